@@ -1,0 +1,120 @@
+/*
+ * b200ann.h -- C ABI of the B200-native exact nearest-neighbour engine.
+ *
+ * This is the drop-in boundary for ONE path of sagspot/the-algorithm: the exact dense scan behind
+ * com.twitter.ann.brute_force.BruteForceIndex and the ann.common Queryable / Appendable contracts.
+ * Plain pointers and sizes only; no C++ or torch types.  A JVM binds it the way the reference binds
+ * Faiss: an opaque native handle + caller-owned flat buffers
+ * (ann/src/main/java/com/twitter/ann/faiss/swig/Index.java:12-37,95-101; swigfaissJNI.java:267-269).
+ * The Scala-side binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every call returns ANN_OK (0) or a negative ann_status; nothing throws, aborts or exits.
+ *     ann_last_error() gives the thread-local message of the last failure on the calling thread.
+ *   - host buffers are caller-owned and only borrowed for the duration of the call; outputs are
+ *     fully written before return.  `_device` variants take device pointers on the index's GPU and a
+ *     cudaStream_t (passed as void*); they enqueue work and return without synchronising.
+ *   - results: nearest first, ascending (Float.compare(distance), id) -- the deterministic refinement
+ *     of the reference's heap order (BruteForceIndex.scala:73-89).  Row q of the outputs has
+ *     out_count[q] = min(max(k,0), size) valid entries; unused slots hold id = -1, distance = +inf.
+ *   - there is no CPU fallback: every compute entry point fails with ANN_ERR_NO_DEVICE / ANN_ERR_CUDA
+ *     when no sm_100 device is usable.
+ *   - a handle may be used from several threads; calls on one handle are serialised internally.  A query
+ *     observes every append whose call returned before the query was issued.
+ */
+#ifndef B200ANN_H_
+#define B200ANN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define ANN_API __attribute__((visibility("default")))
+#else
+#define ANN_API
+#endif
+
+/* Metric ordinals = thrift DistanceMetric (ann/src/main/thrift/.../ann_common.thrift:16-19);
+ * semantics = ann/src/main/scala/com/twitter/ann/common/Metric.scala:88-94 (L2), :119-125 (Cosine),
+ * :150-158 (InnerProduct).  EditDistance (:187-261) is a string metric and is out of scope. */
+typedef enum ann_metric { ANN_METRIC_L2 = 0, ANN_METRIC_COSINE = 1, ANN_METRIC_INNER_PRODUCT = 2 } ann_metric;
+
+typedef enum ann_status {
+    ANN_OK = 0,
+    ANN_ERR_INVALID_ARGUMENT = -1,   /* bad metric / dim / config field                                  */
+    ANN_ERR_NULL_POINTER = -2,       /* a required pointer was NULL                                      */
+    ANN_ERR_DIMENSION_MISMATCH = -3, /* mirrors BadRequest VECTOR_DIMENSION_MISMATCH, ann_common.thrift:146-161 */
+    ANN_ERR_NEGATIVE_K = -4,         /* k < 0 (k == 0 is a success with empty results, BruteForceIndex.scala:83) */
+    ANN_ERR_NO_DEVICE = -5,          /* no CUDA device / not sm_100                                      */
+    ANN_ERR_CUDA = -6,               /* a CUDA runtime or driver call failed (message has the detail)    */
+    ANN_ERR_OUT_OF_MEMORY = -7,      /* host or device allocation failed                                 */
+    ANN_ERR_CANDIDATE_OVERFLOW = -8, /* more near-ties around rank k than the exact selector can hold    */
+    ANN_ERR_UNKNOWN_OPTION = -9
+} ann_status;
+
+/* flags for ann_config.flags */
+#define ANN_FLAG_L2_SQUARED 0x1u /* return squared L2 (Faiss METRIC_L2 style, QueryableIndexAdapter.scala:174) */
+#define ANN_FLAG_NO_SHADOW 0x2u  /* do not keep the bf16 shadow matrix: batched tensor-core path disabled */
+
+typedef struct ann_config {
+    int32_t metric;        /* ann_metric                                                          */
+    int32_t dim;           /* embedding dimension, 1..4096                                        */
+    int64_t capacity_hint; /* rows to reserve up front (0 = grow on demand)                       */
+    int32_t device;        /* CUDA device ordinal                                                 */
+    uint32_t flags;        /* ANN_FLAG_*                                                          */
+} ann_config;
+
+typedef struct ann_index ann_index; /* opaque; owns device memory */
+
+/* BruteForceIndex.apply(metric, futurePool, initialEmbeddings) -- BruteForceIndex.scala:29-37.
+ * The FuturePool stays on the JVM side; initialEmbeddings become one ann_append_batch call. */
+ANN_API int ann_create(const ann_config *cfg, ann_index **out);
+
+/* Releases device memory.  NULL is ignored.  (swig Index.delete(), Index.java:24-37) */
+ANN_API void ann_destroy(ann_index *ix);
+
+/* Appendable.append (Api.scala:133-145; BruteForceIndex.scala:48-52), batched: n rows at once.
+ * ids[n] (NULL => insertion index), rows[n*dim] row-major fp32.  Nothing is validated beyond the
+ * buffer shape (duplicates and non-finite values are stored as given, like the reference). */
+ANN_API int ann_append_batch(ann_index *ix, const int64_t *ids, const float *rows, int64_t n);
+ANN_API int ann_append_batch_device(ann_index *ix, const int64_t *d_ids, const float *d_rows, int64_t n,
+                                    void *stream);
+
+/* Number of rows visible to queries (linkedQueue size, BruteForceIndex.scala:34-36). */
+ANN_API int ann_size(const ann_index *ix, int64_t *n);
+
+/* Queryable.queryWithDistance (Api.scala:40-50; BruteForceIndex.scala:66-91) for b queries at once.
+ * queries[b*dim]; out_ids[b*k], out_dist[b*k], out_count[b] (out_count may be NULL).
+ * Queryable.query (BruteForceIndex.scala:56-64) is the same call with out_dist ignored by the caller.
+ * dim is passed again so that a mismatching caller is refused instead of reading out of bounds. */
+ANN_API int ann_query_batch(ann_index *ix, const float *queries, int32_t b, int32_t dim, int32_t k,
+                            int64_t *out_ids, float *out_dist, int32_t *out_count);
+ANN_API int ann_query_batch_device(ann_index *ix, const float *d_queries, int32_t b, int32_t dim, int32_t k,
+                                   int64_t *d_out_ids, float *d_out_dist, int32_t *d_out_count, void *stream);
+
+/* ComposedQueryable.queryWithDistance (ShardApi.scala:72-86): merge `shards` per-shard result sets
+ * (laid out [shards][b][k], counts [shards][b]) into the global top-k per query, canonical order.
+ * Device pointers: this is the kernel that runs after the NCCL all-gather of each rank's local top-k. */
+ANN_API int ann_merge_topk_device(int32_t device, const int64_t *d_ids, const float *d_dist, const int32_t *d_count,
+                                  int32_t shards, int32_t b, int32_t k, int64_t *d_out_ids, float *d_out_dist,
+                                  int32_t *d_out_count, void *stream);
+
+/* Tuning / introspection.  Options: "path" (0 auto, 1 streaming scan, 2 tensor-core GEMM filter),
+ * "gemm_min_batch".  Stats: "launches" (kernels launched so far), "last_path", "last_candidates",
+ * "scan_fallback_queries", "shadow_bytes", "row_bytes", "n_special". */
+ANN_API int ann_set_option(ann_index *ix, const char *name, int64_t value);
+ANN_API int ann_get_stat(const ann_index *ix, const char *name, int64_t *value);
+
+/* Thread-local message for the last non-zero status returned on this thread ("" if none). */
+ANN_API const char *ann_last_error(void);
+
+/* Library version as major*10000 + minor*100 + patch. */
+ANN_API int ann_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ANN_H_ */

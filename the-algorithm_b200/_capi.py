@@ -1,0 +1,88 @@
+"""ctypes binding of include/b200ann.h -- the same C ABI a JVM would bind through JNI.
+
+Fails loudly when libb200ann.so is missing: there is no CPU fallback behind this module.
+"""
+from __future__ import annotations
+
+import ctypes
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "lib" / "libb200ann.so"
+
+ANN_OK = 0
+ANN_ERR_INVALID_ARGUMENT = -1
+ANN_ERR_NULL_POINTER = -2
+ANN_ERR_DIMENSION_MISMATCH = -3
+ANN_ERR_NEGATIVE_K = -4
+ANN_ERR_NO_DEVICE = -5
+ANN_ERR_CUDA = -6
+ANN_ERR_OUT_OF_MEMORY = -7
+ANN_ERR_CANDIDATE_OVERFLOW = -8
+ANN_ERR_UNKNOWN_OPTION = -9
+
+ANN_FLAG_L2_SQUARED = 0x1
+ANN_FLAG_NO_SHADOW = 0x2
+
+# every symbol include/b200ann.h declares (tests/test_capi_symbols.py checks header <-> library <-> this list)
+SYMBOLS = (
+    "ann_create", "ann_destroy", "ann_append_batch", "ann_append_batch_device", "ann_size", "ann_query_batch",
+    "ann_query_batch_device", "ann_merge_topk_device", "ann_set_option", "ann_get_stat", "ann_last_error", "ann_version",
+)
+
+
+class AnnConfig(ctypes.Structure):
+    _fields_ = [("metric", ctypes.c_int32), ("dim", ctypes.c_int32), ("capacity_hint", ctypes.c_int64),
+                ("device", ctypes.c_int32), ("flags", ctypes.c_uint32)]
+
+
+class AnnError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"b200ann error {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python the-algorithm_b200/build.py` "
+                "(there is no CPU fallback for the CUDA engine)")
+        L = ctypes.CDLL(str(LIB_PATH))
+        vp, i32, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+        L.ann_create.restype = ctypes.c_int
+        L.ann_create.argtypes = [ctypes.POINTER(AnnConfig), ctypes.POINTER(vp)]
+        L.ann_destroy.restype = None
+        L.ann_destroy.argtypes = [vp]
+        L.ann_append_batch.restype = ctypes.c_int
+        L.ann_append_batch.argtypes = [vp, vp, vp, i64]
+        L.ann_append_batch_device.restype = ctypes.c_int
+        L.ann_append_batch_device.argtypes = [vp, vp, vp, i64, vp]
+        L.ann_size.restype = ctypes.c_int
+        L.ann_size.argtypes = [vp, ctypes.POINTER(i64)]
+        L.ann_query_batch.restype = ctypes.c_int
+        L.ann_query_batch.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
+        L.ann_query_batch_device.restype = ctypes.c_int
+        L.ann_query_batch_device.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
+        L.ann_merge_topk_device.restype = ctypes.c_int
+        L.ann_merge_topk_device.argtypes = [i32, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
+        L.ann_set_option.restype = ctypes.c_int
+        L.ann_set_option.argtypes = [vp, ctypes.c_char_p, i64]
+        L.ann_get_stat.restype = ctypes.c_int
+        L.ann_get_stat.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(i64)]
+        L.ann_last_error.restype = ctypes.c_char_p
+        L.ann_last_error.argtypes = []
+        L.ann_version.restype = ctypes.c_int
+        L.ann_version.argtypes = []
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != ANN_OK:
+        raise AnnError(rc, lib().ann_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,269 @@
+"""Host-side mirror of com.twitter.ann.brute_force.BruteForceIndex over the CUDA engine
+(ann/src/main/scala/com/twitter/ann/brute_force/BruteForceIndex.scala:24-92).
+
+    BruteForceIndex.apply(metric, future_pool, initial_embeddings)   <- object BruteForceIndex.apply   (:29-37)
+    index.append(EntityEmbedding(id, embedding)) -> Future[None]     <- append                          (:48-52)
+    index.to_queryable()                                             <- toQueryable                     (:54)
+    index.query(embedding, k, BruteForceRuntimeParams)               <- query                           (:56-64)
+    index.query_with_distance(embedding, k, BruteForceRuntimeParams) <- queryWithDistance               (:66-91)
+plus what a device-resident index adds: append_batch / batch_query_with_distance (whole batches in one call) and
+the raw device-pointer entry points used by the multi-GPU merge and by bench.py.
+
+Every compute call goes through the C ABI (include/b200ann.h); nothing here does distance arithmetic or
+selection on the host, and the module raises if the CUDA library is missing.
+"""
+from __future__ import annotations
+
+import ctypes
+import threading
+from concurrent.futures import Future
+from typing import Iterable, Iterator, List, Optional
+
+import numpy as np
+
+from .. import _capi
+from .common import (Appendable, EntityEmbedding, FuturePool, Metric, NeighborWithDistance, Queryable, RuntimeParams)
+
+
+class _BruteForceRuntimeParams(RuntimeParams):
+    """object BruteForceRuntimeParams extends RuntimeParams (BruteForceIndex.scala:24): no knobs, search is exact."""
+
+    def __repr__(self):
+        return "BruteForceRuntimeParams"
+
+
+BruteForceRuntimeParams = _BruteForceRuntimeParams()
+
+_I64_MIN, _I64_MAX = -(2 ** 63), 2 ** 63 - 1
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+class BruteForceIndex(Appendable, Queryable):
+    DataFileName = "BruteForceFileData"
+    _PENDING_FLUSH = 4096
+
+    def __init__(self, metric: Metric, future_pool: FuturePool, device: int = 0, capacity_hint: int = 0,
+                 l2_squared: bool = False, shadow: bool = True):
+        self.metric = metric
+        self.future_pool = future_pool
+        self.device = device
+        self.dim: Optional[int] = None
+        self._h = ctypes.c_void_p()
+        self._cfg = dict(capacity_hint=capacity_hint, flags=(_capi.ANN_FLAG_L2_SQUARED if l2_squared else 0) |
+                         (0 if shadow else _capi.ANN_FLAG_NO_SHADOW))
+        self._lock = threading.RLock()
+        self._pending_ids: List = []
+        self._pending_rows: List[np.ndarray] = []
+        # generic id type T: ids that are not int64 live in a host table, the device sees the insertion slot
+        self.native_ids = True
+        self._id_table: Optional[List] = None
+        self._n = 0
+
+    # ---- construction -------------------------------------------------------------------------------------
+    @staticmethod
+    def apply(metric: Metric, future_pool: FuturePool, initial_embeddings: Iterable[EntityEmbedding] = (), *,
+              device: int = 0, capacity_hint: int = 0, l2_squared: bool = False, shadow: bool = True) -> "BruteForceIndex":
+        ix = BruteForceIndex(metric, future_pool, device, capacity_hint, l2_squared, shadow)
+        ids, rows = [], []
+        for e in initial_embeddings:
+            ids.append(e.id)
+            rows.append(np.asarray(e.embedding, dtype=np.float32))
+        if rows:
+            ix.append_batch(ids, np.stack(rows))
+        return ix
+
+    def _ensure(self, dim: int):
+        if self._h:
+            if dim != self.dim:
+                raise _capi.AnnError(_capi.ANN_ERR_DIMENSION_MISMATCH,
+                                     f"embedding dimension {dim} != index dimension {self.dim}")
+            return
+        cfg = _capi.AnnConfig(self.metric.ordinal, dim, self._cfg["capacity_hint"], self.device, self._cfg["flags"])
+        _capi.check(_capi.lib().ann_create(ctypes.byref(cfg), ctypes.byref(self._h)))
+        self.dim = dim
+
+    def close(self):
+        with self._lock:
+            if self._h:
+                _capi.lib().ann_destroy(self._h)
+                self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- Appendable ----------------------------------------------------------------------------------------
+    def append(self, entity: EntityEmbedding) -> Future:
+        """One row.  Rows are gathered on the host and reach the device as one batch at the next query / size /
+        flush (or every 4096 rows), so a query still observes every append that returned before it was issued."""
+        def run():
+            with self._lock:
+                self._pending_ids.append(entity.id)
+                self._pending_rows.append(np.asarray(entity.embedding, dtype=np.float32))
+                if len(self._pending_rows) >= self._PENDING_FLUSH:
+                    self.flush()
+        return self.future_pool(run)
+
+    def flush(self):
+        with self._lock:
+            if not self._pending_rows:
+                return
+            ids, rows = self._pending_ids, self._pending_rows
+            self._pending_ids, self._pending_rows = [], []
+            dims = {r.shape[-1] for r in rows}
+            if len(dims) != 1:
+                raise _capi.AnnError(_capi.ANN_ERR_DIMENSION_MISMATCH, "appended embeddings differ in dimension")
+            self.append_batch(ids, np.stack(rows))
+
+    def _device_ids(self, ids, n: int) -> np.ndarray:
+        if ids is None:
+            dev = np.arange(self._n, self._n + n, dtype=np.int64)
+            if self._id_table is not None:
+                self._id_table.extend(dev.tolist())
+            return dev
+        if isinstance(ids, np.ndarray) and ids.dtype.kind in "iu" and self._id_table is None:
+            return np.ascontiguousarray(ids, dtype=np.int64)
+        ids = list(ids)
+        if self._id_table is None and all(isinstance(i, (int, np.integer)) and _I64_MIN <= int(i) <= _I64_MAX for i in ids):
+            return np.asarray(ids, dtype=np.int64)
+        # generic T: slot table.  Ties then break by insertion slot (documented in DESIGN.md).
+        if self._id_table is None:
+            if self._n:
+                raise TypeError("cannot mix native int64 ids with generic ids in one index")
+            self._id_table = []
+            self.native_ids = False
+        self._id_table.extend(ids)
+        return np.arange(self._n, self._n + n, dtype=np.int64)
+
+    def append_batch(self, ids, rows) -> None:
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        if rows.ndim != 2:
+            raise ValueError("rows must be [n, dim]")
+        n = rows.shape[0]
+        with self._lock:
+            if n == 0:
+                return
+            self._ensure(rows.shape[1])
+            dev_ids = self._device_ids(ids, n)
+            if dev_ids.shape[0] != n:
+                raise ValueError("ids and rows differ in length")
+            _capi.check(_capi.lib().ann_append_batch(self._h, _ptr(dev_ids), _ptr(rows), n))
+            self._n += n
+
+    def append_batch_device(self, ids_t, rows_t, stream: int = 0) -> None:
+        """rows_t: CUDA float32 [n, dim] tensor, ids_t: CUDA int64 [n] tensor (or None) on this index's device."""
+        with self._lock:
+            n = int(rows_t.shape[0])
+            if n == 0:
+                return
+            self._ensure(int(rows_t.shape[1]))
+            if self._id_table is not None:
+                raise TypeError("device appends need native int64 ids")
+            _capi.check(_capi.lib().ann_append_batch_device(
+                self._h, None if ids_t is None else ctypes.c_void_p(ids_t.data_ptr()), ctypes.c_void_p(rows_t.data_ptr()),
+                n, ctypes.c_void_p(stream)))
+            self._n += n
+
+    def to_queryable(self) -> "BruteForceIndex":
+        return self
+
+    def size(self) -> int:
+        with self._lock:
+            self.flush()
+            if not self._h:
+                return 0
+            n = ctypes.c_int64()
+            _capi.check(_capi.lib().ann_size(self._h, ctypes.byref(n)))
+            return int(n.value)
+
+    # ---- Queryable -----------------------------------------------------------------------------------------
+    def id_of(self, raw):
+        raw = int(raw)
+        return raw if self._id_table is None else self._id_table[raw]
+
+    def batch_query_with_distance(self, embeddings, num_of_neighbors: int):
+        """b queries in one call.  Returns (ids [b,k] int64 (device ids), distances [b,k] fp32, counts [b])."""
+        q = np.ascontiguousarray(embeddings, dtype=np.float32)
+        if q.ndim != 2:
+            raise ValueError("embeddings must be [b, dim]")
+        b, k = q.shape[0], int(num_of_neighbors)
+        with self._lock:
+            self.flush()
+            kk = max(k, 0)
+            out_ids = np.full((b, kk), -1, dtype=np.int64)
+            out_dist = np.full((b, kk), np.inf, dtype=np.float32)
+            out_cnt = np.zeros(b, dtype=np.int32)
+            if k < 0:
+                raise _capi.AnnError(_capi.ANN_ERR_NEGATIVE_K, "numOfNeighbours < 0")
+            if not self._h:  # nothing appended yet: BruteForceIndex.scala:76-89 yields an empty list
+                return out_ids, out_dist, out_cnt
+            _capi.check(_capi.lib().ann_query_batch(self._h, _ptr(q), b, q.shape[1], k, _ptr(out_ids), _ptr(out_dist),
+                                                    _ptr(out_cnt)))
+            return out_ids, out_dist, out_cnt
+
+    def query_batch_device(self, queries_t, k: int, out_ids_t, out_dist_t, out_count_t, stream: int = 0) -> None:
+        """Device-pointer query: CUDA tensors in, CUDA tensors out, enqueued on `stream` without synchronising.
+        Call raise_pending_error() after the stream has been synchronised."""
+        with self._lock:
+            self.flush()
+            _capi.check(_capi.lib().ann_query_batch_device(
+                self._h, ctypes.c_void_p(queries_t.data_ptr()), int(queries_t.shape[0]), int(queries_t.shape[1]), int(k),
+                ctypes.c_void_p(out_ids_t.data_ptr()), ctypes.c_void_p(out_dist_t.data_ptr()),
+                None if out_count_t is None else ctypes.c_void_p(out_count_t.data_ptr()), ctypes.c_void_p(stream)))
+
+    def raise_pending_error(self) -> None:
+        v = ctypes.c_int64()
+        _capi.check(_capi.lib().ann_get_stat(self._h, b"pending_error", ctypes.byref(v)))
+
+    def query_with_distance(self, embedding, num_of_neighbors: int, runtime_params=BruteForceRuntimeParams) -> Future:
+        def run():
+            e = np.asarray(embedding, dtype=np.float32).reshape(1, -1)
+            if num_of_neighbors <= 0:  # every push is popped again (BruteForceIndex.scala:83-85)
+                return []
+            ids, dist, cnt = self.batch_query_with_distance(e, num_of_neighbors)
+            return [NeighborWithDistance(self.id_of(ids[0, j]), self.metric.from_absolute_distance(dist[0, j]))
+                    for j in range(int(cnt[0]))]
+        return self.future_pool(run)
+
+    def query(self, embedding, num_of_neighbors: int, runtime_params=BruteForceRuntimeParams) -> Future:
+        def run():
+            e = np.asarray(embedding, dtype=np.float32).reshape(1, -1)
+            if num_of_neighbors <= 0:
+                return []
+            ids, _, cnt = self.batch_query_with_distance(e, num_of_neighbors)
+            return [self.id_of(ids[0, j]) for j in range(int(cnt[0]))]
+        return self.future_pool(run)
+
+    # ---- tuning / introspection ------------------------------------------------------------------------------
+    def set_option(self, name: str, value: int) -> None:
+        _capi.check(_capi.lib().ann_set_option(self._h, name.encode(), int(value)))
+
+    def stat(self, name: str) -> int:
+        v = ctypes.c_int64()
+        _capi.check(_capi.lib().ann_get_stat(self._h, name.encode(), ctypes.byref(v)))
+        return int(v.value)
+
+
+def merge_topk_device(ids_t, dist_t, count_t, k: int, stream: int = 0):
+    """K5 on CUDA tensors: ids/dist [S, b, k], counts [S, b] -> (ids [b,k], dist [b,k], counts [b]) on the same device.
+    Replaces ComposedQueryable's flatten/sort/take (ShardApi.scala:77-85)."""
+    import torch
+
+    s, b = int(ids_t.shape[0]), int(ids_t.shape[1])
+    kk = int(ids_t.shape[2])
+    dev = ids_t.device
+    out_ids = torch.full((b, kk), -1, dtype=torch.int64, device=dev)
+    out_dist = torch.full((b, kk), float("inf"), dtype=torch.float32, device=dev)
+    out_cnt = torch.zeros((b,), dtype=torch.int32, device=dev)
+    if k > 0 and b > 0:
+        assert kk == k
+        _capi.check(_capi.lib().ann_merge_topk_device(
+            dev.index or 0, ctypes.c_void_p(ids_t.data_ptr()), ctypes.c_void_p(dist_t.data_ptr()),
+            ctypes.c_void_p(count_t.data_ptr()), s, b, k, ctypes.c_void_p(out_ids.data_ptr()),
+            ctypes.c_void_p(out_dist.data_ptr()), ctypes.c_void_p(out_cnt.data_ptr()), ctypes.c_void_p(stream)))
+    return out_ids, out_dist, out_cnt

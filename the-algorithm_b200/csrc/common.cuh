@@ -1,0 +1,101 @@
+// common.cuh -- shared device helpers for the exact-kNN kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace b200ann {
+
+constexpr int kMetricL2 = 0, kMetricCosine = 1, kMetricIP = 2;
+
+// Candidate entry: (orderable(g) << 32) | local_row, g = "badness" (smaller is nearer).
+//   InnerProduct: g = -dot      Cosine: g = -dot/|a|      L2: g = sum (a-b)^2  (scan)  or  |a|^2/2 - a.b (gemm)
+// Sorting entries as u64 ascending orders by g then row.
+typedef unsigned long long entry_t;
+
+// java.lang.Float.compare as an unsigned key (ann/.../common/Metric.scala:17-36):
+// -0.0 < +0.0, +inf < NaN, all NaN equal.
+__host__ __device__ __forceinline__ uint32_t float_order_key(float f) {
+#ifdef __CUDA_ARCH__
+    uint32_t b = __float_as_uint(f);
+#else
+    union { float f; uint32_t u; } c; c.f = f; uint32_t b = c.u;
+#endif
+    if (f != f) return 0xFFFFFFFFu;
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float float_from_order_key(uint32_t k) {
+    uint32_t b = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(b);
+#else
+    union { float f; uint32_t u; } c; c.u = b; return c.f;
+#endif
+}
+
+__device__ __forceinline__ entry_t make_entry(float g, uint32_t row) {
+    return ((entry_t)float_order_key(g) << 32) | (entry_t)row;
+}
+__device__ __forceinline__ float entry_g(entry_t e) { return float_from_order_key((uint32_t)(e >> 32)); }
+__device__ __forceinline__ uint32_t entry_row(entry_t e) { return (uint32_t)(e & 0xFFFFFFFFull); }
+
+constexpr entry_t kEntryPad = 0xFFFFFFFFFFFFFFFFull;
+
+// ---- per-query state shared by the scan, the GEMM filter, compaction and finalize -----------------
+// tau_key: orderable key of the current acceptance threshold on g (accept g <= tau).  Starts at +inf.
+struct QueryState {
+    float eps_abs;   // absolute slack on g covering approximate-score error + fp32 tie granularity
+    float eps_rel;   // relative slack on |g|
+    float qnorm;     // |b|
+    float qnorm2;    // |b|^2
+    uint32_t tau_key;
+    uint32_t pool_count;     // entries written to this query's pool (may exceed capacity => overflow)
+    uint32_t special_count;  // rows whose approximate score was not finite (always rescored exactly)
+    uint32_t flags;          // bit0: pool overflow, bit1: special overflow, bit2: survivor overflow
+};
+
+constexpr uint32_t kFlagPoolOverflow = 1u, kFlagSpecialOverflow = 2u, kFlagSurvivorOverflow = 4u;
+constexpr int kSpecialCap = 256;  // per query
+
+// threshold with margin: everything with g <= kth + margin(kth) may still belong to the exact top-k
+__device__ __forceinline__ float widen(float kth, float eps_abs, float eps_rel) {
+    return kth + (2.0f * eps_abs + 2.0f * eps_rel * fabsf(kth));
+}
+
+// ---- mbarrier / bulk-copy PTX (Hopper+; the only async-copy path used by the scan) -----------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+}  // namespace b200ann

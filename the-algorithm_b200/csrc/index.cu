@@ -1,0 +1,594 @@
+// index.cu -- the C ABI (include/b200ann.h): device-resident index storage, batched append, query dispatch.
+//
+// Mirrors, for one GPU shard, com.twitter.ann.brute_force.BruteForceIndex
+// (ann/src/main/scala/com/twitter/ann/brute_force/BruteForceIndex.scala:26-92):
+//   storage  : ConcurrentLinkedQueue[EntityEmbedding[T]]  ->  row-major fp32 matrix [n][pitch] in HBM, 128-byte
+//              aligned base, int64 ids, per-row norms, optional bf16 shadow operand for the tensor-core filter
+//   append   : linkedQueue.add(e) per row                 ->  one H2D copy + one norms/shadow kernel per batch
+//   query    : per-query scan + PriorityQueue             ->  approximate filter (streaming scan or tcgen05 GEMM)
+//              whose survivors are rescored exactly and ordered by (Float.compare(distance), id)
+// There is no CPU fallback: without a usable sm_100 device every compute entry point returns an error.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/b200ann.h"
+#include "kernels.h"
+
+using namespace b200ann;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                         \
+    do {                                                                                                       \
+        cudaError_t _e = (expr);                                                                               \
+        if (_e != cudaSuccess) {                                                                               \
+            char _b[512];                                                                                      \
+            snprintf(_b, sizeof(_b), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            (void)cudaGetLastError();                                                                          \
+            return fail(_e == cudaErrorMemoryAllocation ? ANN_ERR_OUT_OF_MEMORY : ANN_ERR_CUDA, _b);           \
+        }                                                                                                      \
+    } while (0)
+
+constexpr int kMaxDim = 1024;
+constexpr int kMaxK = 1024;
+constexpr int kScanGroup = 64;       // queries finalized together on the scan path
+constexpr int kScanPoolCap = 16384;  // pool entries per query, scan path
+constexpr int kGemmPoolCap = 4096;   // pool entries per query, gemm path
+constexpr int kPubStride = 256;
+
+struct DeviceScalars {
+    uint32_t max_norm_bits;
+    uint32_t error_flags;
+    unsigned long long n_special;
+    unsigned long long bad_queries;
+};
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;  // elements
+    cudaError_t ensure(size_t want) {
+        if (want <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e == cudaSuccess) n = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+__global__ void iota_ids_kernel(int64_t* ids, long long row0, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        ids[row0 + i] = row0 + i;
+}
+
+__global__ void collect_flags_kernel(const QueryState* qs, int b, DeviceScalars* sc) {
+    uint32_t f = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < b; i += gridDim.x * blockDim.x) f |= qs[i].flags;
+    f = __reduce_or_sync(0xFFFFFFFFu, f);
+    if ((threadIdx.x & 31) == 0 && f) atomicOr(&sc->error_flags, f);
+}
+
+}  // namespace
+
+struct ann_index {
+    ann_config cfg{};
+    int dim = 0, pitch = 0, kp = 0, metric = 0;
+    bool l2_squared = false, use_shadow = true;
+    int device = 0, sm_count = 0;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+
+    long long cap = 0, n = 0;
+    float* rows = nullptr;
+    int64_t* ids = nullptr;
+    float* inv_norm = nullptr;
+    float* row_norm = nullptr;
+    __nv_bfloat16* shadow = nullptr;
+    DeviceScalars* scalars = nullptr;
+    unsigned long long n_special = 0;
+
+    // scratch
+    DevBuf<float> q_in, q_padded, out_dist;
+    DevBuf<__nv_bfloat16> q_shadow;
+    DevBuf<QueryState> qstate;
+    DevBuf<entry_t> pool;
+    DevBuf<uint32_t> special_rows, pub_keys;
+    DevBuf<int64_t> out_ids;
+    DevBuf<int32_t> out_count;
+    DevBuf<int64_t> stage_ids;
+    DevBuf<float> stage_rows;
+
+    // options / stats
+    int path_opt = 0, gemm_min_batch = 16;
+    long long launches = 0, last_path = 0, scan_fallback_queries = 0;
+};
+
+namespace {
+
+int set_device(const ann_index* ix) {
+    CUDA_TRY(cudaSetDevice(ix->device));
+    return ANN_OK;
+}
+
+int grow(ann_index* ix, long long need, cudaStream_t st) {
+    if (need <= ix->cap) return ANN_OK;
+    long long ncap = std::max<long long>({need, ix->cap * 2, 1024});
+    ncap = (ncap + 127) / 128 * 128;
+    float* nrows = nullptr;
+    int64_t* nids = nullptr;
+    float *ninv = nullptr, *nnorm = nullptr;
+    __nv_bfloat16* nsh = nullptr;
+    CUDA_TRY(cudaMalloc(&nrows, (size_t)ncap * ix->pitch * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&nids, (size_t)ncap * sizeof(int64_t)));
+    CUDA_TRY(cudaMalloc(&nnorm, (size_t)ncap * sizeof(float)));
+    if (ix->metric == kMetricCosine) CUDA_TRY(cudaMalloc(&ninv, (size_t)ncap * sizeof(float)));
+    if (ix->use_shadow) CUDA_TRY(cudaMalloc(&nsh, (size_t)ncap * ix->kp * sizeof(__nv_bfloat16)));
+    if (ix->n > 0) {
+        CUDA_TRY(cudaMemcpyAsync(nrows, ix->rows, (size_t)ix->n * ix->pitch * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(nids, ix->ids, (size_t)ix->n * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(nnorm, ix->row_norm, (size_t)ix->n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        if (ninv) CUDA_TRY(cudaMemcpyAsync(ninv, ix->inv_norm, (size_t)ix->n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        if (nsh)
+            CUDA_TRY(cudaMemcpyAsync(nsh, ix->shadow, (size_t)ix->n * ix->kp * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice, st));
+    }
+    // zero the tail: pad columns of `rows` and the whole shadow tail must read as 0
+    CUDA_TRY(cudaMemsetAsync(nrows + (size_t)ix->n * ix->pitch, 0, (size_t)(ncap - ix->n) * ix->pitch * sizeof(float), st));
+    if (nsh) CUDA_TRY(cudaMemsetAsync(nsh + (size_t)ix->n * ix->kp, 0, (size_t)(ncap - ix->n) * ix->kp * sizeof(__nv_bfloat16), st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    cudaFree(ix->rows);
+    cudaFree(ix->ids);
+    cudaFree(ix->row_norm);
+    cudaFree(ix->inv_norm);
+    cudaFree(ix->shadow);
+    ix->rows = nrows;
+    ix->ids = nids;
+    ix->row_norm = nnorm;
+    ix->inv_norm = ninv;
+    ix->shadow = nsh;
+    ix->cap = ncap;
+    return ANN_OK;
+}
+
+// rows/ids already on the device (or staged there); place them and run K1
+int append_device_core(ann_index* ix, const int64_t* d_ids, const float* d_rows, long long n_new, cudaStream_t st) {
+    int rc = grow(ix, ix->n + n_new, st);
+    if (rc) return rc;
+    float* dst = ix->rows + (size_t)ix->n * ix->pitch;
+    if (ix->pitch == ix->dim) {
+        CUDA_TRY(cudaMemcpyAsync(dst, d_rows, (size_t)n_new * ix->dim * sizeof(float), cudaMemcpyDefault, st));
+    } else {
+        CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)ix->pitch * sizeof(float), d_rows, (size_t)ix->dim * sizeof(float),
+                                   (size_t)ix->dim * sizeof(float), (size_t)n_new, cudaMemcpyDefault, st));
+    }
+    if (d_ids) {
+        CUDA_TRY(cudaMemcpyAsync(ix->ids + ix->n, d_ids, (size_t)n_new * sizeof(int64_t), cudaMemcpyDefault, st));
+    } else {
+        int blocks = (int)std::min<long long>((n_new + 255) / 256, 1024);
+        iota_ids_kernel<<<blocks, 256, 0, st>>>(ix->ids, ix->n, n_new);
+        CUDA_TRY(cudaGetLastError());
+        ix->launches++;
+    }
+    AppendParams ap{};
+    ap.rows = ix->rows;
+    ap.row0 = ix->n;
+    ap.n_new = n_new;
+    ap.dim = ix->dim;
+    ap.pitch = ix->pitch;
+    ap.metric = ix->metric;
+    ap.inv_norm = ix->inv_norm;
+    ap.row_norm = ix->row_norm;
+    ap.shadow = ix->shadow;
+    ap.kp = ix->kp;
+    ap.max_norm_bits = &ix->scalars->max_norm_bits;
+    ap.n_special = &ix->scalars->n_special;
+    CUDA_TRY(launch_append(ap, st));
+    ix->launches++;
+    return ANN_OK;
+}
+
+struct ScanPlan {
+    int qb, warps, cap, grid, r_pub, j_pub;
+    size_t smem;
+};
+
+int plan_scan(const ann_index* ix, int b, int k_eff, ScanPlan* pl) {
+    int cap = 1024;
+    while (cap < 4 * k_eff) cap <<= 1;
+    int qb = b >= 8 ? 8 : (b > 2 ? 4 : b);
+    while (qb > 1 && (size_t)qb * cap * 8 > 64 * 1024) qb >>= 1;
+    const size_t tile_bytes = (size_t)32 * ix->pitch * sizeof(float);
+    int warps = 0;
+    for (;;) {
+        size_t fixed = scan_smem_bytes(qb, ix->pitch, 0, cap);
+        if (fixed + tile_bytes <= ix->smem_optin) {
+            warps = (int)std::min<size_t>(8, (ix->smem_optin - fixed) / tile_bytes);
+            break;
+        }
+        if (qb == 1) break;
+        qb >>= 1;
+    }
+    if (warps < 1) return fail(ANN_ERR_INVALID_ARGUMENT, "dimension too large for the streaming scan");
+    long long n_tiles = (ix->n + 31) / 32;
+    int grid = (int)std::min<long long>(ix->sm_count, std::max<long long>(1, (n_tiles + warps - 1) / warps));
+    grid = std::min(grid, kPubStride);
+    pl->qb = qb;
+    pl->warps = warps;
+    pl->cap = cap;
+    pl->grid = grid;
+    pl->j_pub = std::max(1, std::min(k_eff, (3 * grid) / 4));
+    pl->r_pub = (k_eff + pl->j_pub - 1) / pl->j_pub;
+    pl->smem = scan_smem_bytes(qb, ix->pitch, warps, cap);
+    return ANN_OK;
+}
+
+int query_scan(ann_index* ix, const float* d_queries, int b, int k_eff, int k_out, int64_t* d_out_ids, float* d_out_dist,
+               int32_t* d_out_count, cudaStream_t st) {
+    ScanPlan pl;
+    int rc = plan_scan(ix, b, k_eff, &pl);
+    if (rc) return rc;
+    CUDA_TRY(ix->q_padded.ensure((size_t)b * ix->pitch));
+    CUDA_TRY(ix->qstate.ensure((size_t)b));
+    CUDA_TRY(ix->pub_keys.ensure((size_t)b * kPubStride));
+    const int group = std::min(b, kScanGroup);
+    CUDA_TRY(ix->pool.ensure((size_t)group * kScanPoolCap));
+    CUDA_TRY(ix->special_rows.ensure((size_t)std::max(group, 1) * kSpecialCap));
+
+    PrepParams pp{};
+    pp.queries = d_queries;
+    pp.b = b;
+    pp.dim = ix->dim;
+    pp.pitch = ix->pitch;
+    pp.metric = ix->metric;
+    pp.kp = ix->kp;
+    pp.q_padded = ix->q_padded.p;
+    pp.q_shadow = nullptr;
+    pp.qstate = ix->qstate.p;
+    pp.max_norm_bits = &ix->scalars->max_norm_bits;
+    pp.path = 1;
+    pp.pub_keys = ix->pub_keys.p;
+    pp.pub_stride = kPubStride;
+    pp.bad_queries = &ix->scalars->bad_queries;
+    CUDA_TRY(launch_prep_queries(pp, st));
+    ix->launches++;
+
+    for (int g0 = 0; g0 < b; g0 += group) {
+        const int gn = std::min(group, b - g0);
+        for (int q0 = 0; q0 < gn; q0 += pl.qb) {
+            ScanParams sp{};
+            sp.rows = ix->rows;
+            sp.n_rows = ix->n;
+            sp.pitch = ix->pitch;
+            sp.metric = ix->metric;
+            sp.inv_norm = ix->inv_norm;
+            sp.queries = ix->q_padded.p + (size_t)(g0 + q0) * ix->pitch;
+            sp.nq = std::min(pl.qb, gn - q0);
+            sp.qstate = ix->qstate.p + g0 + q0;
+            sp.pool = ix->pool.p + (size_t)q0 * kScanPoolCap;
+            sp.pool_cap = kScanPoolCap;
+            sp.special_rows = ix->special_rows.p + (size_t)q0 * kSpecialCap;
+            sp.pub_keys = ix->pub_keys.p + (size_t)(g0 + q0) * kPubStride;
+            sp.pub_stride = kPubStride;
+            sp.k = k_eff;
+            sp.r_pub = pl.r_pub;
+            sp.j_pub = pl.j_pub;
+            sp.warps = pl.warps;
+            sp.cap = pl.cap;
+            CUDA_TRY(launch_scan(sp, pl.qb, pl.grid, pl.smem, st));
+            ix->launches++;
+        }
+        SelectParams fp{};
+        fp.qstate = ix->qstate.p + g0;
+        fp.pool = ix->pool.p;
+        fp.pool_cap = kScanPoolCap;
+        fp.special_rows = ix->special_rows.p;
+        fp.pub_keys = ix->pub_keys.p + (size_t)g0 * kPubStride;
+        fp.pub_stride = kPubStride;
+        fp.pub_count = pl.grid;
+        fp.j_pub = pl.j_pub;
+        fp.k = k_eff;
+        fp.rows = ix->rows;
+        fp.ids = ix->ids;
+        fp.n_rows = ix->n;
+        fp.dim = ix->dim;
+        fp.pitch = ix->pitch;
+        fp.metric = ix->metric;
+        fp.l2_squared = ix->l2_squared ? 1 : 0;
+        fp.queries = ix->q_padded.p + (size_t)g0 * ix->pitch;
+        fp.q_pitch = ix->pitch;
+        fp.out_ids = d_out_ids + (size_t)g0 * k_out;
+        fp.out_dist = d_out_dist + (size_t)g0 * k_out;
+        fp.out_count = d_out_count ? d_out_count + g0 : nullptr;
+        fp.k_out = k_out;
+        CUDA_TRY(launch_finalize(fp, gn, st));
+        ix->launches++;
+    }
+    collect_flags_kernel<<<std::min(64, (b + 255) / 256), 256, 0, st>>>(ix->qstate.p, b, ix->scalars);
+    CUDA_TRY(cudaGetLastError());
+    ix->launches++;
+    ix->last_path = 1;
+    return ANN_OK;
+}
+
+int query_core(ann_index* ix, const float* d_queries, int b, int k, int64_t* d_out_ids, float* d_out_dist,
+               int32_t* d_out_count, cudaStream_t st) {
+    if (b == 0) return ANN_OK;
+    const long long n = ix->n;
+    if (k == 0 || n == 0) {
+        if (k > 0 || d_out_count) {
+            CUDA_TRY(launch_fill_empty(d_out_ids, d_out_dist, d_out_count, b, k, st));
+            ix->launches++;
+        }
+        return ANN_OK;
+    }
+    const int k_eff = (int)std::min<long long>(k, n);
+    if (k_eff > kMaxK) return fail(ANN_ERR_INVALID_ARGUMENT, "min(k, size) > 1024 is not supported");
+    return query_scan(ix, d_queries, b, k_eff, k, d_out_ids, d_out_dist, d_out_count, st);
+}
+
+// read and clear the sticky device error word; call after a synchronisation point
+int check_device_flags(ann_index* ix, cudaStream_t st) {
+    DeviceScalars h{};
+    CUDA_TRY(cudaMemcpyAsync(&h, ix->scalars, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    ix->n_special = h.n_special;
+    if (h.error_flags) {
+        CUDA_TRY(cudaMemsetAsync(&ix->scalars->error_flags, 0, sizeof(uint32_t), st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        char msg[256];
+        snprintf(msg, sizeof(msg),
+                 "exact selector overflow (flags=0x%x): too many rows tie within the error margin of rank k, or too many "
+                 "non-finite scores",
+                 h.error_flags);
+        return fail(ANN_ERR_CANDIDATE_OVERFLOW, msg);
+    }
+    return ANN_OK;
+}
+
+}  // namespace
+
+// ================================================================== C ABI =====================================
+
+extern "C" {
+
+int ann_version(void) { return 100; }
+
+const char* ann_last_error(void) { return g_last_error.c_str(); }
+
+int ann_create(const ann_config* cfg, ann_index** out) {
+    if (!cfg || !out) return fail(ANN_ERR_NULL_POINTER, "ann_create: cfg/out is NULL");
+    *out = nullptr;
+    if (cfg->metric < 0 || cfg->metric > 2) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_create: unknown metric ordinal");
+    if (cfg->dim < 1 || cfg->dim > kMaxDim) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_create: dim must be in 1..1024");
+    if (cfg->capacity_hint < 0) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_create: negative capacity_hint");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        (void)cudaGetLastError();
+        return fail(ANN_ERR_NO_DEVICE, "ann_create: no CUDA device (this engine has no CPU fallback)");
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_create: bad device ordinal");
+    cudaDeviceProp prop{};
+    CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) {
+        char msg[160];
+        snprintf(msg, sizeof(msg), "ann_create: device %d is sm_%d%d; this library is built for sm_100a only", cfg->device,
+                 prop.major, prop.minor);
+        return fail(ANN_ERR_NO_DEVICE, msg);
+    }
+    ann_index* ix = new (std::nothrow) ann_index();
+    if (!ix) return fail(ANN_ERR_OUT_OF_MEMORY, "ann_create: host allocation failed");
+    ix->cfg = *cfg;
+    ix->dim = cfg->dim;
+    ix->metric = cfg->metric;
+    ix->pitch = (cfg->dim + 3) / 4 * 4;
+    ix->l2_squared = (cfg->flags & ANN_FLAG_L2_SQUARED) != 0;
+    ix->use_shadow = (cfg->flags & ANN_FLAG_NO_SHADOW) == 0;
+    ix->kp = (cfg->dim + (cfg->metric == kMetricL2 ? 3 : 0) + 7) / 8 * 8;
+    ix->device = cfg->device;
+    ix->sm_count = prop.multiProcessorCount;
+    ix->smem_optin = prop.sharedMemPerBlockOptin;
+    auto cleanup = [&](int rc) {
+        ann_destroy(ix);
+        return rc;
+    };
+    if (cudaSetDevice(ix->device) != cudaSuccess) return cleanup(fail(ANN_ERR_CUDA, "cudaSetDevice failed"));
+    if (cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking) != cudaSuccess)
+        return cleanup(fail(ANN_ERR_CUDA, "cudaStreamCreate failed"));
+    if (cudaMalloc(&ix->scalars, sizeof(DeviceScalars)) != cudaSuccess)
+        return cleanup(fail(ANN_ERR_OUT_OF_MEMORY, "cudaMalloc failed"));
+    if (cudaMemsetAsync(ix->scalars, 0, sizeof(DeviceScalars), ix->stream) != cudaSuccess)
+        return cleanup(fail(ANN_ERR_CUDA, "cudaMemset failed"));
+    if (cfg->capacity_hint > 0) {
+        int rc = grow(ix, cfg->capacity_hint, ix->stream);
+        if (rc) return cleanup(rc);
+    }
+    if (cudaStreamSynchronize(ix->stream) != cudaSuccess) return cleanup(fail(ANN_ERR_CUDA, "stream sync failed"));
+    *out = ix;
+    return ANN_OK;
+}
+
+void ann_destroy(ann_index* ix) {
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    if (ix->stream) cudaStreamSynchronize(ix->stream);
+    cudaFree(ix->rows);
+    cudaFree(ix->ids);
+    cudaFree(ix->inv_norm);
+    cudaFree(ix->row_norm);
+    cudaFree(ix->shadow);
+    cudaFree(ix->scalars);
+    ix->q_in.release();
+    ix->q_padded.release();
+    ix->out_dist.release();
+    ix->q_shadow.release();
+    ix->qstate.release();
+    ix->pool.release();
+    ix->special_rows.release();
+    ix->pub_keys.release();
+    ix->out_ids.release();
+    ix->out_count.release();
+    ix->stage_ids.release();
+    ix->stage_rows.release();
+    if (ix->stream) cudaStreamDestroy(ix->stream);
+    (void)cudaGetLastError();
+    delete ix;
+}
+
+int ann_size(const ann_index* ix, int64_t* n) {
+    if (!ix || !n) return fail(ANN_ERR_NULL_POINTER, "ann_size: NULL argument");
+    *n = ix->n;
+    return ANN_OK;
+}
+
+int ann_append_batch(ann_index* ix, const int64_t* ids, const float* rows, int64_t n) {
+    if (!ix) return fail(ANN_ERR_NULL_POINTER, "ann_append_batch: index is NULL");
+    if (n < 0) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_append_batch: n < 0");
+    if (n == 0) return ANN_OK;
+    if (!rows) return fail(ANN_ERR_NULL_POINTER, "ann_append_batch: rows is NULL");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    int rc = set_device(ix);
+    if (rc) return rc;
+    // host pointers go straight into place (cudaMemcpyDefault): no staging copy of the batch
+    rc = append_device_core(ix, ids, rows, n, ix->stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaStreamSynchronize(ix->stream));
+    ix->n += n;
+    return check_device_flags(ix, ix->stream);
+}
+
+int ann_append_batch_device(ann_index* ix, const int64_t* d_ids, const float* d_rows, int64_t n, void* stream) {
+    if (!ix) return fail(ANN_ERR_NULL_POINTER, "ann_append_batch_device: index is NULL");
+    if (n < 0) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_append_batch_device: n < 0");
+    if (n == 0) return ANN_OK;
+    if (!d_rows) return fail(ANN_ERR_NULL_POINTER, "ann_append_batch_device: rows is NULL");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    int rc = set_device(ix);
+    if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    rc = append_device_core(ix, d_ids, d_rows, n, st);
+    if (rc) return rc;
+    // the special-row census decides which query kernels are legal, so it must be current
+    CUDA_TRY(cudaStreamSynchronize(st));
+    ix->n += n;
+    return check_device_flags(ix, st);
+}
+
+int ann_query_batch_device(ann_index* ix, const float* d_queries, int32_t b, int32_t dim, int32_t k, int64_t* d_out_ids,
+                           float* d_out_dist, int32_t* d_out_count, void* stream) {
+    if (!ix) return fail(ANN_ERR_NULL_POINTER, "ann_query_batch_device: index is NULL");
+    if (b < 0) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_query_batch_device: b < 0");
+    if (k < 0) return fail(ANN_ERR_NEGATIVE_K, "ann_query_batch_device: k < 0");
+    if (dim != ix->dim) return fail(ANN_ERR_DIMENSION_MISMATCH, "ann_query_batch_device: query dimension != index dimension");
+    if (b == 0) return ANN_OK;
+    if (!d_queries || (k > 0 && (!d_out_ids || !d_out_dist)))
+        return fail(ANN_ERR_NULL_POINTER, "ann_query_batch_device: NULL buffer");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    int rc = set_device(ix);
+    if (rc) return rc;
+    cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    return query_core(ix, d_queries, b, k, d_out_ids, d_out_dist, d_out_count, st);
+}
+
+int ann_query_batch(ann_index* ix, const float* queries, int32_t b, int32_t dim, int32_t k, int64_t* out_ids, float* out_dist,
+                    int32_t* out_count) {
+    if (!ix) return fail(ANN_ERR_NULL_POINTER, "ann_query_batch: index is NULL");
+    if (b < 0) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_query_batch: b < 0");
+    if (k < 0) return fail(ANN_ERR_NEGATIVE_K, "ann_query_batch: k < 0");
+    if (dim != ix->dim) return fail(ANN_ERR_DIMENSION_MISMATCH, "ann_query_batch: query dimension != index dimension");
+    if (b == 0) return ANN_OK;
+    if (!queries || (k > 0 && (!out_ids || !out_dist))) return fail(ANN_ERR_NULL_POINTER, "ann_query_batch: NULL buffer");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    int rc = set_device(ix);
+    if (rc) return rc;
+    cudaStream_t st = ix->stream;
+    const size_t nk = (size_t)b * (size_t)std::max(k, 1);
+    CUDA_TRY(ix->q_in.ensure((size_t)b * ix->dim));
+    CUDA_TRY(ix->out_ids.ensure(nk));
+    CUDA_TRY(ix->out_dist.ensure(nk));
+    CUDA_TRY(ix->out_count.ensure((size_t)b));
+    CUDA_TRY(cudaMemcpyAsync(ix->q_in.p, queries, (size_t)b * ix->dim * sizeof(float), cudaMemcpyHostToDevice, st));
+    rc = query_core(ix, ix->q_in.p, b, k, ix->out_ids.p, ix->out_dist.p, ix->out_count.p, st);
+    if (rc) return rc;
+    if (k > 0) {
+        CUDA_TRY(cudaMemcpyAsync(out_ids, ix->out_ids.p, (size_t)b * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(out_dist, ix->out_dist.p, (size_t)b * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+    }
+    if (out_count) CUDA_TRY(cudaMemcpyAsync(out_count, ix->out_count.p, (size_t)b * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return check_device_flags(ix, st);
+}
+
+int ann_merge_topk_device(int32_t device, const int64_t* d_ids, const float* d_dist, const int32_t* d_count, int32_t shards,
+                          int32_t b, int32_t k, int64_t* d_out_ids, float* d_out_dist, int32_t* d_out_count, void* stream) {
+    if (shards < 1 || b < 0) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_merge_topk_device: shards < 1 or b < 0");
+    if (k < 0) return fail(ANN_ERR_NEGATIVE_K, "ann_merge_topk_device: k < 0");
+    if (b == 0 || k == 0) return ANN_OK;
+    if (!d_ids || !d_dist || !d_count || !d_out_ids || !d_out_dist)
+        return fail(ANN_ERR_NULL_POINTER, "ann_merge_topk_device: NULL buffer");
+    if ((long long)shards * k > 16384) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_merge_topk_device: shards*k > 16384");
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(launch_merge(d_ids, d_dist, d_count, shards, b, k, d_out_ids, d_out_dist, d_out_count, (cudaStream_t)stream));
+    return ANN_OK;
+}
+
+int ann_set_option(ann_index* ix, const char* name, int64_t value) {
+    if (!ix || !name) return fail(ANN_ERR_NULL_POINTER, "ann_set_option: NULL argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (!strcmp(name, "path")) {
+        if (value < 0 || value > 2) return fail(ANN_ERR_INVALID_ARGUMENT, "path must be 0 (auto), 1 (scan) or 2 (gemm)");
+        ix->path_opt = (int)value;
+        return ANN_OK;
+    }
+    if (!strcmp(name, "gemm_min_batch")) {
+        if (value < 1) return fail(ANN_ERR_INVALID_ARGUMENT, "gemm_min_batch must be >= 1");
+        ix->gemm_min_batch = (int)value;
+        return ANN_OK;
+    }
+    return fail(ANN_ERR_UNKNOWN_OPTION, std::string("unknown option: ") + name);
+}
+
+int ann_get_stat(const ann_index* ix, const char* name, int64_t* value) {
+    if (!ix || !name || !value) return fail(ANN_ERR_NULL_POINTER, "ann_get_stat: NULL argument");
+    if (!strcmp(name, "pending_error")) {
+        // synchronise the device and surface (then clear) the sticky selector-overflow word
+        ann_index* m = const_cast<ann_index*>(ix);
+        std::lock_guard<std::mutex> lk(m->mu);
+        CUDA_TRY(cudaSetDevice(m->device));
+        CUDA_TRY(cudaDeviceSynchronize());
+        *value = 0;
+        return check_device_flags(m, m->stream);
+    }
+    if (!strcmp(name, "launches")) *value = ix->launches;
+    else if (!strcmp(name, "last_path")) *value = ix->last_path;
+    else if (!strcmp(name, "scan_fallback_queries")) *value = ix->scan_fallback_queries;
+    else if (!strcmp(name, "n_special")) *value = (int64_t)ix->n_special;
+    else if (!strcmp(name, "row_bytes")) *value = (int64_t)ix->n * ix->pitch * 4;
+    else if (!strcmp(name, "shadow_bytes")) *value = ix->shadow ? (int64_t)ix->n * ix->kp * 2 : 0;
+    else if (!strcmp(name, "capacity")) *value = ix->cap;
+    else if (!strcmp(name, "sm_count")) *value = ix->sm_count;
+    else return fail(ANN_ERR_UNKNOWN_OPTION, std::string("unknown stat: ") + name);
+    return ANN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,107 @@
+// kernels.h -- host-visible launch interfaces of the CUDA kernels (internal to libb200ann.so).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "common.cuh"
+
+namespace b200ann {
+
+// ---------------------------------------------------------------- K1: append (norms, shadow, flags)
+struct AppendParams {
+    const float* rows;      // [n_new][pitch] already in place inside the index matrix
+    long long row0;         // first new row (global index inside the shard)
+    long long n_new;
+    int dim, pitch, metric;
+    float* inv_norm;        // [cap]  1/|a|            (Cosine only, else nullptr)
+    float* row_norm;        // [cap]  |a| rounded up   (always)
+    __nv_bfloat16* shadow;  // [cap][kp] or nullptr
+    int kp;                 // shadow pitch in elements (multiple of 8)
+    uint32_t* max_norm_bits;  // running max of |a| (float bits, non-negative => integer order)
+    unsigned long long* n_special;   // rows with non-finite entries or (Cosine) zero norm
+};
+cudaError_t launch_append(const AppendParams& p, cudaStream_t stream);
+
+// ---------------------------------------------------------------- query preparation
+struct PrepParams {
+    const float* queries;   // [b][dim]
+    int b, dim, pitch, metric, kp;
+    float* q_padded;        // [b][pitch]  zero padded fp32 copy (scan path)
+    __nv_bfloat16* q_shadow;  // [b_pad][kp] bf16 operand (gemm path) or nullptr
+    QueryState* qstate;     // [b]
+    const uint32_t* max_norm_bits;
+    int path;               // 1 = scan (fp32 error model), 2 = gemm (bf16 error model)
+    uint32_t* pub_keys;     // [b][pub_stride] reset to 0xFFFFFFFF (scan path) or nullptr
+    int pub_stride;
+    unsigned long long* bad_queries;  // count of queries with non-finite entries / zero norm under Cosine
+};
+cudaError_t launch_prep_queries(const PrepParams& p, cudaStream_t stream);
+
+// ---------------------------------------------------------------- K2: streaming scan
+struct ScanParams {
+    const float* rows;
+    long long n_rows;
+    int pitch, metric;
+    const float* inv_norm;
+    const float* queries;   // [nq][pitch] padded
+    int nq;
+    QueryState* qstate;     // [nq]
+    entry_t* pool;          // [nq][pool_cap]
+    int pool_cap;
+    uint32_t* special_rows; // [nq][kSpecialCap]
+    uint32_t* pub_keys;     // [nq][pub_stride]
+    int pub_stride;
+    int k, r_pub, j_pub;
+    int warps, cap;
+};
+size_t scan_smem_bytes(int qb, int pitch, int warps, int cap);
+cudaError_t launch_scan(const ScanParams& p, int qb, int grid, size_t smem, cudaStream_t stream);
+
+// ---------------------------------------------------------------- selection: compaction + exact finalize
+struct SelectParams {
+    QueryState* qstate;     // [b]
+    entry_t* pool;          // [b][pool_cap]
+    int pool_cap;
+    const uint32_t* special_rows;  // [b][kSpecialCap]
+    const uint32_t* pub_keys;      // [b][pub_stride] or nullptr
+    int pub_stride, pub_count, j_pub;
+    int k;
+    // exact rescoring inputs
+    const float* rows;
+    const int64_t* ids;
+    long long n_rows;
+    int dim, pitch, metric, l2_squared;
+    const float* queries;   // [b][q_pitch] fp32
+    int q_pitch;
+    int64_t* out_ids;       // [b][k_out]
+    float* out_dist;
+    int32_t* out_count;
+    int k_out;
+};
+// approx-only: sort the pool, keep everything within the margin of the k-th best, tighten tau
+cudaError_t launch_compact_pool(const SelectParams& p, int b, cudaStream_t stream);
+// compaction + exact fp64 rescoring + (distance, id) ordering + output
+cudaError_t launch_finalize(const SelectParams& p, int b, cudaStream_t stream);
+// fill outputs for k == 0 / empty index
+cudaError_t launch_fill_empty(int64_t* out_ids, float* out_dist, int32_t* out_count, int b, int k_out, cudaStream_t stream);
+
+// ---------------------------------------------------------------- K5: shard merge
+cudaError_t launch_merge(const int64_t* ids, const float* dist, const int32_t* count, int shards, int b, int k,
+                         int64_t* out_ids, float* out_dist, int32_t* out_count, cudaStream_t stream);
+
+// ---------------------------------------------------------------- K3: tcgen05 GEMM filter
+struct GemmParams {
+    const void* tmap_rows;     // CUtensorMap* (host copy passed by value inside launch)
+    const void* tmap_queries;
+    long long row_begin, row_end;   // chunk of corpus rows
+    int b_pad;                      // queries padded to a multiple of 128
+    int b;
+    int k_steps;                    // number of 16-wide MMA k-steps
+    QueryState* qstate;
+    entry_t* pool;
+    int pool_cap;
+    const float* row_norm;          // per-row |a| for the error bound (nullptr => global bound in eps_abs)
+};
+cudaError_t launch_gemm_filter(const GemmParams& p, int grid, cudaStream_t stream);
+size_t gemm_smem_bytes();
+
+}  // namespace b200ann
