@@ -1,0 +1,451 @@
+// gemm_filter.cu -- K3: batched candidate filter on the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
+//
+// Replaces, for a whole batch of queries at once, the per-row `metric.distance(row, query)` + heap push of
+// BruteForceIndex.queryWithDistance (ann/src/main/scala/com/twitter/ann/brute_force/BruteForceIndex.scala:76-86).
+// The (queries x rows) score matrix is a dense contraction; it is computed tile by tile in bf16 with fp32
+// accumulation and NEVER written to memory: the epilogue compares every score against the query's running
+// threshold (held in a register, one TMEM lane = one query) and only the rare survivors are appended to the
+// query's candidate pool.  finalize_kernel later rescales the survivors exactly.
+//
+//   D[q, r] = sum_k Qs[q, k] * Rs[r, k]         Qs = bf16 query operand, Rs = bf16 shadow rows (append_kernels.cu)
+//   score s = D, badness g = -s, survive iff g <= tau_q  (tau_q already carries the 2*eps margin)
+//
+// Tiling: queries are the MMA M dimension (128 per CTA = 128 TMEM lanes), corpus rows the N dimension
+// (128 per CTA).  With CG = 2 two CTAs of a cluster pair up (tcgen05 cta_group::2, M = N = 256): each CTA
+// stages only its half of both operands and the pair's tensor cores read both halves.  A row tile stays in
+// shared memory while every query tile streams past it (queries come from L2), so the shadow matrix is read
+// from HBM exactly once per batch.  Both operands are double buffered (TMA -> smem, mbarrier full/empty), the
+// accumulator is double buffered in TMEM (2 x N columns), and 8 epilogue warps drain one accumulator while
+// the next tile's MMAs run.
+//
+// K is not padded to the 128-byte swizzle width in HBM: a K of e.g. 208 is staged as 3 blocks of 64 (128B
+// swizzle) + 1 block of 16 (32B swizzle), each with its own tensor map / UMMA descriptor, TMA zero-filling
+// the tail columns.
+#include <cuda.h>
+
+#include <cstring>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200ann {
+
+namespace {
+
+constexpr int kGemmThreads = 384;     // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 spare, 4..11 epilogue
+constexpr int kEpiWarp0 = 4;
+constexpr int kNumEpiWarps = 8;
+constexpr int kTileRows = 128;        // rows (and queries) staged per CTA per tile
+
+struct alignas(64) GemmTmaps {
+    CUtensorMap q64, q32, q16, r64, r32, r16;
+};
+
+struct GemmArgs {
+    long long row_begin, row_end;     // corpus rows of this launch
+    int b, n_qt;                      // real queries, query tiles of 128*CG
+    int kp_mma;                       // K rounded up to 16
+    QueryState* qstate;
+    entry_t* pool;
+    int pool_cap;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address: "CTA 0 of my pair"
+
+template <int CG>
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    if constexpr (CG == 1) {
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                smem_u32(dst)),
+            "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+            : "memory");
+    } else {
+        asm volatile(
+            "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+                "r"(smem_u32(dst)),
+            "l"(map), "r"(smem_u32(bar) & kPeerMask), "r"(c0), "r"(c1)
+            : "memory");
+    }
+}
+
+template <int CG>
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    if constexpr (CG == 1) {
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    } else {
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                         smem_u32(bar)),
+                     "h"((uint16_t)3)
+                     : "memory");
+    }
+}
+
+template <int CG>
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (CG == 1) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    }
+}
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout type [61,64).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t sbo_bytes, uint32_t layout_type) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFFu);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)layout_type << 61;
+    return d;
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t* r = reinterpret_cast<uint32_t*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+          "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+          "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+struct KBlocks {
+    int nb64, has32, has16;
+    __device__ __forceinline__ explicit KBlocks(int kp_mma) {
+        nb64 = kp_mma >> 6;
+        int rem = kp_mma & 63;
+        has32 = rem >= 32;
+        has16 = (rem & 31) >= 16;
+    }
+};
+
+}  // namespace
+
+template <int CG>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    constexpr int N_TILE = kTileRows * CG;          // MMA N (and M)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x / CG;
+    const int n_clusters = gridDim.x / CG;
+
+    const uint32_t tile_bytes = (uint32_t)kTileRows * a.kp_mma * 2;
+    const uint32_t tile_stride = (tile_bytes + 1023u) & ~1023u;
+    unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char* smA[2] = {base, base + tile_stride};
+    unsigned char* smB[2] = {base + 2 * tile_stride, base + 3 * tile_stride};
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + 4 * tile_stride);
+    uint64_t* a_full = bars + 0;
+    uint64_t* a_empty = bars + 2;
+    uint64_t* b_full = bars + 4;
+    uint64_t* b_empty = bars + 6;
+    uint64_t* t_full = bars + 8;
+    uint64_t* t_empty = bars + 10;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+    const KBlocks kb(a.kp_mma);
+    const long long chunk_rows = a.row_end - a.row_begin;
+    const int n_rt = (int)((chunk_rows + N_TILE - 1) / N_TILE);
+    constexpr uint32_t kTmemCols = 2 * N_TILE;       // 256 (CG=1) or 512 (CG=2)
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.q64) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.r64) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&a_full[i], 1);
+            mbar_init(&a_empty[i], 1);
+            mbar_init(&b_full[i], 1);
+            mbar_init(&b_empty[i], 1);
+            mbar_init(&t_full[i], 1);
+            mbar_init(&t_empty[i], kNumEpiWarps * CG);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) {
+        if constexpr (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        }
+    }
+    tc_fence_before();
+    if constexpr (CG == 2) cluster_sync_all();
+    else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            uint32_t ga = 0, it = 0;
+            for (int rt = cluster_id; rt < n_rt; rt += n_clusters, ++it) {
+                const uint32_t bs = it & 1;
+                mbar_wait(&b_empty[bs], ((it >> 1) & 1) ^ 1);
+                if (leader) mbar_expect_tx(&b_full[bs], tile_bytes * CG);
+                {
+                    const int row0 = (int)(a.row_begin + (long long)rt * N_TILE + rank * kTileRows);
+                    unsigned char* dst = smB[bs];
+                    for (int i = 0; i < kb.nb64; ++i) tma_load_2d<CG>(&tm.r64, &b_full[bs], dst + i * 16384, i * 64, row0);
+                    int off = kb.nb64 * 16384, col = kb.nb64 * 64;
+                    if (kb.has32) {
+                        tma_load_2d<CG>(&tm.r32, &b_full[bs], dst + off, col, row0);
+                        off += 8192;
+                        col += 32;
+                    }
+                    if (kb.has16) tma_load_2d<CG>(&tm.r16, &b_full[bs], dst + off, col, row0);
+                }
+                for (int qt = 0; qt < a.n_qt; ++qt, ++ga) {
+                    const uint32_t s = ga & 1;
+                    mbar_wait(&a_empty[s], ((ga >> 1) & 1) ^ 1);
+                    if (leader) mbar_expect_tx(&a_full[s], tile_bytes * CG);
+                    const int q0 = qt * N_TILE + rank * kTileRows;
+                    unsigned char* dst = smA[s];
+                    for (int i = 0; i < kb.nb64; ++i) tma_load_2d<CG>(&tm.q64, &a_full[s], dst + i * 16384, i * 64, q0);
+                    int off = kb.nb64 * 16384, col = kb.nb64 * 64;
+                    if (kb.has32) {
+                        tma_load_2d<CG>(&tm.q32, &a_full[s], dst + off, col, q0);
+                        off += 8192;
+                        col += 32;
+                    }
+                    if (kb.has16) tma_load_2d<CG>(&tm.q16, &a_full[s], dst + off, col, q0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer (leader CTA, one thread) ================================
+        if (leader && lane == 0) {
+            // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7, 10), K-major both, N>>3 at 17, M>>4 at 24
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_TILE >> 3) << 17) | ((uint32_t)(N_TILE >> 4) << 24);
+            uint32_t ga = 0, it = 0;
+            for (int rt = cluster_id; rt < n_rt; rt += n_clusters, ++it) {
+                const uint32_t bs = it & 1;
+                mbar_wait(&b_full[bs], (it >> 1) & 1);
+                const uint32_t b_addr = smem_u32(smB[bs]);
+                for (int qt = 0; qt < a.n_qt; ++qt, ++ga) {
+                    const uint32_t s = ga & 1;
+                    mbar_wait(&a_full[s], (ga >> 1) & 1);
+                    mbar_wait(&t_empty[s], ((ga >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smA[s]);
+                    const uint32_t d_tmem = tmem_base + s * N_TILE;
+                    uint32_t acc = 0;
+                    for (int i = 0; i < kb.nb64; ++i) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            umma_bf16<CG>(d_tmem, smem_desc(a_addr + i * 16384 + j * 32, 1024, 2),
+                                          smem_desc(b_addr + i * 16384 + j * 32, 1024, 2), idesc, acc);
+                            acc = 1;
+                        }
+                    }
+                    uint32_t off = kb.nb64 * 16384;
+                    if (kb.has32) {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            umma_bf16<CG>(d_tmem, smem_desc(a_addr + off + j * 32, 512, 4), smem_desc(b_addr + off + j * 32, 512, 4),
+                                          idesc, acc);
+                            acc = 1;
+                        }
+                        off += 8192;
+                    }
+                    if (kb.has16) {
+                        umma_bf16<CG>(d_tmem, smem_desc(a_addr + off, 256, 6), smem_desc(b_addr + off, 256, 6), idesc, acc);
+                        acc = 1;
+                    }
+                    umma_commit<CG>(&a_empty[s]);   // operands of this query tile consumed
+                    umma_commit<CG>(&t_full[s]);    // accumulator ready for the epilogue
+                }
+                umma_commit<CG>(&b_empty[bs]);      // row tile consumed
+            }
+        }
+    } else if (warp >= kEpiWarp0) {
+        // ================================ epilogue: TMEM -> registers -> threshold filter ================================
+        const int e = warp - kEpiWarp0;
+        const int quarter = warp & 3;                 // TMEM lanes 32*quarter .. +31 are the ones this warp may touch
+        const int half = e >> 2;                      // which half of the N columns
+        constexpr int COLS_PER_WARP = N_TILE / 2;
+        uint32_t ge = 0;
+        for (int rt = cluster_id; rt < n_rt; rt += n_clusters) {
+            const long long tile_row0 = a.row_begin + (long long)rt * N_TILE;
+            const int valid_cols = (int)min((long long)N_TILE, a.row_end - tile_row0);
+            for (int qt = 0; qt < a.n_qt; ++qt, ++ge) {
+                const uint32_t s = ge & 1;
+                const int q = qt * N_TILE + (int)rank * kTileRows + quarter * 32 + lane;
+                const bool q_ok = q < a.b;
+                float thr = INFINITY;                 // scores >= thr survive; +inf rejects everything (padding query)
+                if (q_ok) {
+                    uint32_t tk = __ldcg(&a.qstate[q].tau_key);
+                    thr = (tk >= 0xFF800000u) ? -INFINITY : -float_from_order_key(tk);
+                }
+                mbar_wait(&t_full[s], (ge >> 1) & 1);
+                tc_fence_after();
+                const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + s * N_TILE + half * COLS_PER_WARP;
+#pragma unroll 1
+                for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 32) {
+                    float v[32];
+                    tmem_ld32(t_lane + c0, v);
+                    tmem_ld_wait();
+                    const int col0 = half * COLS_PER_WARP + c0;
+                    bool any = false;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) any |= (v[j] >= thr);
+                    if (any && col0 < valid_cols) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (v[j] >= thr && col0 + j < valid_cols) {
+                                uint32_t slot = atomicAdd(&a.qstate[q].pool_count, 1u);
+                                if (slot < (uint32_t)a.pool_cap)
+                                    a.pool[(size_t)q * a.pool_cap + slot] = make_entry(-v[j], (uint32_t)(tile_row0 + col0 + j));
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (CG == 1) mbar_arrive(&t_empty[s]);
+                    else asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(&t_empty[s]) & kPeerMask) : "memory");
+                }
+            }
+        }
+    }
+
+    // ---- teardown ----
+    __syncwarp();   // single-lane roles: reconverge the warp before the .aligned barriers below
+    tc_fence_before();
+    if constexpr (CG == 2) cluster_sync_all();
+    else __syncthreads();
+    if (warp == 2) {
+        if constexpr (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side: tensor maps through the driver entry point (no link-time dependency on libcuda)
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+bool make_map(CUtensorMap* m, const void* gptr, long long n_rows, int kp, int box_cols, CUtensorMapSwizzle sw) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)kp, (cuuint64_t)n_rows};
+    cuuint64_t strides[1] = {(cuuint64_t)kp * 2};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)kTileRows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+}  // namespace
+
+size_t gemm_smem_bytes(int kp_mma) {
+    size_t tile = ((size_t)kTileRows * kp_mma * 2 + 1023) & ~(size_t)1023;
+    return 4 * tile + 13 * 8 + 16 + 1024;
+}
+
+cudaError_t launch_gemm_filter(const GemmLaunch& g, cudaStream_t stream) {
+    GemmTmaps tm;
+    memset(&tm, 0, sizeof(tm));
+    const int kp = g.kp;
+    bool ok = make_map(&tm.q64, g.q_shadow, g.b_pad, kp, 64, CU_TENSOR_MAP_SWIZZLE_128B) &&
+              make_map(&tm.q32, g.q_shadow, g.b_pad, kp, 32, CU_TENSOR_MAP_SWIZZLE_64B) &&
+              make_map(&tm.q16, g.q_shadow, g.b_pad, kp, 16, CU_TENSOR_MAP_SWIZZLE_32B) &&
+              make_map(&tm.r64, g.shadow, g.n_rows_total, kp, 64, CU_TENSOR_MAP_SWIZZLE_128B) &&
+              make_map(&tm.r32, g.shadow, g.n_rows_total, kp, 32, CU_TENSOR_MAP_SWIZZLE_64B) &&
+              make_map(&tm.r16, g.shadow, g.n_rows_total, kp, 16, CU_TENSOR_MAP_SWIZZLE_32B);
+    if (!ok) return cudaErrorInvalidValue;
+    const int cg = g.cta_group;
+    const int n_tile = kTileRows * cg;
+    GemmArgs a{};
+    a.row_begin = g.row_begin;
+    a.row_end = g.row_end;
+    a.b = g.b;
+    a.n_qt = (g.b + n_tile - 1) / n_tile;
+    a.kp_mma = (kp + 15) / 16 * 16;
+    a.qstate = g.qstate;
+    a.pool = g.pool;
+    a.pool_cap = g.pool_cap;
+    const long long rows = g.row_end - g.row_begin;
+    const int n_rt = (int)((rows + n_tile - 1) / n_tile);
+    if (n_rt <= 0 || a.n_qt <= 0) return cudaSuccess;
+    int clusters = g.sm_count / cg;
+    if (clusters > n_rt) clusters = n_rt;
+    const size_t smem = gemm_smem_bytes(a.kp_mma);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(clusters * cg);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cg;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e;
+    if (cg == 1) {
+        e = cudaFuncSetAttribute(gemm_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaLaunchKernelEx(&cfg, gemm_filter_kernel<1>, tm, a);
+    } else {
+        e = cudaFuncSetAttribute(gemm_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaLaunchKernelEx(&cfg, gemm_filter_kernel<2>, tm, a);
+    }
+    if (e != cudaSuccess) return e;
+    return cudaGetLastError();
+}
+
+}  // namespace b200ann

@@ -121,7 +121,8 @@ struct ann_index {
     DevBuf<float> stage_rows;
 
     // options / stats
-    int path_opt = 0, gemm_min_batch = 16;
+    int path_opt = 0, gemm_min_batch = 16, gemm_cta_group = 2;
+    long long last_candidates = 0;
     long long launches = 0, last_path = 0, scan_fallback_queries = 0;
 };
 
@@ -331,6 +332,98 @@ int query_scan(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
     return ANN_OK;
 }
 
+
+// K3 flow: geometric row chunks, each scored by the tensor-core filter against the thresholds learnt from the rows
+// before it; an approximate compaction between chunks; one exact finalize at the end.
+int query_gemm(ann_index* ix, const float* d_queries, int b, int k_eff, int k_out, int64_t* d_out_ids, float* d_out_dist,
+               int32_t* d_out_count, cudaStream_t st) {
+    const int b_pad = (b + 127) / 128 * 128;
+    CUDA_TRY(ix->q_padded.ensure((size_t)b * ix->pitch));
+    CUDA_TRY(ix->q_shadow.ensure((size_t)b_pad * ix->kp));
+    CUDA_TRY(ix->qstate.ensure((size_t)b));
+    CUDA_TRY(ix->pool.ensure((size_t)b * kGemmPoolCap));
+    CUDA_TRY(ix->special_rows.ensure((size_t)kSpecialCap));
+
+    PrepParams pp{};
+    pp.queries = d_queries;
+    pp.b = b;
+    pp.dim = ix->dim;
+    pp.pitch = ix->pitch;
+    pp.metric = ix->metric;
+    pp.kp = ix->kp;
+    pp.q_padded = ix->q_padded.p;
+    pp.q_shadow = ix->q_shadow.p;
+    pp.qstate = ix->qstate.p;
+    pp.max_norm_bits = &ix->scalars->max_norm_bits;
+    pp.path = 2;
+    pp.pub_keys = nullptr;
+    pp.pub_stride = 0;
+    pp.bad_queries = &ix->scalars->bad_queries;
+    CUDA_TRY(launch_prep_queries(pp, st));
+    ix->launches++;
+
+    SelectParams fp{};
+    fp.qstate = ix->qstate.p;
+    fp.pool = ix->pool.p;
+    fp.pool_cap = kGemmPoolCap;
+    fp.special_rows = ix->special_rows.p;
+    fp.pub_keys = nullptr;
+    fp.k = k_eff;
+    fp.rows = ix->rows;
+    fp.ids = ix->ids;
+    fp.n_rows = ix->n;
+    fp.dim = ix->dim;
+    fp.pitch = ix->pitch;
+    fp.metric = ix->metric;
+    fp.l2_squared = ix->l2_squared ? 1 : 0;
+    fp.queries = ix->q_padded.p;
+    fp.q_pitch = ix->pitch;
+    fp.out_ids = d_out_ids;
+    fp.out_dist = d_out_dist;
+    fp.out_count = d_out_count;
+    fp.k_out = k_out;
+
+    // chunk schedule: the first chunk is scored with tau = +inf (every row is a candidate), so it must fit the pool;
+    // afterwards a chunk `growth` times the rows seen so far adds ~ (growth-1) * k * (margin inflation) candidates.
+    const long long first = std::min<long long>(ix->n, kGemmPoolCap / 2);
+    int growth = (int)std::min<long long>(8, std::max<long long>(2, 2400 / std::max(1, k_eff)));
+    long long begin = 0, end = first;
+    for (;;) {
+        GemmLaunch g{};
+        g.q_shadow = ix->q_shadow.p;
+        g.shadow = ix->shadow;
+        g.n_rows_total = ix->n;
+        g.row_begin = begin;
+        g.row_end = end;
+        g.b = b;
+        g.b_pad = b_pad;
+        g.kp = ix->kp;
+        g.cta_group = ix->gemm_cta_group;
+        g.sm_count = ix->sm_count;
+        g.qstate = ix->qstate.p;
+        g.pool = ix->pool.p;
+        g.pool_cap = kGemmPoolCap;
+        CUDA_TRY(launch_gemm_filter(g, st));
+        ix->launches++;
+        if (end >= ix->n) break;
+        CUDA_TRY(launch_compact_pool(fp, b, st));
+        ix->launches++;
+        begin = end;
+        end = std::min<long long>(ix->n, end * growth);
+    }
+    CUDA_TRY(launch_finalize(fp, b, st));
+    ix->launches++;
+    collect_flags_kernel<<<std::min(64, (b + 255) / 256), 256, 0, st>>>(ix->qstate.p, b, ix->scalars);
+    CUDA_TRY(cudaGetLastError());
+    ix->launches++;
+    ix->last_path = 2;
+    return ANN_OK;
+}
+
+bool gemm_eligible(const ann_index* ix, int b, int k_eff) {
+    return ix->shadow != nullptr && ix->n_special == 0 && k_eff <= 256 && ix->n >= 1024 && b >= 1;
+}
+
 int query_core(ann_index* ix, const float* d_queries, int b, int k, int64_t* d_out_ids, float* d_out_dist,
                int32_t* d_out_count, cudaStream_t st) {
     if (b == 0) return ANN_OK;
@@ -344,6 +437,12 @@ int query_core(ann_index* ix, const float* d_queries, int b, int k, int64_t* d_o
     }
     const int k_eff = (int)std::min<long long>(k, n);
     if (k_eff > kMaxK) return fail(ANN_ERR_INVALID_ARGUMENT, "min(k, size) > 1024 is not supported");
+    int path = ix->path_opt;
+    if (path == 2 && !gemm_eligible(ix, b, k_eff))
+        return fail(ANN_ERR_INVALID_ARGUMENT,
+                    "path=2 (tensor-core filter) needs the bf16 shadow, no non-finite/zero-norm rows, size >= 1024 and k <= 256");
+    if (path == 0) path = (gemm_eligible(ix, b, k_eff) && b >= ix->gemm_min_batch) ? 2 : 1;
+    if (path == 2) return query_gemm(ix, d_queries, b, k_eff, k, d_out_ids, d_out_dist, d_out_count, st);
     return query_scan(ix, d_queries, b, k_eff, k, d_out_ids, d_out_dist, d_out_count, st);
 }
 
@@ -558,6 +657,11 @@ int ann_set_option(ann_index* ix, const char* name, int64_t value) {
     if (!strcmp(name, "path")) {
         if (value < 0 || value > 2) return fail(ANN_ERR_INVALID_ARGUMENT, "path must be 0 (auto), 1 (scan) or 2 (gemm)");
         ix->path_opt = (int)value;
+        return ANN_OK;
+    }
+    if (!strcmp(name, "gemm_cta_group")) {
+        if (value != 1 && value != 2) return fail(ANN_ERR_INVALID_ARGUMENT, "gemm_cta_group must be 1 or 2");
+        ix->gemm_cta_group = (int)value;
         return ANN_OK;
     }
     if (!strcmp(name, "gemm_min_batch")) {

@@ -89,19 +89,19 @@ cudaError_t launch_merge(const int64_t* ids, const float* dist, const int32_t* c
                          int64_t* out_ids, float* out_dist, int32_t* out_count, cudaStream_t stream);
 
 // ---------------------------------------------------------------- K3: tcgen05 GEMM filter
-struct GemmParams {
-    const void* tmap_rows;     // CUtensorMap* (host copy passed by value inside launch)
-    const void* tmap_queries;
-    long long row_begin, row_end;   // chunk of corpus rows
-    int b_pad;                      // queries padded to a multiple of 128
-    int b;
-    int k_steps;                    // number of 16-wide MMA k-steps
+struct GemmLaunch {
+    const void* q_shadow;       // bf16 [b_pad][kp]
+    const void* shadow;         // bf16 [n_rows_total][kp]
+    long long n_rows_total;
+    long long row_begin, row_end;   // chunk of corpus rows scored by this launch
+    int b, b_pad, kp;
+    int cta_group;              // 1 or 2 (tcgen05 cta_group)
+    int sm_count;
     QueryState* qstate;
     entry_t* pool;
     int pool_cap;
-    const float* row_norm;          // per-row |a| for the error bound (nullptr => global bound in eps_abs)
 };
-cudaError_t launch_gemm_filter(const GemmParams& p, int grid, cudaStream_t stream);
-size_t gemm_smem_bytes();
+cudaError_t launch_gemm_filter(const GemmLaunch& g, cudaStream_t stream);
+size_t gemm_smem_bytes(int kp_mma);
 
 }  // namespace b200ann

@@ -53,7 +53,7 @@ def parity(metric, n, d, b, k, seed, dup=False, ids_mode="iota"):
 
 
 all_ok = True
-for metric in (InnerProduct, Cosine, L2):
+for metric in ((InnerProduct, Cosine, L2) if "--no-parity" not in sys.argv else ()):
     for (n, d, b, k) in [(1000, 16, 3, 10), (5000, 200, 9, 100), (100_000, 200, 16, 100), (70_001, 128, 5, 100),
                          (3000, 100, 4, 7), (257, 36, 2, 300), (50, 8, 1, 100), (200_000, 64, 1, 200)]:
         all_ok &= parity(metric, n, d, b, k, seed=n + d)
@@ -79,17 +79,19 @@ for (metric, n, d) in [(L2, 10_000_000, 128), (InnerProduct, 10_000_000, 200)]:
         oi = torch.empty((b, 100), dtype=torch.int64, device=dev)
         od = torch.empty((b, 100), dtype=torch.float32, device=dev)
         oc = torch.empty((b,), dtype=torch.int32, device=dev)
-        st = torch.cuda.current_stream().cuda_stream
+        ts = torch.cuda.Stream(dev)
+        st = ts.cuda_stream
+        torch.cuda.synchronize()
         for _ in range(3):
             ix.query_batch_device(q, 100, oi, od, oc, st)
         torch.cuda.synchronize()
         ix.raise_pending_error()
         reps = 20
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        e0.record(ts)
         for _ in range(reps):
             ix.query_batch_device(q, 100, oi, od, oc, st)
-        e1.record()
+        e1.record(ts)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
         gbs = n * d * 4 / (ms * 1e-3) / 1e9
