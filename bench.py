@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of BASELINE.json on N B200s of one node.
+
+    python bench.py --gpus 1 --steps K --warmup W                      (default arm: the CUDA engine)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --gpus N --steps K --warmup W     (reference arm: CPU restatement, rank 0 only)
+
+metric  : exact top-100 queries/sec over a 10M x 200 fp32 corpus (BASELINE.json `metric`, configs[1]:
+          InnerProduct, query batch 4096, tcgen05 GEMM path)
+step    : one batch of 4096 synthetic queries through the whole query path (prep -> GEMM filter chunks ->
+          compaction -> exact fp64 finalize; with N > 1 also the NCCL all-gather of the local top-k + K5 merge)
+value   : whole-job queries/s with queries and outputs resident in HBM (CUDA events on the launching stream,
+          barrier + synchronize on both sides, max over ranks)
+e2e     : the same through the host-buffer C-ABI call ann_query_batch (pinned host queries in, host results out,
+          H2D / D2H inside the timed region)
+N > 1   : STRONG scaling on the same 10M-row corpus -- rows sharded contiguously across ranks, queries replicated,
+          one exchange step (all-gather of b*k*(8+4)+b*4 bytes per rank) followed by the K5 merge kernel.
+roofline: dominant kernel = gemm_filter (tensor bound); achieved = 2*N_local*d*B flop / its CUDA-event time.
+cpu_baseline / --impl reference: the reference-faithful C restatement (oracle/oracle.c: linked list of heap rows,
+          Scala PriorityQueue mechanics) on the host cores, one query per thread, bounded sample of the same workload.
+          The Scala original cannot run here (no JVM, unshipped deps) -- kind = "port".
+Synthetic data: rows ~ N(0, 1/d) (TwHIN-like dense, unnormalised), queries ~ U[-1, 1) (Warmup.scala:46-47).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "exact top-100 queries/sec, 10Mx200 fp32 corpus, InnerProduct, query batch 4096"
+UNIT = "queries/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=10_000_000, help="total corpus rows (sharded across ranks)")
+    ap.add_argument("--dim", type=int, default=200)
+    ap.add_argument("--batch", type=int, default=4096)
+    ap.add_argument("--k", type=int, default=100)
+    ap.add_argument("--metric", default="InnerProduct")
+    ap.add_argument("--path", type=int, default=0, help="0 auto, 1 streaming scan, 2 tensor-core GEMM filter")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-queries", type=int, default=0, help="queries in the CPU sample (0 = one per host thread)")
+    return ap.parse_args()
+
+
+def config_dict(a, n_gpus):
+    return {
+        "workload": f"configs[1]: exact {a.metric} top-{a.k} over {a.rows}x{a.dim} fp32 corpus, query batch {a.batch}",
+        "rows": a.rows, "dim": a.dim, "batch": a.batch, "k": a.k, "distance": a.metric,
+        "sharding": "single GPU" if n_gpus == 1 else f"rows sharded contiguously over {n_gpus} ranks, queries replicated, "
+                    "NCCL all-gather of local top-k + merge kernel",
+        "l2_flush": "none needed: every step streams the corpus shadow (>= 4 GB per 10M rows) through a 126 MB L2",
+    }
+
+
+# ------------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm, mx, reasons = [], 0.0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------- CPU baseline
+def cpu_baseline_run(corpus_np, ids_np, queries_np, metric_ord: int, k: int, steps: int, warmup: int):
+    """Times the reference-faithful restatement (oracle.FaithfulIndex) with one whole query per host thread."""
+    import oracle
+
+    cores = oracle.max_threads()
+    ix = oracle.FaithfulIndex(metric_ord, corpus_np.shape[1])
+    t0 = time.time()
+    chunk = 1_000_000
+    for c0 in range(0, corpus_np.shape[0], chunk):
+        ix.append(ids_np[c0:c0 + chunk], corpus_np[c0:c0 + chunk])
+    build_s = time.time() - t0
+    nq = queries_np.shape[0]
+    per_step = []
+    for s in range(warmup + steps):
+        t0 = time.time()
+        ix.query(queries_np, k, nthreads=cores)
+        dt = time.time() - t0
+        if s >= warmup:
+            per_step.append(dt)
+    ix.close()
+    tot = sum(per_step)
+    return {"value": nq * len(per_step) / tot, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{nq} queries per step x {len(per_step)} step(s) against the full {corpus_np.shape[0]}x{corpus_np.shape[1]} "
+                      f"corpus, one query per thread; linked-list build {build_s:.1f}s not timed",
+            "ms_per_step": 1000.0 * tot / len(per_step)}
+
+
+def gen_host_data(a, device_ok: bool):
+    """Synthetic corpus/queries on the host for the CPU arm (generated on the GPU when present, for speed)."""
+    import numpy as np
+    import torch
+
+    if device_ok:
+        dev = torch.device("cuda", 0)
+        g = torch.Generator(device=dev)
+        g.manual_seed(0x5EED0001)
+        parts = []
+        for c0 in range(0, a.rows, 1_000_000):
+            m = min(1_000_000, a.rows - c0)
+            parts.append((torch.randn((m, a.dim), generator=g, device=dev) / a.dim ** 0.5).cpu())
+        corpus = torch.cat(parts).numpy()
+        g.manual_seed(0x5EED0002)
+        q = (torch.rand((a.batch, a.dim), generator=g, device=dev) * 2 - 1).cpu().numpy()
+    else:
+        g = torch.Generator()
+        g.manual_seed(0x5EED0001)
+        corpus = (torch.randn((a.rows, a.dim), generator=g) / a.dim ** 0.5).numpy()
+        g.manual_seed(0x5EED0002)
+        q = (torch.rand((a.batch, a.dim), generator=g) * 2 - 1).numpy()
+    return corpus, np.arange(a.rows, dtype=np.int64), q
+
+
+def run_reference(a):
+    """--impl reference: the reference's CPU implementation of the path (restated, see module docstring)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import oracle
+    import torch
+
+    from oracle import METRIC_BY_NAME
+    cores = oracle.max_threads()
+    corpus, ids, q = gen_host_data(a, torch.cuda.is_available())
+    nq = a.cpu_queries or cores
+    res = cpu_baseline_run(corpus, ids, q[:nq], METRIC_BY_NAME[a.metric], a.k, a.steps, a.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32 (fp64 accumulate)", "data": "synthetic", "config": config_dict(a, a.gpus),
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference arm = C restatement of BruteForceIndex.scala:66-91 (JVM + unshipped deps cannot run here)",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def run_ours(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import _pkg
+    _pkg.load()
+    from the_algorithm_b200.ann.brute_force import BruteForceIndex, merge_topk_device
+    from the_algorithm_b200.ann.common import FuturePool, Metric
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+
+    metric = Metric.from_string(a.metric)
+    n, d, b, k = a.rows, a.dim, a.batch, a.k
+    lo = rank * n // world
+    hi = (rank + 1) * n // world
+    n_local = hi - lo
+
+    # ---- build the shard (not timed): same generator stream on every rank, each keeps its own row range ----
+    ix = BruteForceIndex(metric, FuturePool.immediate_pool(), device=local_rank, capacity_hint=n_local)
+    g = torch.Generator(device=dev)
+    g.manual_seed(0x5EED0001)
+    for c0 in range(0, n, 1_000_000):
+        m = min(1_000_000, n - c0)
+        rows = torch.randn((m, d), generator=g, device=dev) / d ** 0.5
+        s, e = max(c0, lo), min(c0 + m, hi)
+        if s < e:
+            ix.append_batch_device(torch.arange(s, e, device=dev, dtype=torch.int64), rows[s - c0:e - c0].contiguous())
+    del rows
+    g.manual_seed(0x5EED0002)
+    q_dev = (torch.rand((b, d), generator=g, device=dev) * 2 - 1).contiguous()
+    if a.path:
+        ix.set_option("path", a.path)
+
+    out_ids = torch.empty((b, k), dtype=torch.int64, device=dev)
+    out_dist = torch.empty((b, k), dtype=torch.float32, device=dev)
+    out_cnt = torch.empty((b,), dtype=torch.int32, device=dev)
+    if world > 1:
+        g_ids = torch.empty((world, b, k), dtype=torch.int64, device=dev)
+        g_dist = torch.empty((world, b, k), dtype=torch.float32, device=dev)
+        g_cnt = torch.empty((world, b), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step_device(queries):
+        ix.query_batch_device(queries, k, out_ids, out_dist, out_cnt, stream.cuda_stream)
+        if world == 1:
+            return out_ids, out_dist, out_cnt
+        dist.all_gather_into_tensor(g_ids, out_ids)
+        dist.all_gather_into_tensor(g_dist, out_dist)
+        dist.all_gather_into_tensor(g_cnt, out_cnt)
+        return merge_topk_device(g_ids, g_dist, g_cnt, k, stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # ---- warm-up, then the device-resident measurement ----
+    for _ in range(max(a.warmup, 3)):
+        res = step_device(q_dev)
+    barrier()
+    ix.raise_pending_error()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ix.stat("launches")
+    ix.set_option("timing", 1)
+    ms_total = timed(lambda: step_device(q_dev), a.steps)
+    kernel_us = ix.stat("kernel_us")
+    kernel_n = ix.stat("kernel_launches_timed")
+    ix.set_option("timing", 0)
+    launches = ix.stat("launches") - launches0 + (a.steps if world > 1 else 0)
+    ix.raise_pending_error()
+    last_path = ix.stat("last_path")
+    ms_step = ms_total / a.steps
+    value = b / (ms_step * 1e-3)
+
+    # ---- end to end through the host-buffer C-ABI call: pinned queries in, host results out ----
+    q_pin = q_dev.cpu().pin_memory()
+    h_ids = torch.empty((b, k), dtype=torch.int64).pin_memory()
+    h_dist = torch.empty((b, k), dtype=torch.float32).pin_memory()
+    h_cnt = torch.empty((b,), dtype=torch.int32).pin_memory()
+    q_np = q_pin.numpy()
+
+    def step_e2e():
+        if world == 1:
+            return ix.batch_query_with_distance(q_np, k)     # ann_query_batch: H2D, query path, D2H, all inside the call
+        qd = q_pin.to(dev, non_blocking=True)
+        oi, od, oc = step_device(qd)
+        h_ids.copy_(oi, non_blocking=True)
+        h_dist.copy_(od, non_blocking=True)
+        h_cnt.copy_(oc, non_blocking=True)
+        stream.synchronize()
+        return h_ids, h_dist, h_cnt
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        step_e2e()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / a.steps
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline of the dominant kernel (CUDA events around each launch, on the launching stream) ----
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    if last_path == 2:
+        flops_step = 2.0 * n_local * d * b
+        achieved = flops_step * a.steps / (kernel_us * 1e-6) / 1e12 if kernel_us else None
+        peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        roofline = {"bound": "tensor", "kernel": "gemm_filter_kernel<2> (tcgen05.mma kind::f16, bf16 in / fp32 accumulate)",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+                    if peaks else "fallback 1.4 PFLOP/s sustained",
+                    "traffic": None, "kernel_ms_per_step": kernel_us / 1e3 / a.steps,
+                    "launches_per_step": kernel_n / a.steps,
+                    "algorithmic_flops_per_step": flops_step}
+    else:
+        bytes_step = float(n_local) * d * 4 * ((b + 7) // 8)
+        achieved = bytes_step * a.steps / (kernel_us * 1e-6) / 1e9 if kernel_us else None
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        roofline = {"bound": "hbm", "kernel": "scan_topk_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": (achieved / peak) if achieved else None, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
+                    "kernel_ms_per_step": kernel_us / 1e3 / a.steps, "launches_per_step": kernel_n / a.steps}
+
+    # ---- CPU baseline on the host cores (rank 0, N = 1 only; bounded sample) ----
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        try:
+            import oracle
+            from oracle import METRIC_BY_NAME
+            cores = oracle.max_threads()
+            nq = a.cpu_queries or cores
+            parts = []
+            # the device-resident corpus itself, copied back: the CPU arm sees exactly the rows the GPU scanned
+            g.manual_seed(0x5EED0001)
+            for c0 in range(0, n, 1_000_000):
+                m = min(1_000_000, n - c0)
+                parts.append((torch.randn((m, d), generator=g, device=dev) / d ** 0.5).cpu())
+            corpus_np = torch.cat(parts).numpy()
+            del parts
+            r = cpu_baseline_run(corpus_np, np.arange(n, dtype=np.int64), q_np[:nq], METRIC_BY_NAME[a.metric], k, 1, 0)
+            cpu = {kk: r[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
+            del corpus_np
+        except Exception as e:  # the baseline is a report, never a reason to lose the measurement
+            cpu = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {e!r}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "bf16 filter (tcgen05, fp32 accumulate) + exact fp64-accumulated fp32 distances" if last_path == 2
+                     else "f32 scan + exact fp64-accumulated fp32 distances",
+            "data": "synthetic", "config": config_dict(a, n_gpus),
+            "e2e": {"value": b / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": b * d * 4,
+                    "d2h_bytes_per_step": b * k * 12 + b * 4, "ms_per_step": e2e_ms,
+                    "api": "ann_query_batch (host buffers)" if world == 1 else "pinned H2D + ann_query_batch_device + all-gather + merge + D2H"},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "path": {1: "scan", 2: "gemm"}.get(last_path, str(last_path)),
+        }
+        print(json.dumps(line), flush=True)
+    ix.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+    return run_ours(a)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -13,7 +13,8 @@
  *     ann_last_error() gives the thread-local message of the last failure on the calling thread.
  *   - host buffers are caller-owned and only borrowed for the duration of the call; outputs are
  *     fully written before return.  `_device` variants take device pointers on the index's GPU and a
- *     cudaStream_t (passed as void*); they enqueue work and return without synchronising.
+ *     cudaStream_t (passed as void*; NULL is the legacy default stream); they enqueue work on that stream, so
+ *     they are ordered after whatever produced their inputs there, and return without synchronising.
  *   - results: nearest first, ascending (Float.compare(distance), id) -- the deterministic refinement
  *     of the reference's heap order (BruteForceIndex.scala:73-89).  Row q of the outputs has
  *     out_count[q] = min(max(k,0), size) valid entries; unused slots hold id = -1, distance = +inf.
@@ -61,7 +62,7 @@ typedef enum ann_status {
 
 typedef struct ann_config {
     int32_t metric;        /* ann_metric                                                          */
-    int32_t dim;           /* embedding dimension, 1..4096                                        */
+    int32_t dim;           /* embedding dimension, 1..1024                                        */
     int64_t capacity_hint; /* rows to reserve up front (0 = grow on demand)                       */
     int32_t device;        /* CUDA device ordinal                                                 */
     uint32_t flags;        /* ANN_FLAG_*                                                          */
@@ -102,9 +103,12 @@ ANN_API int ann_merge_topk_device(int32_t device, const int64_t *d_ids, const fl
                                   int32_t shards, int32_t b, int32_t k, int64_t *d_out_ids, float *d_out_dist,
                                   int32_t *d_out_count, void *stream);
 
-/* Tuning / introspection.  Options: "path" (0 auto, 1 streaming scan, 2 tensor-core GEMM filter),
- * "gemm_min_batch".  Stats: "launches" (kernels launched so far), "last_path", "last_candidates",
- * "scan_fallback_queries", "shadow_bytes", "row_bytes", "n_special". */
+/* Tuning / introspection.
+ * Options: "path" (0 auto, 1 streaming scan, 2 tensor-core GEMM filter), "gemm_min_batch", "gemm_cta_group" (1|2),
+ *          "timing" (1 = bracket every scan / GEMM-filter launch with CUDA events on its stream).
+ * Stats:   "launches" (kernels launched so far), "last_path", "shadow_bytes", "row_bytes", "n_special", "capacity",
+ *          "sm_count", "kernel_us" / "kernel_launches_timed" (accumulated since "timing" was set; synchronises),
+ *          "pending_error" (synchronises the device and returns the sticky selector-overflow status, if any). */
 ANN_API int ann_set_option(ann_index *ix, const char *name, int64_t value);
 ANN_API int ann_get_stat(const ann_index *ix, const char *name, int64_t *value);
 

@@ -1,0 +1,350 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same seeded inputs.
+Bar: neighbour ids bit-identical (ties by id), distances bit-identical (the finalize kernel reproduces the oracle's
+fp64-accumulate / round-once arithmetic operation for operation), so the 1e-5 relative tolerance of BASELINE.json is met
+with zero slack; the tolerance is still asserted explicitly below."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import oracle_np as onp
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5  # BASELINE.json north_star: distances within 1e-5 relative error in fp32
+
+
+def _imports():
+    from the_algorithm_b200 import _capi
+    from the_algorithm_b200.ann.brute_force import BruteForceIndex, BruteForceRuntimeParams, merge_topk_device
+    from the_algorithm_b200.ann.common import (ComposedQueryable, Cosine, EmbeddingProducer, EntityEmbedding, FuturePool,
+                                               InnerProduct, L2, Metric, QueryableByIdImplementation,
+                                               RoundRobinShardFunction, ShardedAppendable)
+    return locals()
+
+
+G = None
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _g():
+    global G
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    G = _imports()
+    yield
+
+
+def metrics():
+    return [G["InnerProduct"], G["Cosine"], G["L2"]]
+
+
+def make(n, d, b, seed, dup=False, perm_ids=True, scale=1.0):
+    rng = np.random.default_rng(seed)
+    corpus = (rng.standard_normal((n, d)) * scale / np.sqrt(d)).astype(np.float32)
+    if dup and n >= 100:
+        m = n // 100 + 1
+        corpus[n // 2: n // 2 + m] = corpus[:m]
+    q = rng.uniform(-1, 1, (b, d)).astype(np.float32)
+    ids = (rng.permutation(n).astype(np.int64) * 13 - 17) if perm_ids else np.arange(n, dtype=np.int64)
+    return corpus, ids, q
+
+
+def check(metric, corpus, ids, q, k, path=0, cg=None):
+    ix = G["BruteForceIndex"].apply(metric, G["FuturePool"].immediate_pool())
+    ix.append_batch(ids, corpus)
+    if path:
+        ix.set_option("path", path)
+    if cg:
+        ix.set_option("gemm_cta_group", cg)
+    gi, gd, gc = ix.batch_query_with_distance(q, k)
+    used = ix.stat("last_path")
+    ix.close()
+    oi, od, oc = oracle.query_canonical(metric.ordinal, corpus, ids, q, k)
+    assert (gc == oc).all()
+    assert (gi == oi).all(), f"ids differ at {np.argwhere(gi != oi)[:4].tolist()}"
+    assert (onp.float_order_key(gd) == onp.float_order_key(od)).all()
+    fin = np.isfinite(od)
+    assert np.all(np.abs(gd[fin] - od[fin]) <= REL_TOL * np.abs(od[fin]))
+    if path:
+        assert used == path
+    return used
+
+
+# ------------------------------------------------------------------------------------------------ streaming scan (K2)
+@pytest.mark.parametrize("mi", [0, 1, 2])
+@pytest.mark.parametrize("n,d,b,k", [(1000, 16, 3, 10), (5000, 200, 9, 100), (70_001, 128, 5, 100), (3000, 100, 4, 7),
+                                     (257, 36, 2, 300), (50, 8, 1, 100), (200_000, 64, 1, 200), (33, 3, 2, 5),
+                                     (4097, 1, 2, 9), (9000, 999, 2, 50)])
+def test_scan_path_matches_oracle(mi, n, d, b, k):
+    corpus, ids, q = make(n, d, b, seed=n * 7 + d)
+    check(metrics()[mi], corpus, ids, q, k, path=1)
+
+
+@pytest.mark.parametrize("mi", [0, 1, 2])
+def test_scan_path_duplicates_tie_break_by_id(mi):
+    corpus, ids, q = make(20_000, 200, 8, seed=5, dup=True)
+    check(metrics()[mi], corpus, ids, q, 100, path=1)
+
+
+# ------------------------------------------------------------------------------------------------ tcgen05 GEMM filter (K3)
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("mi", [0, 1, 2])
+@pytest.mark.parametrize("n,d,b,k", [(4096, 64, 128, 10), (50_000, 200, 300, 100), (33_333, 128, 257, 100),
+                                     (20_000, 72, 64, 17), (2000, 200, 1, 100), (131_073, 40, 130, 256)])
+def test_gemm_path_matches_oracle(cg, mi, n, d, b, k):
+    corpus, ids, q = make(n, d, b, seed=n + d + b, dup=(n == 33_333))
+    check(metrics()[mi], corpus, ids, q, k, path=2, cg=cg)
+
+
+def test_auto_path_picks_gemm_for_batches_and_scan_for_single_queries():
+    corpus, ids, q = make(30_000, 200, 64, seed=1)
+    assert check(G["InnerProduct"], corpus, ids, q, 100) == 2
+    assert check(G["InnerProduct"], corpus, ids, q[:1], 100) == 1
+
+
+# ------------------------------------------------------------------------------------------------ config 1 of BASELINE.json
+def test_config1_cosine_100k_x_200_1000_queries():
+    corpus, ids, q = make(100_000, 200, 1000, seed=0x5EED, perm_ids=False)
+    check(G["Cosine"], corpus, ids, q, 100)
+
+
+# ------------------------------------------------------------------------------------------------ edge cases
+@pytest.mark.parametrize("mi", [0, 1, 2])
+def test_k_edge_cases(mi):
+    metric = metrics()[mi]
+    corpus, ids, q = make(300, 24, 4, seed=9)
+    ix = G["BruteForceIndex"].apply(metric, G["FuturePool"].immediate_pool())
+    ix.append_batch(ids, corpus)
+    i, d, c = ix.batch_query_with_distance(q, 0)                          # k == 0: success, empty
+    assert i.shape == (4, 0) and c.tolist() == [0, 0, 0, 0]
+    i, d, c = ix.batch_query_with_distance(q, 301)                        # k > n: n results, padded
+    oi, od, oc = oracle.query_canonical(metric.ordinal, corpus, ids, q, 301)
+    assert c.tolist() == [300] * 4 and (i == oi).all() and (i[:, 300] == -1).all() and np.isinf(d[:, 300]).all()
+    with pytest.raises(G["_capi"].AnnError) as e:
+        ix.batch_query_with_distance(q, -1)
+    assert e.value.code == G["_capi"].ANN_ERR_NEGATIVE_K
+    with pytest.raises(G["_capi"].AnnError) as e:
+        ix.batch_query_with_distance(q[:, :23], 5)
+    assert e.value.code == G["_capi"].ANN_ERR_DIMENSION_MISMATCH
+    with pytest.raises(G["_capi"].AnnError) as e:
+        ix.append_batch([1], np.zeros((1, 25), np.float32))
+    assert e.value.code == G["_capi"].ANN_ERR_DIMENSION_MISMATCH
+    assert ix.query(q[0], 0).result() == [] and ix.query_with_distance(q[0], -3).result() == []
+    ix.close()
+
+
+def test_empty_index_and_single_row():
+    ix = G["BruteForceIndex"].apply(G["L2"], G["FuturePool"].immediate_pool())
+    assert ix.size() == 0
+    assert ix.query(np.zeros(4, np.float32), 5).result() == []
+    ix.append(G["EntityEmbedding"](42, np.array([1, 2, 3, 4], np.float32))).result()
+    assert ix.size() == 1
+    res = ix.query_with_distance(np.array([1, 2, 3, 5], np.float32), 5).result()
+    assert [(n.neighbor, n.distance.distance) for n in res] == [(42, 1.0)]
+    ix.close()
+
+
+@pytest.mark.parametrize("mi", [0, 1, 2])
+def test_special_values_nan_inf_zero_rows(mi):
+    metric = metrics()[mi]
+    rng = np.random.default_rng(3)
+    corpus = rng.standard_normal((2000, 12)).astype(np.float32)
+    corpus[3] = 0.0
+    corpus[7, 2] = np.nan
+    corpus[9, 1] = np.inf
+    corpus[11, 0] = -np.inf
+    corpus[13] = -0.0
+    corpus[1500, 5] = np.nan
+    q = rng.standard_normal((33, 12)).astype(np.float32)
+    ids = rng.permutation(2000).astype(np.int64)
+    used = check(metric, corpus, ids, q, 100)         # batch of 33 would pick the GEMM path: special rows force the scan
+    assert used == 1
+    check(metric, corpus[:1000], ids[:1000], q[:3], 1000, path=1)   # every row returned: NaN distances last, in id order
+    ix = G["BruteForceIndex"].apply(metric, G["FuturePool"].immediate_pool())
+    ix.append_batch(ids, corpus)
+    ix.set_option("path", 2)
+    with pytest.raises(G["_capi"].AnnError):          # the tensor-core filter refuses an index with non-finite rows
+        ix.batch_query_with_distance(q, 10)
+    ix.close()
+
+
+def test_tiny_and_huge_magnitudes():
+    for scale in (1e-3, 1e4):
+        corpus, ids, q = make(5000, 64, 40, seed=11, scale=scale)
+        for m in metrics():
+            check(m, corpus, ids, q * (1.0 if scale < 1 else 100.0), 50)
+
+
+def test_massive_ties_raise_instead_of_returning_wrong_results():
+    """100k identical rows: every row ties at rank k.  The exact selector holds a bounded candidate set, so this must be
+    reported (ANN_ERR_CANDIDATE_OVERFLOW), never answered approximately."""
+    corpus = np.ones((100_000, 16), np.float32)
+    ix = G["BruteForceIndex"].apply(G["InnerProduct"], G["FuturePool"].immediate_pool())
+    ix.append_batch(None, corpus)
+    with pytest.raises(G["_capi"].AnnError) as e:
+        ix.batch_query_with_distance(np.ones((1, 16), np.float32), 10)
+    assert e.value.code == G["_capi"].ANN_ERR_CANDIDATE_OVERFLOW
+    # a tie group that fits is answered exactly: ids ascending
+    small = G["BruteForceIndex"].apply(G["InnerProduct"], G["FuturePool"].immediate_pool())
+    small.append_batch(np.arange(900, 0, -1, dtype=np.int64), np.ones((900, 16), np.float32))
+    i, d, c = small.batch_query_with_distance(np.ones((1, 16), np.float32), 10)
+    assert i[0].tolist() == list(range(1, 11))
+    ix.close()
+    small.close()
+
+
+# ------------------------------------------------------------------------------------------------ Appendable semantics
+def test_incremental_appends_grow_and_are_visible():
+    metric = G["Cosine"]
+    corpus, ids, q = make(30_000, 48, 20, seed=21)
+    ix = G["BruteForceIndex"].apply(metric, G["FuturePool"].immediate_pool())
+    cuts = [0, 1, 100, 1023, 1025, 7000, 30_000]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        ix.append_batch(ids[a:b], corpus[a:b])
+        assert ix.size() == b
+        gi, gd, gc = ix.batch_query_with_distance(q, 10)
+        oi, od, oc = oracle.query_canonical(metric.ordinal, corpus[:b], ids[:b], q, 10)
+        assert (gi == oi).all() and (gc == oc).all()
+    # single-row appends through the Appendable trait are visible to the next query
+    extra = q[0] * 3
+    ix.append(G["EntityEmbedding"](10 ** 12, extra)).result()
+    assert ix.query(extra, 1).result() == [10 ** 12]
+    ix.close()
+
+
+def test_generic_id_type_uses_slot_table():
+    rng = np.random.default_rng(4)
+    rows = rng.standard_normal((50, 6)).astype(np.float32)
+    names = [f"user-{i}" for i in range(50)]
+    ix = G["BruteForceIndex"].apply(G["L2"], G["FuturePool"].immediate_pool(),
+                                    (G["EntityEmbedding"](n, r) for n, r in zip(names, rows)))
+    got = ix.query(rows[17], 3).result()
+    oi, _, _ = oracle.query_canonical(oracle.L2, rows, None, rows[17:18], 3)
+    assert got == [names[j] for j in oi[0]]
+    ix.close()
+
+
+def test_device_pointer_entry_points_and_threaded_pool():
+    import torch
+
+    metric = G["InnerProduct"]
+    corpus, ids, q = make(40_000, 200, 96, seed=31)
+    dev = torch.device("cuda", 0)
+    ix = G["BruteForceIndex"](metric, G["FuturePool"](4), capacity_hint=50_000)
+    ix.append_batch_device(torch.from_numpy(ids).to(dev), torch.from_numpy(corpus).to(dev))
+    qd = torch.from_numpy(q).to(dev)
+    oi_t = torch.empty((96, 100), dtype=torch.int64, device=dev)
+    od_t = torch.empty((96, 100), dtype=torch.float32, device=dev)
+    oc_t = torch.empty((96,), dtype=torch.int32, device=dev)
+    ix.query_batch_device(qd, 100, oi_t, od_t, oc_t, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    ix.raise_pending_error()
+    oi, od, oc = oracle.query_canonical(metric.ordinal, corpus, ids, q, 100)
+    assert (oi_t.cpu().numpy() == oi).all() and (od_t.cpu().numpy().view(np.uint32) == od.view(np.uint32)).all()
+    futs = [ix.query(q[j], 10) for j in range(16)]                       # FuturePool(threads): concurrent single queries
+    for j, f in enumerate(futs):
+        assert f.result() == oi[j, :10].tolist()
+    ix.close()
+
+
+# ------------------------------------------------------------------------------------------------ by-id + sharding on the GPU
+def test_queryable_by_id_batches_on_device():
+    rng = np.random.default_rng(8)
+    corpus, ids, _ = make(20_000, 64, 1, seed=8)
+    users = {u: rng.uniform(-1, 1, 64).astype(np.float32) for u in range(40)}
+
+    class Producer(G["EmbeddingProducer"]):
+        def produce_embedding(self, input):
+            return users.get(input)
+
+    ix = G["BruteForceIndex"].apply(G["Cosine"], G["FuturePool"].immediate_pool())
+    ix.append_batch(ids, corpus)
+    byid = G["QueryableByIdImplementation"](Producer(), ix)
+    seeds = [3, 999, 7, 11]                                             # 999 has no embedding
+    res = byid.batch_query_with_distance_by_id(seeds, 20, None).result()
+    assert [r.seed for r in res] == [3] * 20 + [7] * 20 + [11] * 20
+    for s in (3, 7, 11):
+        oi, od, _ = oracle.query_canonical(oracle.COSINE, corpus, ids, users[s].reshape(1, -1), 20)
+        mine = [r for r in res if r.seed == s]
+        assert [r.neighbor for r in mine] == oi[0].tolist()
+        assert [np.float32(r.distance.distance) for r in mine] == od[0].tolist()
+    ix.close()
+
+
+@pytest.mark.parametrize("mi", [0, 1, 2])
+def test_composed_queryable_over_gpu_shards_equals_single_index(mi):
+    metric = metrics()[mi]
+    corpus, ids, q = make(9000, 32, 37, seed=13, dup=True)
+    pool = G["FuturePool"].immediate_pool()
+    shards = [G["BruteForceIndex"].apply(metric, pool) for _ in range(3)]
+    parts = np.array_split(np.arange(9000), 3)
+    for s, p in zip(shards, parts):
+        s.append_batch(ids[p], corpus[p])
+    composed = G["ComposedQueryable"](shards)
+    gi, gd, gc = composed.batch_query_with_distance(q, 50)
+    oi, od, oc = oracle.query_canonical(metric.ordinal, corpus, ids, q, 50)
+    assert (gi == oi).all() and (gd.view(np.uint32) == od.view(np.uint32)).all() and (gc == oc).all()
+    one = composed.query_with_distance(q[0], 5).result()
+    assert [n.neighbor for n in one] == oi[0, :5].tolist()
+    for s in shards:
+        s.close()
+
+
+def test_merge_kernel_matches_oracle_merge():
+    import torch
+
+    rng = np.random.default_rng(17)
+    s, b, k = 8, 19, 100
+    dist = np.sort(rng.standard_normal((s, b, k)).astype(np.float32), axis=2)
+    dist[:, :, ::7] = np.round(dist[:, :, ::7], 1)                      # cross-shard ties
+    dist = np.sort(dist, axis=2)
+    ids = rng.permutation(s * b * k).astype(np.int64).reshape(s, b, k)
+    cnt = rng.integers(0, k + 1, (s, b)).astype(np.int32)
+    cnt[0] = k
+    dist[3, 2, :5] = np.nan
+    dev = torch.device("cuda", 0)
+    oi, od, oc = G["merge_topk_device"](torch.from_numpy(ids).to(dev), torch.from_numpy(dist).to(dev),
+                                        torch.from_numpy(cnt).to(dev), k)
+    torch.cuda.synchronize()
+    oi, od, oc = oi.cpu().numpy(), od.cpu().numpy(), oc.cpu().numpy()
+    for qi in range(b):
+        # valid prefix of every shard list, canonical order
+        ei, ed, ec = oracle.merge(ids[:, qi], dist[:, qi], cnt[:, qi], k)
+        assert oc[qi] == ec and (oi[qi] == ei).all()
+        assert (onp.float_order_key(od[qi]) == onp.float_order_key(ed)).all()
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+def test_full_size_properties_10m_rows():
+    """At BASELINE's full size the oracle is too slow, so check size-independent properties on a 10M x 128 L2 index:
+    (1) a stored row queried back finds itself first at distance exactly 0; (2) the tensor-core path and the
+    streaming path (two unrelated kernels) return bit-identical lists; (3) lists are sorted under (distance, id);
+    (4) appending the exact query as a new row makes it the new top-1 (visibility at scale)."""
+    import torch
+
+    dev = torch.device("cuda", 0)
+    n, d, k = 10_000_000, 128, 100
+    g = torch.Generator(device=dev)
+    g.manual_seed(123)
+    ix = G["BruteForceIndex"](G["L2"], G["FuturePool"].immediate_pool(), capacity_hint=n + 16)
+    probe_rows = {}
+    for c0 in range(0, n, 1_000_000):
+        rows = torch.randn((1_000_000, d), generator=g, device=dev) / d ** 0.5
+        ix.append_batch_device(torch.arange(c0, c0 + 1_000_000, device=dev, dtype=torch.int64), rows)
+        probe_rows[c0 + 4321] = rows[4321].cpu().numpy()
+    probes = np.stack(list(probe_rows.values()))
+    ix.set_option("path", 1)
+    i1, d1, c1 = ix.batch_query_with_distance(probes, k)
+    assert i1[:, 0].tolist() == list(probe_rows.keys()) and (d1[:, 0] == 0).all()
+    q = (torch.rand((160, d), generator=g, device=dev) * 2 - 1).cpu().numpy()
+    si, sd, _ = ix.batch_query_with_distance(q[:8], k)
+    ix.set_option("path", 2)
+    gi, gd, _ = ix.batch_query_with_distance(q, k)
+    assert (gi[:8] == si).all() and (gd[:8].view(np.uint32) == sd.view(np.uint32)).all()
+    keys = onp.float_order_key(gd).astype(np.int64)
+    assert ((keys[:, 1:] > keys[:, :-1]) | ((keys[:, 1:] == keys[:, :-1]) & (gi[:, 1:] > gi[:, :-1]))).all()
+    ix.append_batch(np.array([n + 7], np.int64), q[5:6])
+    gi2, gd2, _ = ix.batch_query_with_distance(q, k)
+    assert gi2[5, 0] == n + 7 and gd2[5, 0] == 0 and (gi2[5, 1:] == gi[5, :-1]).all()
+    ix.close()

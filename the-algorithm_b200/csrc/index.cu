@@ -12,10 +12,12 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/b200ann.h"
@@ -122,6 +124,12 @@ struct ann_index {
 
     // options / stats
     int path_opt = 0, gemm_min_batch = 16, gemm_cta_group = 2;
+    // optional CUDA-event timing of the dominant kernel of each path, on the launching stream (bench.py roofline)
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pairs;
+    size_t ev_used = 0;
+    double kernel_ms_total = 0.0;
+    long long kernel_launches_timed = 0;
     long long last_candidates = 0;
     long long launches = 0, last_path = 0, scan_fallback_queries = 0;
 };
@@ -207,6 +215,40 @@ int append_device_core(ann_index* ix, const int64_t* d_ids, const float* d_rows,
     CUDA_TRY(launch_append(ap, st));
     ix->launches++;
     return ANN_OK;
+}
+
+
+// ---- optional per-launch CUDA-event timing (enabled with ann_set_option("timing", 1)) ----
+struct TimedScope {
+    ann_index* ix;
+    cudaStream_t st;
+    std::pair<cudaEvent_t, cudaEvent_t>* pr = nullptr;
+    TimedScope(ann_index* i, cudaStream_t s) : ix(i), st(s) {
+        if (!ix->timing) return;
+        if (ix->ev_used == ix->ev_pairs.size()) {
+            cudaEvent_t a, b;
+            if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+            ix->ev_pairs.emplace_back(a, b);
+        }
+        pr = &ix->ev_pairs[ix->ev_used++];
+        cudaEventRecord(pr->first, st);
+    }
+    ~TimedScope() {
+        if (pr) cudaEventRecord(pr->second, st);
+    }
+};
+
+// fold finished event pairs into kernel_ms_total (call after the stream has been synchronised)
+void harvest_timing(ann_index* ix) {
+    for (size_t i = 0; i < ix->ev_used; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ix->ev_pairs[i].first, ix->ev_pairs[i].second) == cudaSuccess) {
+            ix->kernel_ms_total += ms;
+            ix->kernel_launches_timed++;
+        }
+    }
+    ix->ev_used = 0;
+    (void)cudaGetLastError();
 }
 
 struct ScanPlan {
@@ -296,7 +338,10 @@ int query_scan(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
             sp.j_pub = pl.j_pub;
             sp.warps = pl.warps;
             sp.cap = pl.cap;
-            CUDA_TRY(launch_scan(sp, pl.qb, pl.grid, pl.smem, st));
+            {
+                TimedScope ts(ix, st);
+                CUDA_TRY(launch_scan(sp, pl.qb, pl.grid, pl.smem, st));
+            }
             ix->launches++;
         }
         SelectParams fp{};
@@ -386,7 +431,7 @@ int query_gemm(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
     // chunk schedule: the first chunk is scored with tau = +inf (every row is a candidate), so it must fit the pool;
     // afterwards a chunk `growth` times the rows seen so far adds ~ (growth-1) * k * (margin inflation) candidates.
     const long long first = std::min<long long>(ix->n, kGemmPoolCap / 2);
-    int growth = (int)std::min<long long>(8, std::max<long long>(2, 2400 / std::max(1, k_eff)));
+    int growth = (int)std::min<long long>(8, std::max<long long>(2, 1400 / std::max(1, k_eff)));
     long long begin = 0, end = first;
     for (;;) {
         GemmLaunch g{};
@@ -403,8 +448,25 @@ int query_gemm(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
         g.qstate = ix->qstate.p;
         g.pool = ix->pool.p;
         g.pool_cap = kGemmPoolCap;
-        CUDA_TRY(launch_gemm_filter(g, st));
+        {
+            TimedScope ts(ix, st);
+            CUDA_TRY(launch_gemm_filter(g, st));
+        }
         ix->launches++;
+        if (getenv("B200ANN_DEBUG")) {
+            std::vector<QueryState> h(b);
+            CUDA_TRY(cudaStreamSynchronize(st));
+            CUDA_TRY(cudaMemcpy(h.data(), ix->qstate.p, sizeof(QueryState) * b, cudaMemcpyDeviceToHost));
+            uint32_t mx = 0, mn = ~0u;
+            double sum = 0;
+            for (auto& x : h) {
+                mx = std::max(mx, x.pool_count);
+                mn = std::min(mn, x.pool_count);
+                sum += x.pool_count;
+            }
+            fprintf(stderr, "[b200ann] chunk [%lld,%lld): pool_count min %u mean %.1f max %u  eps_abs[0]=%g tau[0]=%g\n", begin, end,
+                    mn, sum / b, mx, h[0].eps_abs, float_from_order_key(h[0].tau_key));
+        }
         if (end >= ix->n) break;
         CUDA_TRY(launch_compact_pool(fp, b, st));
         ix->launches++;
@@ -549,6 +611,10 @@ void ann_destroy(ann_index* ix) {
     ix->out_count.release();
     ix->stage_ids.release();
     ix->stage_rows.release();
+    for (auto& pr : ix->ev_pairs) {
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
     if (ix->stream) cudaStreamDestroy(ix->stream);
     (void)cudaGetLastError();
     delete ix;
@@ -584,7 +650,7 @@ int ann_append_batch_device(ann_index* ix, const int64_t* d_ids, const float* d_
     std::lock_guard<std::mutex> lk(ix->mu);
     int rc = set_device(ix);
     if (rc) return rc;
-    cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    cudaStream_t st = (cudaStream_t)stream;  // NULL = the legacy default stream, as everywhere in CUDA
     rc = append_device_core(ix, d_ids, d_rows, n, st);
     if (rc) return rc;
     // the special-row census decides which query kernels are legal, so it must be current
@@ -605,7 +671,7 @@ int ann_query_batch_device(ann_index* ix, const float* d_queries, int32_t b, int
     std::lock_guard<std::mutex> lk(ix->mu);
     int rc = set_device(ix);
     if (rc) return rc;
-    cudaStream_t st = stream ? (cudaStream_t)stream : ix->stream;
+    cudaStream_t st = (cudaStream_t)stream;  // NULL = the legacy default stream
     return query_core(ix, d_queries, b, k, d_out_ids, d_out_dist, d_out_count, st);
 }
 
@@ -659,6 +725,13 @@ int ann_set_option(ann_index* ix, const char* name, int64_t value) {
         ix->path_opt = (int)value;
         return ANN_OK;
     }
+    if (!strcmp(name, "timing")) {
+        ix->timing = value != 0;
+        ix->kernel_ms_total = 0.0;
+        ix->kernel_launches_timed = 0;
+        ix->ev_used = 0;
+        return ANN_OK;
+    }
     if (!strcmp(name, "gemm_cta_group")) {
         if (value != 1 && value != 2) return fail(ANN_ERR_INVALID_ARGUMENT, "gemm_cta_group must be 1 or 2");
         ix->gemm_cta_group = (int)value;
@@ -682,6 +755,16 @@ int ann_get_stat(const ann_index* ix, const char* name, int64_t* value) {
         CUDA_TRY(cudaDeviceSynchronize());
         *value = 0;
         return check_device_flags(m, m->stream);
+    }
+    if (!strcmp(name, "kernel_us") || !strcmp(name, "kernel_launches_timed")) {
+        // dominant-kernel time accumulated since timing was switched on; synchronises the device
+        ann_index* m = const_cast<ann_index*>(ix);
+        std::lock_guard<std::mutex> lk(m->mu);
+        CUDA_TRY(cudaSetDevice(m->device));
+        CUDA_TRY(cudaDeviceSynchronize());
+        harvest_timing(m);
+        *value = !strcmp(name, "kernel_us") ? (int64_t)(m->kernel_ms_total * 1000.0) : m->kernel_launches_timed;
+        return ANN_OK;
     }
     if (!strcmp(name, "launches")) *value = ix->launches;
     else if (!strcmp(name, "last_path")) *value = ix->last_path;

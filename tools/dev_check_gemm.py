@@ -91,7 +91,7 @@ if mode == "time":
     oi = torch.empty((b, k), dtype=torch.int64, device=dev)
     od = torch.empty((b, k), dtype=torch.float32, device=dev)
     oc = torch.empty((b,), dtype=torch.int32, device=dev)
-    ts = torch.cuda.Stream(dev)
+    ts = torch.cuda.current_stream()
     st = ts.cuda_stream
     torch.cuda.synchronize()
     for _ in range(2):

@@ -79,7 +79,7 @@ for (metric, n, d) in [(L2, 10_000_000, 128), (InnerProduct, 10_000_000, 200)]:
         oi = torch.empty((b, 100), dtype=torch.int64, device=dev)
         od = torch.empty((b, 100), dtype=torch.float32, device=dev)
         oc = torch.empty((b,), dtype=torch.int32, device=dev)
-        ts = torch.cuda.Stream(dev)
+        ts = torch.cuda.current_stream()
         st = ts.cuda_stream
         torch.cuda.synchronize()
         for _ in range(3):
