@@ -170,28 +170,46 @@ def test_special_values_nan_inf_zero_rows(mi):
 
 
 def test_tiny_and_huge_magnitudes():
-    for scale in (1e-3, 1e4):
+    for scale in (1e-6, 1e6):
         corpus, ids, q = make(5000, 64, 40, seed=11, scale=scale)
         for m in metrics():
             check(m, corpus, ids, q * (1.0 if scale < 1 else 100.0), 50)
 
 
-def test_massive_ties_raise_instead_of_returning_wrong_results():
-    """100k identical rows: every row ties at rank k.  The exact selector holds a bounded candidate set, so this must be
-    reported (ANN_ERR_CANDIDATE_OVERFLOW), never answered approximately."""
+def test_massive_ties_are_answered_exactly_by_the_fallback():
+    """100k identical rows: every row ties at rank k, far more than the bounded selector holds.  The host entry point
+    re-answers such queries with the exact fallback (exact distance for every row + radix select on (distance, id)); the
+    asynchronous device entry point reports them instead of guessing."""
+    import torch
+
     corpus = np.ones((100_000, 16), np.float32)
+    ids = np.random.default_rng(0).permutation(100_000).astype(np.int64)
     ix = G["BruteForceIndex"].apply(G["InnerProduct"], G["FuturePool"].immediate_pool())
-    ix.append_batch(None, corpus)
+    ix.append_batch(ids, corpus)
+    q = np.ones((2, 16), np.float32)
+    q[1, 0] = 0.5
+    i, d, c = ix.batch_query_with_distance(q, 10)
+    assert i.tolist() == [list(range(10))] * 2 and c.tolist() == [10, 10]
+    assert d[0].tolist() == [-15.0] * 10 and d[1].tolist() == [-14.5] * 10
+    assert ix.stat("exact_fallback_queries") == 2
+    dev = torch.device("cuda", 0)
+    oi = torch.empty((2, 10), dtype=torch.int64, device=dev)
+    od = torch.empty((2, 10), dtype=torch.float32, device=dev)
+    ix.query_batch_device(torch.from_numpy(q).to(dev), 10, oi, od, None)
     with pytest.raises(G["_capi"].AnnError) as e:
-        ix.batch_query_with_distance(np.ones((1, 16), np.float32), 10)
+        ix.raise_pending_error()
     assert e.value.code == G["_capi"].ANN_ERR_CANDIDATE_OVERFLOW
-    # a tie group that fits is answered exactly: ids ascending
-    small = G["BruteForceIndex"].apply(G["InnerProduct"], G["FuturePool"].immediate_pool())
-    small.append_batch(np.arange(900, 0, -1, dtype=np.int64), np.ones((900, 16), np.float32))
-    i, d, c = small.batch_query_with_distance(np.ones((1, 16), np.float32), 10)
-    assert i[0].tolist() == list(range(1, 11))
     ix.close()
-    small.close()
+
+
+@pytest.mark.parametrize("mi", [0, 1, 2])
+def test_degenerate_queries_nan_and_zero(mi):
+    """A NaN query makes every distance NaN (all tie, order by id); a zero query does the same under Cosine."""
+    metric = metrics()[mi]
+    corpus, ids, q = make(7000, 20, 3, seed=77)
+    q[0, 3] = np.nan
+    q[1] = 0.0
+    check(metric, corpus, ids, q, 25)
 
 
 # ------------------------------------------------------------------------------------------------ Appendable semantics

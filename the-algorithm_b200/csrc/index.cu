@@ -119,8 +119,7 @@ struct ann_index {
     DevBuf<uint32_t> special_rows, pub_keys;
     DevBuf<int64_t> out_ids;
     DevBuf<int32_t> out_count;
-    DevBuf<int64_t> stage_ids;
-    DevBuf<float> stage_rows;
+    DevBuf<unsigned char> fb_scratch;
 
     // options / stats
     int path_opt = 0, gemm_min_batch = 16, gemm_cta_group = 2;
@@ -131,7 +130,7 @@ struct ann_index {
     double kernel_ms_total = 0.0;
     long long kernel_launches_timed = 0;
     long long last_candidates = 0;
-    long long launches = 0, last_path = 0, scan_fallback_queries = 0;
+    long long launches = 0, last_path = 0, exact_fallback_queries = 0;
 };
 
 namespace {
@@ -508,6 +507,45 @@ int query_core(ann_index* ix, const float* d_queries, int b, int k, int64_t* d_o
     return query_scan(ix, d_queries, b, k_eff, k, d_out_ids, d_out_dist, d_out_count, st);
 }
 
+
+// Queries the bounded selector flagged (QueryState.flags != 0) are answered again, exactly, by exact_fallback.cu.
+// Needs the per-query flags on the host, so it synchronises `st`; used by the host-buffer entry point.
+int resolve_flagged(ann_index* ix, const float* d_queries, int b, int k, int64_t* d_out_ids, float* d_out_dist,
+                    int32_t* d_out_count, cudaStream_t st) {
+    if (b == 0 || k == 0 || ix->n == 0) return ANN_OK;
+    DeviceScalars hs{};
+    CUDA_TRY(cudaMemcpyAsync(&hs, ix->scalars, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (!hs.error_flags) return ANN_OK;
+    std::vector<QueryState> h((size_t)b);
+    CUDA_TRY(cudaMemcpyAsync(h.data(), ix->qstate.p, sizeof(QueryState) * (size_t)b, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    const int k_eff = (int)std::min<long long>(k, ix->n);
+    CUDA_TRY(ix->fb_scratch.ensure(fallback_scratch_bytes(ix->n, k_eff)));
+    for (int q = 0; q < b; ++q) {
+        if (!h[q].flags) continue;
+        FallbackParams fp{};
+        fp.rows = ix->rows;
+        fp.ids = ix->ids;
+        fp.n_rows = ix->n;
+        fp.pitch = ix->pitch;
+        fp.dim = ix->dim;
+        fp.metric = ix->metric;
+        fp.l2_squared = ix->l2_squared ? 1 : 0;
+        fp.query = d_queries + (size_t)q * ix->dim;
+        fp.scratch = ix->fb_scratch.p;
+        fp.k = k_eff;
+        fp.k_out = k;
+        fp.out_ids = d_out_ids + (size_t)q * k;
+        fp.out_dist = d_out_dist + (size_t)q * k;
+        fp.out_count = d_out_count ? d_out_count + q : nullptr;
+        CUDA_TRY(launch_exact_fallback(fp, st, &ix->launches));
+        ix->exact_fallback_queries++;
+    }
+    CUDA_TRY(cudaMemsetAsync(&ix->scalars->error_flags, 0, sizeof(uint32_t), st));
+    return ANN_OK;
+}
+
 // read and clear the sticky device error word; call after a synchronisation point
 int check_device_flags(ann_index* ix, cudaStream_t st) {
     DeviceScalars h{};
@@ -609,8 +647,7 @@ void ann_destroy(ann_index* ix) {
     ix->pub_keys.release();
     ix->out_ids.release();
     ix->out_count.release();
-    ix->stage_ids.release();
-    ix->stage_rows.release();
+    ix->fb_scratch.release();
     for (auto& pr : ix->ev_pairs) {
         cudaEventDestroy(pr.first);
         cudaEventDestroy(pr.second);
@@ -695,6 +732,8 @@ int ann_query_batch(ann_index* ix, const float* queries, int32_t b, int32_t dim,
     CUDA_TRY(cudaMemcpyAsync(ix->q_in.p, queries, (size_t)b * ix->dim * sizeof(float), cudaMemcpyHostToDevice, st));
     rc = query_core(ix, ix->q_in.p, b, k, ix->out_ids.p, ix->out_dist.p, ix->out_count.p, st);
     if (rc) return rc;
+    rc = resolve_flagged(ix, ix->q_in.p, b, k, ix->out_ids.p, ix->out_dist.p, ix->out_count.p, st);
+    if (rc) return rc;
     if (k > 0) {
         CUDA_TRY(cudaMemcpyAsync(out_ids, ix->out_ids.p, (size_t)b * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaMemcpyAsync(out_dist, ix->out_dist.p, (size_t)b * k * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -768,7 +807,7 @@ int ann_get_stat(const ann_index* ix, const char* name, int64_t* value) {
     }
     if (!strcmp(name, "launches")) *value = ix->launches;
     else if (!strcmp(name, "last_path")) *value = ix->last_path;
-    else if (!strcmp(name, "scan_fallback_queries")) *value = ix->scan_fallback_queries;
+    else if (!strcmp(name, "exact_fallback_queries")) *value = ix->exact_fallback_queries;
     else if (!strcmp(name, "n_special")) *value = (int64_t)ix->n_special;
     else if (!strcmp(name, "row_bytes")) *value = (int64_t)ix->n * ix->pitch * 4;
     else if (!strcmp(name, "shadow_bytes")) *value = ix->shadow ? (int64_t)ix->n * ix->kp * 2 : 0;

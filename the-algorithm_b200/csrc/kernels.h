@@ -88,6 +88,22 @@ cudaError_t launch_fill_empty(int64_t* out_ids, float* out_dist, int32_t* out_co
 cudaError_t launch_merge(const int64_t* ids, const float* dist, const int32_t* count, int shards, int b, int k,
                          int64_t* out_ids, float* out_dist, int32_t* out_count, cudaStream_t stream);
 
+// ---------------------------------------------------------------- exact fallback (degenerate ties, NaN queries)
+struct FallbackParams {
+    const float* rows;
+    const int64_t* ids;
+    long long n_rows;
+    int pitch, dim, metric, l2_squared;
+    const float* query;     // [dim] fp32 on the device
+    void* scratch;          // fallback_scratch_bytes(n_rows, k)
+    int k, k_out;           // k = min(requested k, n_rows)
+    int64_t* out_ids;       // [k_out] slots of this query
+    float* out_dist;
+    int32_t* out_count;     // may be nullptr
+};
+size_t fallback_scratch_bytes(long long n, int k);
+cudaError_t launch_exact_fallback(const FallbackParams& p, cudaStream_t stream, long long* launches);
+
 // ---------------------------------------------------------------- K3: tcgen05 GEMM filter
 struct GemmLaunch {
     const void* q_shadow;       // bf16 [b_pad][kp]
