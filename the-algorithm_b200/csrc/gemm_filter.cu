@@ -23,6 +23,7 @@
 // the tail columns.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -48,6 +49,7 @@ struct GemmArgs {
     QueryState* qstate;
     entry_t* pool;
     int pool_cap;
+    int debug_nohit;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -133,6 +135,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
           "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr)
         : "memory");
+}
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, float* v) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+    *v = __uint_as_float(r);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -293,26 +300,57 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
         }
     } else if (warp >= kEpiWarp0) {
         // ================================ epilogue: TMEM -> registers -> threshold filter ================================
+        // One TMEM lane = one query, so the query's threshold lives in a register and a score costs one compare
+        // (the compiler folds 32 compares into a max tree).  Thresholds are constant for the launch; the one for the
+        // next query tile is prefetched while the current tile is scanned.  Survivors are rare: a thread parks up to
+        // kHitRegs of them in registers, releases the accumulator, reserves pool slots with ONE atomic, and writes
+        // the entries one tile later, when the atomic's round trip has long completed.
+        constexpr int kHitRegs = 4;
         const int e = warp - kEpiWarp0;
         const int quarter = warp & 3;                 // TMEM lanes 32*quarter .. +31 are the ones this warp may touch
         const int half = e >> 2;                      // which half of the N columns
         constexpr int COLS_PER_WARP = N_TILE / 2;
+        const int q_lane = (int)rank * kTileRows + quarter * 32 + lane;
+        auto load_tau = [&](int qt) -> uint32_t {
+            const int q = qt * N_TILE + q_lane;
+            return q < a.b ? __ldcg(&a.qstate[q].tau_key) : 0u;
+        };
+        auto emit_now = [&](int q, float v, uint32_t row) {
+            uint32_t slot = atomicAdd(&a.qstate[q].pool_count, 1u);
+            if (slot < (uint32_t)a.pool_cap) a.pool[(size_t)q * a.pool_cap + slot] = make_entry(-v, row);
+        };
+        // deferred hits of the previous tile
+        float pv[kHitRegs];
+        uint32_t pr[kHitRegs];
+        int pcnt = 0, pq = 0;
+        uint32_t pslot = 0;
+        auto flush_prev = [&]() {
+            if (pcnt) {
+#pragma unroll
+                for (int i = 0; i < kHitRegs; ++i)
+                    if (i < pcnt && pslot + i < (uint32_t)a.pool_cap) a.pool[(size_t)pq * a.pool_cap + pslot + i] = make_entry(-pv[i], pr[i]);
+            }
+            pcnt = 0;
+        };
         uint32_t ge = 0;
+        uint32_t tk_next = (cluster_id < n_rt) ? load_tau(0) : 0u;
         for (int rt = cluster_id; rt < n_rt; rt += n_clusters) {
             const long long tile_row0 = a.row_begin + (long long)rt * N_TILE;
             const int valid_cols = (int)min((long long)N_TILE, a.row_end - tile_row0);
             for (int qt = 0; qt < a.n_qt; ++qt, ++ge) {
                 const uint32_t s = ge & 1;
-                const int q = qt * N_TILE + (int)rank * kTileRows + quarter * 32 + lane;
+                const int q = qt * N_TILE + q_lane;
                 const bool q_ok = q < a.b;
-                float thr = INFINITY;                 // scores >= thr survive; +inf rejects everything (padding query)
-                if (q_ok) {
-                    uint32_t tk = __ldcg(&a.qstate[q].tau_key);
-                    thr = (tk >= 0xFF800000u) ? -INFINITY : -float_from_order_key(tk);
-                }
+                const uint32_t tk = tk_next;
+                tk_next = load_tau(qt + 1 < a.n_qt ? qt + 1 : 0);   // in flight while this tile is scanned
+                // scores >= thr survive; +inf rejects everything (padding query), -inf accepts everything (tau = +inf)
+                const float thr = (!q_ok || a.debug_nohit) ? INFINITY : (tk >= 0xFF800000u ? -INFINITY : -float_from_order_key(tk));
                 mbar_wait(&t_full[s], (ge >> 1) & 1);
                 tc_fence_after();
                 const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + s * N_TILE + half * COLS_PER_WARP;
+                float cv[kHitRegs];
+                uint32_t cr[kHitRegs];
+                int ccnt = 0;
 #pragma unroll 1
                 for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 32) {
                     float v[32];
@@ -322,25 +360,60 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
                     bool any = false;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) any |= (v[j] >= thr);
-                    if (any && col0 < valid_cols) {
+                    // Rare path, kept small on purpose (a 32x unrolled hit handler blew the instruction cache and
+                    // stalled the MMA warp): build this lane's hit mask, OR it across the warp, and for every column
+                    // some lane hit re-read that single column from TMEM (warp-uniform address).
+                    if (__any_sync(0xFFFFFFFFu, any) && col0 < valid_cols) {
+                        uint32_t mask = 0;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (v[j] >= thr && col0 + j < valid_cols) {
-                                uint32_t slot = atomicAdd(&a.qstate[q].pool_count, 1u);
-                                if (slot < (uint32_t)a.pool_cap)
-                                    a.pool[(size_t)q * a.pool_cap + slot] = make_entry(-v[j], (uint32_t)(tile_row0 + col0 + j));
+                        for (int j = 0; j < 32; ++j) mask |= (v[j] >= thr) ? (1u << j) : 0u;
+                        const int left = valid_cols - col0;
+                        if (left < 32) mask &= (1u << left) - 1u;
+                        uint32_t um = __reduce_or_sync(0xFFFFFFFFu, mask);
+                        while (um) {
+                            const int j = __ffs(um) - 1;
+                            um &= um - 1;
+                            float x;
+                            tmem_ld1(t_lane + c0 + j, &x);
+                            tmem_ld_wait();
+                            if ((mask >> j) & 1u) {
+                                const uint32_t row = (uint32_t)(tile_row0 + col0 + j);
+                                if (ccnt < kHitRegs) {
+#pragma unroll
+                                    for (int i = 0; i < kHitRegs; ++i)
+                                        if (i == ccnt) {
+                                            cv[i] = x;
+                                            cr[i] = row;
+                                        }
+                                    ++ccnt;
+                                } else {
+                                    emit_now(q, x, row);   // dense regions (first chunk): straight to the pool
+                                }
                             }
                         }
                     }
                 }
+                // accumulator fully read: hand it back to the MMA warp before touching global memory
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) {
                     if constexpr (CG == 1) mbar_arrive(&t_empty[s]);
                     else asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(&t_empty[s]) & kPeerMask) : "memory");
                 }
+                flush_prev();                          // previous tile's slots were reserved one tile ago
+                if (ccnt) {
+                    pslot = atomicAdd(&a.qstate[q].pool_count, (uint32_t)ccnt);
+                    pq = q;
+                    pcnt = ccnt;
+#pragma unroll
+                    for (int i = 0; i < kHitRegs; ++i) {
+                        pv[i] = cv[i];
+                        pr[i] = cr[i];
+                    }
+                }
             }
         }
+        flush_prev();
     }
 
     // ---- teardown ----
@@ -416,6 +489,7 @@ cudaError_t launch_gemm_filter(const GemmLaunch& g, cudaStream_t stream) {
     a.qstate = g.qstate;
     a.pool = g.pool;
     a.pool_cap = g.pool_cap;
+    a.debug_nohit = getenv("B200ANN_NOHIT") ? 1 : 0;
     const long long rows = g.row_end - g.row_begin;
     const int n_rt = (int)((rows + n_tile - 1) / n_tile);
     if (n_rt <= 0 || a.n_qt <= 0) return cudaSuccess;

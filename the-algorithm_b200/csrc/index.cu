@@ -447,14 +447,28 @@ int query_gemm(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
         g.qstate = ix->qstate.p;
         g.pool = ix->pool.p;
         g.pool_cap = kGemmPoolCap;
+        cudaEvent_t dbg0 = nullptr, dbg1 = nullptr;
+        const bool dbg = getenv("B200ANN_DEBUG") != nullptr;
+        if (dbg) {
+            cudaEventCreate(&dbg0);
+            cudaEventCreate(&dbg1);
+            cudaEventRecord(dbg0, st);
+        }
         {
             TimedScope ts(ix, st);
             CUDA_TRY(launch_gemm_filter(g, st));
         }
         ix->launches++;
-        if (getenv("B200ANN_DEBUG")) {
+        if (dbg) {
             std::vector<QueryState> h(b);
+            cudaEventRecord(dbg1, st);
             CUDA_TRY(cudaStreamSynchronize(st));
+            float dms = 0.f;
+            cudaEventElapsedTime(&dms, dbg0, dbg1);
+            fprintf(stderr, "[b200ann] gemm launch %.3f ms, %.1f TFLOP/s\n", dms,
+                    2.0 * (double)(end - begin) * ix->dim * b / (dms * 1e-3) / 1e12);
+            cudaEventDestroy(dbg0);
+            cudaEventDestroy(dbg1);
             CUDA_TRY(cudaMemcpy(h.data(), ix->qstate.p, sizeof(QueryState) * b, cudaMemcpyDeviceToHost));
             uint32_t mx = 0, mn = ~0u;
             double sum = 0;

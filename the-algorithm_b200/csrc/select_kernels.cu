@@ -19,25 +19,6 @@ constexpr int kSelThreads = 512;
 constexpr int kSortCap = 4096;    // approximate-stage sort capacity per query
 constexpr int kExactCap = 2048;   // survivors + specials rescored exactly (power of two)
 
-__device__ void bitonic_sort_entries(entry_t* a, int n2) {
-    for (int k = 2; k <= n2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < n2; i += blockDim.x) {
-                int ixj = i ^ j;
-                if (ixj > i) {
-                    entry_t x = a[i], y = a[ixj];
-                    bool up = ((i & k) == 0);
-                    if ((x > y) == up) {
-                        a[i] = y;
-                        a[ixj] = x;
-                    }
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
-
 __device__ __forceinline__ bool pair_greater(uint32_t ka, long long ia, uint32_t kb, long long ib) {
     return ka > kb || (ka == kb && ia > ib);
 }
@@ -105,13 +86,65 @@ __device__ float exact_distance(int metric, const float* __restrict__ a, const f
     return __fsub_rn(1.0f, __double2float_rn(cs));
 }
 
-// Shared front end of compaction and finalize: filter the pool by the current threshold, sort, find the
-// survivors (everything within the margin of the k-th best).  Returns the survivor count in *n_surv and the
-// tightened threshold in *tau_out; entries are left sorted in `buf`.  Returns false on overflow.
-__device__ bool select_survivors(const SelectParams& p, int q, entry_t* buf, int* n_surv, float* tau_out) {
+// k-th smallest 32-bit key among the n entries of `buf` (k >= 1, n >= k): 4 MSB-first passes of 8 bits, each a
+// 256-bin shared-memory histogram over the entries still matching the prefix and a one-warp scan that picks the bin.
+__device__ uint32_t kth_key_radix(const entry_t* buf, int n, int k, uint32_t* hist) {
+    __shared__ uint32_t prefix_s, krem_s;
+    if (threadIdx.x == 0) {
+        prefix_s = 0;
+        krem_s = (uint32_t)k;
+    }
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        const uint32_t prefix = prefix_s;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint32_t key = (uint32_t)(buf[i] >> 32);
+            if (pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            uint32_t c[8], sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                c[j] = hist[lane * 8 + j];
+                sum += c[j];
+            }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const uint32_t excl = incl - sum, krem = krem_s;
+            // exactly one lane has excl < krem <= incl
+            if (excl < krem && krem <= incl) {
+                uint32_t cum = excl;
+                int bin = lane * 8 + 7;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (cum + c[j] >= krem) {
+                        bin = lane * 8 + j;
+                        break;
+                    }
+                    cum += c[j];
+                }
+                prefix_s = prefix | ((uint32_t)bin << shift);
+                krem_s = krem - cum;
+            }
+        }
+        __syncthreads();
+    }
+    return prefix_s;
+}
+
+// Shared front end of compaction and finalize: load the pool entries that pass the current threshold into `buf`
+// (unsorted), find the k-th best approximate badness with a radix select, tighten the threshold to k-th + margin.
+// Everything with g <= *tau_out may still belong to the exact top-k.  Returns false on overflow.
+__device__ bool load_and_threshold(const SelectParams& p, int q, entry_t* buf, uint32_t* hist, int* n_out, float* tau_out) {
     __shared__ int n_s;
-    __shared__ float tau_s;
-    __shared__ int ok_s;
     QueryState* qs = p.qstate + q;
     const float eps_abs = qs->eps_abs, eps_rel = qs->eps_rel;
     const int pool_n = min((int)qs->pool_count, p.pool_cap);
@@ -122,10 +155,7 @@ __device__ bool select_survivors(const SelectParams& p, int q, entry_t* buf, int
         uint32_t gk = cta_kth_smallest_key(p.pub_keys + (size_t)q * p.pub_stride, p.pub_count, p.j_pub, nullptr);
         if (gk < 0xFF800000u) tau = fminf(tau, widen(float_from_order_key(gk), eps_abs, eps_rel));
     }
-    if (threadIdx.x == 0) {
-        n_s = 0;
-        ok_s = 1;
-    }
+    if (threadIdx.x == 0) n_s = 0;
     __syncthreads();
     const entry_t* pool = p.pool + (size_t)q * p.pool_cap;
     for (int i = threadIdx.x; i < pool_n; i += blockDim.x) {
@@ -136,37 +166,18 @@ __device__ bool select_survivors(const SelectParams& p, int q, entry_t* buf, int
         }
     }
     __syncthreads();
-    int n = n_s;
+    const int n = n_s;
     if (n > kSortCap) {
         if (threadIdx.x == 0) atomicOr(&qs->flags, kFlagSurvivorOverflow);
         return false;
     }
-    int n2 = 2;
-    while (n2 < n) n2 <<= 1;
-    for (int i = n + threadIdx.x; i < n2; i += blockDim.x) buf[i] = kEntryPad;
-    __syncthreads();
-    bitonic_sort_entries(buf, n2);
-    if (threadIdx.x == 0) {
-        float t = tau;
-        if (n >= p.k && p.k > 0) t = fminf(t, widen(entry_g(buf[p.k - 1]), eps_abs, eps_rel));
-        tau_s = t;
+    if (n >= p.k && p.k > 0) {
+        const uint32_t kk = kth_key_radix(buf, n, p.k, hist);
+        tau = fminf(tau, widen(float_from_order_key(kk), eps_abs, eps_rel));
     }
-    __syncthreads();
-    tau = tau_s;
-    // survivors = sorted prefix with g <= tau : binary search by one thread
-    if (threadIdx.x == 0) {
-        int lo = 0, hi = n;
-        while (lo < hi) {
-            int mid = (lo + hi) >> 1;
-            if (entry_g(buf[mid]) <= tau) lo = mid + 1;
-            else hi = mid;
-        }
-        n_s = lo;
-    }
-    __syncthreads();
-    *n_surv = n_s;
+    *n_out = n;
     *tau_out = tau;
-    return ok_s != 0;
+    return true;
 }
 
 }  // namespace
@@ -175,19 +186,27 @@ __device__ bool select_survivors(const SelectParams& p, int q, entry_t* buf, int
 __global__ void __launch_bounds__(kSelThreads) compact_pool_kernel(SelectParams p) {
     extern __shared__ __align__(16) unsigned char sm[];
     entry_t* buf = reinterpret_cast<entry_t*>(sm);
+    __shared__ uint32_t hist[256];
+    __shared__ int n_keep;
     const int q = blockIdx.x;
     QueryState* qs = p.qstate + q;
     if (qs->pool_count > (uint32_t)p.pool_cap) {
         if (threadIdx.x == 0) atomicOr(&qs->flags, kFlagPoolOverflow);
         return;
     }
-    int n_surv;
+    int n;
     float tau;
-    if (!select_survivors(p, q, buf, &n_surv, &tau)) return;
+    if (!load_and_threshold(p, q, buf, hist, &n, &tau)) return;
+    if (threadIdx.x == 0) n_keep = 0;
+    __syncthreads();
     entry_t* pool = p.pool + (size_t)q * p.pool_cap;
-    for (int i = threadIdx.x; i < n_surv; i += blockDim.x) pool[i] = buf[i];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const entry_t e = buf[i];
+        if (entry_g(e) <= tau) pool[atomicAdd(&n_keep, 1)] = e;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        qs->pool_count = n_surv;
+        qs->pool_count = n_keep;
         qs->tau_key = float_order_key(tau);
     }
 }
@@ -198,6 +217,8 @@ __global__ void __launch_bounds__(kSelThreads) finalize_kernel(SelectParams p) {
     entry_t* buf = reinterpret_cast<entry_t*>(sm);                       // kSortCap entries
     long long* cid = reinterpret_cast<long long*>(sm + kSortCap * 8);      // kExactCap ids
     uint32_t* ckey = reinterpret_cast<uint32_t*>(sm + kSortCap * 8 + kExactCap * 8);  // kExactCap keys
+    __shared__ uint32_t hist[256];
+    __shared__ int n_cand_s;
     const int q = blockIdx.x;
     QueryState* qs = p.qstate + q;
     int64_t* oid = p.out_ids + (size_t)q * p.k_out;
@@ -216,25 +237,43 @@ __global__ void __launch_bounds__(kSelThreads) finalize_kernel(SelectParams p) {
         fail_fill();
         return;
     }
-    int n_surv;
+    int n;
     float tau;
-    if (!select_survivors(p, q, buf, &n_surv, &tau)) {
+    if (!load_and_threshold(p, q, buf, hist, &n, &tau)) {
         fail_fill();
         return;
     }
+    if (qs->flags & (kFlagPoolOverflow | kFlagSpecialOverflow)) {
+        fail_fill();
+        return;
+    }
+    // exact rescoring of every survivor (g <= tau) and every special row; unordered, the final sort orders them
     const int n_spec = min((int)qs->special_count, kSpecialCap);
-    const int n_cand = n_surv + n_spec;
-    if (n_cand > kExactCap || (qs->flags & (kFlagPoolOverflow | kFlagSpecialOverflow))) {
-        if (threadIdx.x == 0 && n_cand > kExactCap) atomicOr(&qs->flags, kFlagSurvivorOverflow);
+    if (threadIdx.x == 0) n_cand_s = 0;
+    __syncthreads();
+    const float* qv = p.queries + (size_t)q * p.q_pitch;
+    for (int i = threadIdx.x; i < n + n_spec; i += blockDim.x) {
+        uint32_t row;
+        if (i < n) {
+            const entry_t e = buf[i];
+            if (!(entry_g(e) <= tau)) continue;
+            row = entry_row(e);
+        } else {
+            row = p.special_rows[(size_t)q * kSpecialCap + (i - n)];
+        }
+        const int slot = atomicAdd(&n_cand_s, 1);
+        if (slot < kExactCap) {
+            float dist = exact_distance(p.metric, p.rows + (size_t)row * p.pitch, qv, p.dim, p.l2_squared);
+            ckey[slot] = float_order_key(dist);
+            cid[slot] = p.ids[row];
+        }
+    }
+    __syncthreads();
+    const int n_cand = n_cand_s;
+    if (n_cand > kExactCap) {
+        if (threadIdx.x == 0) atomicOr(&qs->flags, kFlagSurvivorOverflow);
         fail_fill();
         return;
-    }
-    const float* qv = p.queries + (size_t)q * p.q_pitch;
-    for (int i = threadIdx.x; i < n_cand; i += blockDim.x) {
-        uint32_t row = i < n_surv ? entry_row(buf[i]) : p.special_rows[(size_t)q * kSpecialCap + (i - n_surv)];
-        float dist = exact_distance(p.metric, p.rows + (size_t)row * p.pitch, qv, p.dim, p.l2_squared);
-        ckey[i] = float_order_key(dist);
-        cid[i] = p.ids[row];
     }
     int n2 = 2;
     while (n2 < n_cand) n2 <<= 1;
