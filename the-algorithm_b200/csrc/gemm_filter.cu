@@ -155,7 +155,7 @@ struct KBlocks {
 
 }  // namespace
 
-template <int CG>
+template <int CG, bool SEED>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -357,12 +357,25 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
                     tmem_ld32(t_lane + c0, v);
                     tmem_ld_wait();
                     const int col0 = half * COLS_PER_WARP + c0;
+                    if constexpr (SEED) {
+                        // threshold seeding: the best score of each 32-row group goes to a fixed pool slot.  The k-th best
+                        // of these group maxima bounds the k-th best row from below (k distinct groups => k rows).
+                        const int left = valid_cols - col0;
+                        float m = -INFINITY;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) m = fmaxf(m, j < left ? v[j] : -INFINITY);
+                        if (q_ok && left > 0) {
+                            const uint32_t slot = (uint32_t)((tile_row0 - a.row_begin + col0) >> 5);
+                            if (slot < (uint32_t)a.pool_cap) a.pool[(size_t)q * a.pool_cap + slot] = make_entry(-m, 0xFFFFFFFFu);
+                        }
+                        continue;
+                    }
                     bool any = false;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) any |= (v[j] >= thr);
                     // Rare path, kept small on purpose (a 32x unrolled hit handler blew the instruction cache and
-                    // stalled the MMA warp): build this lane's hit mask, OR it across the warp, and for every column
-                    // some lane hit re-read that single column from TMEM (warp-uniform address).
+                    // stalled the MMA warp): build this lane's hit mask, OR it across the warp, and visit every column
+                    // some lane hit by re-reading that single column from TMEM (warp-uniform address; a 32-way select on v[] was slower).
                     if (__any_sync(0xFFFFFFFFu, any) && col0 < valid_cols) {
                         uint32_t mask = 0;
 #pragma unroll
@@ -509,15 +522,11 @@ cudaError_t launch_gemm_filter(const GemmLaunch& g, cudaStream_t stream) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaError_t e;
-    if (cg == 1) {
-        e = cudaFuncSetAttribute(gemm_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaLaunchKernelEx(&cfg, gemm_filter_kernel<1>, tm, a);
-    } else {
-        e = cudaFuncSetAttribute(gemm_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        e = cudaLaunchKernelEx(&cfg, gemm_filter_kernel<2>, tm, a);
-    }
+    void (*fn)(GemmTmaps, GemmArgs) = cg == 1 ? (g.seed_mode ? gemm_filter_kernel<1, true> : gemm_filter_kernel<1, false>)
+                                              : (g.seed_mode ? gemm_filter_kernel<2, true> : gemm_filter_kernel<2, false>);
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    e = cudaLaunchKernelEx(&cfg, fn, tm, a);
     if (e != cudaSuccess) return e;
     return cudaGetLastError();
 }

@@ -427,12 +427,7 @@ int query_gemm(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
     fp.out_count = d_out_count;
     fp.k_out = k_out;
 
-    // chunk schedule: the first chunk is scored with tau = +inf (every row is a candidate), so it must fit the pool;
-    // afterwards a chunk `growth` times the rows seen so far adds ~ (growth-1) * k * (margin inflation) candidates.
-    const long long first = std::min<long long>(ix->n, kGemmPoolCap / 2);
-    int growth = (int)std::min<long long>(8, std::max<long long>(2, 1400 / std::max(1, k_eff)));
-    long long begin = 0, end = first;
-    for (;;) {
+    auto gemm_launch = [&](long long begin, long long end, int seed_mode) -> int {
         GemmLaunch g{};
         g.q_shadow = ix->q_shadow.p;
         g.shadow = ix->shadow;
@@ -443,6 +438,7 @@ int query_gemm(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
         g.b_pad = b_pad;
         g.kp = ix->kp;
         g.cta_group = ix->gemm_cta_group;
+        g.seed_mode = seed_mode;
         g.sm_count = ix->sm_count;
         g.qstate = ix->qstate.p;
         g.pool = ix->pool.p;
@@ -465,8 +461,6 @@ int query_gemm(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
             CUDA_TRY(cudaStreamSynchronize(st));
             float dms = 0.f;
             cudaEventElapsedTime(&dms, dbg0, dbg1);
-            fprintf(stderr, "[b200ann] gemm launch %.3f ms, %.1f TFLOP/s\n", dms,
-                    2.0 * (double)(end - begin) * ix->dim * b / (dms * 1e-3) / 1e12);
             cudaEventDestroy(dbg0);
             cudaEventDestroy(dbg1);
             CUDA_TRY(cudaMemcpy(h.data(), ix->qstate.p, sizeof(QueryState) * b, cudaMemcpyDeviceToHost));
@@ -477,9 +471,41 @@ int query_gemm(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
                 mn = std::min(mn, x.pool_count);
                 sum += x.pool_count;
             }
-            fprintf(stderr, "[b200ann] chunk [%lld,%lld): pool_count min %u mean %.1f max %u  eps_abs[0]=%g tau[0]=%g\n", begin, end,
-                    mn, sum / b, mx, h[0].eps_abs, float_from_order_key(h[0].tau_key));
+            fprintf(stderr, "[b200ann] gemm%s [%lld,%lld): %.3f ms %.1f TFLOP/s; pool_count min %u mean %.1f max %u tau[0]=%g\n",
+                    seed_mode ? " seed" : "", begin, end, dms, 2.0 * (double)(end - begin) * ix->dim * b / (dms * 1e-3) / 1e12, mn,
+                    sum / b, mx, float_from_order_key(h[0].tau_key));
         }
+        return ANN_OK;
+    };
+
+    // Chunk schedule.  Thresholds only tighten between launches, so the work is cut into geometrically growing row
+    // ranges; each launch filters against the k-th best seen so far (+ margin) and a compaction follows it.
+    //   seed   : over the first S rows only the best score of every 32-row group is kept (fixed slots, no atomics); the
+    //            k-th best group maximum is a valid threshold, as tight as having seen ~S rows.  Needs S/32 >= 4k groups.
+    //   chunks : then [0, c1), [c1, c2), ... sized so that each adds roughly kHitBudget candidates per query.
+    const int kHitBudget = 1400;
+    const long long seed_rows = std::min<long long>(ix->n / 256 * 256, (long long)kGemmPoolCap * 32);
+    const bool use_seed = seed_rows >= 128LL * k_eff && seed_rows >= 4096;
+    int growth = (int)std::min<long long>(8, std::max<long long>(2, kHitBudget / std::max(1, k_eff)));
+    long long begin = 0, end;
+    if (use_seed) {
+        int rc2 = gemm_launch(0, seed_rows, 1);
+        if (rc2) return rc2;
+        SelectParams sp = fp;
+        sp.seed_count = (int)(seed_rows / 32);
+        CUDA_TRY(launch_compact_pool(sp, b, st));
+        ix->launches++;
+        // a threshold learnt from S rows lets through about 2.2 * k / S of the rows (group loss 1.13 x margin ~1.9)
+        end = std::min<long long>(ix->n, std::max<long long>(seed_rows, (long long)((double)kHitBudget * seed_rows / (2.2 * k_eff))));
+        end = (end + 255) / 256 * 256;
+        if (end > ix->n) end = ix->n;
+    } else {
+        // no seed: the first chunk is scored with tau = +inf (every row is a candidate), so it must fit the pool
+        end = std::min<long long>(ix->n, kGemmPoolCap / 2);
+    }
+    for (;;) {
+        int rc2 = gemm_launch(begin, end, 0);
+        if (rc2) return rc2;
         if (end >= ix->n) break;
         CUDA_TRY(launch_compact_pool(fp, b, st));
         ix->launches++;

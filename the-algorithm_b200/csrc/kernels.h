@@ -65,6 +65,7 @@ struct SelectParams {
     const uint32_t* pub_keys;      // [b][pub_stride] or nullptr
     int pub_stride, pub_count, j_pub;
     int k;
+    int seed_count;         // > 0: the pool holds exactly this many seed entries (group maxima); derive tau, discard them
     // exact rescoring inputs
     const float* rows;
     const int64_t* ids;
@@ -112,6 +113,7 @@ struct GemmLaunch {
     long long row_begin, row_end;   // chunk of corpus rows scored by this launch
     int b, b_pad, kp;
     int cta_group;              // 1 or 2 (tcgen05 cta_group)
+    int seed_mode;              // 1: threshold seeding launch (group maxima at fixed pool slots)
     int sm_count;
     QueryState* qstate;
     entry_t* pool;

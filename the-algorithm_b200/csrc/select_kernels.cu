@@ -147,7 +147,7 @@ __device__ bool load_and_threshold(const SelectParams& p, int q, entry_t* buf, u
     __shared__ int n_s;
     QueryState* qs = p.qstate + q;
     const float eps_abs = qs->eps_abs, eps_rel = qs->eps_rel;
-    const int pool_n = min((int)qs->pool_count, p.pool_cap);
+    const int pool_n = p.seed_count > 0 ? min(p.seed_count, p.pool_cap) : min((int)qs->pool_count, p.pool_cap);
     float tau = INFINITY;
     uint32_t tk = qs->tau_key;
     if (tk < 0xFF800000u) tau = float_from_order_key(tk);
@@ -190,13 +190,20 @@ __global__ void __launch_bounds__(kSelThreads) compact_pool_kernel(SelectParams 
     __shared__ int n_keep;
     const int q = blockIdx.x;
     QueryState* qs = p.qstate + q;
-    if (qs->pool_count > (uint32_t)p.pool_cap) {
+    if (p.seed_count == 0 && qs->pool_count > (uint32_t)p.pool_cap) {
         if (threadIdx.x == 0) atomicOr(&qs->flags, kFlagPoolOverflow);
         return;
     }
     int n;
     float tau;
     if (!load_and_threshold(p, q, buf, hist, &n, &tau)) return;
+    if (p.seed_count > 0) {   // seed entries carry no row: keep only the threshold
+        if (threadIdx.x == 0) {
+            qs->pool_count = 0;
+            qs->tau_key = float_order_key(tau);
+        }
+        return;
+    }
     if (threadIdx.x == 0) n_keep = 0;
     __syncthreads();
     entry_t* pool = p.pool + (size_t)q * p.pool_cap;
