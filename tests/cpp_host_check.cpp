@@ -1,0 +1,31 @@
+// Compile-and-link check of the C++ host mirror (the-algorithm_b200/host/cpp/b200ann.hpp) against libb200ann.so.
+// Without a GPU every compute entry point must fail loudly: the constructor throws AnnError(ANN_ERR_NO_DEVICE).
+// With a GPU it runs a three-row known-answer query (InnerProduct distances 1 - a.b).
+#include <cstdio>
+
+#include "../the-algorithm_b200/host/cpp/b200ann.hpp"
+
+int main() {
+    using namespace ann;
+    if (metric_from_string("Cosine") != Metric::Cosine) return 10;
+    if (!(Distance{-0.0f} < Distance{0.0f}) || !(Distance{1e30f} < Distance{std::numeric_limits<float>::quiet_NaN()})) return 11;
+    try {
+        BruteForceIndex<int64_t> ix(Metric::InnerProduct, 2);
+        const int64_t ids[3] = {7, 8, 9};
+        const float rows[6] = {1, 0, 0, 1, 2, 0};
+        ix.appendBatch(ids, rows, 3);
+        auto res = ix.queryWithDistance({1.0f, 0.0f}, 2).get();
+        if (res.size() != 2 || res[0].neighbor != 9 || res[0].distance.distance != -1.0f || res[1].neighbor != 7) return 12;
+        auto only = ix.query({1.0f, 0.0f}, 0).get();
+        if (!only.empty()) return 13;
+        std::printf("gpu ok\n");
+        return 0;
+    } catch (const AnnError& e) {
+        if (e.code == ANN_ERR_NO_DEVICE || e.code == ANN_ERR_CUDA) {
+            std::printf("no device: %s\n", e.what());
+            return 0;
+        }
+        std::printf("unexpected: %s\n", e.what());
+        return 14;
+    }
+}

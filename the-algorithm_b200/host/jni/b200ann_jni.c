@@ -1,0 +1,61 @@
+/* b200ann_jni.c -- JNI shim between com.twitter.ann.brute_force.B200AnnNative (host/scala/GpuBruteForceIndex.scala) and
+ * the C ABI (include/b200ann.h).  One function per entry point, no logic: direct ByteBuffers are unwrapped to plain
+ * pointers and passed through.  Same boundary shape as the reference's SWIG Faiss binding
+ * (ann/src/main/java/com/twitter/ann/faiss/swig/swigfaissJNI.java:267-269: opaque long handle + flat buffers).
+ *
+ * Build (where a JDK exists):  gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux \
+ *                                  b200ann_jni.c -L../../lib -lb200ann -o libb200ann_jni.so
+ * This image has no jni.h, so the body is compiled only when the header is present; the guard keeps `make` green. */
+#if defined(__has_include)
+#if __has_include(<jni.h>)
+#define B200ANN_HAVE_JNI 1
+#endif
+#endif
+
+#ifdef B200ANN_HAVE_JNI
+#include <jni.h>
+
+#include "../../../include/b200ann.h"
+
+#define NATIVE(ret, name) JNIEXPORT ret JNICALL Java_com_twitter_ann_brute_1force_B200AnnNative_00024_##name
+
+static void *addr(JNIEnv *env, jobject buf) { return buf ? (*env)->GetDirectBufferAddress(env, buf) : NULL; }
+
+NATIVE(jlong, create)(JNIEnv *env, jobject self, jint metric, jint dim, jlong capacity_hint, jint device, jint flags) {
+    (void)env; (void)self;
+    ann_config cfg = {metric, dim, capacity_hint, device, (uint32_t)flags};
+    ann_index *ix = NULL;
+    return ann_create(&cfg, &ix) == ANN_OK ? (jlong)(intptr_t)ix : 0;
+}
+
+NATIVE(void, destroy)(JNIEnv *env, jobject self, jlong handle) {
+    (void)env; (void)self;
+    ann_destroy((ann_index *)(intptr_t)handle);
+}
+
+NATIVE(jint, appendBatch)(JNIEnv *env, jobject self, jlong handle, jobject ids, jobject rows, jlong n) {
+    (void)self;
+    return ann_append_batch((ann_index *)(intptr_t)handle, (const int64_t *)addr(env, ids), (const float *)addr(env, rows), n);
+}
+
+NATIVE(jlong, size)(JNIEnv *env, jobject self, jlong handle) {
+    (void)env; (void)self;
+    int64_t n = 0;
+    return ann_size((const ann_index *)(intptr_t)handle, &n) == ANN_OK ? (jlong)n : -1;
+}
+
+NATIVE(jint, queryBatch)(JNIEnv *env, jobject self, jlong handle, jobject queries, jint b, jint dim, jint k, jobject out_ids,
+                         jobject out_dist, jobject out_count) {
+    (void)self;
+    return ann_query_batch((ann_index *)(intptr_t)handle, (const float *)addr(env, queries), b, dim, k,
+                           (int64_t *)addr(env, out_ids), (float *)addr(env, out_dist), (int32_t *)addr(env, out_count));
+}
+
+NATIVE(jstring, lastError)(JNIEnv *env, jobject self) {
+    (void)self;
+    return (*env)->NewStringUTF(env, ann_last_error());
+}
+#else
+/* no JDK in this image: nothing to compile */
+typedef int b200ann_jni_not_built_here;
+#endif

@@ -1,0 +1,159 @@
+package com.twitter.ann.brute_force
+
+// Drop-in for com.twitter.ann.brute_force.BruteForceIndex (BruteForceIndex.scala:26-92) backed by the B200 engine.
+// Same traits, same factory shape; swap the constructor call at the call sites listed in INTEGRATION.md.
+//
+// NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no JVM / scalac / jni.h (SURVEY.md F4).  It is the thin,
+// mechanical binding of include/b200ann.h that a maintainer adds next to the reference class; every behaviour it relies
+// on is exercised through the same C ABI by tests/ (Python ctypes) and tests/cpp_host_check.cpp (C++).
+
+import com.twitter.ann.common.Appendable
+import com.twitter.ann.common.Distance
+import com.twitter.ann.common.EmbeddingType._
+import com.twitter.ann.common.EntityEmbedding
+import com.twitter.ann.common.Metric
+import com.twitter.ann.common.NeighborWithDistance
+import com.twitter.ann.common.Queryable
+import com.twitter.ann.common.{Cosine, InnerProduct, L2}
+import com.twitter.util.Future
+import com.twitter.util.FuturePool
+import java.nio.{ByteBuffer, ByteOrder}
+
+/** JNI surface: one static native per C-ABI entry point (include/b200ann.h).  Buffers are direct ByteBuffers so the
+ * GC can neither move nor free them during a call (the hazard noted at faiss/QueryableIndexAdapter.scala:128-132). */
+object B200AnnNative {
+  // natives are unpacked from the jar and System.load'ed exactly like swigfaiss (faiss/NativeUtils.java:93-111)
+  System.loadLibrary("b200ann_jni")
+  @native def create(metric: Int, dim: Int, capacityHint: Long, device: Int, flags: Int): Long // 0 => see lastError
+  @native def destroy(handle: Long): Unit
+  @native def appendBatch(handle: Long, ids: ByteBuffer, rows: ByteBuffer, n: Long): Int
+  @native def size(handle: Long): Long
+  @native def queryBatch(handle: Long, queries: ByteBuffer, b: Int, dim: Int, k: Int,
+    outIds: ByteBuffer, outDist: ByteBuffer, outCount: ByteBuffer): Int
+  @native def lastError(): String
+}
+
+object GpuBruteForceIndex {
+  val DataFileName = "BruteForceFileData"
+
+  private def ordinal(metric: Metric[_]): Int = metric match { // thrift DistanceMetric, ann_common.thrift:16-19
+    case L2 => 0
+    case Cosine => 1
+    case InnerProduct => 2
+    case other => throw new IllegalArgumentException(s"metric $other is not a dense-vector metric")
+  }
+
+  /** Same shape as BruteForceIndex.apply (BruteForceIndex.scala:29-37).  `T` is carried through `idInjection`:
+   * Long ids go to the device as they are (ties break by id); any other T is mapped to its insertion slot. */
+  def apply[T, D <: Distance[D]](
+    metric: Metric[D],
+    futurePool: FuturePool,
+    initialEmbeddings: Iterator[EntityEmbedding[T]] = Iterator(),
+    device: Int = 0
+  ): GpuBruteForceIndex[T, D] = {
+    val index = new GpuBruteForceIndex[T, D](metric, futurePool, device)
+    initialEmbeddings.grouped(65536).foreach(batch => index.appendBatch(batch))
+    index
+  }
+}
+
+class GpuBruteForceIndex[T, D <: Distance[D]] private (
+  metric: Metric[D],
+  futurePool: FuturePool,
+  device: Int)
+    extends Appendable[T, BruteForceRuntimeParams.type, D]
+    with Queryable[T, BruteForceRuntimeParams.type, D]
+    with AutoCloseable {
+
+  private[this] var handle: Long = 0L
+  private[this] var dim: Int = -1
+  private[this] val slotTable = new java.util.ArrayList[T]() // used only when T is not Long
+  private[this] var nativeIds = true
+
+  private[this] def check(rc: Int): Unit =
+    if (rc != 0) throw new RuntimeException(s"b200ann error $rc: ${B200AnnNative.lastError()}")
+
+  private[this] def ensure(d: Int): Unit = synchronized {
+    if (handle == 0L) {
+      handle = B200AnnNative.create(GpuBruteForceIndex.ordinal(metric), d, 0L, device, 0)
+      if (handle == 0L) throw new RuntimeException(B200AnnNative.lastError())
+      dim = d
+    } else if (d != dim) {
+      throw new IllegalArgumentException(s"embedding dimension $d != index dimension $dim")
+    }
+  }
+
+  private[this] def direct(bytes: Int): ByteBuffer = ByteBuffer.allocateDirect(bytes).order(ByteOrder.nativeOrder())
+
+  /** Batched Appendable path: one host->device copy and one kernel per batch. */
+  def appendBatch(batch: Seq[EntityEmbedding[T]]): Unit = synchronized {
+    if (batch.nonEmpty) {
+      val d = batch.head.embedding.length
+      ensure(d)
+      val ids = direct(batch.size * 8)
+      val rows = direct(batch.size * d * 4)
+      batch.foreach { e =>
+        e.id match {
+          case l: Long if nativeIds => ids.putLong(l)
+          case other =>
+            nativeIds = false
+            ids.putLong(slotTable.size.toLong)
+            slotTable.add(other)
+        }
+        var i = 0
+        while (i < d) { rows.putFloat(e.embedding(i)); i += 1 }
+      }
+      check(B200AnnNative.appendBatch(handle, ids, rows, batch.size.toLong))
+    }
+  }
+
+  // Appendable.append, BruteForceIndex.scala:48-52
+  override def append(embedding: EntityEmbedding[T]): Future[Unit] = futurePool { appendBatch(Seq(embedding)) }
+
+  override def toQueryable: Queryable[T, BruteForceRuntimeParams.type, D] = this
+
+  /** b queries in one device call; the extra entry point callers that can batch should use (SURVEY.md 3.3). */
+  def batchQueryWithDistance(
+    embeddings: Seq[EmbeddingVector],
+    numOfNeighbours: Int
+  ): Seq[List[NeighborWithDistance[T, D]]] = {
+    if (numOfNeighbours <= 0 || handle == 0L || embeddings.isEmpty) return embeddings.map(_ => Nil)
+    val b = embeddings.size
+    val q = direct(b * dim * 4)
+    embeddings.foreach { e => var i = 0; while (i < dim) { q.putFloat(e(i)); i += 1 } }
+    val outIds = direct(b * numOfNeighbours * 8)
+    val outDist = direct(b * numOfNeighbours * 4)
+    val outCount = direct(b * 4)
+    check(B200AnnNative.queryBatch(handle, q, b, dim, numOfNeighbours, outIds, outDist, outCount))
+    (0 until b).map { qi =>
+      (0 until outCount.getInt(qi * 4)).map { j =>
+        val raw = outIds.getLong((qi * numOfNeighbours + j) * 8)
+        val id = if (nativeIds) raw.asInstanceOf[T] else slotTable.get(raw.toInt)
+        NeighborWithDistance(id, metric.fromAbsoluteDistance(outDist.getFloat((qi * numOfNeighbours + j) * 4)))
+      }.toList
+    }
+  }
+
+  // Queryable.queryWithDistance, BruteForceIndex.scala:66-91: nearest first; ties by id instead of by heap history
+  override def queryWithDistance(
+    embedding: EmbeddingVector,
+    numOfNeighbours: Int,
+    runtimeParams: BruteForceRuntimeParams.type
+  ): Future[List[NeighborWithDistance[T, D]]] =
+    futurePool { batchQueryWithDistance(Seq(embedding), numOfNeighbours).head }
+
+  // Queryable.query, BruteForceIndex.scala:56-64
+  override def query(
+    embedding: EmbeddingVector,
+    numOfNeighbours: Int,
+    runtimeParams: BruteForceRuntimeParams.type
+  ): Future[List[T]] =
+    queryWithDistance(embedding, numOfNeighbours, runtimeParams).map(_.map(_.neighbor))
+
+  def size: Long = synchronized { if (handle == 0L) 0L else B200AnnNative.size(handle) }
+
+  // explicit release, idempotent -- the swig Index.delete() contract (faiss/swig/Index.java:24-37)
+  override def close(): Unit = synchronized {
+    if (handle != 0L) { B200AnnNative.destroy(handle); handle = 0L }
+  }
+}
