@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(PrepParams p, int b_p
     for (int q = warp; q < b_pad; q += nwarps) {
         if (q >= p.b) {  // padding rows of the GEMM operand
             if (p.q_shadow)
-                for (int i = lane; i < p.kp; i += 32) p.q_shadow[(size_t)q * p.kp + i] = __float2bfloat16_rn(0.f);
+                for (int i = lane; i < p.qkp; i += 32) p.q_shadow[(size_t)q * p.qkp + i] = __float2bfloat16_rn(0.f);
             continue;
         }
         const float* src = p.queries + (size_t)q * p.dim;
@@ -102,11 +102,11 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(PrepParams p, int b_p
         n2 = warp_sum(n2);
         finite = __all_sync(0xFFFFFFFFu, finite);
         if (p.q_shadow) {
-            for (int i = lane; i < p.kp; i += 32) {
+            for (int i = lane; i < p.qkp; i += 32) {
                 float v = 0.f;
                 if (i < p.dim) v = src[i];
                 else if (p.metric == kMetricL2 && i < p.dim + 3) v = 1.0f;
-                p.q_shadow[(size_t)q * p.kp + i] = __float2bfloat16_rn(v);
+                p.q_shadow[(size_t)q * p.qkp + i] = __float2bfloat16_rn(v);
             }
         }
         if (p.pub_keys)

@@ -62,6 +62,59 @@ __device__ __forceinline__ float widen(float kth, float eps_abs, float eps_rel) 
     return kth + (2.0f * eps_abs + 2.0f * eps_rel * fabsf(kth));
 }
 
+// ---- exact distance, operation for operation the oracle's distance_f64 (oracle/oracle.c): fp64 accumulation in index
+// order, explicit round-to-nearest mul/add (no contraction), one rounding to fp32, `1 - x` in fp32.  The row is read in
+// blocks of four 128-bit loads, double buffered, so that a thread walking one row has 64 bytes in flight instead of
+// one dependent 4-byte load per step (rows are gathered from random places in HBM).  `a` must be 16-byte aligned with
+// `pitch4` float4 of storage; `b` is read element-wise (broadcast across the threads of a CTA).
+struct ExactAcc {
+    double s0, s1, s2;   // L2: sum (a-b)^2 ; dot products: a.b, a.a, b.b
+};
+
+__device__ __forceinline__ void exact_step(int metric, float x, float y, ExactAcc& acc) {
+    const double dx = (double)x, dy = (double)y;
+    if (metric == kMetricL2) {
+        const double diff = __dsub_rn(dx, dy);
+        acc.s0 = __dadd_rn(acc.s0, __dmul_rn(diff, diff));
+    } else {
+        acc.s0 = __dadd_rn(acc.s0, __dmul_rn(dx, dy));
+        if (metric == kMetricCosine) {
+            acc.s1 = __dadd_rn(acc.s1, __dmul_rn(dx, dx));
+            acc.s2 = __dadd_rn(acc.s2, __dmul_rn(dy, dy));
+        }
+    }
+}
+
+__device__ __forceinline__ float exact_distance_rows(int metric, const float* __restrict__ a, int pitch4, const float* __restrict__ b,
+                                                     int d, int l2_squared) {
+    const float4* a4 = reinterpret_cast<const float4*>(a);
+    const int n4 = (d + 3) >> 2;              // float4 that hold at least one valid element (n4 <= pitch4)
+    ExactAcc acc{0.0, 0.0, 0.0};
+    float4 cur[4], nxt[4];
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cur[j] = (j < n4) ? __ldg(a4 + j) : zero;
+    for (int base = 0; base < n4; base += 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) nxt[j] = (base + 4 + j < n4) ? __ldg(a4 + base + 4 + j) : zero;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int i = (base + j) << 2;
+            if (i < d) exact_step(metric, cur[j].x, b[i], acc);
+            if (i + 1 < d) exact_step(metric, cur[j].y, b[i + 1], acc);
+            if (i + 2 < d) exact_step(metric, cur[j].z, b[i + 2], acc);
+            if (i + 3 < d) exact_step(metric, cur[j].w, b[i + 3], acc);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
+    }
+    (void)pitch4;
+    if (metric == kMetricL2) return __double2float_rn(l2_squared ? acc.s0 : __dsqrt_rn(acc.s0));
+    if (metric == kMetricIP) return __fsub_rn(1.0f, __double2float_rn(acc.s0));
+    const double cs = __ddiv_rn(acc.s0, __dmul_rn(__dsqrt_rn(acc.s1), __dsqrt_rn(acc.s2)));
+    return __fsub_rn(1.0f, __double2float_rn(cs));
+}
+
 // ---- mbarrier / bulk-copy PTX (Hopper+; the only async-copy path used by the scan) -----------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

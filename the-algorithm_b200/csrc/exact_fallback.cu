@@ -31,32 +31,13 @@ struct SelectState {
 
 __device__ __forceinline__ unsigned long long id_key(long long id) { return (unsigned long long)id ^ 0x8000000000000000ull; }
 
-__device__ float exact_distance_fb(int metric, const float* __restrict__ a, const float* __restrict__ b, int d, int l2_squared) {
-    if (metric == kMetricL2) {
-        double acc = 0.0;
-        for (int i = 0; i < d; ++i) {
-            double diff = __dsub_rn((double)a[i], (double)b[i]);
-            acc = __dadd_rn(acc, __dmul_rn(diff, diff));
-        }
-        return __double2float_rn(l2_squared ? acc : __dsqrt_rn(acc));
-    }
-    double dot = 0.0;
-    for (int i = 0; i < d; ++i) dot = __dadd_rn(dot, __dmul_rn((double)a[i], (double)b[i]));
-    if (metric == kMetricIP) return __fsub_rn(1.0f, __double2float_rn(dot));
-    double na = 0.0, nb = 0.0;
-    for (int i = 0; i < d; ++i) na = __dadd_rn(na, __dmul_rn((double)a[i], (double)a[i]));
-    for (int i = 0; i < d; ++i) nb = __dadd_rn(nb, __dmul_rn((double)b[i], (double)b[i]));
-    double cs = __ddiv_rn(dot, __dmul_rn(__dsqrt_rn(na), __dsqrt_rn(nb)));
-    return __fsub_rn(1.0f, __double2float_rn(cs));
-}
-
 __global__ void __launch_bounds__(256) exact_all_kernel(const float* __restrict__ rows, long long n, int pitch, int dim, int metric,
                                                         int l2_squared, const float* __restrict__ query, uint32_t* __restrict__ dkey) {
     extern __shared__ float qs[];
     for (int i = threadIdx.x; i < dim; i += blockDim.x) qs[i] = query[i];
     __syncthreads();
     for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x)
-        dkey[r] = float_order_key(exact_distance_fb(metric, rows + (size_t)r * pitch, qs, dim, l2_squared));
+        dkey[r] = float_order_key(exact_distance_rows(metric, rows + (size_t)r * pitch, pitch >> 2, qs, dim, l2_squared));
 }
 
 __global__ void init_state_kernel(SelectState* st, uint32_t k) {

@@ -461,11 +461,11 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-bool make_map(CUtensorMap* m, const void* gptr, long long n_rows, int kp, int box_cols, CUtensorMapSwizzle sw) {
+bool make_map(CUtensorMap* m, const void* gptr, long long n_rows, int kp, int pitch_elems, int box_cols, CUtensorMapSwizzle sw) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     cuuint64_t dims[2] = {(cuuint64_t)kp, (cuuint64_t)n_rows};
-    cuuint64_t strides[1] = {(cuuint64_t)kp * 2};
+    cuuint64_t strides[1] = {(cuuint64_t)pitch_elems * 2};
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)kTileRows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(gptr), dims, strides, box, estr,
@@ -484,12 +484,12 @@ cudaError_t launch_gemm_filter(const GemmLaunch& g, cudaStream_t stream) {
     GemmTmaps tm;
     memset(&tm, 0, sizeof(tm));
     const int kp = g.kp;
-    bool ok = make_map(&tm.q64, g.q_shadow, g.b_pad, kp, 64, CU_TENSOR_MAP_SWIZZLE_128B) &&
-              make_map(&tm.q32, g.q_shadow, g.b_pad, kp, 32, CU_TENSOR_MAP_SWIZZLE_64B) &&
-              make_map(&tm.q16, g.q_shadow, g.b_pad, kp, 16, CU_TENSOR_MAP_SWIZZLE_32B) &&
-              make_map(&tm.r64, g.shadow, g.n_rows_total, kp, 64, CU_TENSOR_MAP_SWIZZLE_128B) &&
-              make_map(&tm.r32, g.shadow, g.n_rows_total, kp, 32, CU_TENSOR_MAP_SWIZZLE_64B) &&
-              make_map(&tm.r16, g.shadow, g.n_rows_total, kp, 16, CU_TENSOR_MAP_SWIZZLE_32B);
+    bool ok = make_map(&tm.q64, g.q_shadow, g.b_pad, kp, g.qkp, 64, CU_TENSOR_MAP_SWIZZLE_128B) &&
+              make_map(&tm.q32, g.q_shadow, g.b_pad, kp, g.qkp, 32, CU_TENSOR_MAP_SWIZZLE_64B) &&
+              make_map(&tm.q16, g.q_shadow, g.b_pad, kp, g.qkp, 16, CU_TENSOR_MAP_SWIZZLE_32B) &&
+              make_map(&tm.r64, g.shadow, g.n_rows_total, kp, kp, 64, CU_TENSOR_MAP_SWIZZLE_128B) &&
+              make_map(&tm.r32, g.shadow, g.n_rows_total, kp, kp, 32, CU_TENSOR_MAP_SWIZZLE_64B) &&
+              make_map(&tm.r16, g.shadow, g.n_rows_total, kp, kp, 16, CU_TENSOR_MAP_SWIZZLE_32B);
     if (!ok) return cudaErrorInvalidValue;
     const int cg = g.cta_group;
     const int n_tile = kTileRows * cg;

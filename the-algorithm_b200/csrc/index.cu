@@ -383,7 +383,8 @@ int query_gemm(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
                int32_t* d_out_count, cudaStream_t st) {
     const int b_pad = (b + 127) / 128 * 128;
     CUDA_TRY(ix->q_padded.ensure((size_t)b * ix->pitch));
-    CUDA_TRY(ix->q_shadow.ensure((size_t)b_pad * ix->kp));
+    const int qkp = (ix->kp + 63) / 64 * 64;
+    CUDA_TRY(ix->q_shadow.ensure((size_t)b_pad * qkp));
     CUDA_TRY(ix->qstate.ensure((size_t)b));
     CUDA_TRY(ix->pool.ensure((size_t)b * kGemmPoolCap));
     CUDA_TRY(ix->special_rows.ensure((size_t)kSpecialCap));
@@ -397,6 +398,7 @@ int query_gemm(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
     pp.kp = ix->kp;
     pp.q_padded = ix->q_padded.p;
     pp.q_shadow = ix->q_shadow.p;
+    pp.qkp = qkp;
     pp.qstate = ix->qstate.p;
     pp.max_norm_bits = &ix->scalars->max_norm_bits;
     pp.path = 2;
@@ -430,6 +432,7 @@ int query_gemm(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
     auto gemm_launch = [&](long long begin, long long end, int seed_mode) -> int {
         GemmLaunch g{};
         g.q_shadow = ix->q_shadow.p;
+        g.qkp = qkp;
         g.shadow = ix->shadow;
         g.n_rows_total = ix->n;
         g.row_begin = begin;
@@ -483,10 +486,12 @@ int query_gemm(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
     //   seed   : over the first S rows only the best score of every 32-row group is kept (fixed slots, no atomics); the
     //            k-th best group maximum is a valid threshold, as tight as having seen ~S rows.  Needs S/32 >= 4k groups.
     //   chunks : then [0, c1), [c1, c2), ... sized so that each adds roughly kHitBudget candidates per query.
-    const int kHitBudget = 1400;
+    int kHitBudget = 500;
+    if (const char* hb = getenv("B200ANN_HIT_BUDGET")) kHitBudget = std::max(100, atoi(hb));
     const long long seed_rows = std::min<long long>(ix->n / 256 * 256, (long long)kGemmPoolCap * 32);
     const bool use_seed = seed_rows >= 128LL * k_eff && seed_rows >= 4096;
-    int growth = (int)std::min<long long>(8, std::max<long long>(2, kHitBudget / std::max(1, k_eff)));
+    // a chunk `growth` times the rows seen so far adds about (growth - 1) * 1.9 * k candidates per query
+    int growth = (int)std::min<double>(8.0, std::max<double>(2.0, 1.0 + kHitBudget / (1.9 * std::max(1, k_eff))));
     long long begin = 0, end;
     if (use_seed) {
         int rc2 = gemm_launch(0, seed_rows, 1);

@@ -26,7 +26,8 @@ struct PrepParams {
     const float* queries;   // [b][dim]
     int b, dim, pitch, metric, kp;
     float* q_padded;        // [b][pitch]  zero padded fp32 copy (scan path)
-    __nv_bfloat16* q_shadow;  // [b_pad][kp] bf16 operand (gemm path) or nullptr
+    __nv_bfloat16* q_shadow;  // [b_pad][qkp] bf16 operand (gemm path) or nullptr; only the first kp columns are used
+    int qkp;                  // query operand pitch in elements: kp rounded up to 64 (128-byte aligned rows => 4 sectors per box row)
     QueryState* qstate;     // [b]
     const uint32_t* max_norm_bits;
     int path;               // 1 = scan (fp32 error model), 2 = gemm (bf16 error model)
@@ -107,7 +108,8 @@ cudaError_t launch_exact_fallback(const FallbackParams& p, cudaStream_t stream, 
 
 // ---------------------------------------------------------------- K3: tcgen05 GEMM filter
 struct GemmLaunch {
-    const void* q_shadow;       // bf16 [b_pad][kp]
+    const void* q_shadow;       // bf16 [b_pad][qkp]
+    int qkp;
     const void* shadow;         // bf16 [n_rows_total][kp]
     long long n_rows_total;
     long long row_begin, row_end;   // chunk of corpus rows scored by this launch

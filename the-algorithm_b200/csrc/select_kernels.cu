@@ -65,27 +65,6 @@ __device__ uint32_t cta_kth_smallest_key(const uint32_t* v, int count, int J, ui
     return x;
 }
 
-// exact distance, operation for operation the oracle's distance_f64 (oracle/oracle.c)
-__device__ float exact_distance(int metric, const float* __restrict__ a, const float* __restrict__ b, int d, int l2_squared) {
-    if (metric == kMetricL2) {
-        double acc = 0.0;
-        for (int i = 0; i < d; ++i) {
-            double diff = __dsub_rn((double)a[i], (double)b[i]);
-            double sq = __dmul_rn(diff, diff);
-            acc = __dadd_rn(acc, sq);
-        }
-        return __double2float_rn(l2_squared ? acc : __dsqrt_rn(acc));
-    }
-    double dot = 0.0;
-    for (int i = 0; i < d; ++i) dot = __dadd_rn(dot, __dmul_rn((double)a[i], (double)b[i]));
-    if (metric == kMetricIP) return __fsub_rn(1.0f, __double2float_rn(dot));
-    double na = 0.0, nb = 0.0;
-    for (int i = 0; i < d; ++i) na = __dadd_rn(na, __dmul_rn((double)a[i], (double)a[i]));
-    for (int i = 0; i < d; ++i) nb = __dadd_rn(nb, __dmul_rn((double)b[i], (double)b[i]));
-    double cs = __ddiv_rn(dot, __dmul_rn(__dsqrt_rn(na), __dsqrt_rn(nb)));
-    return __fsub_rn(1.0f, __double2float_rn(cs));
-}
-
 // k-th smallest 32-bit key among the n entries of `buf` (k >= 1, n >= k): 4 MSB-first passes of 8 bits, each a
 // 256-bin shared-memory histogram over the entries still matching the prefix and a one-warp scan that picks the bin.
 __device__ uint32_t kth_key_radix(const entry_t* buf, int n, int k, uint32_t* hist) {
@@ -270,7 +249,7 @@ __global__ void __launch_bounds__(kSelThreads) finalize_kernel(SelectParams p) {
         }
         const int slot = atomicAdd(&n_cand_s, 1);
         if (slot < kExactCap) {
-            float dist = exact_distance(p.metric, p.rows + (size_t)row * p.pitch, qv, p.dim, p.l2_squared);
+            float dist = exact_distance_rows(p.metric, p.rows + (size_t)row * p.pitch, p.pitch >> 2, qv, p.dim, p.l2_squared);
             ckey[slot] = float_order_key(dist);
             cid[slot] = p.ids[row];
         }
