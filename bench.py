@@ -35,8 +35,13 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-METRIC = "exact top-100 queries/sec, 10Mx200 fp32 corpus, InnerProduct, query batch 4096"
 UNIT = "queries/s"
+
+
+def metric_name(a) -> str:
+    """BASELINE.json's metric for the default arguments; the same sentence with the actual shape otherwise."""
+    rows = f"{a.rows // 1_000_000}M" if a.rows % 1_000_000 == 0 else str(a.rows)
+    return f"exact top-{a.k} queries/sec, {rows}x{a.dim} fp32 corpus, {a.metric}, query batch {a.batch}"
 
 
 def parse():
@@ -178,7 +183,7 @@ def run_reference(a):
     nq = a.cpu_queries or cores
     res = cpu_baseline_run(corpus, ids, q[:nq], METRIC_BY_NAME[a.metric], a.k, a.steps, a.warmup)
     line = {
-        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "impl": "reference", "metric": metric_name(a), "value": res["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32 (fp64 accumulate)", "data": "synthetic", "config": config_dict(a, a.gpus),
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -374,7 +379,7 @@ def run_ours(a):
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "metric": metric_name(a), "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16 filter (tcgen05, fp32 accumulate) + exact fp64-accumulated fp32 distances" if last_path == 2
                      else "f32 scan + exact fp64-accumulated fp32 distances",

@@ -1,0 +1,121 @@
+"""BASELINE.json configs 3 and 5 on one B200 (run under gpurun; writes JSON lines to gpurun_out/).
+
+    python tools/config_runs.py latency   [--rows 10000000 --dim 128 --metric L2 --queries 1000]
+        config 3: single-query top-100, one query per call through the HOST entry point (H2D + scan + finalize + D2H +
+        synchronise inside every call); p50 / p90 / p99 latency and the algorithmic scan GB/s they imply.
+    python tools/config_runs.py streaming [--rows 6250000 --appends 125000 --append-batch 512 --query-batch 256]
+        config 5 (one rank's share of 50M rows + 1M appends over 8 ranks): batched appends interleaved with batched
+        queries; append rows/s, query QPS and a visibility check (a row appended before a query is found by it).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+import _pkg  # noqa: E402
+
+_pkg.load()
+from the_algorithm_b200.ann.brute_force import BruteForceIndex  # noqa: E402
+from the_algorithm_b200.ann.common import FuturePool, Metric  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("mode", choices=["latency", "streaming"])
+ap.add_argument("--rows", type=int, default=None)
+ap.add_argument("--dim", type=int, default=None)
+ap.add_argument("--metric", default=None)
+ap.add_argument("--k", type=int, default=100)
+ap.add_argument("--queries", type=int, default=1000)
+ap.add_argument("--appends", type=int, default=125_000)
+ap.add_argument("--append-batch", type=int, default=512)
+ap.add_argument("--query-batch", type=int, default=256)
+a = ap.parse_args()
+dev = torch.device("cuda", 0)
+OUT = ROOT / "gpurun_out"
+OUT.mkdir(exist_ok=True)
+
+
+def build(metric, n, d, extra=0):
+    g = torch.Generator(device=dev)
+    g.manual_seed(0x5EED0001)
+    ix = BruteForceIndex(metric, FuturePool.immediate_pool(), capacity_hint=n + extra)
+    for c0 in range(0, n, 1_000_000):
+        m = min(1_000_000, n - c0)
+        rows = torch.randn((m, d), generator=g, device=dev) / d ** 0.5
+        ix.append_batch_device(torch.arange(c0, c0 + m, device=dev, dtype=torch.int64), rows)
+    return ix, g
+
+
+if a.mode == "latency":
+    n, d = a.rows or 10_000_000, a.dim or 128
+    metric = Metric.from_string(a.metric or "L2")
+    ix, g = build(metric, n, d)
+    q = (torch.rand((a.queries + 20, d), generator=g, device=dev) * 2 - 1).cpu().numpy()
+    for i in range(20):
+        ix.batch_query_with_distance(q[i:i + 1], a.k)
+    lat = []
+    for i in range(20, 20 + a.queries):
+        t0 = time.perf_counter()
+        ix.batch_query_with_distance(q[i:i + 1], a.k)
+        lat.append((time.perf_counter() - t0) * 1e3)
+    lat = np.sort(np.array(lat))
+    p = lambda x: float(lat[min(len(lat) - 1, int(x * len(lat)))])
+    peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    bytes_q = n * d * 4
+    rec = {"config": f"config 3: single-query {metric.name} top-{a.k}, {n}x{d} fp32, one query per host call", "queries": a.queries,
+           "p50_ms": p(0.5), "p90_ms": p(0.9), "p99_ms": p(0.99), "mean_ms": float(lat.mean()), "qps_single_stream": 1e3 / float(lat.mean()),
+           "scan_GBps_at_p50": bytes_q / (p(0.5) * 1e-3) / 1e9, "hbm_peak_GBps_measured": hbm,
+           "frac_of_measured_hbm_at_p50": bytes_q / (p(0.5) * 1e-3) / 1e9 / hbm, "frac_of_nominal_8TBps_at_p50": bytes_q / (p(0.5) * 1e-3) / 8e12,
+           "path": {1: "scan", 2: "gemm"}[ix.stat("last_path")], "includes": "H2D query, scan, finalize, D2H results, stream sync"}
+    print(json.dumps(rec), flush=True)
+    (OUT / "config3_latency.json").write_text(json.dumps(rec, indent=1))
+
+if a.mode == "streaming":
+    n, d = a.rows or 6_250_000, a.dim or 200
+    metric = Metric.from_string(a.metric or "InnerProduct")
+    ix, g = build(metric, n, d, extra=a.appends + 16)
+    nb = a.appends // a.append_batch
+    new_rows = (torch.randn((nb * a.append_batch, d), generator=g, device=dev) / d ** 0.5).cpu().numpy()
+    queries = (torch.rand((a.query_batch, d), generator=g, device=dev) * 2 - 1).cpu().numpy()
+    ix.batch_query_with_distance(queries, a.k)  # warm-up
+    t_app = t_q = 0.0
+    n_q = 0
+    visible_ok = True
+    next_id = n
+    t_all = time.perf_counter()
+    for bi in range(nb):
+        rows = new_rows[bi * a.append_batch:(bi + 1) * a.append_batch]
+        ids = np.arange(next_id, next_id + a.append_batch, dtype=np.int64)
+        t0 = time.perf_counter()
+        ix.append_batch(ids, rows)               # host rows -> device matrix + norms/shadow kernel, returns when visible
+        t_app += time.perf_counter() - t0
+        next_id += a.append_batch
+        if bi % 8 == 7:                          # a query batch every 8 append batches
+            qb = queries.copy()
+            if metric.name != "InnerProduct":
+                qb[0] = rows[-1]                 # visibility probe: the row appended just before this query (distance 0)
+            else:
+                qb[0] = rows[-1] * 64.0          # InnerProduct: make the fresh row the clear winner for its own direction
+            t0 = time.perf_counter()
+            ids_out, dist_out, _ = ix.batch_query_with_distance(qb, a.k)
+            t_q += time.perf_counter() - t0
+            n_q += a.query_batch
+            visible_ok &= bool(ids_out[0, 0] == ids[-1]) if metric.name != "InnerProduct" else bool(ids[-1] in ids_out[0])
+    wall = time.perf_counter() - t_all
+    rec = {"config": f"config 5 (one rank's share): {n} preloaded rows x {d}, {nb * a.append_batch} rows appended in batches of "
+                     f"{a.append_batch}, {metric.name} top-{a.k} query batches of {a.query_batch} every 8 append batches",
+           "append_rows_per_s": nb * a.append_batch / t_app, "append_ms_per_batch": 1e3 * t_app / nb,
+           "query_qps": n_q / t_q if t_q else None, "query_ms_per_batch": 1e3 * t_q / max(1, n_q // a.query_batch),
+           "wall_s": wall, "final_size": ix.size(), "appended_rows_visible_to_next_query": visible_ok,
+           "path": {1: "scan", 2: "gemm"}[ix.stat("last_path")]}
+    print(json.dumps(rec), flush=True)
+    (OUT / "config5_streaming.json").write_text(json.dumps(rec, indent=1))
+    sys.exit(0 if visible_ok else 1)
