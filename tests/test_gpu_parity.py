@@ -91,7 +91,8 @@ def test_scan_path_duplicates_tie_break_by_id(mi):
 @pytest.mark.parametrize("cg", [1, 2])
 @pytest.mark.parametrize("mi", [0, 1, 2])
 @pytest.mark.parametrize("n,d,b,k", [(4096, 64, 128, 10), (50_000, 200, 300, 100), (33_333, 128, 257, 100),
-                                     (20_000, 72, 64, 17), (2000, 200, 1, 100), (131_073, 40, 130, 256)])
+                                     (20_000, 72, 64, 17), (2000, 200, 1, 100), (131_073, 40, 130, 256),
+                                     (30_000, 256, 150, 100), (25_000, 285, 140, 50)])
 def test_gemm_path_matches_oracle(cg, mi, n, d, b, k):
     corpus, ids, q = make(n, d, b, seed=n + d + b, dup=(n == 33_333))
     check(metrics()[mi], corpus, ids, q, k, path=2, cg=cg)
@@ -101,6 +102,9 @@ def test_auto_path_picks_gemm_for_batches_and_scan_for_single_queries():
     corpus, ids, q = make(30_000, 200, 64, seed=1)
     assert check(G["InnerProduct"], corpus, ids, q, 100) == 2
     assert check(G["InnerProduct"], corpus, ids, q[:1], 100) == 1
+    # operand tiles of a 300-d index do not fit the tensor-core kernel's shared memory: batches use the scan, correctly
+    corpus, ids, q = make(20_000, 300, 40, seed=2)
+    assert check(G["Cosine"], corpus, ids, q, 100) == 1
 
 
 # ------------------------------------------------------------------------------------------------ config 1 of BASELINE.json
@@ -199,6 +203,11 @@ def test_massive_ties_are_answered_exactly_by_the_fallback():
     with pytest.raises(G["_capi"].AnnError) as e:
         ix.raise_pending_error()
     assert e.value.code == G["_capi"].ANN_ERR_CANDIDATE_OVERFLOW
+    ix.set_option("device_fallback", 1)               # opt in: the device entry point synchronises and answers exactly
+    ix.query_batch_device(torch.from_numpy(q).to(dev), 10, oi, od, None)
+    torch.cuda.synchronize()
+    ix.raise_pending_error()
+    assert oi.cpu().numpy().tolist() == [list(range(10))] * 2
     ix.close()
 
 

@@ -50,6 +50,7 @@ struct GemmArgs {
     entry_t* pool;
     int pool_cap;
     int debug_nohit;
+    int nb_stages;                    // row-tile buffers: 2 when four operand tiles fit in shared memory, else 1
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -170,8 +171,8 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
     const uint32_t tile_stride = (tile_bytes + 1023u) & ~1023u;
     unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     unsigned char* smA[2] = {base, base + tile_stride};
-    unsigned char* smB[2] = {base + 2 * tile_stride, base + 3 * tile_stride};
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base + 4 * tile_stride);
+    unsigned char* smB[2] = {base + 2 * tile_stride, base + (a.nb_stages > 1 ? 3 : 2) * tile_stride};
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + (2 + a.nb_stages) * tile_stride);
     uint64_t* a_full = bars + 0;
     uint64_t* a_empty = bars + 2;
     uint64_t* b_full = bars + 4;
@@ -220,8 +221,8 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
         if (lane == 0) {
             uint32_t ga = 0, it = 0;
             for (int rt = cluster_id; rt < n_rt; rt += n_clusters, ++it) {
-                const uint32_t bs = it & 1;
-                mbar_wait(&b_empty[bs], ((it >> 1) & 1) ^ 1);
+                const uint32_t bs = a.nb_stages > 1 ? (it & 1) : 0;
+                mbar_wait(&b_empty[bs], ((a.nb_stages > 1 ? (it >> 1) : it) & 1) ^ 1);
                 if (leader) mbar_expect_tx(&b_full[bs], tile_bytes * CG);
                 {
                     const int row0 = (int)(a.row_begin + (long long)rt * N_TILE + rank * kTileRows);
@@ -259,8 +260,8 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_TILE >> 3) << 17) | ((uint32_t)(N_TILE >> 4) << 24);
             uint32_t ga = 0, it = 0;
             for (int rt = cluster_id; rt < n_rt; rt += n_clusters, ++it) {
-                const uint32_t bs = it & 1;
-                mbar_wait(&b_full[bs], (it >> 1) & 1);
+                const uint32_t bs = a.nb_stages > 1 ? (it & 1) : 0;
+                mbar_wait(&b_full[bs], (a.nb_stages > 1 ? (it >> 1) : it) & 1);
                 const uint32_t b_addr = smem_u32(smB[bs]);
                 for (int qt = 0; qt < a.n_qt; ++qt, ++ga) {
                     const uint32_t s = ga & 1;
@@ -475,9 +476,18 @@ bool make_map(CUtensorMap* m, const void* gptr, long long n_rows, int kp, int pi
 
 }  // namespace
 
-size_t gemm_smem_bytes(int kp_mma) {
+size_t gemm_smem_bytes(int kp_mma, int nb_stages) {
     size_t tile = ((size_t)kTileRows * kp_mma * 2 + 1023) & ~(size_t)1023;
-    return 4 * tile + 13 * 8 + 16 + 1024;
+    return (2 + nb_stages) * tile + 13 * 8 + 16 + 1024;
+}
+
+// 2 row-tile buffers when they fit next to the 2 query stages, else 1 (the row tile reload is then exposed once per
+// row tile); 0 = the operand tiles do not fit at all and the caller must use the streaming scan.
+int gemm_row_stages(int kp, size_t smem_optin) {
+    const int kp_mma = (kp + 15) / 16 * 16;
+    if (gemm_smem_bytes(kp_mma, 2) <= smem_optin) return 2;
+    if (gemm_smem_bytes(kp_mma, 1) <= smem_optin) return 1;
+    return 0;
 }
 
 cudaError_t launch_gemm_filter(const GemmLaunch& g, cudaStream_t stream) {
@@ -508,7 +518,8 @@ cudaError_t launch_gemm_filter(const GemmLaunch& g, cudaStream_t stream) {
     if (n_rt <= 0 || a.n_qt <= 0) return cudaSuccess;
     int clusters = g.sm_count / cg;
     if (clusters > n_rt) clusters = n_rt;
-    const size_t smem = gemm_smem_bytes(a.kp_mma);
+    a.nb_stages = g.nb_stages;
+    const size_t smem = gemm_smem_bytes(a.kp_mma, a.nb_stages);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(clusters * cg);
     cfg.blockDim = dim3(kGemmThreads);

@@ -123,6 +123,7 @@ struct ann_index {
 
     // options / stats
     int path_opt = 0, gemm_min_batch = 16, gemm_cta_group = 2;
+    bool device_fallback = false;   // device entry point: synchronise and run the exact fallback for flagged queries
     // optional CUDA-event timing of the dominant kernel of each path, on the launching stream (bench.py roofline)
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pairs;
@@ -442,6 +443,7 @@ int query_gemm(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
         g.kp = ix->kp;
         g.cta_group = ix->gemm_cta_group;
         g.seed_mode = seed_mode;
+        g.nb_stages = gemm_row_stages(ix->kp, ix->smem_optin);
         g.sm_count = ix->sm_count;
         g.qstate = ix->qstate.p;
         g.pool = ix->pool.p;
@@ -527,7 +529,8 @@ int query_gemm(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
 }
 
 bool gemm_eligible(const ann_index* ix, int b, int k_eff) {
-    return ix->shadow != nullptr && ix->n_special == 0 && k_eff <= 256 && ix->n >= 1024 && b >= 1;
+    return ix->shadow != nullptr && ix->n_special == 0 && k_eff <= 256 && ix->n >= 1024 && b >= 1 &&
+           gemm_row_stages(ix->kp, ix->smem_optin) > 0;
 }
 
 int query_core(ann_index* ix, const float* d_queries, int b, int k, int64_t* d_out_ids, float* d_out_dist,
@@ -546,7 +549,7 @@ int query_core(ann_index* ix, const float* d_queries, int b, int k, int64_t* d_o
     int path = ix->path_opt;
     if (path == 2 && !gemm_eligible(ix, b, k_eff))
         return fail(ANN_ERR_INVALID_ARGUMENT,
-                    "path=2 (tensor-core filter) needs the bf16 shadow, no non-finite/zero-norm rows, size >= 1024 and k <= 256");
+                    "path=2 (tensor-core filter) needs the bf16 shadow, no non-finite/zero-norm rows, size >= 1024, k <= 256 and dim <= 288");
     if (path == 0) path = (gemm_eligible(ix, b, k_eff) && b >= ix->gemm_min_batch) ? 2 : 1;
     if (path == 2) return query_gemm(ix, d_queries, b, k_eff, k, d_out_ids, d_out_dist, d_out_count, st);
     return query_scan(ix, d_queries, b, k_eff, k, d_out_ids, d_out_dist, d_out_count, st);
@@ -754,7 +757,9 @@ int ann_query_batch_device(ann_index* ix, const float* d_queries, int32_t b, int
     int rc = set_device(ix);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;  // NULL = the legacy default stream
-    return query_core(ix, d_queries, b, k, d_out_ids, d_out_dist, d_out_count, st);
+    rc = query_core(ix, d_queries, b, k, d_out_ids, d_out_dist, d_out_count, st);
+    if (rc == ANN_OK && ix->device_fallback) rc = resolve_flagged(ix, d_queries, b, k, d_out_ids, d_out_dist, d_out_count, st);
+    return rc;
 }
 
 int ann_query_batch(ann_index* ix, const float* queries, int32_t b, int32_t dim, int32_t k, int64_t* out_ids, float* out_dist,
@@ -814,6 +819,10 @@ int ann_set_option(ann_index* ix, const char* name, int64_t value) {
         ix->kernel_ms_total = 0.0;
         ix->kernel_launches_timed = 0;
         ix->ev_used = 0;
+        return ANN_OK;
+    }
+    if (!strcmp(name, "device_fallback")) {
+        ix->device_fallback = value != 0;
         return ANN_OK;
     }
     if (!strcmp(name, "gemm_cta_group")) {

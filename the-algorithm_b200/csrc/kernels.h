@@ -116,12 +116,14 @@ struct GemmLaunch {
     int b, b_pad, kp;
     int cta_group;              // 1 or 2 (tcgen05 cta_group)
     int seed_mode;              // 1: threshold seeding launch (group maxima at fixed pool slots)
+    int nb_stages;              // from gemm_row_stages()
     int sm_count;
     QueryState* qstate;
     entry_t* pool;
     int pool_cap;
 };
 cudaError_t launch_gemm_filter(const GemmLaunch& g, cudaStream_t stream);
-size_t gemm_smem_bytes(int kp_mma);
+size_t gemm_smem_bytes(int kp_mma, int nb_stages);
+int gemm_row_stages(int kp, size_t smem_optin);   // 2, 1 or 0 (operands do not fit: use the scan)
 
 }  // namespace b200ann
