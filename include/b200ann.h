@@ -84,6 +84,10 @@ ANN_API int ann_append_batch(ann_index *ix, const int64_t *ids, const float *row
 ANN_API int ann_append_batch_device(ann_index *ix, const int64_t *d_ids, const float *d_rows, int64_t n,
                                     void *stream);
 
+/* Reads rows [start, start+n) and their ids back into host buffers (out_ids[n], out_rows[n*dim], either may be NULL).
+ * What SerializableBruteForceIndex.toDirectory iterates to persist the index (BruteForceIndex.scala:142-161). */
+ANN_API int ann_read_rows(ann_index *ix, int64_t start, int64_t n, int64_t *out_ids, float *out_rows);
+
 /* Number of rows visible to queries (linkedQueue size, BruteForceIndex.scala:34-36). */
 ANN_API int ann_size(const ann_index *ix, int64_t *n);
 

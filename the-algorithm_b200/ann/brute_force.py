@@ -239,6 +239,16 @@ class BruteForceIndex(Appendable, Queryable):
             return [self.id_of(ids[0, j]) for j in range(int(cnt[0]))]
         return self.future_pool(run)
 
+    def read_rows(self, start: int, n: int):
+        """Rows [start, start+n) and their device ids, in insertion order (what toDirectory iterates)."""
+        with self._lock:
+            self.flush()
+            ids = np.empty(n, dtype=np.int64)
+            rows = np.empty((n, self.dim or 0), dtype=np.float32)
+            if n:
+                _capi.check(_capi.lib().ann_read_rows(self._h, start, n, _ptr(ids), _ptr(rows)))
+            return ids, rows
+
     # ---- tuning / introspection ------------------------------------------------------------------------------
     def set_option(self, name: str, value: int) -> None:
         _capi.check(_capi.lib().ann_set_option(self._h, name.encode(), int(value)))
@@ -267,3 +277,70 @@ def merge_topk_device(ids_t, dist_t, count_t, k: int, stream: int = 0):
             ctypes.c_void_p(count_t.data_ptr()), s, b, k, ctypes.c_void_p(out_ids.data_ptr()),
             ctypes.c_void_p(out_dist.data_ptr()), ctypes.c_void_p(out_cnt.data_ptr()), ctypes.c_void_p(stream)))
     return out_ids, out_dist, out_cnt
+
+
+# ------------------------------------------------------------------------------------------------ persistence
+_MAGIC = b"B200ANN\x01"
+
+
+class SerializableBruteForceIndex:
+    """Mirror of SerializableBruteForceIndex / BruteForceDeserialization (BruteForceIndex.scala:94-162;
+    BruteForceDeserialization.scala:18-64): one data file `BruteForceFileData` inside a directory, `_SUCCESS` marker
+    (common/IndexOutputFile.scala:60).
+
+    The reference streams TBinaryProtocol `PersistedEmbedding{1: binary id, 2: embedding.Embedding}` structs with no header
+    (ThriftIteratorIO.scala:14-22); the inner `embedding.Embedding` thrift struct is not in the open-source tree, so byte
+    compatibility cannot be pinned.  This is the native raw format instead (little endian):
+        magic "B200ANN\x01" | int32 metric ordinal | int32 dim | int64 n | int64 ids[n] | float32 rows[n][dim]
+    Only native int64 ids are persisted."""
+
+    DataFileName = BruteForceIndex.DataFileName
+    SuccessMarker = "_SUCCESS"
+
+    @staticmethod
+    def to_directory(index: BruteForceIndex, directory, chunk_rows: int = 1 << 20) -> None:
+        import os
+        from pathlib import Path
+
+        if not index.native_ids:
+            raise TypeError("only native int64 ids can be persisted")
+        d = Path(directory)
+        d.mkdir(parents=True, exist_ok=True)
+        n = index.size()
+        dim = index.dim or 0
+        with open(d / SerializableBruteForceIndex.DataFileName, "wb") as f:
+            f.write(_MAGIC)
+            f.write(np.array([index.metric.ordinal, dim], dtype="<i4").tobytes())
+            f.write(np.array([n], dtype="<i8").tobytes())
+            for s in range(0, n, chunk_rows):          # ids first, then rows, each streamed in chunks
+                ids, _ = index.read_rows(s, min(chunk_rows, n - s))
+                f.write(ids.astype("<i8").tobytes())
+            for s in range(0, n, chunk_rows):
+                _, rows = index.read_rows(s, min(chunk_rows, n - s))
+                f.write(rows.astype("<f4").tobytes())
+        (d / SerializableBruteForceIndex.SuccessMarker).write_bytes(b"")
+
+    toDirectory = to_directory
+
+    @staticmethod
+    def from_directory(directory, metric: Metric, future_pool: FuturePool, *, device: int = 0,
+                       chunk_rows: int = 1 << 20) -> BruteForceIndex:
+        from pathlib import Path
+
+        d = Path(directory)
+        with open(d / SerializableBruteForceIndex.DataFileName, "rb") as f:
+            if f.read(8) != _MAGIC:
+                raise ValueError("not a b200ann BruteForceFileData file")
+            ordinal, dim = np.frombuffer(f.read(8), dtype="<i4")
+            (n,) = np.frombuffer(f.read(8), dtype="<i8")
+            if int(ordinal) != metric.ordinal:
+                raise ValueError(f"index was written with metric ordinal {ordinal}, asked to load as {metric}")
+            ids = np.frombuffer(f.read(int(n) * 8), dtype="<i8")
+            index = BruteForceIndex(metric, future_pool, device=device, capacity_hint=int(n))
+            for s in range(0, int(n), chunk_rows):
+                m = min(chunk_rows, int(n) - s)
+                rows = np.frombuffer(f.read(m * int(dim) * 4), dtype="<f4").reshape(m, int(dim))
+                index.append_batch(ids[s:s + m], rows)
+        return index
+
+    fromDirectory = from_directory

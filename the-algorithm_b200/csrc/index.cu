@@ -550,7 +550,13 @@ int query_core(ann_index* ix, const float* d_queries, int b, int k, int64_t* d_o
     if (path == 2 && !gemm_eligible(ix, b, k_eff))
         return fail(ANN_ERR_INVALID_ARGUMENT,
                     "path=2 (tensor-core filter) needs the bf16 shadow, no non-finite/zero-norm rows, size >= 1024, k <= 256 and dim <= 288");
-    if (path == 0) path = (gemm_eligible(ix, b, k_eff) && b >= ix->gemm_min_batch) ? 2 : 1;
+    // measured on 10M x 200 (profiles/r01_crossover.txt): the scan costs 1.2 / 1.2 / 1.7 / 3.1 ms for 1 / 2 / 4 / 8 queries and
+    // another 3.1 ms per further 8; the tensor-core path is flat at ~2.0 ms up to 64 queries but pays ~12 launches, which
+    // only amortise on a large shard.
+    if (path == 0) {
+        const bool big = b >= ix->gemm_min_batch || (b >= 5 && ix->n >= 2000000);
+        path = (gemm_eligible(ix, b, k_eff) && big) ? 2 : 1;
+    }
     if (path == 2) return query_gemm(ix, d_queries, b, k_eff, k, d_out_ids, d_out_dist, d_out_count, st);
     return query_scan(ix, d_queries, b, k_eff, k, d_out_ids, d_out_dist, d_out_count, st);
 }
@@ -708,6 +714,22 @@ void ann_destroy(ann_index* ix) {
 int ann_size(const ann_index* ix, int64_t* n) {
     if (!ix || !n) return fail(ANN_ERR_NULL_POINTER, "ann_size: NULL argument");
     *n = ix->n;
+    return ANN_OK;
+}
+
+int ann_read_rows(ann_index* ix, int64_t start, int64_t n, int64_t* out_ids, float* out_rows) {
+    if (!ix) return fail(ANN_ERR_NULL_POINTER, "ann_read_rows: index is NULL");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (start < 0 || n < 0 || start + n > ix->n) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_read_rows: range outside [0, size)");
+    if (n == 0) return ANN_OK;
+    int rc = set_device(ix);
+    if (rc) return rc;
+    if (out_ids) CUDA_TRY(cudaMemcpyAsync(out_ids, ix->ids + start, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost, ix->stream));
+    if (out_rows)
+        CUDA_TRY(cudaMemcpy2DAsync(out_rows, (size_t)ix->dim * sizeof(float), ix->rows + (size_t)start * ix->pitch,
+                                   (size_t)ix->pitch * sizeof(float), (size_t)ix->dim * sizeof(float), (size_t)n,
+                                   cudaMemcpyDeviceToHost, ix->stream));
+    CUDA_TRY(cudaStreamSynchronize(ix->stream));
     return ANN_OK;
 }
 
