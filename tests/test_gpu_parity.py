@@ -375,3 +375,56 @@ def test_full_size_properties_10m_rows():
     gi2, gd2, _ = ix.batch_query_with_distance(q, k)
     assert gi2[5, 0] == n + 7 and gd2[5, 0] == 0 and (gi2[5, 1:] == gi[5, :-1]).all()
     ix.close()
+
+
+# ------------------------------------------------------------------------------------------------ large batches, threads
+def test_batch_larger_than_one_gemm_slice():
+    """20k queries in one call: the tensor-core path runs them in slices of 16384 with per-query state kept for all."""
+    corpus, ids, q = make(8192, 32, 20_000, seed=41)
+    corpus[100:140] = corpus[0]                      # a tie group so that some queries need the margin logic
+    check(G["InnerProduct"], corpus, ids, q, 10)
+
+
+def test_concurrent_appends_and_queries_from_threads():
+    """Appendable / Queryable are used from FuturePool threads in the reference (BruteForceIndex.scala:49,71): concurrent
+    appends and queries on one handle must stay consistent; every query sees a prefix-closed set of completed appends."""
+    import threading
+
+    metric = G["L2"]
+    rng = np.random.default_rng(9)
+    base, ids0, q = make(20_000, 48, 32, seed=90)
+    extra = (rng.standard_normal((16, 500, 48)) / 7).astype(np.float32)
+    ix = G["BruteForceIndex"].apply(metric, G["FuturePool"](8))
+    ix.append_batch(ids0, base)
+    errors = []
+
+    def appender(t):
+        try:
+            for j in range(4):
+                blk = t * 4 + j
+                ix.append_batch(np.arange(10 ** 9 + blk * 500, 10 ** 9 + (blk + 1) * 500, dtype=np.int64), extra[blk])
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    def querier():
+        try:
+            for _ in range(6):
+                i, d, c = ix.batch_query_with_distance(q, 20)
+                assert (c == 20).all() and (np.diff(d, axis=1) >= 0).all()
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=appender, args=(t,)) for t in range(4)] + [threading.Thread(target=querier) for _ in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    assert ix.size() == 20_000 + 16 * 500
+    # appends from different threads interleave, so compare against the oracle on the same multiset of rows
+    all_ids, all_rows = ix.read_rows(0, ix.size())
+    gi, gd, gc = ix.batch_query_with_distance(q, 50)
+    oi, od, oc = oracle.query_canonical(metric.ordinal, all_rows, all_ids, q, 50)
+    assert (gi == oi).all() and (gd.view(np.uint32) == od.view(np.uint32)).all()
+    assert sorted(all_ids.tolist()) == sorted(ids0.tolist() + list(range(10 ** 9, 10 ** 9 + 8000)))
+    ix.close()

@@ -63,55 +63,67 @@ __device__ __forceinline__ float widen(float kth, float eps_abs, float eps_rel) 
 }
 
 // ---- exact distance, operation for operation the oracle's distance_f64 (oracle/oracle.c): fp64 accumulation in index
-// order, explicit round-to-nearest mul/add (no contraction), one rounding to fp32, `1 - x` in fp32.  The row is read in
-// blocks of four 128-bit loads, double buffered, so that a thread walking one row has 64 bytes in flight instead of
-// one dependent 4-byte load per step (rows are gathered from random places in HBM).  `a` must be 16-byte aligned with
-// `pitch4` float4 of storage; `b` is read element-wise (broadcast across the threads of a CTA).
-struct ExactAcc {
-    double s0, s1, s2;   // L2: sum (a-b)^2 ; dot products: a.b, a.a, b.b
+// order, explicit round-to-nearest mul/add (no contraction), one rounding to fp32, `1 - x` in fp32.
+// The query is pre-converted to fp64 once per CTA (`b64`, shared memory) together with its squared norm `nb` (the same
+// sequential sum for every row).  Per block of 16 elements the independent work (convert, subtract / multiply) is done
+// first and only the additions form the dependent chain; the row itself is read with 128-bit loads, double buffered.
+struct ExactQuery {
+    const double* b64;   // [d] query as doubles
+    double nb;           // sum b_i^2 in index order (Cosine)
 };
 
-__device__ __forceinline__ void exact_step(int metric, float x, float y, ExactAcc& acc) {
-    const double dx = (double)x, dy = (double)y;
-    if (metric == kMetricL2) {
-        const double diff = __dsub_rn(dx, dy);
-        acc.s0 = __dadd_rn(acc.s0, __dmul_rn(diff, diff));
-    } else {
-        acc.s0 = __dadd_rn(acc.s0, __dmul_rn(dx, dy));
-        if (metric == kMetricCosine) {
-            acc.s1 = __dadd_rn(acc.s1, __dmul_rn(dx, dx));
-            acc.s2 = __dadd_rn(acc.s2, __dmul_rn(dy, dy));
-        }
-    }
+// sequential sum of squares of the query, exactly as the oracle accumulates it
+__device__ __forceinline__ double exact_query_norm2(const double* b64, int d) {
+    double nb = 0.0;
+    for (int i = 0; i < d; ++i) nb = __dadd_rn(nb, __dmul_rn(b64[i], b64[i]));
+    return nb;
 }
 
-__device__ __forceinline__ float exact_distance_rows(int metric, const float* __restrict__ a, int pitch4, const float* __restrict__ b,
-                                                     int d, int l2_squared) {
+template <bool kGlobal = true>
+__device__ __forceinline__ float exact_distance_rows(int metric, const float* __restrict__ a, const ExactQuery& q, int d, int l2_squared) {
     const float4* a4 = reinterpret_cast<const float4*>(a);
-    const int n4 = (d + 3) >> 2;              // float4 that hold at least one valid element (n4 <= pitch4)
-    ExactAcc acc{0.0, 0.0, 0.0};
+    auto ld = [&](int i) -> float4 { return kGlobal ? __ldg(a4 + i) : a4[i]; };
+    const int n4 = (d + 3) >> 2;       // float4 holding at least one valid element
+    const int full = d >> 4;           // blocks of 16 elements with no tail
+    double s0 = 0.0, s1 = 0.0;         // L2: sum (a-b)^2 ; otherwise a.b and (Cosine) a.a
     float4 cur[4], nxt[4];
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto step = [&](float xf, double y) {
+        const double x = (double)xf;
+        if (metric == kMetricL2) {
+            const double df = __dsub_rn(x, y);
+            s0 = __dadd_rn(s0, __dmul_rn(df, df));
+        } else {
+            s0 = __dadd_rn(s0, __dmul_rn(x, y));
+            if (metric == kMetricCosine) s1 = __dadd_rn(s1, __dmul_rn(x, x));
+        }
+    };
 #pragma unroll
-    for (int j = 0; j < 4; ++j) cur[j] = (j < n4) ? __ldg(a4 + j) : zero;
-    for (int base = 0; base < n4; base += 4) {
+    for (int j = 0; j < 4; ++j) cur[j] = (j < n4) ? ld(j) : zero;
+    for (int blk = 0; blk < full; ++blk) {
+        const int base4 = blk << 2;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) nxt[j] = (base + 4 + j < n4) ? __ldg(a4 + base + 4 + j) : zero;
+        for (int j = 0; j < 4; ++j) nxt[j] = (base4 + 4 + j < n4) ? ld(base4 + 4 + j) : zero;
+        const double* bq = q.b64 + (blk << 4);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int i = (base + j) << 2;
-            if (i < d) exact_step(metric, cur[j].x, b[i], acc);
-            if (i + 1 < d) exact_step(metric, cur[j].y, b[i + 1], acc);
-            if (i + 2 < d) exact_step(metric, cur[j].z, b[i + 2], acc);
-            if (i + 3 < d) exact_step(metric, cur[j].w, b[i + 3], acc);
+            step(cur[j].x, bq[4 * j]);
+            step(cur[j].y, bq[4 * j + 1]);
+            step(cur[j].z, bq[4 * j + 2]);
+            step(cur[j].w, bq[4 * j + 3]);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
     }
-    (void)pitch4;
-    if (metric == kMetricL2) return __double2float_rn(l2_squared ? acc.s0 : __dsqrt_rn(acc.s0));
-    if (metric == kMetricIP) return __fsub_rn(1.0f, __double2float_rn(acc.s0));
-    const double cs = __ddiv_rn(acc.s0, __dmul_rn(__dsqrt_rn(acc.s1), __dsqrt_rn(acc.s2)));
+    // tail: fewer than 16 elements, all already in `cur`
+    for (int i = full << 4; i < d; ++i) {
+        const int j = (i >> 2) & 3, c = i & 3;
+        const float xf = c == 0 ? cur[j].x : c == 1 ? cur[j].y : c == 2 ? cur[j].z : cur[j].w;
+        step(xf, q.b64[i]);
+    }
+    if (metric == kMetricL2) return __double2float_rn(l2_squared ? s0 : __dsqrt_rn(s0));
+    if (metric == kMetricIP) return __fsub_rn(1.0f, __double2float_rn(s0));
+    const double cs = __ddiv_rn(s0, __dmul_rn(__dsqrt_rn(s1), __dsqrt_rn(q.nb)));
     return __fsub_rn(1.0f, __double2float_rn(cs));
 }
 

@@ -33,11 +33,15 @@ __device__ __forceinline__ unsigned long long id_key(long long id) { return (uns
 
 __global__ void __launch_bounds__(256) exact_all_kernel(const float* __restrict__ rows, long long n, int pitch, int dim, int metric,
                                                         int l2_squared, const float* __restrict__ query, uint32_t* __restrict__ dkey) {
-    extern __shared__ float qs[];
-    for (int i = threadIdx.x; i < dim; i += blockDim.x) qs[i] = query[i];
+    extern __shared__ double q64[];
+    __shared__ double nb_s;
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) q64[i] = (double)query[i];
     __syncthreads();
+    if (threadIdx.x == 0) nb_s = (metric == kMetricCosine) ? exact_query_norm2(q64, dim) : 0.0;
+    __syncthreads();
+    const ExactQuery eq{q64, nb_s};
     for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x)
-        dkey[r] = float_order_key(exact_distance_rows(metric, rows + (size_t)r * pitch, pitch >> 2, qs, dim, l2_squared));
+        dkey[r] = float_order_key(exact_distance_rows(metric, rows + (size_t)r * pitch, eq, dim, l2_squared));
 }
 
 __global__ void init_state_kernel(SelectState* st, uint32_t k) {
@@ -195,7 +199,7 @@ cudaError_t launch_exact_fallback(const FallbackParams& p, cudaStream_t stream, 
     off += (size_t)2 * p.k * 8;
     uint32_t* lkey = reinterpret_cast<uint32_t*>(base + off);
     const int grid = (int)std::min<long long>((p.n_rows + 255) / 256, 148 * 8);
-    exact_all_kernel<<<grid, 256, p.dim * sizeof(float), stream>>>(p.rows, p.n_rows, p.pitch, p.dim, p.metric, p.l2_squared, p.query, dkey);
+    exact_all_kernel<<<grid, 256, p.dim * sizeof(double), stream>>>(p.rows, p.n_rows, p.pitch, p.dim, p.metric, p.l2_squared, p.query, dkey);
     init_state_kernel<<<1, 256, 0, stream>>>(st, (uint32_t)p.k);
     for (int pass = 0; pass < 12; ++pass) {
         radix_hist_kernel<<<grid, 256, 0, stream>>>(dkey, p.ids, p.n_rows, st, pass);

@@ -380,13 +380,12 @@ int query_scan(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
 
 // K3 flow: geometric row chunks, each scored by the tensor-core filter against the thresholds learnt from the rows
 // before it; an approximate compaction between chunks; one exact finalize at the end.
-int query_gemm(ann_index* ix, const float* d_queries, int b, int k_eff, int k_out, int64_t* d_out_ids, float* d_out_dist,
-               int32_t* d_out_count, cudaStream_t st) {
+int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b, int k_eff, int k_out, int64_t* d_out_ids,
+               float* d_out_dist, int32_t* d_out_count, cudaStream_t st) {
     const int b_pad = (b + 127) / 128 * 128;
     CUDA_TRY(ix->q_padded.ensure((size_t)b * ix->pitch));
     const int qkp = (ix->kp + 63) / 64 * 64;
     CUDA_TRY(ix->q_shadow.ensure((size_t)b_pad * qkp));
-    CUDA_TRY(ix->qstate.ensure((size_t)b));
     CUDA_TRY(ix->pool.ensure((size_t)b * kGemmPoolCap));
     CUDA_TRY(ix->special_rows.ensure((size_t)kSpecialCap));
 
@@ -400,7 +399,7 @@ int query_gemm(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
     pp.q_padded = ix->q_padded.p;
     pp.q_shadow = ix->q_shadow.p;
     pp.qkp = qkp;
-    pp.qstate = ix->qstate.p;
+    pp.qstate = qs_base;
     pp.max_norm_bits = &ix->scalars->max_norm_bits;
     pp.path = 2;
     pp.pub_keys = nullptr;
@@ -410,7 +409,7 @@ int query_gemm(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
     ix->launches++;
 
     SelectParams fp{};
-    fp.qstate = ix->qstate.p;
+    fp.qstate = qs_base;
     fp.pool = ix->pool.p;
     fp.pool_cap = kGemmPoolCap;
     fp.special_rows = ix->special_rows.p;
@@ -445,7 +444,7 @@ int query_gemm(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
         g.seed_mode = seed_mode;
         g.nb_stages = gemm_row_stages(ix->kp, ix->smem_optin);
         g.sm_count = ix->sm_count;
-        g.qstate = ix->qstate.p;
+        g.qstate = qs_base;
         g.pool = ix->pool.p;
         g.pool_cap = kGemmPoolCap;
         cudaEvent_t dbg0 = nullptr, dbg1 = nullptr;
@@ -468,7 +467,7 @@ int query_gemm(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
             cudaEventElapsedTime(&dms, dbg0, dbg1);
             cudaEventDestroy(dbg0);
             cudaEventDestroy(dbg1);
-            CUDA_TRY(cudaMemcpy(h.data(), ix->qstate.p, sizeof(QueryState) * b, cudaMemcpyDeviceToHost));
+            CUDA_TRY(cudaMemcpy(h.data(), qs_base, sizeof(QueryState) * b, cudaMemcpyDeviceToHost));
             uint32_t mx = 0, mn = ~0u;
             double sum = 0;
             for (auto& x : h) {
@@ -521,7 +520,7 @@ int query_gemm(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
     }
     CUDA_TRY(launch_finalize(fp, b, st));
     ix->launches++;
-    collect_flags_kernel<<<std::min(64, (b + 255) / 256), 256, 0, st>>>(ix->qstate.p, b, ix->scalars);
+    collect_flags_kernel<<<std::min(64, (b + 255) / 256), 256, 0, st>>>(qs_base, b, ix->scalars);
     CUDA_TRY(cudaGetLastError());
     ix->launches++;
     ix->last_path = 2;
@@ -557,7 +556,18 @@ int query_core(ann_index* ix, const float* d_queries, int b, int k, int64_t* d_o
         const bool big = b >= ix->gemm_min_batch || (b >= 5 && ix->n >= 2000000);
         path = (gemm_eligible(ix, b, k_eff) && big) ? 2 : 1;
     }
-    if (path == 2) return query_gemm(ix, d_queries, b, k_eff, k, d_out_ids, d_out_dist, d_out_count, st);
+    if (path == 2) {
+        // bound the per-call scratch (pool = 32 KB per query): very large batches go through in slices
+        constexpr int kMaxGemmBatch = 16384;
+        CUDA_TRY(ix->qstate.ensure((size_t)b));   // per-query state of the WHOLE batch stays addressable for the fallback
+        for (int q0 = 0; q0 < b; q0 += kMaxGemmBatch) {
+            const int nb = std::min(kMaxGemmBatch, b - q0);
+            int rc = query_gemm(ix, ix->qstate.p + q0, d_queries + (size_t)q0 * ix->dim, nb, k_eff, k, d_out_ids + (size_t)q0 * k,
+                                d_out_dist + (size_t)q0 * k, d_out_count ? d_out_count + q0 : nullptr, st);
+            if (rc) return rc;
+        }
+        return ANN_OK;
+    }
     return query_scan(ix, d_queries, b, k_eff, k, d_out_ids, d_out_dist, d_out_count, st);
 }
 

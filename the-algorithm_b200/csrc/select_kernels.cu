@@ -15,7 +15,7 @@ namespace b200ann {
 
 namespace {
 
-constexpr int kSelThreads = 512;
+constexpr int kSelThreads = 256;
 constexpr int kSortCap = 4096;    // approximate-stage sort capacity per query
 constexpr int kExactCap = 2048;   // survivors + specials rescored exactly (power of two)
 
@@ -162,7 +162,7 @@ __device__ bool load_and_threshold(const SelectParams& p, int q, entry_t* buf, u
 }  // namespace
 
 // ---- approx-only compaction between GEMM chunks: pool <- survivors, tau <- k-th best + margin --------------
-__global__ void __launch_bounds__(kSelThreads) compact_pool_kernel(SelectParams p) {
+__global__ void __launch_bounds__(kSelThreads, 4) compact_pool_kernel(SelectParams p) {
     extern __shared__ __align__(16) unsigned char sm[];
     entry_t* buf = reinterpret_cast<entry_t*>(sm);
     __shared__ uint32_t hist[256];
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(kSelThreads) compact_pool_kernel(SelectParams 
 }
 
 // ---- finalize: survivors + specials -> exact distances -> (distance, id) order -> outputs -------------------
-__global__ void __launch_bounds__(kSelThreads) finalize_kernel(SelectParams p) {
+__global__ void __launch_bounds__(kSelThreads, 4) finalize_kernel(SelectParams p) {
     extern __shared__ __align__(16) unsigned char sm[];
     entry_t* buf = reinterpret_cast<entry_t*>(sm);                       // kSortCap entries
     long long* cid = reinterpret_cast<long long*>(sm + kSortCap * 8);      // kExactCap ids
@@ -233,11 +233,12 @@ __global__ void __launch_bounds__(kSelThreads) finalize_kernel(SelectParams p) {
         fail_fill();
         return;
     }
-    // exact rescoring of every survivor (g <= tau) and every special row; unordered, the final sort orders them
+    // Exact rescoring of every survivor (g <= tau) and every special row; unordered, the final sort orders them.
+    // The candidate rows are scattered over the whole matrix, so every chain is a sequence of dependent DRAM misses.
     const int n_spec = min((int)qs->special_count, kSpecialCap);
     if (threadIdx.x == 0) n_cand_s = 0;
     __syncthreads();
-    const float* qv = p.queries + (size_t)q * p.q_pitch;
+    uint32_t* crow = ckey;   // row indices first, replaced by the distance keys
     for (int i = threadIdx.x; i < n + n_spec; i += blockDim.x) {
         uint32_t row;
         if (i < n) {
@@ -248,11 +249,7 @@ __global__ void __launch_bounds__(kSelThreads) finalize_kernel(SelectParams p) {
             row = p.special_rows[(size_t)q * kSpecialCap + (i - n)];
         }
         const int slot = atomicAdd(&n_cand_s, 1);
-        if (slot < kExactCap) {
-            float dist = exact_distance_rows(p.metric, p.rows + (size_t)row * p.pitch, p.pitch >> 2, qv, p.dim, p.l2_squared);
-            ckey[slot] = float_order_key(dist);
-            cid[slot] = p.ids[row];
-        }
+        if (slot < kExactCap) crow[slot] = row;
     }
     __syncthreads();
     const int n_cand = n_cand_s;
@@ -260,6 +257,29 @@ __global__ void __launch_bounds__(kSelThreads) finalize_kernel(SelectParams p) {
         if (threadIdx.x == 0) atomicOr(&qs->flags, kFlagSurvivorOverflow);
         fail_fill();
         return;
+    }
+    {
+        // the query as doubles (and its squared norm) once per CTA, in the shared memory the approximate entries occupied
+        double* q64 = reinterpret_cast<double*>(buf);                                  // <= 8 KB (dim <= 1024)
+        uint32_t* okey = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(buf) + 8192);   // kExactCap keys
+        __shared__ double nb_s;
+        const float* qv = p.queries + (size_t)q * p.q_pitch;
+        for (int i = threadIdx.x; i < p.dim; i += blockDim.x) q64[i] = (double)qv[i];
+        __syncthreads();
+        if (threadIdx.x == 0) nb_s = (p.metric == kMetricCosine) ? exact_query_norm2(q64, p.dim) : 0.0;
+        __syncthreads();
+        const ExactQuery eq{q64, nb_s};
+        // one thread per candidate row, all candidates in parallel; several CTAs per SM overlap each other's
+        // dependent-miss chains (the kernel is latency bound, so occupancy -- not per-thread ILP -- is what pays)
+        for (int c = threadIdx.x; c < n_cand; c += blockDim.x) {
+            const uint32_t row = crow[c];
+            const float dist = exact_distance_rows(p.metric, p.rows + (size_t)row * p.pitch, eq, p.dim, p.l2_squared);
+            cid[c] = p.ids[row];
+            okey[c] = float_order_key(dist);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < n_cand; i += blockDim.x) ckey[i] = okey[i];
+        __syncthreads();
     }
     int n2 = 2;
     while (n2 < n_cand) n2 <<= 1;
