@@ -84,6 +84,11 @@ ANN_API int ann_append_batch(ann_index *ix, const int64_t *ids, const float *row
 ANN_API int ann_append_batch_device(ann_index *ix, const int64_t *d_ids, const float *d_rows, int64_t n,
                                     void *stream);
 
+/* Updatable.update (Api.scala:148-150; the HNSW backend implements it, hnsw/Hnsw.scala:149-182): overwrite the embeddings
+ * stored at `slots` (insertion indices, 0 <= slot < size; ids keep their value) with rows[n*dim] and refresh their norms /
+ * bf16 shadow rows.  The id -> slot map is the caller's (the host mirrors keep one). */
+ANN_API int ann_update_batch(ann_index *ix, const int64_t *slots, const float *rows, int64_t n);
+
 /* Reads rows [start, start+n) and their ids back into host buffers (out_ids[n], out_rows[n*dim], either may be NULL).
  * What SerializableBruteForceIndex.toDirectory iterates to persist the index (BruteForceIndex.scala:142-161). */
 ANN_API int ann_read_rows(ann_index *ix, int64_t start, int64_t n, int64_t *out_ids, float *out_rows);

@@ -428,3 +428,65 @@ def test_concurrent_appends_and_queries_from_threads():
     assert (gi == oi).all() and (gd.view(np.uint32) == od.view(np.uint32)).all()
     assert sorted(all_ids.tolist()) == sorted(ids0.tolist() + list(range(10 ** 9, 10 ** 9 + 8000)))
     ix.close()
+
+
+# ------------------------------------------------------------------------------------------------ Updatable
+@pytest.mark.parametrize("mi", [0, 1, 2])
+def test_update_overwrites_in_place_and_appends_unknown_ids(mi):
+    """trait Updatable (Api.scala:148-150): after update(entity) the index answers as if it had been built with the new
+    embedding; the row keeps its slot and id."""
+    metric = metrics()[mi]
+    corpus, ids, q = make(12_000, 40, 64, seed=55)
+    ix = G["BruteForceIndex"].apply(metric, G["FuturePool"].immediate_pool())
+    ix.append_batch(ids, corpus)
+    rng = np.random.default_rng(56)
+    pick = rng.choice(12_000, 700, replace=False)
+    new_rows = (rng.standard_normal((700, 40)) / 6).astype(np.float32)
+    new_rows[:3] = q[:3] * 0.9                                    # make a few updated rows clear winners
+    extra_ids = np.array([10 ** 12 + 1, 10 ** 12 + 2], dtype=np.int64)
+    extra_rows = (rng.standard_normal((2, 40)) / 6).astype(np.float32)
+    ix.update_batch(np.concatenate([ids[pick], extra_ids]), np.concatenate([new_rows, extra_rows]))
+    ix.update(G["EntityEmbedding"](int(ids[5]), corpus[5] * 2)).result()
+    want_rows = corpus.copy()
+    want_rows[pick] = new_rows
+    want_rows[5] = corpus[5] * 2 if 5 not in pick else want_rows[5]
+    if 5 in pick:
+        want_rows[5] = corpus[5] * 2
+    all_rows = np.concatenate([want_rows, extra_rows])
+    all_ids = np.concatenate([ids, extra_ids])
+    assert ix.size() == 12_002
+    for path in (1, 2):
+        ix.set_option("path", path)
+        gi, gd, gc = ix.batch_query_with_distance(q, 30)
+        oi, od, oc = oracle.query_canonical(metric.ordinal, all_rows, all_ids, q, 30)
+        assert (gi == oi).all() and (gd.view(np.uint32) == od.view(np.uint32)).all()
+    ix.close()
+
+
+# ------------------------------------------------------------------------------------------------ query-service shell
+def test_micro_batching_queryable_coalesces_concurrent_single_queries():
+    """Concurrent single-vector callers behind the unchanged Queryable trait are answered in device batches."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from the_algorithm_b200.ann.service import MicroBatchingQueryable, warmup
+
+    metric = G["Cosine"]
+    corpus, ids, q = make(40_000, 64, 600, seed=71)
+    ix = G["BruteForceIndex"].apply(metric, G["FuturePool"].immediate_pool())
+    ix.append_batch(ids, corpus)
+    mb = MicroBatchingQueryable(ix, max_batch=128, max_delay_ms=2.0)
+    assert warmup(mb, 64, k=100, successes=20, timeout_ms=500) >= 20
+    before = mb.batches
+    with ThreadPoolExecutor(32) as ex:
+        futs = [ex.submit(lambda j=j: mb.query_with_distance(q[j], 10 if j % 3 else 25).result(timeout=60)) for j in range(600)]
+        res = [f.result() for f in futs]
+    oi10, od10, _ = oracle.query_canonical(oracle.COSINE, corpus, ids, q, 10)
+    oi25, od25, _ = oracle.query_canonical(oracle.COSINE, corpus, ids, q, 25)
+    for j, r in enumerate(res):
+        want_i, want_d = (oi10, od10) if j % 3 else (oi25, od25)
+        assert [n.neighbor for n in r] == want_i[j].tolist()
+        assert [np.float32(n.distance.distance) for n in r] == want_d[j].tolist()
+    assert mb.batches - before < 600 / 4                      # far fewer device calls than requests
+    assert mb.query(q[0], 0).result() == []
+    mb.close()
+    ix.close()

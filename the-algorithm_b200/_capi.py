@@ -26,7 +26,7 @@ ANN_FLAG_NO_SHADOW = 0x2
 
 # every symbol include/b200ann.h declares (tests/test_capi_symbols.py checks header <-> library <-> this list)
 SYMBOLS = (
-    "ann_create", "ann_destroy", "ann_append_batch", "ann_append_batch_device", "ann_read_rows", "ann_size", "ann_query_batch",
+    "ann_create", "ann_destroy", "ann_append_batch", "ann_append_batch_device", "ann_update_batch", "ann_read_rows", "ann_size", "ann_query_batch",
     "ann_query_batch_device", "ann_merge_topk_device", "ann_set_option", "ann_get_stat", "ann_last_error", "ann_version",
 )
 
@@ -63,6 +63,8 @@ def lib() -> ctypes.CDLL:
         L.ann_append_batch.argtypes = [vp, vp, vp, i64]
         L.ann_append_batch_device.restype = ctypes.c_int
         L.ann_append_batch_device.argtypes = [vp, vp, vp, i64, vp]
+        L.ann_update_batch.restype = ctypes.c_int
+        L.ann_update_batch.argtypes = [vp, vp, vp, i64]
         L.ann_read_rows.restype = ctypes.c_int
         L.ann_read_rows.argtypes = [vp, i64, i64, vp, vp]
         L.ann_size.restype = ctypes.c_int

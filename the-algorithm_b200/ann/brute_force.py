@@ -169,6 +169,40 @@ class BruteForceIndex(Appendable, Queryable):
                 n, ctypes.c_void_p(stream)))
             self._n += n
 
+    # ---- Updatable (Api.scala:148-150) ---------------------------------------------------------------------------
+    def _slot_map(self):
+        """id -> insertion slot, built on first use from the ids stored on the device (later appends keep it current)."""
+        if getattr(self, "_slots", None) is None or len(self._slots) != self._n:
+            if self._id_table is not None:
+                self._slots = {i: s for s, i in enumerate(self._id_table)}
+            else:
+                ids, _ = self.read_rows(0, self._n) if self._n else (np.zeros(0, np.int64), None)
+                self._slots = {int(i): s for s, i in enumerate(ids)}
+        return self._slots
+
+    def update_batch(self, ids, rows) -> None:
+        """Overwrite the embeddings of existing ids in place; unknown ids are appended (Hnsw.update semantics,
+        hnsw/Hnsw.scala:149-182).  With duplicate ids in the index the first inserted one is updated."""
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        with self._lock:
+            self.flush()
+            smap = self._slot_map() if self._n else {}
+            ids = list(ids)
+            known = [j for j, i in enumerate(ids) if (i if self._id_table is not None else int(i)) in smap]
+            fresh = [j for j in range(len(ids)) if j not in set(known)]
+            if known:
+                slots = np.asarray([smap[ids[j] if self._id_table is not None else int(ids[j])] for j in known], dtype=np.int64)
+                sub = np.ascontiguousarray(rows[known])
+                if sub.shape[1] != self.dim:
+                    raise _capi.AnnError(_capi.ANN_ERR_DIMENSION_MISMATCH, "embedding dimension != index dimension")
+                _capi.check(_capi.lib().ann_update_batch(self._h, _ptr(slots), _ptr(sub), len(known)))
+            if fresh:
+                self.append_batch([ids[j] for j in fresh], rows[fresh])
+                self._slots = None
+
+    def update(self, entity: EntityEmbedding) -> Future:
+        return self.future_pool(lambda: self.update_batch([entity.id], np.asarray(entity.embedding, np.float32).reshape(1, -1)))
+
     def to_queryable(self) -> "BruteForceIndex":
         return self
 

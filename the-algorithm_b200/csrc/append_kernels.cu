@@ -29,8 +29,13 @@ __global__ void __launch_bounds__(256) append_rows_kernel(AppendParams p) {
     float local_max = 0.f;
     unsigned long long local_special = 0;
     for (long long r = warp; r < p.n_new; r += nwarps) {
-        const long long row = p.row0 + r;
-        const float* a = p.rows + (size_t)row * p.pitch;
+        const long long row = p.slots ? p.slots[r] : p.row0 + r;
+        float* a = const_cast<float*>(p.rows) + (size_t)row * p.pitch;
+        if (p.slots) {  // in-place update: move the staged embedding into the matrix first
+            const float* src = p.staged + (size_t)r * p.dim;
+            for (int i = lane; i < p.dim; i += 32) a[i] = src[i];
+            __syncwarp();
+        }
         double n2 = 0.0;
         bool finite = true;
         for (int i = lane; i < p.dim; i += 32) {

@@ -120,6 +120,8 @@ struct ann_index {
     DevBuf<int64_t> out_ids;
     DevBuf<int32_t> out_count;
     DevBuf<unsigned char> fb_scratch;
+    DevBuf<float> upd_rows;
+    DevBuf<long long> upd_slots;
 
     // options / stats
     int path_opt = 0, gemm_min_batch = 16, gemm_cta_group = 2;
@@ -712,6 +714,8 @@ void ann_destroy(ann_index* ix) {
     ix->out_ids.release();
     ix->out_count.release();
     ix->fb_scratch.release();
+    ix->upd_rows.release();
+    ix->upd_slots.release();
     for (auto& pr : ix->ev_pairs) {
         cudaEventDestroy(pr.first);
         cudaEventDestroy(pr.second);
@@ -725,6 +729,42 @@ int ann_size(const ann_index* ix, int64_t* n) {
     if (!ix || !n) return fail(ANN_ERR_NULL_POINTER, "ann_size: NULL argument");
     *n = ix->n;
     return ANN_OK;
+}
+
+int ann_update_batch(ann_index* ix, const int64_t* slots, const float* rows, int64_t n) {
+    if (!ix) return fail(ANN_ERR_NULL_POINTER, "ann_update_batch: index is NULL");
+    if (n < 0) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_update_batch: n < 0");
+    if (n == 0) return ANN_OK;
+    if (!slots || !rows) return fail(ANN_ERR_NULL_POINTER, "ann_update_batch: NULL buffer");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    for (int64_t i = 0; i < n; ++i)
+        if (slots[i] < 0 || slots[i] >= ix->n) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_update_batch: slot outside [0, size)");
+    int rc = set_device(ix);
+    if (rc) return rc;
+    cudaStream_t st = ix->stream;
+    CUDA_TRY(ix->upd_rows.ensure((size_t)n * ix->dim));
+    CUDA_TRY(ix->upd_slots.ensure((size_t)n));
+    CUDA_TRY(cudaMemcpyAsync(ix->upd_rows.p, rows, (size_t)n * ix->dim * sizeof(float), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ix->upd_slots.p, slots, (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, st));
+    AppendParams ap{};
+    ap.rows = ix->rows;
+    ap.row0 = 0;
+    ap.slots = ix->upd_slots.p;
+    ap.staged = ix->upd_rows.p;
+    ap.n_new = n;
+    ap.dim = ix->dim;
+    ap.pitch = ix->pitch;
+    ap.metric = ix->metric;
+    ap.inv_norm = ix->inv_norm;
+    ap.row_norm = ix->row_norm;
+    ap.shadow = ix->shadow;
+    ap.kp = ix->kp;
+    ap.max_norm_bits = &ix->scalars->max_norm_bits;   // only ever grows: the error bounds stay valid (looser)
+    ap.n_special = &ix->scalars->n_special;           // conservative: a repaired row does not lower the census
+    CUDA_TRY(launch_append(ap, st));
+    ix->launches++;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return check_device_flags(ix, st);
 }
 
 int ann_read_rows(ann_index* ix, int64_t start, int64_t n, int64_t* out_ids, float* out_rows) {

@@ -10,6 +10,8 @@ namespace b200ann {
 struct AppendParams {
     const float* rows;      // [n_new][pitch] already in place inside the index matrix
     long long row0;         // first new row (global index inside the shard)
+    const long long* slots; // optional: row r lives at slots[r] instead of row0 + r (Updatable.update)
+    const float* staged;    // with slots: the new embeddings [n_new][dim], scattered into `rows` by the kernel
     long long n_new;
     int dim, pitch, metric;
     float* inv_norm;        // [cap]  1/|a|            (Cosine only, else nullptr)
