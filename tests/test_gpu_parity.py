@@ -162,7 +162,7 @@ def test_special_values_nan_inf_zero_rows(mi):
     corpus[1500, 5] = np.nan
     q = rng.standard_normal((33, 12)).astype(np.float32)
     ids = rng.permutation(2000).astype(np.int64)
-    used = check(metric, corpus, ids, q, 100)         # batch of 33 would pick the GEMM path: special rows force the scan
+    used = check(metric, corpus, ids, q, 100)         # a batch would pick the GEMM path: special rows force the scan
     assert used == 1
     check(metric, corpus[:1000], ids[:1000], q[:3], 1000, path=1)   # every row returned: NaN distances last, in id order
     ix = G["BruteForceIndex"].apply(metric, G["FuturePool"].immediate_pool())

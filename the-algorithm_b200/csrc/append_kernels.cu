@@ -153,9 +153,13 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(PrepParams p, int b_p
             st.tau_key = 0xFF800000u;  // +inf
             st.pool_count = 0;
             st.special_count = 0;
-            st.flags = 0;
+            // Degenerate queries cannot be served by an approximate filter: a non-finite entry (every distance NaN), a zero
+            // Cosine query (0/0), or magnitudes whose products could overflow fp32 in the tensor core.  They are flagged
+            // up front and answered by the exact fallback (exact_fallback.cu).
+            const bool bad = !finite || !((nb - nb) == 0.0f) || (p.metric == kMetricCosine && n2 == 0.0) ||
+                             (p.path == 2 && !(amax * nb < 1e30f && amax < 1e37f));
+            st.flags = bad ? kFlagSpecialOverflow : 0u;
             p.qstate[q] = st;
-            const bool bad = !finite || !((nb - nb) == 0.0f) || (p.metric == kMetricCosine && n2 == 0.0);
             if (bad) atomicAdd(p.bad_queries, 1ull);
         }
     }

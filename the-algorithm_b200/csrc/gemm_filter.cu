@@ -50,7 +50,7 @@ struct GemmArgs {
     entry_t* pool;
     int pool_cap;
     int debug_nohit;
-    int nb_stages;                    // row-tile buffers: 2 when four operand tiles fit in shared memory, else 1
+    int na_stages, nb_stages;         // query-tile / row-tile buffers.  na = 1: a single query tile stays resident (batch fits one tile)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -170,16 +170,20 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
     const uint32_t tile_bytes = (uint32_t)kTileRows * a.kp_mma * 2;
     const uint32_t tile_stride = (tile_bytes + 1023u) & ~1023u;
     unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    unsigned char* smA[2] = {base, base + tile_stride};
-    unsigned char* smB[2] = {base + 2 * tile_stride, base + (a.nb_stages > 1 ? 3 : 2) * tile_stride};
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base + (2 + a.nb_stages) * tile_stride);
+    const int na = a.na_stages, nb = a.nb_stages;
+    const bool a_resident = na == 1;                 // one query tile for the whole launch: loaded once, never released
+    unsigned char* smA[2] = {base, base + (na > 1 ? 1 : 0) * tile_stride};
+    unsigned char* smB[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) smB[i] = base + (size_t)(na + (i < nb ? i : 0)) * tile_stride;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)(na + nb) * tile_stride);
     uint64_t* a_full = bars + 0;
     uint64_t* a_empty = bars + 2;
-    uint64_t* b_full = bars + 4;
-    uint64_t* b_empty = bars + 6;
-    uint64_t* t_full = bars + 8;
-    uint64_t* t_empty = bars + 10;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t* b_full = bars + 4;     // 3
+    uint64_t* b_empty = bars + 7;    // 3
+    uint64_t* t_full = bars + 10;
+    uint64_t* t_empty = bars + 12;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
     const KBlocks kb(a.kp_mma);
     const long long chunk_rows = a.row_end - a.row_begin;
@@ -194,10 +198,12 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
         for (int i = 0; i < 2; ++i) {
             mbar_init(&a_full[i], 1);
             mbar_init(&a_empty[i], 1);
-            mbar_init(&b_full[i], 1);
-            mbar_init(&b_empty[i], 1);
             mbar_init(&t_full[i], 1);
             mbar_init(&t_empty[i], kNumEpiWarps * CG);
+        }
+        for (int i = 0; i < 3; ++i) {
+            mbar_init(&b_full[i], 1);
+            mbar_init(&b_empty[i], 1);
         }
         mbar_fence_init();
     }
@@ -221,8 +227,8 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
         if (lane == 0) {
             uint32_t ga = 0, it = 0;
             for (int rt = cluster_id; rt < n_rt; rt += n_clusters, ++it) {
-                const uint32_t bs = a.nb_stages > 1 ? (it & 1) : 0;
-                mbar_wait(&b_empty[bs], ((a.nb_stages > 1 ? (it >> 1) : it) & 1) ^ 1);
+                const uint32_t bs = it % nb;
+                mbar_wait(&b_empty[bs], ((it / nb) & 1) ^ 1);
                 if (leader) mbar_expect_tx(&b_full[bs], tile_bytes * CG);
                 {
                     const int row0 = (int)(a.row_begin + (long long)rt * N_TILE + rank * kTileRows);
@@ -237,8 +243,9 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
                     if (kb.has16) tma_load_2d<CG>(&tm.r16, &b_full[bs], dst + off, col, row0);
                 }
                 for (int qt = 0; qt < a.n_qt; ++qt, ++ga) {
-                    const uint32_t s = ga & 1;
-                    mbar_wait(&a_empty[s], ((ga >> 1) & 1) ^ 1);
+                    if (a_resident && ga > 0) continue;          // the only query tile is already (being) loaded
+                    const uint32_t s = a_resident ? 0 : (ga & 1);
+                    if (!a_resident) mbar_wait(&a_empty[s], ((ga >> 1) & 1) ^ 1);
                     if (leader) mbar_expect_tx(&a_full[s], tile_bytes * CG);
                     const int q0 = qt * N_TILE + rank * kTileRows;
                     unsigned char* dst = smA[s];
@@ -260,15 +267,17 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_TILE >> 3) << 17) | ((uint32_t)(N_TILE >> 4) << 24);
             uint32_t ga = 0, it = 0;
             for (int rt = cluster_id; rt < n_rt; rt += n_clusters, ++it) {
-                const uint32_t bs = a.nb_stages > 1 ? (it & 1) : 0;
-                mbar_wait(&b_full[bs], (a.nb_stages > 1 ? (it >> 1) : it) & 1);
+                const uint32_t bs = it % nb;
+                mbar_wait(&b_full[bs], (it / nb) & 1);
                 const uint32_t b_addr = smem_u32(smB[bs]);
                 for (int qt = 0; qt < a.n_qt; ++qt, ++ga) {
-                    const uint32_t s = ga & 1;
-                    mbar_wait(&a_full[s], (ga >> 1) & 1);
+                    const uint32_t s = ga & 1;                    // accumulator stage
+                    const uint32_t as = a_resident ? 0 : s;       // query-tile stage
+                    if (!a_resident) mbar_wait(&a_full[as], (ga >> 1) & 1);
+                    else if (ga == 0) mbar_wait(&a_full[0], 0);
                     mbar_wait(&t_empty[s], ((ga >> 1) & 1) ^ 1);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smA[s]);
+                    const uint32_t a_addr = smem_u32(smA[as]);
                     const uint32_t d_tmem = tmem_base + s * N_TILE;
                     uint32_t acc = 0;
                     for (int i = 0; i < kb.nb64; ++i) {
@@ -293,7 +302,7 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
                         umma_bf16<CG>(d_tmem, smem_desc(a_addr + off, 256, 6), smem_desc(b_addr + off, 256, 6), idesc, acc);
                         acc = 1;
                     }
-                    umma_commit<CG>(&a_empty[s]);   // operands of this query tile consumed
+                    if (!a_resident) umma_commit<CG>(&a_empty[as]);   // operands of this query tile consumed
                     umma_commit<CG>(&t_full[s]);    // accumulator ready for the epilogue
                 }
                 umma_commit<CG>(&b_empty[bs]);      // row tile consumed
@@ -476,17 +485,17 @@ bool make_map(CUtensorMap* m, const void* gptr, long long n_rows, int kp, int pi
 
 }  // namespace
 
-size_t gemm_smem_bytes(int kp_mma, int nb_stages) {
+size_t gemm_smem_bytes(int kp_mma, int n_tiles) {
     size_t tile = ((size_t)kTileRows * kp_mma * 2 + 1023) & ~(size_t)1023;
-    return (2 + nb_stages) * tile + 13 * 8 + 16 + 1024;
+    return (size_t)n_tiles * tile + 15 * 8 + 16 + 1024;
 }
 
 // 2 row-tile buffers when they fit next to the 2 query stages, else 1 (the row tile reload is then exposed once per
 // row tile); 0 = the operand tiles do not fit at all and the caller must use the streaming scan.
 int gemm_row_stages(int kp, size_t smem_optin) {
     const int kp_mma = (kp + 15) / 16 * 16;
-    if (gemm_smem_bytes(kp_mma, 2) <= smem_optin) return 2;
-    if (gemm_smem_bytes(kp_mma, 1) <= smem_optin) return 1;
+    if (gemm_smem_bytes(kp_mma, 4) <= smem_optin) return 2;
+    if (gemm_smem_bytes(kp_mma, 3) <= smem_optin) return 1;
     return 0;
 }
 
@@ -518,8 +527,12 @@ cudaError_t launch_gemm_filter(const GemmLaunch& g, cudaStream_t stream) {
     if (n_rt <= 0 || a.n_qt <= 0) return cudaSuccess;
     int clusters = g.sm_count / cg;
     if (clusters > n_rt) clusters = n_rt;
-    a.nb_stages = g.nb_stages;
-    const size_t smem = gemm_smem_bytes(a.kp_mma, a.nb_stages);
+    // g.nb_stages (from gemm_row_stages) says how many operand tiles fit: 2 -> four tiles, 1 -> three.  With a single query
+    // tile (batch <= one M tile) the tile saved on the query side deepens the row pipeline instead.
+    const int tiles = g.nb_stages + 2;
+    a.na_stages = a.n_qt == 1 ? 1 : 2;
+    a.nb_stages = tiles - a.na_stages;
+    const size_t smem = gemm_smem_bytes(a.kp_mma, tiles);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(clusters * cg);
     cfg.blockDim = dim3(kGemmThreads);

@@ -124,7 +124,7 @@ struct ann_index {
     DevBuf<long long> upd_slots;
 
     // options / stats
-    int path_opt = 0, gemm_min_batch = 16, gemm_cta_group = 2;
+    int path_opt = 0, gemm_min_batch = 2, gemm_cta_group = 2;
     bool device_fallback = false;   // device entry point: synchronise and run the exact fallback for flagged queries
     // optional CUDA-event timing of the dominant kernel of each path, on the launching stream (bench.py roofline)
     bool timing = false;
@@ -551,13 +551,11 @@ int query_core(ann_index* ix, const float* d_queries, int b, int k, int64_t* d_o
     if (path == 2 && !gemm_eligible(ix, b, k_eff))
         return fail(ANN_ERR_INVALID_ARGUMENT,
                     "path=2 (tensor-core filter) needs the bf16 shadow, no non-finite/zero-norm rows, size >= 1024, k <= 256 and dim <= 288");
-    // measured on 10M x 200 (profiles/r01_crossover.txt): the scan costs 1.2 / 1.2 / 1.7 / 3.1 ms for 1 / 2 / 4 / 8 queries and
-    // another 3.1 ms per further 8; the tensor-core path is flat at ~2.0 ms up to 64 queries but pays ~12 launches, which
-    // only amortise on a large shard.
-    if (path == 0) {
-        const bool big = b >= ix->gemm_min_batch || (b >= 5 && ix->n >= 2000000);
-        path = (gemm_eligible(ix, b, k_eff) && big) ? 2 : 1;
-    }
+    // profiles/r01_crossover.txt: with the resident-query pipeline the tensor-core path is at least as fast as the scan for
+    // every batch >= 2 at every shard size measured (100K .. 10M rows).  Single queries stay on the HBM-streaming scan by
+    // default (the fp32 matrix itself is scanned, nothing approximate is involved); gemm_min_batch = 1 routes them to the
+    // tensor-core path too, which reads the half-size bf16 shadow (0.85 vs 1.22 ms at 10M x 200).
+    if (path == 0) path = (gemm_eligible(ix, b, k_eff) && b >= ix->gemm_min_batch) ? 2 : 1;
     if (path == 2) {
         // bound the per-call scratch (pool = 32 KB per query): very large batches go through in slices
         constexpr int kMaxGemmBatch = 16384;
