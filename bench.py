@@ -303,10 +303,11 @@ def run_ours(a):
     h_dist = torch.empty((b, k), dtype=torch.float32).pin_memory()
     h_cnt = torch.empty((b,), dtype=torch.int32).pin_memory()
     q_np = q_pin.numpy()
+    out_np = (h_ids.numpy(), h_dist.numpy(), h_cnt.numpy())      # pinned result buffers handed to the C ABI
 
     def step_e2e():
         if world == 1:
-            return ix.batch_query_with_distance(q_np, k)     # ann_query_batch: H2D, query path, D2H, all inside the call
+            return ix.batch_query_with_distance(q_np, k, out=out_np)   # ann_query_batch: H2D, query path, D2H inside the call
         qd = q_pin.to(dev, non_blocking=True)
         oi, od, oc = step_device(qd)
         h_ids.copy_(oi, non_blocking=True)
@@ -335,6 +336,14 @@ def run_ours(a):
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
     except Exception:
         pass
+    traffic = None
+    try:   # DRAM bytes of the same kernel from the committed ncu --set full capture of this command (profiles/)
+        tj = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())
+        if (n, d, b, k, world, a.metric) == (10_000_000, 200, 4096, 100, 1, "InnerProduct"):
+            traffic = {"dram_bytes_per_step": tj["gemm_filter_dram_bytes_per_step"],
+                       "algorithmic_shadow_bytes_per_step": tj["algorithmic_shadow_bytes_per_step"], "source": tj["source"]}
+    except Exception:
+        pass
     if last_path == 2:
         flops_step = 2.0 * n_local * d * b
         achieved = flops_step * a.steps / (kernel_us * 1e-6) / 1e12 if kernel_us else None
@@ -343,7 +352,7 @@ def run_ours(a):
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
                     if peaks else "fallback 1.4 PFLOP/s sustained",
-                    "traffic": None, "kernel_ms_per_step": kernel_us / 1e3 / a.steps,
+                    "traffic": traffic, "kernel_ms_per_step": kernel_us / 1e3 / a.steps,
                     "launches_per_step": kernel_n / a.steps,
                     "algorithmic_flops_per_step": flops_step}
     else:

@@ -220,8 +220,10 @@ class BruteForceIndex(Appendable, Queryable):
         raw = int(raw)
         return raw if self._id_table is None else self._id_table[raw]
 
-    def batch_query_with_distance(self, embeddings, num_of_neighbors: int):
-        """b queries in one call.  Returns (ids [b,k] int64 (device ids), distances [b,k] fp32, counts [b])."""
+    def batch_query_with_distance(self, embeddings, num_of_neighbors: int, out=None):
+        """b queries in one call.  Returns (ids [b,k] int64 (device ids), distances [b,k] fp32, counts [b]).
+        `out` = (ids, dist, counts) lets the caller supply the result buffers (e.g. pinned host memory), which the C ABI
+        fills completely; otherwise fresh arrays are allocated."""
         q = np.ascontiguousarray(embeddings, dtype=np.float32)
         if q.ndim != 2:
             raise ValueError("embeddings must be [b, dim]")
@@ -229,9 +231,15 @@ class BruteForceIndex(Appendable, Queryable):
         with self._lock:
             self.flush()
             kk = max(k, 0)
-            out_ids = np.full((b, kk), -1, dtype=np.int64)
-            out_dist = np.full((b, kk), np.inf, dtype=np.float32)
-            out_cnt = np.zeros(b, dtype=np.int32)
+            if out is not None and self._h and k > 0:
+                out_ids, out_dist, out_cnt = out
+                assert out_ids.shape == (b, kk) and out_ids.dtype == np.int64 and out_ids.flags.c_contiguous
+                assert out_dist.shape == (b, kk) and out_dist.dtype == np.float32 and out_dist.flags.c_contiguous
+                assert out_cnt.shape == (b,) and out_cnt.dtype == np.int32
+            else:
+                out_ids = np.full((b, kk), -1, dtype=np.int64)
+                out_dist = np.full((b, kk), np.inf, dtype=np.float32)
+                out_cnt = np.zeros(b, dtype=np.int32)
             if k < 0:
                 raise _capi.AnnError(_capi.ANN_ERR_NEGATIVE_K, "numOfNeighbours < 0")
             if not self._h:  # nothing appended yet: BruteForceIndex.scala:76-89 yields an empty list
