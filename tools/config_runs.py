@@ -27,7 +27,7 @@ from the_algorithm_b200.ann.brute_force import BruteForceIndex  # noqa: E402
 from the_algorithm_b200.ann.common import FuturePool, Metric  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("mode", choices=["latency", "streaming"])
+ap.add_argument("mode", choices=["latency", "streaming", "config1"])
 ap.add_argument("--rows", type=int, default=None)
 ap.add_argument("--dim", type=int, default=None)
 ap.add_argument("--metric", default=None)
@@ -52,6 +52,53 @@ def build(metric, n, d, extra=0):
         ix.append_batch_device(torch.arange(c0, c0 + m, device=dev, dtype=torch.int64), rows)
     return ix, g
 
+
+if a.mode == "config1":
+    # BASELINE.json configs[0]: Cosine top-100 over 100K x 200, 1K queries -- the reference's own CPU-runnable case.
+    # Full parity against the canonical oracle, and the reference-faithful restatement timed on the host cores.
+    import oracle
+
+    n, d, nq = a.rows or 100_000, a.dim or 200, a.queries
+    metric = Metric.from_string(a.metric or "Cosine")
+    rng = np.random.default_rng(0x5EED)
+    corpus = (rng.standard_normal((n, d)) / np.sqrt(d)).astype(np.float32)
+    ids = np.arange(n, dtype=np.int64)
+    q = rng.uniform(-1, 1, (nq, d)).astype(np.float32)
+    ix = BruteForceIndex.apply(metric, FuturePool.immediate_pool())
+    ix.append_batch(ids, corpus)
+    for _ in range(3):
+        gi, gd, gc = ix.batch_query_with_distance(q, a.k)
+    t0 = time.perf_counter()
+    reps = 20
+    for _ in range(reps):
+        gi, gd, gc = ix.batch_query_with_distance(q, a.k)
+    gpu_s = (time.perf_counter() - t0) / reps
+    lat = []
+    for i in range(200):
+        t0 = time.perf_counter()
+        ix.batch_query_with_distance(q[i:i + 1], a.k)
+        lat.append((time.perf_counter() - t0) * 1e3)
+    oi, od, oc = oracle.query_canonical(metric.ordinal, corpus, ids, q, a.k)
+    fx = oracle.FaithfulIndex(metric.ordinal, d)
+    fx.append(ids, corpus)
+    cores = oracle.max_threads()
+    t0 = time.perf_counter()
+    fi, fd, fc = fx.query(q, a.k, nthreads=1)
+    cpu1_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    fx.query(q, a.k, nthreads=cores)
+    cpuN_s = time.perf_counter() - t0
+    rec = {"config": f"config 1: {metric.name} top-{a.k}, {n}x{d} fp32, {nq} queries",
+           "gpu_batch_qps_host_api": nq / gpu_s, "gpu_ms_per_1k_batch": gpu_s * 1e3,
+           "gpu_single_query_p50_ms": float(np.median(lat)), "gpu_single_query_p99_ms": float(np.sort(lat)[int(0.99 * len(lat))]),
+           "ids_identical_to_oracle": bool((gi == oi).all()), "distance_bits_identical": bool((gd.view(np.uint32) == od.view(np.uint32)).all()),
+           "max_rel_dist_err": float(np.max(np.abs(gd - od) / np.maximum(np.abs(od), 1e-30))),
+           "faithful_heap_vs_canonical_id_mismatches": int((fi != oi).sum()),
+           "cpu_port_qps_1_thread": nq / cpu1_s, f"cpu_port_qps_{cores}_threads": nq / cpuN_s, "cpu_cores": cores,
+           "path": {1: "scan", 2: "gemm"}[ix.stat("last_path")]}
+    print(json.dumps(rec), flush=True)
+    (OUT / "config1.json").write_text(json.dumps(rec, indent=1))
+    sys.exit(0 if rec["ids_identical_to_oracle"] else 1)
 
 if a.mode == "latency":
     n, d = a.rows or 10_000_000, a.dim or 128
