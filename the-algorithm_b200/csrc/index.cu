@@ -575,12 +575,18 @@ int query_core(ann_index* ix, const float* d_queries, int b, int k, int64_t* d_o
 // Queries the bounded selector flagged (QueryState.flags != 0) are answered again, exactly, by exact_fallback.cu.
 // Needs the per-query flags on the host, so it synchronises `st`; used by the host-buffer entry point.
 int resolve_flagged(ann_index* ix, const float* d_queries, int b, int k, int64_t* d_out_ids, float* d_out_dist,
-                    int32_t* d_out_count, cudaStream_t st) {
+                    int32_t* d_out_count, cudaStream_t st, const DeviceScalars* snapshot = nullptr, bool* ran = nullptr) {
+    if (ran) *ran = false;
     if (b == 0 || k == 0 || ix->n == 0) return ANN_OK;
     DeviceScalars hs{};
-    CUDA_TRY(cudaMemcpyAsync(&hs, ix->scalars, sizeof(hs), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    if (snapshot) {
+        hs = *snapshot;
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(&hs, ix->scalars, sizeof(hs), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+    }
     if (!hs.error_flags) return ANN_OK;
+    if (ran) *ran = true;
     std::vector<QueryState> h((size_t)b);
     CUDA_TRY(cudaMemcpyAsync(h.data(), ix->qstate.p, sizeof(QueryState) * (size_t)b, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -852,15 +858,30 @@ int ann_query_batch(ann_index* ix, const float* queries, int32_t b, int32_t dim,
     CUDA_TRY(cudaMemcpyAsync(ix->q_in.p, queries, (size_t)b * ix->dim * sizeof(float), cudaMemcpyHostToDevice, st));
     rc = query_core(ix, ix->q_in.p, b, k, ix->out_ids.p, ix->out_dist.p, ix->out_count.p, st);
     if (rc) return rc;
-    rc = resolve_flagged(ix, ix->q_in.p, b, k, ix->out_ids.p, ix->out_dist.p, ix->out_count.p, st);
+    // one round trip in the common case: results and the sticky flag word come back together
+    DeviceScalars hs{};
+    auto copy_out = [&]() -> int {
+        if (k > 0) {
+            CUDA_TRY(cudaMemcpyAsync(out_ids, ix->out_ids.p, (size_t)b * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(out_dist, ix->out_dist.p, (size_t)b * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+        }
+        if (out_count) CUDA_TRY(cudaMemcpyAsync(out_count, ix->out_count.p, (size_t)b * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(&hs, ix->scalars, sizeof(hs), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return ANN_OK;
+    };
+    rc = copy_out();
     if (rc) return rc;
-    if (k > 0) {
-        CUDA_TRY(cudaMemcpyAsync(out_ids, ix->out_ids.p, (size_t)b * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(out_dist, ix->out_dist.p, (size_t)b * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+    ix->n_special = hs.n_special;
+    if (hs.error_flags) {   // rare: some queries were flagged by the bounded selector -> exact fallback, then copy again
+        bool ran = false;
+        rc = resolve_flagged(ix, ix->q_in.p, b, k, ix->out_ids.p, ix->out_dist.p, ix->out_count.p, st, &hs, &ran);
+        if (rc) return rc;
+        rc = copy_out();
+        if (rc) return rc;
+        if (hs.error_flags) return check_device_flags(ix, st);
     }
-    if (out_count) CUDA_TRY(cudaMemcpyAsync(out_count, ix->out_count.p, (size_t)b * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
-    return check_device_flags(ix, st);
+    return ANN_OK;
 }
 
 int ann_merge_topk_device(int32_t device, const int64_t* d_ids, const float* d_dist, const int32_t* d_count, int32_t shards,
