@@ -49,7 +49,7 @@ struct GemmArgs {
     QueryState* qstate;
     entry_t* pool;
     int pool_cap;
-    int debug_nohit;
+    int debug_nohit, debug_norot;
     int na_stages, nb_stages;         // query-tile / row-tile buffers.  na = 1: a single query tile stays resident (batch fits one tile)
 };
 
@@ -137,11 +137,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
         : "r"(taddr)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld1(uint32_t taddr, float* v) {
-    uint32_t r;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
-    *v = __uint_as_float(r);
-}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct KBlocks {
@@ -185,6 +180,13 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
     uint64_t* t_empty = bars + 12;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
+    // Every cluster walks the query tiles in a different rotation: otherwise all 148 SMs would be on the same 256 queries
+    // at the same moment and their slot-reservation atomics would pile up on the same 256 counters in L2.
+    const int qt_shift = a.debug_norot ? 0 : cluster_id % a.n_qt;
+    auto rot_qt = [&](int qt) {
+        const int t = qt + qt_shift;
+        return t >= a.n_qt ? t - a.n_qt : t;
+    };
     const KBlocks kb(a.kp_mma);
     const long long chunk_rows = a.row_end - a.row_begin;
     const int n_rt = (int)((chunk_rows + N_TILE - 1) / N_TILE);
@@ -247,7 +249,7 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
                     const uint32_t s = a_resident ? 0 : (ga & 1);
                     if (!a_resident) mbar_wait(&a_empty[s], ((ga >> 1) & 1) ^ 1);
                     if (leader) mbar_expect_tx(&a_full[s], tile_bytes * CG);
-                    const int q0 = qt * N_TILE + rank * kTileRows;
+                    const int q0 = rot_qt(qt) * N_TILE + rank * kTileRows;
                     unsigned char* dst = smA[s];
                     for (int i = 0; i < kb.nb64; ++i) tma_load_2d<CG>(&tm.q64, &a_full[s], dst + i * 16384, i * 64, q0);
                     int off = kb.nb64 * 16384, col = kb.nb64 * 64;
@@ -322,7 +324,7 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
         constexpr int COLS_PER_WARP = N_TILE / 2;
         const int q_lane = (int)rank * kTileRows + quarter * 32 + lane;
         auto load_tau = [&](int qt) -> uint32_t {
-            const int q = qt * N_TILE + q_lane;
+            const int q = rot_qt(qt) * N_TILE + q_lane;
             return q < a.b ? __ldcg(&a.qstate[q].tau_key) : 0u;
         };
         auto emit_now = [&](int q, float v, uint32_t row) {
@@ -349,7 +351,7 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
             const int valid_cols = (int)min((long long)N_TILE, a.row_end - tile_row0);
             for (int qt = 0; qt < a.n_qt; ++qt, ++ge) {
                 const uint32_t s = ge & 1;
-                const int q = qt * N_TILE + q_lane;
+                const int q = rot_qt(qt) * N_TILE + q_lane;
                 const bool q_ok = q < a.b;
                 const uint32_t tk = tk_next;
                 tk_next = load_tau(qt + 1 < a.n_qt ? qt + 1 : 0);   // in flight while this tile is scanned
@@ -383,35 +385,41 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
                     bool any = false;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) any |= (v[j] >= thr);
-                    // Rare path, kept small on purpose (a 32x unrolled hit handler blew the instruction cache and
-                    // stalled the MMA warp): build this lane's hit mask, OR it across the warp, and visit every column
-                    // some lane hit by re-reading that single column from TMEM (warp-uniform address; a 32-way select on v[] was slower).
+                    // Rare path, kept SMALL on purpose: the kernel has to stay inside the 32 KB instruction cache (a 32x
+                    // unrolled hit handler -- tried twice, 42-45 KB of code -- costs 5-40 % because it stalls the MMA warp).
+                    // Build this lane's hit mask and walk its own hits; v[j] for a lane-specific j is a 5-level select tree
+                    // on the registers (31 selects), so there is no second trip to TMEM, whose read port is the epilogue's
+                    // bottleneck.
                     if (__any_sync(0xFFFFFFFFu, any) && col0 < valid_cols) {
                         uint32_t mask = 0;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) mask |= (v[j] >= thr) ? (1u << j) : 0u;
                         const int left = valid_cols - col0;
                         if (left < 32) mask &= (1u << left) - 1u;
-                        uint32_t um = __reduce_or_sync(0xFFFFFFFFu, mask);
-                        while (um) {
-                            const int j = __ffs(um) - 1;
-                            um &= um - 1;
-                            float x;
-                            tmem_ld1(t_lane + c0 + j, &x);
-                            tmem_ld_wait();
-                            if ((mask >> j) & 1u) {
-                                const uint32_t row = (uint32_t)(tile_row0 + col0 + j);
-                                if (ccnt < kHitRegs) {
+                        while (mask) {
+                            const int j = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            float t16[16], t8[8], t4[4], t2[2];
 #pragma unroll
-                                    for (int i = 0; i < kHitRegs; ++i)
-                                        if (i == ccnt) {
-                                            cv[i] = x;
-                                            cr[i] = row;
-                                        }
-                                    ++ccnt;
-                                } else {
-                                    emit_now(q, x, row);   // dense regions (first chunk): straight to the pool
-                                }
+                            for (int i = 0; i < 16; ++i) t16[i] = (j & 1) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) t8[i] = (j & 2) ? t16[2 * i + 1] : t16[2 * i];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) t4[i] = (j & 4) ? t8[2 * i + 1] : t8[2 * i];
+#pragma unroll
+                            for (int i = 0; i < 2; ++i) t2[i] = (j & 8) ? t4[2 * i + 1] : t4[2 * i];
+                            const float x = (j & 16) ? t2[1] : t2[0];
+                            const uint32_t row = (uint32_t)(tile_row0 + col0 + j);
+                            if (ccnt < kHitRegs) {
+#pragma unroll
+                                for (int i = 0; i < kHitRegs; ++i)
+                                    if (i == ccnt) {
+                                        cv[i] = x;
+                                        cr[i] = row;
+                                    }
+                                ++ccnt;
+                            } else {
+                                emit_now(q, x, row);   // dense regions: straight to the pool
                             }
                         }
                     }
@@ -522,6 +530,7 @@ cudaError_t launch_gemm_filter(const GemmLaunch& g, cudaStream_t stream) {
     a.pool = g.pool;
     a.pool_cap = g.pool_cap;
     a.debug_nohit = getenv("B200ANN_NOHIT") ? 1 : 0;
+    a.debug_norot = getenv("B200ANN_NOROT") ? 1 : 0;
     const long long rows = g.row_end - g.row_begin;
     const int n_rt = (int)((rows + n_tile - 1) / n_tile);
     if (n_rt <= 0 || a.n_qt <= 0) return cudaSuccess;
