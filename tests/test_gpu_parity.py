@@ -92,7 +92,9 @@ def test_scan_path_duplicates_tie_break_by_id(mi):
 @pytest.mark.parametrize("mi", [0, 1, 2])
 @pytest.mark.parametrize("n,d,b,k", [(4096, 64, 128, 10), (50_000, 200, 300, 100), (33_333, 128, 257, 100),
                                      (20_000, 72, 64, 17), (2000, 200, 1, 100), (131_073, 40, 130, 256),
-                                     (30_000, 256, 150, 100), (25_000, 285, 140, 50)])
+                                     (30_000, 256, 150, 100), (25_000, 285, 140, 50),
+                                     (30_000, 300, 300, 100), (20_000, 384, 140, 50), (16_000, 512, 300, 20),
+                                     (12_000, 637, 130, 20), (9000, 512, 7, 10)])
 def test_gemm_path_matches_oracle(cg, mi, n, d, b, k):
     corpus, ids, q = make(n, d, b, seed=n + d + b, dup=(n == 33_333))
     check(metrics()[mi], corpus, ids, q, k, path=2, cg=cg)
@@ -102,9 +104,12 @@ def test_auto_path_picks_gemm_for_batches_and_scan_for_single_queries():
     corpus, ids, q = make(30_000, 200, 64, seed=1)
     assert check(G["InnerProduct"], corpus, ids, q, 100) == 2
     assert check(G["InnerProduct"], corpus, ids, q[:1], 100) == 1
-    # operand tiles of a 300-d index do not fit the tensor-core kernel's shared memory: batches use the scan, correctly
+    # a 300-d index streams its query tile in two K segments on the tensor-core path
     corpus, ids, q = make(20_000, 300, 40, seed=2)
-    assert check(G["Cosine"], corpus, ids, q, 100) == 1
+    assert check(G["Cosine"], corpus, ids, q, 100) == 2
+    # beyond ~640 dimensions one row tile no longer fits in shared memory: batches use the scan, correctly
+    corpus, ids, q = make(6000, 700, 20, seed=3)
+    assert check(G["Cosine"], corpus, ids, q, 50) == 1
 
 
 # ------------------------------------------------------------------------------------------------ config 1 of BASELINE.json

@@ -50,7 +50,10 @@ struct GemmArgs {
     entry_t* pool;
     int pool_cap;
     int debug_nohit, debug_norot;
-    int na_stages, nb_stages;         // query-tile / row-tile buffers.  na = 1: a single query tile stays resident (batch fits one tile)
+    int nseg;                         // K segments per query tile (1 = the whole K extent is one stage)
+    int na_stages, nb_stages;         // query-segment ring slots / row-tile buffers
+    int a_resident;                   // the batch is one query tile: its segments are loaded once and never released
+    uint32_t a_slot_stride;           // bytes between query-segment slots (1024-aligned)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -165,20 +168,18 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
     const uint32_t tile_bytes = (uint32_t)kTileRows * a.kp_mma * 2;
     const uint32_t tile_stride = (tile_bytes + 1023u) & ~1023u;
     unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int na = a.na_stages, nb = a.nb_stages;
-    const bool a_resident = na == 1;                 // one query tile for the whole launch: loaded once, never released
-    unsigned char* smA[2] = {base, base + (na > 1 ? 1 : 0) * tile_stride};
-    unsigned char* smB[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) smB[i] = base + (size_t)(na + (i < nb ? i : 0)) * tile_stride;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(base + (size_t)(na + nb) * tile_stride);
-    uint64_t* a_full = bars + 0;
-    uint64_t* a_empty = bars + 2;
-    uint64_t* b_full = bars + 4;     // 3
-    uint64_t* b_empty = bars + 7;    // 3
-    uint64_t* t_full = bars + 10;
-    uint64_t* t_empty = bars + 12;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+    const int na = a.na_stages, nb = a.nb_stages, nseg = a.nseg;
+    const bool a_resident = a.a_resident != 0;
+    unsigned char* smA0 = base;                                            // na slots of a.a_slot_stride bytes
+    unsigned char* smB0 = base + (size_t)na * a.a_slot_stride;             // nb full-K row tiles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smB0 + (size_t)nb * tile_stride);
+    uint64_t* a_full = bars + 0;     // 8
+    uint64_t* a_empty = bars + 8;    // 8
+    uint64_t* b_full = bars + 16;    // 3
+    uint64_t* b_empty = bars + 19;   // 3
+    uint64_t* t_full = bars + 22;    // 2
+    uint64_t* t_empty = bars + 24;   // 2
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
 
     // Every cluster walks the query tiles in a different rotation: otherwise all 148 SMs would be on the same 256 queries
     // at the same moment and their slot-reservation atomics would pile up on the same 256 counters in L2.
@@ -188,6 +189,11 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
         return t >= a.n_qt ? t - a.n_qt : t;
     };
     const KBlocks kb(a.kp_mma);
+    // K segments: the 64-wide blocks are dealt out evenly, the narrow tail blocks (32 / 16 wide) go with the last segment
+    const int seg_base = kb.nb64 / nseg, seg_rem = kb.nb64 % nseg;
+    auto seg_first64 = [&](int sg) { return sg * seg_base + min(sg, seg_rem); };
+    auto seg_n64 = [&](int sg) { return seg_base + (sg < seg_rem ? 1 : 0); };
+    const uint32_t tail_bytes = (uint32_t)kTileRows * 2u * (32u * kb.has32 + 16u * kb.has16);
     const long long chunk_rows = a.row_end - a.row_begin;
     const int n_rt = (int)((chunk_rows + N_TILE - 1) / N_TILE);
     constexpr uint32_t kTmemCols = 2 * N_TILE;       // 256 (CG=1) or 512 (CG=2)
@@ -197,9 +203,11 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm.r64) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 8; ++i) {
             mbar_init(&a_full[i], 1);
             mbar_init(&a_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
             mbar_init(&t_full[i], 1);
             mbar_init(&t_empty[i], kNumEpiWarps * CG);
         }
@@ -224,6 +232,21 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // one operand segment: `n64` 128B-swizzled blocks starting at 64-block `first64`, plus the narrow tail blocks if asked
+    auto load_blocks = [&](const CUtensorMap* m64, const CUtensorMap* m32, const CUtensorMap* m16, uint64_t* bar, unsigned char* dst,
+                           int first64, int n64, bool with_tail, int coord_row) {
+        for (int i = 0; i < n64; ++i) tma_load_2d<CG>(m64, bar, dst + i * 16384, (first64 + i) * 64, coord_row);
+        if (with_tail) {
+            int off = n64 * 16384, col = kb.nb64 * 64;
+            if (kb.has32) {
+                tma_load_2d<CG>(m32, bar, dst + off, col, coord_row);
+                off += 8192;
+                col += 32;
+            }
+            if (kb.has16) tma_load_2d<CG>(m16, bar, dst + off, col, coord_row);
+        }
+    };
+
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
@@ -232,33 +255,20 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
                 const uint32_t bs = it % nb;
                 mbar_wait(&b_empty[bs], ((it / nb) & 1) ^ 1);
                 if (leader) mbar_expect_tx(&b_full[bs], tile_bytes * CG);
-                {
-                    const int row0 = (int)(a.row_begin + (long long)rt * N_TILE + rank * kTileRows);
-                    unsigned char* dst = smB[bs];
-                    for (int i = 0; i < kb.nb64; ++i) tma_load_2d<CG>(&tm.r64, &b_full[bs], dst + i * 16384, i * 64, row0);
-                    int off = kb.nb64 * 16384, col = kb.nb64 * 64;
-                    if (kb.has32) {
-                        tma_load_2d<CG>(&tm.r32, &b_full[bs], dst + off, col, row0);
-                        off += 8192;
-                        col += 32;
-                    }
-                    if (kb.has16) tma_load_2d<CG>(&tm.r16, &b_full[bs], dst + off, col, row0);
-                }
-                for (int qt = 0; qt < a.n_qt; ++qt, ++ga) {
-                    if (a_resident && ga > 0) continue;          // the only query tile is already (being) loaded
-                    const uint32_t s = a_resident ? 0 : (ga & 1);
-                    if (!a_resident) mbar_wait(&a_empty[s], ((ga >> 1) & 1) ^ 1);
-                    if (leader) mbar_expect_tx(&a_full[s], tile_bytes * CG);
+                load_blocks(&tm.r64, &tm.r32, &tm.r16, &b_full[bs], smB0 + (size_t)bs * tile_stride, 0, kb.nb64, true,
+                            (int)(a.row_begin + (long long)rt * N_TILE + rank * kTileRows));
+                for (int qt = 0; qt < a.n_qt; ++qt) {
+                    if (a_resident && it > 0) continue;           // the only query tile is already resident
                     const int q0 = rot_qt(qt) * N_TILE + rank * kTileRows;
-                    unsigned char* dst = smA[s];
-                    for (int i = 0; i < kb.nb64; ++i) tma_load_2d<CG>(&tm.q64, &a_full[s], dst + i * 16384, i * 64, q0);
-                    int off = kb.nb64 * 16384, col = kb.nb64 * 64;
-                    if (kb.has32) {
-                        tma_load_2d<CG>(&tm.q32, &a_full[s], dst + off, col, q0);
-                        off += 8192;
-                        col += 32;
+                    for (int sg = 0; sg < nseg; ++sg, ++ga) {
+                        const uint32_t slot = ga % na;
+                        if (!a_resident) mbar_wait(&a_empty[slot], ((ga / na) & 1) ^ 1);
+                        const bool last = sg == nseg - 1;
+                        const uint32_t bytes = (uint32_t)seg_n64(sg) * 16384u + (last ? tail_bytes : 0u);
+                        if (leader) mbar_expect_tx(&a_full[slot], bytes * CG);
+                        load_blocks(&tm.q64, &tm.q32, &tm.q16, &a_full[slot], smA0 + (size_t)slot * a.a_slot_stride, seg_first64(sg),
+                                    seg_n64(sg), last, q0);
                     }
-                    if (kb.has16) tma_load_2d<CG>(&tm.q16, &a_full[s], dst + off, col, q0);
                 }
             }
         }
@@ -267,44 +277,51 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
         if (leader && lane == 0) {
             // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7, 10), K-major both, N>>3 at 17, M>>4 at 24
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_TILE >> 3) << 17) | ((uint32_t)(N_TILE >> 4) << 24);
-            uint32_t ga = 0, it = 0;
+            uint32_t ga = 0, gt = 0, it = 0;
             for (int rt = cluster_id; rt < n_rt; rt += n_clusters, ++it) {
                 const uint32_t bs = it % nb;
                 mbar_wait(&b_full[bs], (it / nb) & 1);
-                const uint32_t b_addr = smem_u32(smB[bs]);
-                for (int qt = 0; qt < a.n_qt; ++qt, ++ga) {
-                    const uint32_t s = ga & 1;                    // accumulator stage
-                    const uint32_t as = a_resident ? 0 : s;       // query-tile stage
-                    if (!a_resident) mbar_wait(&a_full[as], (ga >> 1) & 1);
-                    else if (ga == 0) mbar_wait(&a_full[0], 0);
-                    mbar_wait(&t_empty[s], ((ga >> 1) & 1) ^ 1);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smA[as]);
+                const uint32_t b_addr = smem_u32(smB0 + (size_t)bs * tile_stride);
+                for (int qt = 0; qt < a.n_qt; ++qt, ++gt) {
+                    const uint32_t s = gt & 1;                    // accumulator stage
+                    mbar_wait(&t_empty[s], ((gt >> 1) & 1) ^ 1);
                     const uint32_t d_tmem = tmem_base + s * N_TILE;
                     uint32_t acc = 0;
-                    for (int i = 0; i < kb.nb64; ++i) {
+                    for (int sg = 0; sg < nseg; ++sg, ++ga) {
+                        const uint32_t slot = a_resident ? (uint32_t)sg : ga % na;
+                        if (!a_resident) mbar_wait(&a_full[slot], (ga / na) & 1);
+                        else if (it == 0) mbar_wait(&a_full[slot], 0);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(smA0 + (size_t)slot * a.a_slot_stride);
+                        const int n64 = seg_n64(sg);
+                        const uint32_t b_seg = b_addr + (uint32_t)seg_first64(sg) * 16384u;
+                        for (int i = 0; i < n64; ++i) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            umma_bf16<CG>(d_tmem, smem_desc(a_addr + i * 16384 + j * 32, 1024, 2),
-                                          smem_desc(b_addr + i * 16384 + j * 32, 1024, 2), idesc, acc);
-                            acc = 1;
+                            for (int j = 0; j < 4; ++j) {
+                                umma_bf16<CG>(d_tmem, smem_desc(a_addr + i * 16384 + j * 32, 1024, 2),
+                                              smem_desc(b_seg + i * 16384 + j * 32, 1024, 2), idesc, acc);
+                                acc = 1;
+                            }
                         }
-                    }
-                    uint32_t off = kb.nb64 * 16384;
-                    if (kb.has32) {
+                        if (sg == nseg - 1) {
+                            uint32_t a_off = (uint32_t)n64 * 16384u, b_off = (uint32_t)kb.nb64 * 16384u;
+                            if (kb.has32) {
 #pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            umma_bf16<CG>(d_tmem, smem_desc(a_addr + off + j * 32, 512, 4), smem_desc(b_addr + off + j * 32, 512, 4),
-                                          idesc, acc);
-                            acc = 1;
+                                for (int j = 0; j < 2; ++j) {
+                                    umma_bf16<CG>(d_tmem, smem_desc(a_addr + a_off + j * 32, 512, 4),
+                                                  smem_desc(b_addr + b_off + j * 32, 512, 4), idesc, acc);
+                                    acc = 1;
+                                }
+                                a_off += 8192;
+                                b_off += 8192;
+                            }
+                            if (kb.has16) {
+                                umma_bf16<CG>(d_tmem, smem_desc(a_addr + a_off, 256, 6), smem_desc(b_addr + b_off, 256, 6), idesc, acc);
+                                acc = 1;
+                            }
                         }
-                        off += 8192;
+                        if (!a_resident) umma_commit<CG>(&a_empty[slot]);   // this query segment is consumed
                     }
-                    if (kb.has16) {
-                        umma_bf16<CG>(d_tmem, smem_desc(a_addr + off, 256, 6), smem_desc(b_addr + off, 256, 6), idesc, acc);
-                        acc = 1;
-                    }
-                    if (!a_resident) umma_commit<CG>(&a_empty[as]);   // operands of this query tile consumed
                     umma_commit<CG>(&t_full[s]);    // accumulator ready for the epilogue
                 }
                 umma_commit<CG>(&b_empty[bs]);      // row tile consumed
@@ -493,18 +510,64 @@ bool make_map(CUtensorMap* m, const void* gptr, long long n_rows, int kp, int pi
 
 }  // namespace
 
-size_t gemm_smem_bytes(int kp_mma, int n_tiles) {
-    size_t tile = ((size_t)kTileRows * kp_mma * 2 + 1023) & ~(size_t)1023;
-    return (size_t)n_tiles * tile + 15 * 8 + 16 + 1024;
+namespace {
+
+struct GemmPlan {
+    int nseg, na, nb, a_resident;
+    uint32_t a_slot_stride;
+    size_t smem;
+};
+
+// Shared-memory plan.  Preference: whole-K query stages with double-buffered row tiles (the headline shape); when the
+// operand tiles get too large for that (dim > ~208), the query tile is streamed in K segments through a small ring while
+// one full-K row tile stays resident.  A batch that is a single query tile keeps all its segments resident and spends the
+// rest on a deeper row pipeline.
+bool plan_gemm(int kp, int n_qt, size_t smem_optin, GemmPlan* out) {
+    const int kp_mma = (kp + 15) / 16 * 16;
+    const int nb64 = kp_mma / 64, rem = kp_mma % 64;
+    const size_t tail = (size_t)kTileRows * 2 * ((rem >= 32 ? 32 : 0) + ((rem % 32) >= 16 ? 16 : 0));
+    const size_t tile = (((size_t)kTileRows * kp_mma * 2) + 1023) & ~(size_t)1023;
+    const size_t fixed = 26 * 8 + 16 + 1024;
+    auto slot_bytes = [&](int nseg) {
+        const int base = nb64 / nseg, r = nb64 % nseg;
+        size_t biggest = (size_t)(base + (r ? 1 : 0)) * 16384;
+        size_t last = (size_t)base * 16384 + tail;           // the last segment carries the tail and never the remainder
+        return ((biggest > last ? biggest : last) + 1023) & ~(size_t)1023;
+    };
+    const int segs[] = {1, 2, 4, 8};
+    for (int nseg : segs) {
+        if (nseg > 1 && nb64 < nseg) break;
+        const size_t slot = slot_bytes(nseg);
+        if (n_qt == 1) {   // resident query tile
+            for (int nb = 3; nb >= 1; --nb) {
+                const size_t need = (size_t)nseg * slot + (size_t)nb * tile + fixed;
+                if (need <= smem_optin) {
+                    *out = GemmPlan{nseg, nseg, nb, 1, (uint32_t)slot, need};
+                    return true;
+                }
+            }
+        }
+        {   // streamed query segments (also the fallback for one query tile that is too wide to stay resident)
+            const int na_try[] = {nseg == 1 ? 2 : 3, 2};
+            for (int nb = (nseg == 1 ? 2 : 1); nb >= 1; --nb)
+                for (int na : na_try) {
+                    const size_t need = (size_t)na * slot + (size_t)nb * tile + fixed;
+                    if (need <= smem_optin) {
+                        *out = GemmPlan{nseg, na, nb, 0, (uint32_t)slot, need};
+                        return true;
+                    }
+                }
+        }
+    }
+    return false;
 }
 
-// 2 row-tile buffers when they fit next to the 2 query stages, else 1 (the row tile reload is then exposed once per
-// row tile); 0 = the operand tiles do not fit at all and the caller must use the streaming scan.
+}  // namespace
+
+// 1 when some shared-memory plan exists for this operand width (any batch size), else 0: the caller must use the scan.
 int gemm_row_stages(int kp, size_t smem_optin) {
-    const int kp_mma = (kp + 15) / 16 * 16;
-    if (gemm_smem_bytes(kp_mma, 4) <= smem_optin) return 2;
-    if (gemm_smem_bytes(kp_mma, 3) <= smem_optin) return 1;
-    return 0;
+    GemmPlan p;
+    return (plan_gemm(kp, 2, smem_optin, &p) && plan_gemm(kp, 1, smem_optin, &p)) ? 1 : 0;
 }
 
 cudaError_t launch_gemm_filter(const GemmLaunch& g, cudaStream_t stream) {
@@ -536,12 +599,24 @@ cudaError_t launch_gemm_filter(const GemmLaunch& g, cudaStream_t stream) {
     if (n_rt <= 0 || a.n_qt <= 0) return cudaSuccess;
     int clusters = g.sm_count / cg;
     if (clusters > n_rt) clusters = n_rt;
-    // g.nb_stages (from gemm_row_stages) says how many operand tiles fit: 2 -> four tiles, 1 -> three.  With a single query
-    // tile (batch <= one M tile) the tile saved on the query side deepens the row pipeline instead.
-    const int tiles = g.nb_stages + 2;
-    a.na_stages = a.n_qt == 1 ? 1 : 2;
-    a.nb_stages = tiles - a.na_stages;
-    const size_t smem = gemm_smem_bytes(a.kp_mma, tiles);
+    GemmPlan plan;
+    {
+        cudaDeviceProp prop;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        static size_t optin_cache[16] = {0};
+        if (dev < 16 && !optin_cache[dev]) {
+            cudaGetDeviceProperties(&prop, dev);
+            optin_cache[dev] = prop.sharedMemPerBlockOptin;
+        }
+        if (!plan_gemm(kp, a.n_qt, dev < 16 ? optin_cache[dev] : 232448, &plan)) return cudaErrorInvalidValue;
+    }
+    a.nseg = plan.nseg;
+    a.na_stages = plan.na;
+    a.nb_stages = plan.nb;
+    a.a_resident = plan.a_resident;
+    a.a_slot_stride = plan.a_slot_stride;
+    const size_t smem = plan.smem;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(clusters * cg);
     cfg.blockDim = dim3(kGemmThreads);

@@ -550,7 +550,7 @@ int query_core(ann_index* ix, const float* d_queries, int b, int k, int64_t* d_o
     int path = ix->path_opt;
     if (path == 2 && !gemm_eligible(ix, b, k_eff))
         return fail(ANN_ERR_INVALID_ARGUMENT,
-                    "path=2 (tensor-core filter) needs the bf16 shadow, no non-finite/zero-norm rows, size >= 1024, k <= 256 and dim <= 288");
+                    "path=2 (tensor-core filter) needs the bf16 shadow, no non-finite/zero-norm rows, size >= 1024, k <= 256 and dim <= ~640");
     // profiles/r01_crossover.txt: with the resident-query pipeline the tensor-core path is at least as fast as the scan for
     // every batch >= 2 at every shard size measured (100K .. 10M rows).  Single queries stay on the HBM-streaming scan by
     // default (the fp32 matrix itself is scanned, nothing approximate is involved); gemm_min_batch = 1 routes them to the

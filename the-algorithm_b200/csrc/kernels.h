@@ -125,7 +125,6 @@ struct GemmLaunch {
     int pool_cap;
 };
 cudaError_t launch_gemm_filter(const GemmLaunch& g, cudaStream_t stream);
-size_t gemm_smem_bytes(int kp_mma, int nb_stages);
-int gemm_row_stages(int kp, size_t smem_optin);   // 2, 1 or 0 (operands do not fit: use the scan)
+int gemm_row_stages(int kp, size_t smem_optin);   // 1 when a shared-memory plan exists for this operand width, else 0 (use the scan)
 
 }  // namespace b200ann

@@ -74,7 +74,7 @@ if mode == "time":
 
     n = int(sys.argv[3]) if len(sys.argv) > 3 else 10_000_000
     b = int(sys.argv[4]) if len(sys.argv) > 4 else 4096
-    d, k = 200, 100
+    d, k = (int(sys.argv[5]) if len(sys.argv) > 5 else 200), 100
     dev = torch.device("cuda", 0)
     g = torch.Generator(device=dev)
     g.manual_seed(1)
