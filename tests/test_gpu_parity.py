@@ -495,3 +495,24 @@ def test_micro_batching_queryable_coalesces_concurrent_single_queries():
     assert mb.query(q[0], 0).result() == []
     mb.close()
     ix.close()
+
+
+def test_large_k_and_forced_exact_path():
+    """min(k, size) above the bounded selectors' range (1024) is answered by the exact fallback for every query; path = 3
+    forces that path, which gives an independent on-GPU cross-check of the two fast paths."""
+    corpus, ids, q = make(6000, 24, 5, seed=61, dup=True)
+    for m in metrics():
+        ix = G["BruteForceIndex"].apply(m, G["FuturePool"].immediate_pool())
+        ix.append_batch(ids, corpus)
+        gi, gd, gc = ix.batch_query_with_distance(q, 3000)
+        assert ix.stat("last_path") == 3
+        oi, od, oc = oracle.query_canonical(m.ordinal, corpus, ids, q, 3000)
+        assert (gi == oi).all() and (gd.view(np.uint32) == od.view(np.uint32)).all() and (gc == oc).all()
+        ix.set_option("path", 3)
+        e = ix.batch_query_with_distance(q, 40)
+        ix.set_option("path", 2)
+        g2 = ix.batch_query_with_distance(q, 40)
+        ix.set_option("path", 1)
+        s1 = ix.batch_query_with_distance(q, 40)
+        assert (e[0] == g2[0]).all() and (e[0] == s1[0]).all() and (e[1].view(np.uint32) == g2[1].view(np.uint32)).all()
+        ix.close()

@@ -546,7 +546,32 @@ int query_core(ann_index* ix, const float* d_queries, int b, int k, int64_t* d_o
         return ANN_OK;
     }
     const int k_eff = (int)std::min<long long>(k, n);
-    if (k_eff > kMaxK) return fail(ANN_ERR_INVALID_ARGUMENT, "min(k, size) > 1024 is not supported");
+    if (k_eff > 16384) return fail(ANN_ERR_INVALID_ARGUMENT, "min(k, size) > 16384 is not supported");
+    if (k_eff > kMaxK || ix->path_opt == 3) {
+        // Beyond the bounded selectors' range (or on request, path = 3): the exact fallback for every query -- exact distance
+        // for every row + radix select on (distance, id).  Always correct, ~n*dim*4 + 144*n bytes of HBM traffic per query.
+        CUDA_TRY(ix->fb_scratch.ensure(fallback_scratch_bytes(n, k_eff)));
+        for (int q = 0; q < b; ++q) {
+            FallbackParams fp{};
+            fp.rows = ix->rows;
+            fp.ids = ix->ids;
+            fp.n_rows = n;
+            fp.pitch = ix->pitch;
+            fp.dim = ix->dim;
+            fp.metric = ix->metric;
+            fp.l2_squared = ix->l2_squared ? 1 : 0;
+            fp.query = d_queries + (size_t)q * ix->dim;
+            fp.scratch = ix->fb_scratch.p;
+            fp.k = k_eff;
+            fp.k_out = k;
+            fp.out_ids = d_out_ids + (size_t)q * k;
+            fp.out_dist = d_out_dist + (size_t)q * k;
+            fp.out_count = d_out_count ? d_out_count + q : nullptr;
+            CUDA_TRY(launch_exact_fallback(fp, st, &ix->launches));
+        }
+        ix->last_path = 3;
+        return ANN_OK;
+    }
     int path = ix->path_opt;
     if (path == 2 && !gemm_eligible(ix, b, k_eff))
         return fail(ANN_ERR_INVALID_ARGUMENT,
@@ -901,7 +926,7 @@ int ann_set_option(ann_index* ix, const char* name, int64_t value) {
     if (!ix || !name) return fail(ANN_ERR_NULL_POINTER, "ann_set_option: NULL argument");
     std::lock_guard<std::mutex> lk(ix->mu);
     if (!strcmp(name, "path")) {
-        if (value < 0 || value > 2) return fail(ANN_ERR_INVALID_ARGUMENT, "path must be 0 (auto), 1 (scan) or 2 (gemm)");
+        if (value < 0 || value > 3) return fail(ANN_ERR_INVALID_ARGUMENT, "path must be 0 (auto), 1 (scan), 2 (gemm) or 3 (exact fallback)");
         ix->path_opt = (int)value;
         return ANN_OK;
     }
