@@ -167,13 +167,19 @@ def test_special_values_nan_inf_zero_rows(mi):
     corpus[1500, 5] = np.nan
     q = rng.standard_normal((33, 12)).astype(np.float32)
     ids = rng.permutation(2000).astype(np.int64)
-    used = check(metric, corpus, ids, q, 100)         # a batch would pick the GEMM path: special rows force the scan
-    assert used == 1
+    used = check(metric, corpus, ids, q, 100)         # a batch goes to the tensor-core path even with special rows present:
+    assert used == 2                                   # they score -1e38 there and are rescored exactly from the special list
+    check(metric, corpus, ids, q, 100, path=1)        # the scan finds them through their non-finite scores
     check(metric, corpus[:1000], ids[:1000], q[:3], 1000, path=1)   # every row returned: NaN distances last, in id order
+    check(metric, corpus[:1500], ids[:1500], q, 1200, path=0)       # k > 1024: exact path
+    # more special rows than the list holds (256): the tensor-core path steps aside
+    many = corpus.copy()
+    many[100:400, 0] = np.nan
+    assert check(metric, many, ids, q, 50) == 1
     ix = G["BruteForceIndex"].apply(metric, G["FuturePool"].immediate_pool())
-    ix.append_batch(ids, corpus)
+    ix.append_batch(ids, many)
     ix.set_option("path", 2)
-    with pytest.raises(G["_capi"].AnnError):          # the tensor-core filter refuses an index with non-finite rows
+    with pytest.raises(G["_capi"].AnnError):
         ix.batch_query_with_distance(q, 10)
     ix.close()
 

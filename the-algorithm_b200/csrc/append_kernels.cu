@@ -52,18 +52,25 @@ __global__ void __launch_bounds__(256) append_rows_kernel(AppendParams p) {
         if (lane == 0) {
             p.row_norm[row] = nrm_up;
             if (p.inv_norm) p.inv_norm[row] = inv;
-            if (special) local_special += 1;
-            else local_max = fmaxf(local_max, nrm_up);
+            if (special) {
+                local_special += 1;
+                const unsigned long long slot = atomicAdd(p.n_special, 1ull);
+                if (slot < (unsigned long long)kSpecialCap) p.special_list[slot] = (uint32_t)row;
+            } else {
+                local_max = fmaxf(local_max, nrm_up);
+            }
         }
         if (p.shadow) {
             __nv_bfloat16* s = p.shadow + (size_t)row * p.kp;
             const float scale = (p.metric == kMetricCosine) ? inv : 1.0f;
+            const int aug = p.dim;   // first augmented column: 0 for ordinary rows, -kShadowBig for special ones
             for (int i = lane; i < p.kp; i += 32) {
                 float v = 0.f;
-                if (i < p.dim) v = a[i] * scale;
+                if (i < p.dim && !special) v = a[i] * scale;
+                if (i == aug && special) v = -kShadowBig;
                 s[i] = __float2bfloat16_rn(v);
             }
-            if (p.metric == kMetricL2 && lane == 0) {
+            if (p.metric == kMetricL2 && lane == 0 && !special) {
                 double x = -0.5 * n2;
                 __nv_bfloat16 h1 = __double2bfloat16(x);
                 double r1 = x - (double)__bfloat162float(h1);
@@ -78,7 +85,7 @@ __global__ void __launch_bounds__(256) append_rows_kernel(AppendParams p) {
     }
     if (lane == 0) {
         if (local_max > 0.f) atomicMax(p.max_norm_bits, __float_as_uint(local_max));
-        if (local_special) atomicAdd(p.n_special, local_special);
+        (void)local_special;
     }
 }
 
@@ -110,7 +117,7 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(PrepParams p, int b_p
             for (int i = lane; i < p.qkp; i += 32) {
                 float v = 0.f;
                 if (i < p.dim) v = src[i];
-                else if (p.metric == kMetricL2 && i < p.dim + 3) v = 1.0f;
+                else if (i == p.dim || (p.metric == kMetricL2 && i < p.dim + 3)) v = 1.0f;
                 p.q_shadow[(size_t)q * p.qkp + i] = __float2bfloat16_rn(v);
             }
         }

@@ -56,6 +56,11 @@ struct QueryState {
 
 constexpr uint32_t kFlagPoolOverflow = 1u, kFlagSpecialOverflow = 2u, kFlagSurvivorOverflow = 4u;
 constexpr int kSpecialCap = 256;  // per query
+// Special rows (non-finite entries, zero norm under Cosine) get an all-zero shadow row whose augmented column is -kShadowBig:
+// their tensor-core score is ~ -1e38, so they are never a threshold witness nor a candidate; they are rescored exactly from
+// the index-wide special list instead.  Pool entries with g above kSpecialG are such rows seen before any threshold existed.
+constexpr float kShadowBig = 1.0e38f;
+constexpr float kSpecialG = 1.0e37f;
 
 // threshold with margin: everything with g <= kth + margin(kth) may still belong to the exact top-k
 __device__ __forceinline__ float widen(float kth, float eps_abs, float eps_rel) {

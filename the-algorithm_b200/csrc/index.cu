@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -57,7 +58,9 @@ struct DeviceScalars {
     uint32_t error_flags;
     unsigned long long n_special;
     unsigned long long bad_queries;
+    uint32_t special_list[kSpecialCap];   // indices of the first special rows (see common.cuh)
 };
+constexpr size_t kScalarsHeader = offsetof(DeviceScalars, special_list);   // the part the host polls
 
 template <typename T>
 struct DevBuf {
@@ -125,7 +128,8 @@ struct ann_index {
 
     // options / stats
     int path_opt = 0, gemm_min_batch = 2, gemm_cta_group = 2;
-    bool device_fallback = false;   // device entry point: synchronise and run the exact fallback for flagged queries
+    bool device_fallback = false;
+    bool gemm_blocked_by_update = false;   // device entry point: synchronise and run the exact fallback for flagged queries
     // optional CUDA-event timing of the dominant kernel of each path, on the launching stream (bench.py roofline)
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pairs;
@@ -214,6 +218,7 @@ int append_device_core(ann_index* ix, const int64_t* d_ids, const float* d_rows,
     ap.kp = ix->kp;
     ap.max_norm_bits = &ix->scalars->max_norm_bits;
     ap.n_special = &ix->scalars->n_special;
+    ap.special_list = ix->scalars->special_list;
     CUDA_TRY(launch_append(ap, st));
     ix->launches++;
     return ANN_OK;
@@ -415,6 +420,8 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
     fp.pool = ix->pool.p;
     fp.pool_cap = kGemmPoolCap;
     fp.special_rows = ix->special_rows.p;
+    fp.global_special_rows = ix->scalars->special_list;
+    fp.global_special_count = (int)std::min<unsigned long long>(ix->n_special, (unsigned long long)kSpecialCap);
     fp.pub_keys = nullptr;
     fp.k = k_eff;
     fp.rows = ix->rows;
@@ -530,7 +537,8 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
 }
 
 bool gemm_eligible(const ann_index* ix, int b, int k_eff) {
-    return ix->shadow != nullptr && ix->n_special == 0 && k_eff <= 256 && ix->n >= 1024 && b >= 1 &&
+    return ix->shadow != nullptr && ix->n_special <= (unsigned long long)kSpecialCap && !ix->gemm_blocked_by_update && k_eff <= 256 &&
+           ix->n >= 1024 && b >= 1 &&
            gemm_row_stages(ix->kp, ix->smem_optin) > 0;
 }
 
@@ -575,7 +583,7 @@ int query_core(ann_index* ix, const float* d_queries, int b, int k, int64_t* d_o
     int path = ix->path_opt;
     if (path == 2 && !gemm_eligible(ix, b, k_eff))
         return fail(ANN_ERR_INVALID_ARGUMENT,
-                    "path=2 (tensor-core filter) needs the bf16 shadow, no non-finite/zero-norm rows, size >= 1024, k <= 256 and dim <= ~640");
+                    "path=2 (tensor-core filter) needs the bf16 shadow, at most 256 non-finite/zero-norm rows, size >= 1024, k <= 256 and dim <= ~640");
     // profiles/r01_crossover.txt: with the resident-query pipeline the tensor-core path is at least as fast as the scan for
     // every batch >= 2 at every shard size measured (100K .. 10M rows).  Single queries stay on the HBM-streaming scan by
     // default (the fp32 matrix itself is scanned, nothing approximate is involved); gemm_min_batch = 1 routes them to the
@@ -607,7 +615,7 @@ int resolve_flagged(ann_index* ix, const float* d_queries, int b, int k, int64_t
     if (snapshot) {
         hs = *snapshot;
     } else {
-        CUDA_TRY(cudaMemcpyAsync(&hs, ix->scalars, sizeof(hs), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(&hs, ix->scalars, kScalarsHeader, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
     }
     if (!hs.error_flags) return ANN_OK;
@@ -644,7 +652,7 @@ int resolve_flagged(ann_index* ix, const float* d_queries, int b, int k, int64_t
 // read and clear the sticky device error word; call after a synchronisation point
 int check_device_flags(ann_index* ix, cudaStream_t st) {
     DeviceScalars h{};
-    CUDA_TRY(cudaMemcpyAsync(&h, ix->scalars, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(&h, ix->scalars, kScalarsHeader, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     ix->n_special = h.n_special;
     if (h.error_flags) {
@@ -698,7 +706,7 @@ int ann_create(const ann_config* cfg, ann_index** out) {
     ix->pitch = (cfg->dim + 3) / 4 * 4;
     ix->l2_squared = (cfg->flags & ANN_FLAG_L2_SQUARED) != 0;
     ix->use_shadow = (cfg->flags & ANN_FLAG_NO_SHADOW) == 0;
-    ix->kp = (cfg->dim + (cfg->metric == kMetricL2 ? 3 : 0) + 7) / 8 * 8;
+    ix->kp = (cfg->dim + (cfg->metric == kMetricL2 ? 3 : 1) + 7) / 8 * 8;   // + augmented columns (common.cuh, append_kernels.cu)
     ix->device = cfg->device;
     ix->sm_count = prop.multiProcessorCount;
     ix->smem_optin = prop.sharedMemPerBlockOptin;
@@ -790,6 +798,8 @@ int ann_update_batch(ann_index* ix, const int64_t* slots, const float* rows, int
     ap.kp = ix->kp;
     ap.max_norm_bits = &ix->scalars->max_norm_bits;   // only ever grows: the error bounds stay valid (looser)
     ap.n_special = &ix->scalars->n_special;           // conservative: a repaired row does not lower the census
+    ap.special_list = ix->scalars->special_list;
+    if (ix->n_special > 0) ix->gemm_blocked_by_update = true;   // a repaired special row would be listed AND be a candidate
     CUDA_TRY(launch_append(ap, st));
     ix->launches++;
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -891,7 +901,7 @@ int ann_query_batch(ann_index* ix, const float* queries, int32_t b, int32_t dim,
             CUDA_TRY(cudaMemcpyAsync(out_dist, ix->out_dist.p, (size_t)b * k * sizeof(float), cudaMemcpyDeviceToHost, st));
         }
         if (out_count) CUDA_TRY(cudaMemcpyAsync(out_count, ix->out_count.p, (size_t)b * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(&hs, ix->scalars, sizeof(hs), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(&hs, ix->scalars, kScalarsHeader, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         return ANN_OK;
     };

@@ -20,6 +20,7 @@ struct AppendParams {
     int kp;                 // shadow pitch in elements (multiple of 8)
     uint32_t* max_norm_bits;  // running max of |a| (float bits, non-negative => integer order)
     unsigned long long* n_special;   // rows with non-finite entries or (Cosine) zero norm
+    uint32_t* special_list;          // [kSpecialCap] indices of the first special rows (tensor-core path rescoring list)
 };
 cudaError_t launch_append(const AppendParams& p, cudaStream_t stream);
 
@@ -64,7 +65,9 @@ struct SelectParams {
     QueryState* qstate;     // [b]
     entry_t* pool;          // [b][pool_cap]
     int pool_cap;
-    const uint32_t* special_rows;  // [b][kSpecialCap]
+    const uint32_t* special_rows;  // [b][kSpecialCap]  per-query lists written by the scan
+    const uint32_t* global_special_rows;  // tensor-core path: the index-wide list of special rows, same for every query
+    int global_special_count;
     const uint32_t* pub_keys;      // [b][pub_stride] or nullptr
     int pub_stride, pub_count, j_pub;
     int k;

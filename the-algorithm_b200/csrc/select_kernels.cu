@@ -139,7 +139,8 @@ __device__ bool load_and_threshold(const SelectParams& p, int q, entry_t* buf, u
     const entry_t* pool = p.pool + (size_t)q * p.pool_cap;
     for (int i = threadIdx.x; i < pool_n; i += blockDim.x) {
         entry_t e = pool[i];
-        if (entry_g(e) <= tau) {
+        const float ge = entry_g(e);
+        if (ge <= tau && ge < kSpecialG) {   // special rows scored -1e38 by the tensor-core filter are handled separately
             int slot = atomicAdd(&n_s, 1);
             if (slot < kSortCap) buf[slot] = e;
         }
@@ -235,7 +236,8 @@ __global__ void __launch_bounds__(kSelThreads, 4) finalize_kernel(SelectParams p
     }
     // Exact rescoring of every survivor (g <= tau) and every special row; unordered, the final sort orders them.
     // The candidate rows are scattered over the whole matrix, so every chain is a sequence of dependent DRAM misses.
-    const int n_spec = min((int)qs->special_count, kSpecialCap);
+    const uint32_t* spec_rows = p.global_special_rows ? p.global_special_rows : p.special_rows + (size_t)q * kSpecialCap;
+    const int n_spec = p.global_special_rows ? min(p.global_special_count, kSpecialCap) : min((int)qs->special_count, kSpecialCap);
     if (threadIdx.x == 0) n_cand_s = 0;
     __syncthreads();
     uint32_t* crow = ckey;   // row indices first, replaced by the distance keys
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(kSelThreads, 4) finalize_kernel(SelectParams p
             if (!(entry_g(e) <= tau)) continue;
             row = entry_row(e);
         } else {
-            row = p.special_rows[(size_t)q * kSpecialCap + (i - n)];
+            row = spec_rows[i - n];
         }
         const int slot = atomicAdd(&n_cand_s, 1);
         if (slot < kExactCap) crow[slot] = row;
