@@ -522,3 +522,17 @@ def test_large_k_and_forced_exact_path():
         s1 = ix.batch_query_with_distance(q, 40)
         assert (e[0] == g2[0]).all() and (e[0] == s1[0]).all() and (e[1].view(np.uint32) == g2[1].view(np.uint32)).all()
         ix.close()
+
+
+def test_out_of_memory_is_an_error_code_not_a_crash():
+    """An impossible reservation fails with ANN_ERR_OUT_OF_MEMORY and leaves no handle behind; a later index still works."""
+    import ctypes
+
+    capi = G["_capi"]
+    h = ctypes.c_void_p()
+    cfg = capi.AnnConfig(2, 200, 10 ** 12, 0, 0)          # 10^12 rows x 800 B: cudaMalloc refuses immediately
+    rc = capi.lib().ann_create(ctypes.byref(cfg), ctypes.byref(h))
+    assert rc == capi.ANN_ERR_OUT_OF_MEMORY and not h.value
+    assert b"failed" in capi.lib().ann_last_error()
+    corpus, ids, q = make(3000, 16, 4, seed=3)
+    check(G["InnerProduct"], corpus, ids, q, 10)

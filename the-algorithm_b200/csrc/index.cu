@@ -155,23 +155,42 @@ int grow(ann_index* ix, long long need, cudaStream_t st) {
     int64_t* nids = nullptr;
     float *ninv = nullptr, *nnorm = nullptr;
     __nv_bfloat16* nsh = nullptr;
-    CUDA_TRY(cudaMalloc(&nrows, (size_t)ncap * ix->pitch * sizeof(float)));
-    CUDA_TRY(cudaMalloc(&nids, (size_t)ncap * sizeof(int64_t)));
-    CUDA_TRY(cudaMalloc(&nnorm, (size_t)ncap * sizeof(float)));
-    if (ix->metric == kMetricCosine) CUDA_TRY(cudaMalloc(&ninv, (size_t)ncap * sizeof(float)));
-    if (ix->use_shadow) CUDA_TRY(cudaMalloc(&nsh, (size_t)ncap * ix->kp * sizeof(__nv_bfloat16)));
-    if (ix->n > 0) {
-        CUDA_TRY(cudaMemcpyAsync(nrows, ix->rows, (size_t)ix->n * ix->pitch * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(nids, ix->ids, (size_t)ix->n * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(nnorm, ix->row_norm, (size_t)ix->n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        if (ninv) CUDA_TRY(cudaMemcpyAsync(ninv, ix->inv_norm, (size_t)ix->n * sizeof(float), cudaMemcpyDeviceToDevice, st));
-        if (nsh)
-            CUDA_TRY(cudaMemcpyAsync(nsh, ix->shadow, (size_t)ix->n * ix->kp * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice, st));
+    // allocate everything first; on any failure release what was obtained and leave the index untouched
+    cudaError_t e = cudaMalloc(&nrows, (size_t)ncap * ix->pitch * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&nids, (size_t)ncap * sizeof(int64_t));
+    if (e == cudaSuccess) e = cudaMalloc(&nnorm, (size_t)ncap * sizeof(float));
+    if (e == cudaSuccess && ix->metric == kMetricCosine) e = cudaMalloc(&ninv, (size_t)ncap * sizeof(float));
+    if (e == cudaSuccess && ix->use_shadow) e = cudaMalloc(&nsh, (size_t)ncap * ix->kp * sizeof(__nv_bfloat16));
+    auto copy_all = [&]() -> cudaError_t {
+        cudaError_t c = cudaSuccess;
+        if (ix->n > 0) {
+            c = cudaMemcpyAsync(nrows, ix->rows, (size_t)ix->n * ix->pitch * sizeof(float), cudaMemcpyDeviceToDevice, st);
+            if (c == cudaSuccess) c = cudaMemcpyAsync(nids, ix->ids, (size_t)ix->n * sizeof(int64_t), cudaMemcpyDeviceToDevice, st);
+            if (c == cudaSuccess) c = cudaMemcpyAsync(nnorm, ix->row_norm, (size_t)ix->n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+            if (c == cudaSuccess && ninv) c = cudaMemcpyAsync(ninv, ix->inv_norm, (size_t)ix->n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+            if (c == cudaSuccess && nsh)
+                c = cudaMemcpyAsync(nsh, ix->shadow, (size_t)ix->n * ix->kp * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice, st);
+        }
+        // zero the tail: pad columns of `rows` and the whole shadow tail must read as 0
+        if (c == cudaSuccess)
+            c = cudaMemsetAsync(nrows + (size_t)ix->n * ix->pitch, 0, (size_t)(ncap - ix->n) * ix->pitch * sizeof(float), st);
+        if (c == cudaSuccess && nsh)
+            c = cudaMemsetAsync(nsh + (size_t)ix->n * ix->kp, 0, (size_t)(ncap - ix->n) * ix->kp * sizeof(__nv_bfloat16), st);
+        if (c == cudaSuccess) c = cudaStreamSynchronize(st);
+        return c;
+    };
+    if (e == cudaSuccess) e = copy_all();
+    if (e != cudaSuccess) {
+        cudaFree(nrows);
+        cudaFree(nids);
+        cudaFree(nnorm);
+        cudaFree(ninv);
+        cudaFree(nsh);
+        (void)cudaGetLastError();
+        char msg[256];
+        snprintf(msg, sizeof(msg), "growing the index to %lld rows failed: %s", ncap, cudaGetErrorString(e));
+        return fail(e == cudaErrorMemoryAllocation ? ANN_ERR_OUT_OF_MEMORY : ANN_ERR_CUDA, msg);
     }
-    // zero the tail: pad columns of `rows` and the whole shadow tail must read as 0
-    CUDA_TRY(cudaMemsetAsync(nrows + (size_t)ix->n * ix->pitch, 0, (size_t)(ncap - ix->n) * ix->pitch * sizeof(float), st));
-    if (nsh) CUDA_TRY(cudaMemsetAsync(nsh + (size_t)ix->n * ix->kp, 0, (size_t)(ncap - ix->n) * ix->kp * sizeof(__nv_bfloat16), st));
-    CUDA_TRY(cudaStreamSynchronize(st));
     cudaFree(ix->rows);
     cudaFree(ix->ids);
     cudaFree(ix->row_norm);
