@@ -93,21 +93,11 @@ __device__ __forceinline__ float exact_distance_rows(int metric, const float* __
     double s0 = 0.0, s1 = 0.0;         // L2: sum (a-b)^2 ; otherwise a.b and (Cosine) a.a
     float4 cur[4], nxt[4];
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    // The vector fp64 pipe of this part is narrow (finalize was bound by it), so: (1) float -> double goes through the integer
-    // pipe (exact for normal numbers: re-bias the exponent, shift the mantissa; zeros/denormals/inf/NaN take the real
-    // conversion), (2) dot-product terms use ONE fused multiply-add -- the product of two floats is exact in fp64, so
-    // fma(x, y, s) rounds exactly like s + (x*y) with a rounded product, i.e. like the oracle's mul-then-add.  The L2 term
-    // (a-b)^2 is NOT exact in fp64, so it keeps the oracle's separate, individually rounded sub / mul / add.
-    auto to_double = [](float f) -> double {
-        const uint32_t b = __float_as_uint(f);
-        const uint32_t ex = (b >> 23) & 0xFFu;
-        if (ex == 0u || ex == 0xFFu) return (double)f;
-        const uint32_t hi = (b & 0x80000000u) | ((ex + 896u) << 20) | ((b & 0x007FFFFFu) >> 3);
-        const uint32_t lo = b << 29;
-        return __hiloint2double((int)hi, (int)lo);
-    };
+    // Dot-product terms use ONE fused multiply-add: the product of two floats is exact in fp64, so fma(x, y, s) rounds
+    // exactly like the oracle's mul-then-add.  The L2 term (a-b)^2 is NOT exact in fp64, so it keeps the oracle's
+    // separate, individually rounded sub / mul / add.
     auto step = [&](float xf, double y) {
-        const double x = to_double(xf);
+        const double x = (double)xf;
         if (metric == kMetricL2) {
             const double df = __dsub_rn(x, y);
             s0 = __dadd_rn(s0, __dmul_rn(df, df));
