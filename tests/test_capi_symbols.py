@@ -33,6 +33,17 @@ def test_header_cites_reference_lines():
         assert cite in text
 
 
+def test_header_is_plain_c(tmp_path):
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    subprocess.run([gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-c", "-o", str(tmp_path / "h.o"),
+                    str(ROOT / "tests" / "capi_header_check.c")], check=True)
+
+
 def test_argument_validation_without_gpu(built_lib):
     from the_algorithm_b200 import _capi
 
