@@ -8,7 +8,10 @@ import ctypes
 from pathlib import Path
 
 _HERE = Path(__file__).resolve().parent
-LIB_PATH = _HERE / "lib" / "libb200ann.so"
+import os
+
+# B200ANN_LIB lets a developer A/B two builds of the same ABI in one process environment (tools/ab_build.sh)
+LIB_PATH = Path(os.environ["B200ANN_LIB"]) if os.environ.get("B200ANN_LIB") else _HERE / "lib" / "libb200ann.so"
 
 ANN_OK = 0
 ANN_ERR_INVALID_ARGUMENT = -1
