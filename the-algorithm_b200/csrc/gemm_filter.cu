@@ -49,7 +49,7 @@ struct GemmArgs {
     QueryState* qstate;
     entry_t* pool;
     int pool_cap;
-    int debug_nohit, debug_norot;
+    int debug_nohit;
     int nseg;                         // K segments per query tile (1 = the whole K extent is one stage)
     int na_stages, nb_stages;         // query-segment ring slots / row-tile buffers
     int a_resident;                   // the batch is one query tile: its segments are loaded once and never released
@@ -140,6 +140,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, float* v) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+    *v = __uint_as_float(r);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct KBlocks {
@@ -154,7 +159,10 @@ struct KBlocks {
 
 }  // namespace
 
-template <int CG, bool SEED>
+// SEG = false is the common case (the whole K extent is one query stage, ring of two): segment count, ring size and the
+// slot / phase arithmetic are compile-time there, which keeps the single MMA-issuing thread off the critical path (the
+// generic runtime version cost the headline shape 4 %).
+template <int CG, bool SEED, bool SEG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -168,7 +176,9 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
     const uint32_t tile_bytes = (uint32_t)kTileRows * a.kp_mma * 2;
     const uint32_t tile_stride = (tile_bytes + 1023u) & ~1023u;
     unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int na = a.na_stages, nb = a.nb_stages, nseg = a.nseg;
+    const int na = a.na_stages, nb = a.nb_stages, nseg = SEG ? a.nseg : 1;   // na = slots carved out of shared memory
+    auto a_slot = [&](uint32_t g) -> uint32_t { return SEG ? g % (uint32_t)na : (g & 1u); };       // !SEG: ring of two
+    auto a_phase = [&](uint32_t g) -> uint32_t { return SEG ? (g / (uint32_t)na) & 1u : (g >> 1) & 1u; };
     const bool a_resident = a.a_resident != 0;
     unsigned char* smA0 = base;                                            // na slots of a.a_slot_stride bytes
     unsigned char* smB0 = base + (size_t)na * a.a_slot_stride;             // nb full-K row tiles
@@ -181,13 +191,6 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
     uint64_t* t_empty = bars + 24;   // 2
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
 
-    // Every cluster walks the query tiles in a different rotation: otherwise all 148 SMs would be on the same 256 queries
-    // at the same moment and their slot-reservation atomics would pile up on the same 256 counters in L2.
-    const int qt_shift = a.debug_norot ? 0 : cluster_id % a.n_qt;
-    auto rot_qt = [&](int qt) {
-        const int t = qt + qt_shift;
-        return t >= a.n_qt ? t - a.n_qt : t;
-    };
     const KBlocks kb(a.kp_mma);
     // K segments: the 64-wide blocks are dealt out evenly, the narrow tail blocks (32 / 16 wide) go with the last segment
     const int seg_base = kb.nb64 / nseg, seg_rem = kb.nb64 % nseg;
@@ -259,10 +262,10 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
                             (int)(a.row_begin + (long long)rt * N_TILE + rank * kTileRows));
                 for (int qt = 0; qt < a.n_qt; ++qt) {
                     if (a_resident && it > 0) continue;           // the only query tile is already resident
-                    const int q0 = rot_qt(qt) * N_TILE + rank * kTileRows;
+                    const int q0 = qt * N_TILE + rank * kTileRows;
                     for (int sg = 0; sg < nseg; ++sg, ++ga) {
-                        const uint32_t slot = ga % na;
-                        if (!a_resident) mbar_wait(&a_empty[slot], ((ga / na) & 1) ^ 1);
+                        const uint32_t slot = a_resident ? (uint32_t)sg : a_slot(ga);
+                        if (!a_resident) mbar_wait(&a_empty[slot], a_phase(ga) ^ 1);
                         const bool last = sg == nseg - 1;
                         const uint32_t bytes = (uint32_t)seg_n64(sg) * 16384u + (last ? tail_bytes : 0u);
                         if (leader) mbar_expect_tx(&a_full[slot], bytes * CG);
@@ -288,8 +291,8 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
                     const uint32_t d_tmem = tmem_base + s * N_TILE;
                     uint32_t acc = 0;
                     for (int sg = 0; sg < nseg; ++sg, ++ga) {
-                        const uint32_t slot = a_resident ? (uint32_t)sg : ga % na;
-                        if (!a_resident) mbar_wait(&a_full[slot], (ga / na) & 1);
+                        const uint32_t slot = a_resident ? (uint32_t)sg : a_slot(ga);
+                        if (!a_resident) mbar_wait(&a_full[slot], a_phase(ga));
                         else if (it == 0) mbar_wait(&a_full[slot], 0);
                         tc_fence_after();
                         const uint32_t a_addr = smem_u32(smA0 + (size_t)slot * a.a_slot_stride);
@@ -341,7 +344,7 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
         constexpr int COLS_PER_WARP = N_TILE / 2;
         const int q_lane = (int)rank * kTileRows + quarter * 32 + lane;
         auto load_tau = [&](int qt) -> uint32_t {
-            const int q = rot_qt(qt) * N_TILE + q_lane;
+            const int q = qt * N_TILE + q_lane;
             return q < a.b ? __ldcg(&a.qstate[q].tau_key) : 0u;
         };
         auto emit_now = [&](int q, float v, uint32_t row) {
@@ -368,7 +371,7 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
             const int valid_cols = (int)min((long long)N_TILE, a.row_end - tile_row0);
             for (int qt = 0; qt < a.n_qt; ++qt, ++ge) {
                 const uint32_t s = ge & 1;
-                const int q = rot_qt(qt) * N_TILE + q_lane;
+                const int q = qt * N_TILE + q_lane;
                 const bool q_ok = q < a.b;
                 const uint32_t tk = tk_next;
                 tk_next = load_tau(qt + 1 < a.n_qt ? qt + 1 : 0);   // in flight while this tile is scanned
@@ -404,39 +407,35 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
                     for (int j = 0; j < 32; ++j) any |= (v[j] >= thr);
                     // Rare path, kept SMALL on purpose: the kernel has to stay inside the 32 KB instruction cache (a 32x
                     // unrolled hit handler -- tried twice, 42-45 KB of code -- costs 5-40 % because it stalls the MMA warp).
-                    // Build this lane's hit mask and walk its own hits; v[j] for a lane-specific j is a 5-level select tree
-                    // on the registers (31 selects), so there is no second trip to TMEM, whose read port is the epilogue's
-                    // bottleneck.
+                    // Build this lane's hit mask, OR it across the warp, and visit every column some lane hit by re-reading
+                    // that single column from TMEM (warp-uniform address).  A 32-way select on v[] (switch, or a 5-level
+                    // select tree) measured 1-2 % slower on the whole batch in same-box A/B runs.
                     if (__any_sync(0xFFFFFFFFu, any) && col0 < valid_cols) {
                         uint32_t mask = 0;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) mask |= (v[j] >= thr) ? (1u << j) : 0u;
                         const int left = valid_cols - col0;
                         if (left < 32) mask &= (1u << left) - 1u;
-                        while (mask) {
-                            const int j = __ffs(mask) - 1;
-                            mask &= mask - 1;
-                            float t16[16], t8[8], t4[4], t2[2];
+                        uint32_t um = __reduce_or_sync(0xFFFFFFFFu, mask);
+                        while (um) {
+                            const int j = __ffs(um) - 1;
+                            um &= um - 1;
+                            float x;
+                            tmem_ld1(t_lane + c0 + j, &x);
+                            tmem_ld_wait();
+                            if ((mask >> j) & 1u) {
+                                const uint32_t row = (uint32_t)(tile_row0 + col0 + j);
+                                if (ccnt < kHitRegs) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) t16[i] = (j & 1) ? v[2 * i + 1] : v[2 * i];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) t8[i] = (j & 2) ? t16[2 * i + 1] : t16[2 * i];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) t4[i] = (j & 4) ? t8[2 * i + 1] : t8[2 * i];
-#pragma unroll
-                            for (int i = 0; i < 2; ++i) t2[i] = (j & 8) ? t4[2 * i + 1] : t4[2 * i];
-                            const float x = (j & 16) ? t2[1] : t2[0];
-                            const uint32_t row = (uint32_t)(tile_row0 + col0 + j);
-                            if (ccnt < kHitRegs) {
-#pragma unroll
-                                for (int i = 0; i < kHitRegs; ++i)
-                                    if (i == ccnt) {
-                                        cv[i] = x;
-                                        cr[i] = row;
-                                    }
-                                ++ccnt;
-                            } else {
-                                emit_now(q, x, row);   // dense regions: straight to the pool
+                                    for (int i = 0; i < kHitRegs; ++i)
+                                        if (i == ccnt) {
+                                            cv[i] = x;
+                                            cr[i] = row;
+                                        }
+                                    ++ccnt;
+                                } else {
+                                    emit_now(q, x, row);   // dense regions (first chunk): straight to the pool
+                                }
                             }
                         }
                     }
@@ -593,7 +592,6 @@ cudaError_t launch_gemm_filter(const GemmLaunch& g, cudaStream_t stream) {
     a.pool = g.pool;
     a.pool_cap = g.pool_cap;
     a.debug_nohit = getenv("B200ANN_NOHIT") ? 1 : 0;
-    a.debug_norot = getenv("B200ANN_NOROT") ? 1 : 0;
     const long long rows = g.row_end - g.row_begin;
     const int n_rt = (int)((rows + n_tile - 1) / n_tile);
     if (n_rt <= 0 || a.n_qt <= 0) return cudaSuccess;
@@ -630,8 +628,15 @@ cudaError_t launch_gemm_filter(const GemmLaunch& g, cudaStream_t stream) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaError_t e;
-    void (*fn)(GemmTmaps, GemmArgs) = cg == 1 ? (g.seed_mode ? gemm_filter_kernel<1, true> : gemm_filter_kernel<1, false>)
-                                              : (g.seed_mode ? gemm_filter_kernel<2, true> : gemm_filter_kernel<2, false>);
+    const bool seg = !(plan.nseg == 1 && (plan.a_resident || plan.na == 2));
+    void (*fn)(GemmTmaps, GemmArgs);
+    if (cg == 1) {
+        fn = g.seed_mode ? (seg ? gemm_filter_kernel<1, true, true> : gemm_filter_kernel<1, true, false>)
+                         : (seg ? gemm_filter_kernel<1, false, true> : gemm_filter_kernel<1, false, false>);
+    } else {
+        fn = g.seed_mode ? (seg ? gemm_filter_kernel<2, true, true> : gemm_filter_kernel<2, true, false>)
+                         : (seg ? gemm_filter_kernel<2, false, true> : gemm_filter_kernel<2, false, false>);
+    }
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = cudaLaunchKernelEx(&cfg, fn, tm, a);

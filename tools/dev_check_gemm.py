@@ -98,7 +98,10 @@ if mode == "time":
         ix.query_batch_device(q, k, oi, od, oc, st)
     torch.cuda.synchronize()
     ix.raise_pending_error()
-    reps = 5
+    reps = int(sys.argv[6]) if len(sys.argv) > 6 else 5
+    for _ in range(reps // 2):   # thermal / power steady state before timing long runs
+        ix.query_batch_device(q, k, oi, od, oc, st)
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(ts)
     for _ in range(reps):
