@@ -113,7 +113,7 @@ ANN_API int ann_merge_topk_device(int32_t device, const int64_t *d_ids, const fl
                                   int32_t *d_out_count, void *stream);
 
 /* Tuning / introspection.
- * Options: "path" (0 auto, 1 streaming scan, 2 tensor-core GEMM filter, 3 exact fallback for every query), "gemm_min_batch", "gemm_cta_group" (1|2),
+ * Options: "path" (0 auto, 1 streaming scan, 2 tensor-core GEMM filter, 3 exact fallback for every query), "gemm_min_batch", "gemm_cta_group" (1|2), "gemm_epi_warps" (0 auto, 8, 16),
  *          "timing" (1 = bracket every scan / GEMM-filter launch with CUDA events on its stream),
  *          "device_fallback" (1 = ann_query_batch_device synchronises its stream and re-answers flagged queries with the
  *          exact fallback, like the host entry point always does; 0 = stay asynchronous and report them, default).

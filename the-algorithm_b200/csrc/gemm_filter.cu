@@ -15,7 +15,7 @@
 // stages only its half of both operands and the pair's tensor cores read both halves.  A row tile stays in
 // shared memory while every query tile streams past it (queries come from L2), so the shadow matrix is read
 // from HBM exactly once per batch.  Both operands are double buffered (TMA -> smem, mbarrier full/empty), the
-// accumulator is double buffered in TMEM (2 x N columns), and 8 epilogue warps drain one accumulator while
+// accumulator is double buffered in TMEM (2 x N columns), and 16 epilogue warps drain one accumulator while
 // the next tile's MMAs run.
 //
 // K is not padded to the 128-byte swizzle width in HBM: a K of e.g. 208 is staged as 3 blocks of 64 (128B
@@ -33,9 +33,12 @@ namespace b200ann {
 
 namespace {
 
-constexpr int kGemmThreads = 384;     // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 spare, 4..11 epilogue
+// warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 spare, 4.. epilogue.  The epilogue runs with EW = 8 or 16 warps (template parameter):
+// the filter is a string of dependent compares, and in hit-dense chunks two warps per scheduler leave its fixed latencies
+// exposed (IPC 0.38 in ncu), so those launches use four per scheduler (+25 % there); in hit-sparse chunks the epilogue
+// keeps up anyway and the extra warps only take issue slots from the MMA warp (-1..5 %), so they use eight.
 constexpr int kEpiWarp0 = 4;
-constexpr int kNumEpiWarps = 8;
+constexpr int gemm_threads(int epi_warps) { return 32 * (kEpiWarp0 + epi_warps); }
 constexpr int kTileRows = 128;        // rows (and queries) staged per CTA per tile
 
 struct alignas(64) GemmTmaps {
@@ -162,8 +165,8 @@ struct KBlocks {
 // SEG = false is the common case (the whole K extent is one query stage, ring of two): segment count, ring size and the
 // slot / phase arithmetic are compile-time there, which keeps the single MMA-issuing thread off the critical path (the
 // generic runtime version cost the headline shape 4 %).
-template <int CG, bool SEED, bool SEG>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int CG, bool SEED, bool SEG, int EW>
+__global__ void __launch_bounds__(gemm_threads(EW), 1)
 gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     constexpr int N_TILE = kTileRows * CG;          // MMA N (and M)
@@ -212,7 +215,7 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&t_full[i], 1);
-            mbar_init(&t_empty[i], kNumEpiWarps * CG);
+            mbar_init(&t_empty[i], EW * CG);
         }
         for (int i = 0; i < 3; ++i) {
             mbar_init(&b_full[i], 1);
@@ -340,8 +343,8 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
         constexpr int kHitRegs = 4;
         const int e = warp - kEpiWarp0;
         const int quarter = warp & 3;                 // TMEM lanes 32*quarter .. +31 are the ones this warp may touch
-        const int half = e >> 2;                      // which half of the N columns
-        constexpr int COLS_PER_WARP = N_TILE / 2;
+        const int half = e >> 2;                      // which slice of the N columns
+        constexpr int COLS_PER_WARP = N_TILE / (EW / 4);
         const int q_lane = (int)rank * kTileRows + quarter * 32 + lane;
         auto load_tau = [&](int qt) -> uint32_t {
             const int q = qt * N_TILE + q_lane;
@@ -402,9 +405,16 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
                         }
                         continue;
                     }
-                    bool any = false;
+                    // four independent max chains (one per 8 columns) instead of one 32-long dependent chain: with two
+                    // epilogue warps per scheduler the chain latency is exposed.  fmaxf drops NaN, like `>=` does.
+                    float gm[4];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) any |= (v[j] >= thr);
+                    for (int g = 0; g < 4; ++g) {
+                        gm[g] = fmaxf(v[8 * g], v[8 * g + 1]);
+#pragma unroll
+                        for (int j = 2; j < 8; ++j) gm[g] = fmaxf(gm[g], v[8 * g + j]);
+                    }
+                    const bool any = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3])) >= thr;
                     // Rare path, kept SMALL on purpose: the kernel has to stay inside the 32 KB instruction cache (a 32x
                     // unrolled hit handler -- tried twice, 42-45 KB of code -- costs 5-40 % because it stalls the MMA warp).
                     // Build this lane's hit mask, OR it across the warp, and visit every column some lane hit by re-reading
@@ -413,7 +423,11 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
                     if (__any_sync(0xFFFFFFFFu, any) && col0 < valid_cols) {
                         uint32_t mask = 0;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) mask |= (v[j] >= thr) ? (1u << j) : 0u;
+                        for (int g = 0; g < 4; ++g)
+                            if (gm[g] >= thr) {   // only the 8-column groups that hold a hit are expanded
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) mask |= (v[8 * g + j] >= thr) ? (1u << (8 * g + j)) : 0u;
+                            }
                         const int left = valid_cols - col0;
                         if (left < 32) mask &= (1u << left) - 1u;
                         uint32_t um = __reduce_or_sync(0xFFFFFFFFu, mask);
@@ -440,6 +454,10 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
                         }
                     }
                 }
+                // The next tile's threshold was requested at the top of this tile; pin its arrival HERE, before the slot
+                // reservation below: ptxas puts the load and the atomic on one scoreboard, and a wait placed after the
+                // atomic (13 % of the epilogue's stall samples in a hit-heavy chunk) pays the atomic's whole round trip.
+                asm volatile("" : "+r"(tk_next));
                 // accumulator fully read: hand it back to the MMA warp before touching global memory
                 tc_fence_before();
                 __syncwarp();
@@ -617,7 +635,6 @@ cudaError_t launch_gemm_filter(const GemmLaunch& g, cudaStream_t stream) {
     const size_t smem = plan.smem;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(clusters * cg);
-    cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -629,14 +646,15 @@ cudaError_t launch_gemm_filter(const GemmLaunch& g, cudaStream_t stream) {
     cfg.numAttrs = 1;
     cudaError_t e;
     const bool seg = !(plan.nseg == 1 && (plan.a_resident || plan.na == 2));
+    const int ew = g.epi_warps == 16 ? 16 : 8;
+    cfg.blockDim = dim3(gemm_threads(ew));
     void (*fn)(GemmTmaps, GemmArgs);
-    if (cg == 1) {
-        fn = g.seed_mode ? (seg ? gemm_filter_kernel<1, true, true> : gemm_filter_kernel<1, true, false>)
-                         : (seg ? gemm_filter_kernel<1, false, true> : gemm_filter_kernel<1, false, false>);
-    } else {
-        fn = g.seed_mode ? (seg ? gemm_filter_kernel<2, true, true> : gemm_filter_kernel<2, true, false>)
-                         : (seg ? gemm_filter_kernel<2, false, true> : gemm_filter_kernel<2, false, false>);
-    }
+#define B200ANN_PICK(CGV, EWV)                                                                                     \
+    (g.seed_mode ? (seg ? gemm_filter_kernel<CGV, true, true, EWV> : gemm_filter_kernel<CGV, true, false, EWV>)  \
+                 : (seg ? gemm_filter_kernel<CGV, false, true, EWV> : gemm_filter_kernel<CGV, false, false, EWV>))
+    if (cg == 1) fn = ew == 16 ? B200ANN_PICK(1, 16) : B200ANN_PICK(1, 8);
+    else fn = ew == 16 ? B200ANN_PICK(2, 16) : B200ANN_PICK(2, 8);
+#undef B200ANN_PICK
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = cudaLaunchKernelEx(&cfg, fn, tm, a);

@@ -127,7 +127,7 @@ struct ann_index {
     DevBuf<long long> upd_slots;
 
     // options / stats
-    int path_opt = 0, gemm_min_batch = 2, gemm_cta_group = 2;
+    int path_opt = 0, gemm_min_batch = 2, gemm_cta_group = 2, gemm_epi_warps = 0;
     bool device_fallback = false;
     bool gemm_blocked_by_update = false;   // device entry point: synchronise and run the exact fallback for flagged queries
     // optional CUDA-event timing of the dominant kernel of each path, on the launching stream (bench.py roofline)
@@ -457,6 +457,8 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
     fp.out_count = d_out_count;
     fp.k_out = k_out;
 
+    int kHitBudget = 500;
+    if (const char* hb = getenv("B200ANN_HIT_BUDGET")) kHitBudget = std::max(100, atoi(hb));
     auto gemm_launch = [&](long long begin, long long end, int seed_mode) -> int {
         GemmLaunch g{};
         g.q_shadow = ix->q_shadow.p;
@@ -470,6 +472,13 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
         g.kp = ix->kp;
         g.cta_group = ix->gemm_cta_group;
         g.seed_mode = seed_mode;
+        // a chunk is sized to add about kHitBudget candidates per query, so its hit density is budget / rows; above
+        // ~1.5e-4 hits per score the epilogue is the bottleneck and wants 16 warps (measured crossover, 10M x 200)
+        // a chunk is sized to add about kHitBudget candidates per query, so its hit density is budget / rows; above
+        // ~1.5e-4 hits per score the epilogue is the bottleneck and wants 16 warps (same-process A/B, tools/ab_options.py:
+        // 2.82 -> 2.52 ms per 4096-query batch over 1.25M rows; neutral at 10M rows where sparse chunks dominate)
+        g.epi_warps = ix->gemm_epi_warps ? ix->gemm_epi_warps
+                                         : ((!seed_mode && (double)(end - begin) * 1.5e-4 < (double)kHitBudget) ? 16 : 8);
         g.nb_stages = gemm_row_stages(ix->kp, ix->smem_optin);
         g.sm_count = ix->sm_count;
         g.qstate = qs_base;
@@ -515,8 +524,6 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
     //   seed   : over the first S rows only the best score of every 32-row group is kept (fixed slots, no atomics); the
     //            k-th best group maximum is a valid threshold, as tight as having seen ~S rows.  Needs S/32 >= 4k groups.
     //   chunks : then [0, c1), [c1, c2), ... sized so that each adds roughly kHitBudget candidates per query.
-    int kHitBudget = 500;
-    if (const char* hb = getenv("B200ANN_HIT_BUDGET")) kHitBudget = std::max(100, atoi(hb));
     const long long seed_rows = std::min<long long>(ix->n / 256 * 256, (long long)kGemmPoolCap * 32);
     const bool use_seed = seed_rows >= 128LL * k_eff && seed_rows >= 4096;
     // a chunk `growth` times the rows seen so far adds about (growth - 1) * 1.9 * k candidates per query
@@ -968,6 +975,11 @@ int ann_set_option(ann_index* ix, const char* name, int64_t value) {
     }
     if (!strcmp(name, "device_fallback")) {
         ix->device_fallback = value != 0;
+        return ANN_OK;
+    }
+    if (!strcmp(name, "gemm_epi_warps")) {
+        if (value != 0 && value != 8 && value != 16) return fail(ANN_ERR_INVALID_ARGUMENT, "gemm_epi_warps must be 0 (auto), 8 or 16");
+        ix->gemm_epi_warps = (int)value;
         return ANN_OK;
     }
     if (!strcmp(name, "gemm_cta_group")) {

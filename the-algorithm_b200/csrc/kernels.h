@@ -121,6 +121,7 @@ struct GemmLaunch {
     int b, b_pad, kp;
     int cta_group;              // 1 or 2 (tcgen05 cta_group)
     int seed_mode;              // 1: threshold seeding launch (group maxima at fixed pool slots)
+    int epi_warps;              // 8 or 16 epilogue warps (hit-dense chunks want 16); anything else = 8
     int nb_stages;              // from gemm_row_stages()
     int sm_count;
     QueryState* qstate;
