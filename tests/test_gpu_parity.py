@@ -191,6 +191,32 @@ def test_tiny_and_huge_magnitudes():
             check(m, corpus, ids, q * (1.0 if scale < 1 else 100.0), 50)
 
 
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("mi", [0, 1, 2])
+def test_gemm_filter_survives_worst_case_bf16_rounding(mi, cg):
+    """Adversarial for the tensor-core filter: every element of the true neighbours sits just BELOW a bf16 rounding
+    midpoint (the stored operand under-states each by 2^-8 relative, the worst case), every element of 300 decoys just
+    ABOVE one (over-stated by as much).  Under InnerProduct the 20 victims are the exact top-20 although their approximate
+    scores rank them below all 300 decoys by 0.78 % of |a||b| -- within 1.5 % of the margin the measured-residual error
+    bound grants.  An error model that under-states the rounding error loses them."""
+    d, e = 200, 2.0 ** -20
+    victims = np.full((20, d), 1 + 2.0 ** -8 - e, np.float32)
+    victims[:, -1] = 1 + 2.0 ** -7
+    decoys = np.full((300, d), 1 + 2.0 ** -8 + e, np.float32)
+    rng = np.random.default_rng(5)
+    filler = (0.5 * rng.uniform(0.9, 1.0, (3000, d))).astype(np.float32)
+    corpus = np.concatenate([filler[:1500], decoys[:150], victims, decoys[150:], filler[1500:]])
+    ids = rng.permutation(corpus.shape[0]).astype(np.int64) * 3 + 1
+    q = np.ones((3, d), np.float32)
+    q[1] = 1 + 2.0 ** -8 - e                       # the query operand is rounded too
+    q[2] = rng.uniform(0.5, 1.5, d).astype(np.float32)
+    if mi == 0:   # metrics()[0] is InnerProduct, thrift ordinal 2
+        oi, _, _ = oracle.query_canonical(2, corpus, ids, q[:1], 20)
+        assert sorted(oi[0].tolist()) == sorted(ids[1650:1670].tolist())   # the victims really are the InnerProduct top-20
+    assert check(metrics()[mi], corpus, ids, q, 20, path=2, cg=cg) == 2
+    assert check(metrics()[mi], corpus, ids, q, 100, path=2, cg=cg) == 2
+
+
 def test_massive_ties_are_answered_exactly_by_the_fallback():
     """100k identical rows: every row ties at rank k, far more than the bounded selector holds.  The host entry point
     re-answers such queries with the exact fallback (exact distance for every row + radix select on (distance, id)); the

@@ -56,6 +56,8 @@ constexpr int kPubStride = 256;
 struct DeviceScalars {
     uint32_t max_norm_bits;
     uint32_t error_flags;
+    uint32_t max_resid_bits;   // running max of |a - bf16(a)| over the shadow rows (float bits): the measured rounding error
+    uint32_t reserved;
     unsigned long long n_special;
     unsigned long long bad_queries;
     uint32_t special_list[kSpecialCap];   // indices of the first special rows (see common.cuh)
@@ -236,6 +238,7 @@ int append_device_core(ann_index* ix, const int64_t* d_ids, const float* d_rows,
     ap.shadow = ix->shadow;
     ap.kp = ix->kp;
     ap.max_norm_bits = &ix->scalars->max_norm_bits;
+    ap.max_resid_bits = &ix->scalars->max_resid_bits;
     ap.n_special = &ix->scalars->n_special;
     ap.special_list = ix->scalars->special_list;
     CUDA_TRY(launch_append(ap, st));
@@ -335,6 +338,7 @@ int query_scan(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
     pp.q_shadow = nullptr;
     pp.qstate = ix->qstate.p;
     pp.max_norm_bits = &ix->scalars->max_norm_bits;
+    pp.max_resid_bits = &ix->scalars->max_resid_bits;
     pp.path = 1;
     pp.pub_keys = ix->pub_keys.p;
     pp.pub_stride = kPubStride;
@@ -427,6 +431,7 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
     pp.qkp = qkp;
     pp.qstate = qs_base;
     pp.max_norm_bits = &ix->scalars->max_norm_bits;
+    pp.max_resid_bits = &ix->scalars->max_resid_bits;
     pp.path = 2;
     pp.pub_keys = nullptr;
     pp.pub_stride = 0;
@@ -823,6 +828,7 @@ int ann_update_batch(ann_index* ix, const int64_t* slots, const float* rows, int
     ap.shadow = ix->shadow;
     ap.kp = ix->kp;
     ap.max_norm_bits = &ix->scalars->max_norm_bits;   // only ever grows: the error bounds stay valid (looser)
+    ap.max_resid_bits = &ix->scalars->max_resid_bits; // likewise
     ap.n_special = &ix->scalars->n_special;           // conservative: a repaired row does not lower the census
     ap.special_list = ix->scalars->special_list;
     if (ix->n_special > 0) ix->gemm_blocked_by_update = true;   // a repaired special row would be listed AND be a candidate

@@ -19,6 +19,7 @@ struct AppendParams {
     __nv_bfloat16* shadow;  // [cap][kp] or nullptr
     int kp;                 // shadow pitch in elements (multiple of 8)
     uint32_t* max_norm_bits;  // running max of |a| (float bits, non-negative => integer order)
+    uint32_t* max_resid_bits; // running max of |shadow row - exact operand row|, the measured bf16 rounding error (float bits)
     unsigned long long* n_special;   // rows with non-finite entries or (Cosine) zero norm
     uint32_t* special_list;          // [kSpecialCap] indices of the first special rows (tensor-core path rescoring list)
 };
@@ -33,6 +34,7 @@ struct PrepParams {
     int qkp;                  // query operand pitch in elements: kp rounded up to 64 (128-byte aligned rows => 4 sectors per box row)
     QueryState* qstate;     // [b]
     const uint32_t* max_norm_bits;
+    const uint32_t* max_resid_bits;
     int path;               // 1 = scan (fp32 error model), 2 = gemm (bf16 error model)
     uint32_t* pub_keys;     // [b][pub_stride] reset to 0xFFFFFFFF (scan path) or nullptr
     int pub_stride;
