@@ -8,13 +8,14 @@
 metric  : exact top-100 queries/sec over a 10M x 200 fp32 corpus (BASELINE.json `metric`, configs[1]:
           InnerProduct, query batch 4096, tcgen05 GEMM path)
 step    : one batch of 4096 synthetic queries through the whole query path (prep -> GEMM filter chunks ->
-          compaction -> exact fp64 finalize; with N > 1 also the NCCL all-gather of the local top-k + K5 merge)
+          compaction -> exact fp64 finalize; with N > 1 also the exchange + merge of the per-rank top-k lists)
 value   : whole-job queries/s with queries and outputs resident in HBM (CUDA events on the launching stream,
           barrier + synchronize on both sides, max over ranks)
 e2e     : the same through the host-buffer C-ABI call ann_query_batch (pinned host queries in, host results out,
           H2D / D2H inside the timed region)
 N > 1   : STRONG scaling on the same 10M-row corpus -- rows sharded contiguously across ranks, queries replicated,
-          one exchange step (all-gather of b*k*(8+4)+b*4 bytes per rank) followed by the K5 merge kernel.
+          one exchange step: the fused exchange+merge kernel over NVLink peer memory (each rank pulls, merges and
+          pushes 1/N of the batch; ann/exchange.py), or NCCL all-gather + merge kernel if peers cannot be mapped.
 roofline: dominant kernel = gemm_filter (tensor bound); achieved = 2*N_local*d*B flop / its CUDA-event time.
 cpu_baseline / --impl reference: the reference-faithful C restatement (oracle/oracle.c: linked list of heap rows,
           Scala PriorityQueue mechanics) on the host cores, one query per thread, bounded sample of the same workload.
@@ -61,12 +62,13 @@ def parse():
     return ap.parse_args()
 
 
-def config_dict(a, n_gpus):
+def config_dict(a, n_gpus, route=""):
+    how = {"fused": "one fused exchange+merge kernel over NVLink peer memory (each rank merges 1/N of the batch)",
+           "allgather": "NCCL all-gather of local top-k + merge kernel"}.get(route or "fused", route)
     return {
         "workload": f"configs[1]: exact {a.metric} top-{a.k} over {a.rows}x{a.dim} fp32 corpus, query batch {a.batch}",
         "rows": a.rows, "dim": a.dim, "batch": a.batch, "k": a.k, "distance": a.metric,
-        "sharding": "single GPU" if n_gpus == 1 else f"rows sharded contiguously over {n_gpus} ranks, queries replicated, "
-                    "NCCL all-gather of local top-k + merge kernel",
+        "sharding": "single GPU" if n_gpus == 1 else f"rows sharded contiguously over {n_gpus} ranks, queries replicated, " + how,
         "l2_flush": "none needed: every step streams the corpus shadow (>= 4 GB per 10M rows) through a 126 MB L2",
     }
 
@@ -203,8 +205,9 @@ def run_ours(a):
 
     import _pkg
     _pkg.load()
-    from the_algorithm_b200.ann.brute_force import BruteForceIndex, merge_topk_device
+    from the_algorithm_b200.ann.brute_force import BruteForceIndex
     from the_algorithm_b200.ann.common import FuturePool, Metric
+    from the_algorithm_b200.ann.distributed import ShardedBruteForceIndex, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -219,8 +222,7 @@ def run_ours(a):
 
     metric = Metric.from_string(a.metric)
     n, d, b, k = a.rows, a.dim, a.batch, a.k
-    lo = rank * n // world
-    hi = (rank + 1) * n // world
+    lo, hi = shard_range(n, world, rank)
     n_local = hi - lo
 
     # ---- build the shard (not timed): same generator stream on every rank, each keeps its own row range ----
@@ -242,20 +244,14 @@ def run_ours(a):
     out_ids = torch.empty((b, k), dtype=torch.int64, device=dev)
     out_dist = torch.empty((b, k), dtype=torch.float32, device=dev)
     out_cnt = torch.empty((b,), dtype=torch.int32, device=dev)
-    if world > 1:
-        g_ids = torch.empty((world, b, k), dtype=torch.int64, device=dev)
-        g_dist = torch.empty((world, b, k), dtype=torch.float32, device=dev)
-        g_cnt = torch.empty((world, b), dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream()
+    sx = ShardedBruteForceIndex(ix, device=dev) if world > 1 else None
 
     def step_device(queries):
-        ix.query_batch_device(queries, k, out_ids, out_dist, out_cnt, stream.cuda_stream)
         if world == 1:
+            ix.query_batch_device(queries, k, out_ids, out_dist, out_cnt, stream.cuda_stream)
             return out_ids, out_dist, out_cnt
-        dist.all_gather_into_tensor(g_ids, out_ids)
-        dist.all_gather_into_tensor(g_dist, out_dist)
-        dist.all_gather_into_tensor(g_cnt, out_cnt)
-        return merge_topk_device(g_ids, g_dist, g_cnt, k, stream.cuda_stream)
+        return sx.batch_query_device(queries, k, stream.cuda_stream)   # local query + exchange + merge, on every rank
 
     def barrier():
         if world > 1:
@@ -398,10 +394,10 @@ def run_ours(a):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16 filter (tcgen05, fp32 accumulate) + exact fp64-accumulated fp32 distances" if last_path == 2
                      else "f32 scan + exact fp64-accumulated fp32 distances",
-            "data": "synthetic", "config": config_dict(a, n_gpus),
+            "data": "synthetic", "config": config_dict(a, n_gpus, sx.route if sx else ""),
             "e2e": {"value": b / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": b * d * 4,
                     "d2h_bytes_per_step": b * k * 12 + b * 4, "ms_per_step": e2e_ms,
-                    "api": "ann_query_batch (host buffers)" if world == 1 else "pinned H2D + ann_query_batch_device + all-gather + merge + D2H"},
+                    "api": "ann_query_batch (host buffers)" if world == 1 else "pinned H2D + ann_query_batch_device + exchange/merge + D2H"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "path": {1: "scan", 2: "gemm"}.get(last_path, str(last_path)),
         }

@@ -26,6 +26,7 @@
 #ifndef B200ANN_H_
 #define B200ANN_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -112,8 +113,20 @@ ANN_API int ann_merge_topk_device(int32_t device, const int64_t *d_ids, const fl
                                   int32_t shards, int32_t b, int32_t k, int64_t *d_out_ids, float *d_out_dist,
                                   int32_t *d_out_count, void *stream);
 
+/* The same merge fused with its exchange (one kernel instead of all-gather + merge).  A "result block" for (b, k) is one
+ * device allocation laid out [ids: b*k int64][dist: b*k float][count: b int32] (ann_result_block_bytes).  Every rank lets
+ * ann_query_batch_device write its shard's results into its own local block, all ranks map each other's local and final
+ * blocks (CUDA IPC / symmetric memory; peer_local[s], peer_final[s] are rank s's blocks as seen from this process), and after
+ * a cross-rank barrier each rank calls this with its own slice [q_begin, q_begin + q_count) of the batch: the kernel pulls
+ * the slice's rows from all `world` local blocks over NVLink, merges them in canonical order and pushes the merged rows into
+ * all `world` final blocks.  A second cross-rank barrier makes every final block complete.  world <= 16. */
+ANN_API int ann_exchange_merge_device(int32_t device, const void *const *peer_local, void *const *peer_final, int32_t world,
+                                      int32_t b, int32_t k, int32_t q_begin, int32_t q_count, void *stream);
+ANN_API size_t ann_result_block_bytes(int32_t b, int32_t k);
+
 /* Tuning / introspection.
  * Options: "path" (0 auto, 1 streaming scan, 2 tensor-core GEMM filter, 3 exact fallback for every query), "gemm_min_batch", "gemm_cta_group" (1|2), "gemm_epi_warps" (0 auto, 8, 16),
+ *          "gemm_hit_budget" (candidates one chunk may add per query, default 500), "gemm_seed_rows" (0 = default 65536),
  *          "timing" (1 = bracket every scan / GEMM-filter launch with CUDA events on its stream),
  *          "device_fallback" (1 = ann_query_batch_device synchronises its stream and re-answers flagged queries with the
  *          exact fallback, like the host entry point always does; 0 = stay asynchronous and report them, default).

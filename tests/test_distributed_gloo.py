@@ -1,7 +1,8 @@
-"""world_size-2 `gloo` test of the multi-rank query plumbing on CPU: contiguous row sharding, replicated queries,
-all-gather of each rank's local top-k in the [shards][b][k] layout, canonical merge -> identical to the single-shard
-answer.  The local scan and the merge are oracle-backed test doubles here (no GPU); on a B200 the same layout feeds
-ann_query_batch_device and ann_merge_topk_device (tests/test_gpu_parity.py::test_merge_kernel_*, bench.py --gpus N)."""
+"""world_size-2 `gloo` test of the multi-rank host class on CPU (the-algorithm_b200/ann/distributed.py): contiguous row
+sharding, round-robin batch routing, replicated queries, all-gather of each rank's local top-k in the [shards][b][k]
+layout, canonical merge -> identical to the single-shard answer.  The two DEVICE calls (the shard's query and the merge
+kernel) are oracle-backed test doubles here (no GPU); everything between them is the product's ShardedBruteForceIndex.
+On B200s the same class runs ann_query_batch_device + the fused exchange/merge kernel (tools/dist_check.py, bench.py)."""
 import os
 import socket
 
@@ -22,36 +23,64 @@ def _free_port():
     return p
 
 
-def shard_range(n, world, rank):
-    """bench.py's partitioning: rank r holds rows [r*n//R, (r+1)*n//R)."""
-    return rank * n // world, (rank + 1) * n // world
+class _OracleShard:
+    """Test double for one rank's BruteForceIndex: same two methods, CPU tensors, answers from the oracle."""
+
+    def __init__(self, metric):
+        self.metric, self.ids, self.rows = metric, [], []
+
+    def append_batch(self, ids, rows):
+        self.ids.append(np.asarray(ids, np.int64))
+        self.rows.append(np.asarray(rows, np.float32))
+
+    def query_batch_device(self, queries, k, out_ids, out_dist, out_count, stream=0):
+        d = queries.shape[1]
+        ids = np.concatenate(self.ids) if self.ids else np.zeros((0,), np.int64)
+        rows = np.concatenate(self.rows) if self.rows else np.zeros((0, d), np.float32)
+        li, ld, lc = oracle.query_canonical(self.metric, rows, ids, queries.numpy(), k)
+        out_ids.copy_(torch.from_numpy(li))
+        out_dist.copy_(torch.from_numpy(ld))
+        out_count.copy_(torch.from_numpy(lc))
 
 
-def _worker(rank, world, port, metric, n, d, b, k, ret):
+def _oracle_merge(g_ids, g_dist, g_cnt, k, stream=0):
+    """Test double for merge_topk_device: [S,b,k] -> [b,k] through oracle.merge."""
+    b = g_ids.shape[1]
+    oi, od, oc = np.empty((b, k), np.int64), np.empty((b, k), np.float32), np.empty((b,), np.int32)
+    for qi in range(b):
+        oi[qi], od[qi], oc[qi] = oracle.merge(g_ids[:, qi].numpy(), g_dist[:, qi].numpy(), g_cnt[:, qi].numpy(), k)
+    return torch.from_numpy(oi), torch.from_numpy(od), torch.from_numpy(oc)
+
+
+def _worker(rank, world, port, metric, n, d, b, k, routed, ret):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
+        import _pkg
+        _pkg.load()
+        from the_algorithm_b200.ann.distributed import ShardedBruteForceIndex, shard_range
+
         rng = np.random.default_rng(42)                       # same stream on every rank, like bench.py
         corpus = (rng.standard_normal((n, d)) / np.sqrt(d)).astype(np.float32)
         corpus[n // 2: n // 2 + 5] = corpus[:5]              # ties across the shard boundary
         ids = rng.permutation(n).astype(np.int64)
         q = rng.uniform(-1, 1, (b, d)).astype(np.float32)
-        lo, hi = shard_range(n, world, rank)
-        li, ld, lc = oracle.query_canonical(metric, corpus[lo:hi], ids[lo:hi], q, k)
-        g_ids = torch.empty((world, b, k), dtype=torch.int64)
-        g_dist = torch.empty((world, b, k), dtype=torch.float32)
-        g_cnt = torch.empty((world, b), dtype=torch.int32)
-        # gloo wants the list form; NCCL (bench.py) uses all_gather_into_tensor on the same [shards][b][k] buffers
-        dist.all_gather(list(g_ids.unbind(0)), torch.from_numpy(li))
-        dist.all_gather(list(g_dist.unbind(0)), torch.from_numpy(ld))
-        dist.all_gather(list(g_cnt.unbind(0)), torch.from_numpy(lc))
-        out_i = np.empty((b, k), np.int64)
-        out_d = np.empty((b, k), np.float32)
-        for qi in range(b):
-            mi, md, mc = oracle.merge(g_ids[:, qi].numpy(), g_dist[:, qi].numpy(), g_cnt[:, qi].numpy(), k)
-            out_i[qi], out_d[qi] = mi, md
-        wi, wd, _ = oracle.query_canonical(metric, corpus, ids, q, k)
-        ok = bool((out_i == wi).all() and (out_d.view(np.uint32) == wd.view(np.uint32)).all())
+        sx = ShardedBruteForceIndex(_OracleShard(metric), merge=_oracle_merge)
+        assert (sx.rank, sx.world, sx.route) == (rank, world, "allgather")
+        if routed:                                            # streaming appends: batches of 100 rows, round-robin
+            kept = 0
+            for c0 in range(0, n, 100):
+                kept += int(sx.append_routed(ids[c0:c0 + 100], corpus[c0:c0 + 100]))
+            assert abs(kept - ((n + 99) // 100) / world) <= 1
+        else:
+            lo, hi = shard_range(n, world, rank)
+            sx.append_shard(ids[lo:hi], corpus[lo:hi])
+        ok = True
+        for _ in range(2):                                    # buffers are reused across calls
+            oi, od, oc = sx.batch_query_device(torch.from_numpy(q), k)
+            wi, wd, wc = oracle.query_canonical(metric, corpus, ids, q, k)
+            ok &= bool((oi.numpy() == wi).all() and (od.numpy().view(np.uint32) == wd.view(np.uint32)).all()
+                       and (oc.numpy() == wc).all())
         t = torch.tensor([1 if ok else 0])
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         if rank == 0:
@@ -60,12 +89,13 @@ def _worker(rank, world, port, metric, n, d, b, k, ret):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("routed", [False, True])
 @pytest.mark.parametrize("metric", [oracle.L2, oracle.COSINE, oracle.INNER_PRODUCT])
-def test_two_rank_shard_merge_equals_single_shard(metric):
+def test_two_rank_shard_merge_equals_single_shard(metric, routed):
     ctx = mp.get_context("spawn")
     ret = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, metric, 1001, 24, 5, 16, ret)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, metric, 1001, 24, 5, 16, routed, ret)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
@@ -75,6 +105,16 @@ def test_two_rank_shard_merge_equals_single_shard(metric):
 
 
 def test_shard_ranges_cover_everything():
+    import _pkg
+    _pkg.load()
+    from the_algorithm_b200.ann.distributed import route_batch, shard_range
+    from the_algorithm_b200.ann.exchange import slice_of
+
+    assert [route_batch(i, 3) for i in range(7)] == [0, 1, 2, 0, 1, 2, 0]
+    for b in (1, 5, 4096):
+        for world in (1, 2, 3, 8):
+            sl = [slice_of(r, world, b) for r in range(world)]
+            assert sl[0][0] == 0 and sl[-1][1] == b and all(sl[i][1] == sl[i + 1][0] for i in range(world - 1))
     for n in (0, 1, 7, 1000, 10_000_000):
         for world in (1, 2, 3, 8):
             spans = [shard_range(n, world, r) for r in range(world)]

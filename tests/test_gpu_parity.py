@@ -379,6 +379,54 @@ def test_merge_kernel_matches_oracle_merge():
         assert (onp.float_order_key(od[qi]) == onp.float_order_key(ed)).all()
 
 
+@pytest.mark.parametrize("world,b,k", [(1, 5, 10), (2, 37, 100), (3, 8, 1), (8, 64, 100), (16, 9, 33)])
+def test_fused_exchange_merge_kernel_matches_oracle_merge(world, b, k):
+    """ann_exchange_merge_device with all `world` result blocks on one device: every "rank" merges its slice of the batch
+    from all local blocks and writes it to all final blocks; afterwards every final block must hold oracle.merge's answer
+    (ShardApi.scala:77-85 in canonical order).  Lists are sorted by (distance, id) as the shard queries emit them, with
+    cross-shard ties, duplicate (distance, id) pairs, short lists, empty lists and NaN tails."""
+    import torch
+    from the_algorithm_b200.ann.exchange import ResultBlock, exchange_merge_blocks, result_block_bytes, slice_of
+
+    rng = np.random.default_rng(100 + world)
+    dist = np.round(rng.standard_normal((world, b, k)).astype(np.float32), 1)     # many ties within and across shards
+    ids = rng.integers(0, 50, (world, b, k)).astype(np.int64)                      # and repeated ids
+    cnt = rng.integers(0, k + 1, (world, b)).astype(np.int32)
+    cnt[0] = k
+    if world > 1:
+        cnt[1, 0] = 0
+    for s in range(world):
+        for qi in range(b):
+            c = cnt[s, qi]
+            if c > 2 and (s + qi) % 3 == 0:
+                dist[s, qi, c - 2:c] = np.nan                                       # NaN sorts last (Float.compare)
+            order = np.lexsort((ids[s, qi, :c], onp.float_order_key(dist[s, qi, :c])))
+            dist[s, qi, :c] = dist[s, qi, :c][order]
+            ids[s, qi, :c] = ids[s, qi, :c][order]
+    dev = torch.device("cuda", 0)
+    nb = result_block_bytes(b, k)
+    assert nb == b * k * 12 + b * 4
+    bufs = [torch.zeros(2 * nb + 256, dtype=torch.uint8, device=dev) for _ in range(world)]
+    off = (nb + 255) // 256 * 256
+    locs = [ResultBlock(bufs[s], b, k, 0) for s in range(world)]
+    fins = [ResultBlock(bufs[s], b, k, off) for s in range(world)]
+    for s in range(world):
+        locs[s].ids.copy_(torch.from_numpy(ids[s]))
+        locs[s].dist.copy_(torch.from_numpy(dist[s]))
+        locs[s].count.copy_(torch.from_numpy(cnt[s]))
+    for r in range(world):
+        q0, q1 = slice_of(r, world, b)
+        exchange_merge_blocks([x.ptr for x in locs], [x.ptr for x in fins], b, k, q0, q1 - q0, 0)
+    torch.cuda.synchronize()
+    for s in range(world):
+        oi, od, oc = (t.cpu().numpy() for t in fins[s].tensors)
+        for qi in range(b):
+            ei, ed, ec = oracle.merge(ids[:, qi], dist[:, qi], cnt[:, qi], k)
+            assert oc[qi] == ec
+            assert (oi[qi] == ei).all(), (s, qi)
+            assert (onp.float_order_key(od[qi]) == onp.float_order_key(ed)).all()
+
+
 # ------------------------------------------------------------------------------------------------ full-size properties
 def test_full_size_properties_10m_rows():
     """At BASELINE's full size the oracle is too slow, so check size-independent properties on a 10M x 128 L2 index:

@@ -1,0 +1,116 @@
+"""Row-sharded index across the GPUs of one box, one process per GPU: ShardedAppendable + ComposedQueryable
+(ShardApi.scala:21-48, 58-87) with the shards in different processes.
+
+The reference routes every appended row to one of S sub-indices and, per query, fans out to all S, flattens the S*k
+results, sorts and takes k.  Here rank r of R owns one `BruteForceIndex` shard on its GPU; queries are replicated (every
+rank sees the same batch), each rank answers over its rows, and the per-rank top-k lists are exchanged and merged:
+
+  route "fused"     -- the default on GPUs that can map each other's memory: the shard's results land in a peer-mapped
+                       result block and ONE kernel (`ann_exchange_merge_device`, ann/exchange.py) pulls this rank's slice
+                       of the batch from every peer over NVLink, merges it and pushes the merged rows to every peer.
+  route "allgather" -- `all_gather` of the three result arrays in the [shards][b][k] layout (NCCL; gloo on CPU) followed
+                       by the merge kernel (`ann_merge_topk_device`) over the whole batch on every rank.
+
+Both give every rank the complete merged batch, ordered by (Float.compare(distance), id): with globally unique ids that
+is bit for bit the single-shard answer (tests/test_distributed_gloo.py on CPU with test doubles for the two device
+calls; tools/dist_check.py and bench.py --gpus N on GPUs).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+
+def shard_range(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous row partition: rank r holds rows [r*n//R, (r+1)*n//R); sizes differ by at most one."""
+    return rank * n // world, (rank + 1) * n // world
+
+
+def route_batch(batch_index: int, world: int) -> int:
+    """Streaming appends go to the shards round-robin by batch -- the deterministic stand-in for RandomShardFunction
+    (ShardApi.scala:21-25); shard sizes stay within one batch of each other."""
+    return batch_index % world
+
+
+class ShardedBruteForceIndex:
+    """One rank's handle on the sharded index.  `local` is this rank's shard (a BruteForceIndex, or any object with
+    `query_batch_device(queries, k, out_ids, out_dist, out_count, stream)`); `merge` is the [S,b,k] merge used by the
+    all-gather route (default: the CUDA merge kernel)."""
+
+    def __init__(self, local, group=None, route: str = "auto", merge: Optional[Callable] = None, device=None):
+        import torch
+        import torch.distributed as dist
+
+        self.local = local
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.world = dist.get_world_size(self.group)
+        self.device = torch.device(device) if device is not None else torch.device("cpu")
+        self._merge = merge
+        self._px = {}          # (b, k) -> PeerExchange
+        self._gather = {}      # (b, k) -> gathered buffers
+        self._own = {}         # (b, k) -> this rank's result arrays (all-gather route)
+        self._appended_batches = 0
+        if route not in ("auto", "fused", "allgather"):
+            raise ValueError(f"route must be auto, fused or allgather, not {route!r}")
+        self.route = route
+        self.route_note = ""
+        if route == "auto":
+            self.route = "fused" if (self.device.type == "cuda" and self.world > 1) else "allgather"
+
+    # ------------------------------------------------------------------ appends
+    def append_shard(self, ids, rows) -> None:
+        """Rows the caller has already assigned to this rank (e.g. its `shard_range` of a bulk load)."""
+        self.local.append_batch(ids, rows)
+
+    def append_routed(self, ids, rows) -> bool:
+        """Collective-free streaming append: every rank is offered every batch and keeps the ones routed to it.
+        Returns whether this rank kept the batch."""
+        mine = route_batch(self._appended_batches, self.world) == self.rank
+        self._appended_batches += 1
+        if mine:
+            self.local.append_batch(ids, rows)
+        return mine
+
+    # ------------------------------------------------------------------ queries
+    def _exchange_for(self, b: int, k: int):
+        from .exchange import PeerExchange
+
+        key = (b, k)
+        if key not in self._px:
+            self._px[key] = PeerExchange(b, k, self.device, self.group)
+        return self._px[key]
+
+    def batch_query_device(self, queries, k: int, stream: int = 0):
+        """Collective: every rank passes the same [b, dim] batch (on its own device) and receives the merged
+        (ids [b,k], dist [b,k], count [b]).  The returned tensors are reused by the next call with the same (b, k)."""
+        import torch
+        import torch.distributed as dist
+
+        b = int(queries.shape[0])
+        if self.route == "fused":
+            try:
+                px = self._exchange_for(b, k)
+            except Exception as e:   # the ranks cannot map each other's memory: keep the collective route
+                self.route, self.route_note = "allgather", f"peer mapping unavailable: {type(e).__name__}: {e}"
+            else:
+                self.local.query_batch_device(queries, k, px.local.ids, px.local.dist, px.local.count, stream)
+                return px.exchange_merge(stream)
+        key = (b, k)
+        if key not in self._own:
+            dev = self.device
+            self._own[key] = (torch.empty((b, k), dtype=torch.int64, device=dev), torch.empty((b, k), dtype=torch.float32, device=dev),
+                              torch.empty((b,), dtype=torch.int32, device=dev))
+            self._gather[key] = (torch.empty((self.world, b, k), dtype=torch.int64, device=dev),
+                                 torch.empty((self.world, b, k), dtype=torch.float32, device=dev),
+                                 torch.empty((self.world, b), dtype=torch.int32, device=dev))
+        own, gathered = self._own[key], self._gather[key]
+        self.local.query_batch_device(queries, k, own[0], own[1], own[2], stream)
+        for g, o in zip(gathered, own):
+            if self.device.type == "cuda":
+                dist.all_gather_into_tensor(g, o, group=self.group)
+            else:   # gloo has no all_gather_into_tensor
+                dist.all_gather(list(g.unbind(0)), o, group=self.group)
+        merge = self._merge
+        if merge is None:
+            from .brute_force import merge_topk_device as merge
+        return merge(gathered[0], gathered[1], gathered[2], k, stream)

@@ -1,0 +1,99 @@
+"""Shard merge fused with its exchange: the multi-GPU half of ComposedQueryable (ShardApi.scala:72-86).
+
+The reference fans a query out to S shards, collects S lists of k and sorts the S*k entries on one thread.  Row-sharded
+over the GPUs of one box the same step used to be `all_gather` (every rank receives world*b*k entries) + a merge kernel
+over all b queries on every rank.  Here it is ONE kernel over NVLink peer memory (`ann_exchange_merge_device`): every
+rank's local top-k lives in a result block its peers have mapped, rank r pulls only the rows of ITS slice of the batch
+from the `world` blocks, merges them, and pushes the merged rows into every rank's final block.  Each rank moves and
+merges 1/world of the batch; two stream-ordered cross-rank barriers bracket the kernel.
+
+    px = PeerExchange(b, k, device)                   # collective: allocates + maps the symmetric blocks
+    ix.query_batch_device(q, k, *px.local.tensors, stream)   # the shard's results land in the mapped block directly
+    ids, dist, cnt = px.exchange_merge(stream)        # every rank ends up with the whole merged batch
+
+Peer mapping uses torch's symmetric memory (cuMem allocations exchanged between the ranks of a process group), which is
+plumbing in the same sense as the NCCL communicator; the kernel and the layout are this repo's.  `PeerExchange` raises
+if the ranks cannot map each other (no P2P); callers then keep the all-gather + `merge_topk_device` route.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Sequence, Tuple
+
+from .. import _capi
+
+
+def result_block_bytes(b: int, k: int) -> int:
+    """Size of one result block: [ids b*k int64][dist b*k float32][count b int32] (include/b200ann.h)."""
+    return int(_capi.lib().ann_result_block_bytes(b, k))
+
+
+class ResultBlock:
+    """Typed views of one result block inside a uint8 CUDA tensor."""
+
+    def __init__(self, buf, b: int, k: int, offset: int = 0):
+        import torch
+
+        nb = b * k * 12 + b * 4
+        assert buf.dtype == torch.uint8 and buf.numel() >= offset + nb
+        self.b, self.k, self.offset = b, k, offset
+        raw = buf[offset:offset + nb]
+        self.ids = raw[: b * k * 8].view(torch.int64).view(b, k)
+        self.dist = raw[b * k * 8: b * k * 12].view(torch.float32).view(b, k)
+        self.count = raw[b * k * 12:].view(torch.int32)
+        self.ptr = buf.data_ptr() + offset
+
+    @property
+    def tensors(self) -> Tuple:
+        return self.ids, self.dist, self.count
+
+
+def exchange_merge_blocks(local_ptrs: Sequence[int], final_ptrs: Sequence[int], b: int, k: int, q_begin: int, q_count: int,
+                          device: int, stream: int = 0) -> None:
+    """`ann_exchange_merge_device` on raw block pointers (all mapped into this process)."""
+    world = len(local_ptrs)
+    assert world == len(final_ptrs) and world >= 1
+    arr = ctypes.c_void_p * world
+    _capi.check(_capi.lib().ann_exchange_merge_device(device, arr(*local_ptrs), arr(*final_ptrs), world, b, k, q_begin, q_count,
+                                                      ctypes.c_void_p(stream)))
+
+
+def slice_of(rank: int, world: int, b: int) -> Tuple[int, int]:
+    """The queries rank `rank` merges: [rank*b/world, (rank+1)*b/world) -- together the slices tile the batch."""
+    return rank * b // world, (rank + 1) * b // world
+
+
+class PeerExchange:
+    """Symmetric result blocks of one (b, k) shape across the ranks of a process group + the fused exchange/merge."""
+
+    def __init__(self, b: int, k: int, device, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.b, self.k = b, k
+        self.device = torch.device(device)
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.world = dist.get_world_size(self.group)
+        nb = result_block_bytes(b, k)
+        self._stride = (nb + 255) // 256 * 256
+        self._buf = symm_mem.empty(2 * self._stride, dtype=torch.uint8, device=self.device)
+        self._hdl = symm_mem.rendezvous(self._buf, self.group)
+        ptrs: List[int] = [int(p) for p in self._hdl.buffer_ptrs]
+        assert len(ptrs) == self.world and ptrs[self.rank] == self._buf.data_ptr()
+        self._local_ptrs = ptrs
+        self._final_ptrs = [p + self._stride for p in ptrs]
+        self.local = ResultBlock(self._buf, b, k, 0)
+        self.final = ResultBlock(self._buf, b, k, self._stride)
+        self.q_begin, q_end = slice_of(self.rank, self.world, b)
+        self.q_count = q_end - self.q_begin
+
+    def exchange_merge(self, stream: int = 0):
+        """Collective.  `local` must have been written on the CURRENT torch stream (== `stream`): the barriers are enqueued
+        on torch's current stream, the kernel on `stream`.  Returns the final block's (ids, dist, count) views."""
+        self._hdl.barrier(channel=0)     # every rank's local block is complete
+        exchange_merge_blocks(self._local_ptrs, self._final_ptrs, self.b, self.k, self.q_begin, self.q_count,
+                              self.device.index or 0, stream)
+        self._hdl.barrier(channel=1)     # every rank's slice has landed in every final block; locals may be reused
+        return self.final.tensors

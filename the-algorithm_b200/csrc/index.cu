@@ -130,6 +130,9 @@ struct ann_index {
 
     // options / stats
     int path_opt = 0, gemm_min_batch = 2, gemm_cta_group = 2, gemm_epi_warps = 0;
+    int gemm_hit_budget = 500;        // candidates a chunk of the GEMM path may add per query (sets the chunk schedule)
+    int gemm_small_select = 1;        // GEMM path: 2048 / 1024-entry selector stages (4 CTAs per SM) instead of 4096 / 2048
+    long long gemm_seed_rows = 0;     // rows of the threshold-seeding launch (0 = as many as the pool has slots for)
     bool device_fallback = false;
     bool gemm_blocked_by_update = false;   // device entry point: synchronise and run the exact fallback for flagged queries
     // optional CUDA-event timing of the dominant kernel of each path, on the launching stream (bench.py roofline)
@@ -440,6 +443,10 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
     ix->launches++;
 
     SelectParams fp{};
+    if (ix->gemm_small_select) {   // pools on this path hold a few hundred entries; overflow still falls back exactly
+        fp.sort_cap = 2048;
+        fp.exact_cap = 1024;
+    }
     fp.qstate = qs_base;
     fp.pool = ix->pool.p;
     fp.pool_cap = kGemmPoolCap;
@@ -462,8 +469,7 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
     fp.out_count = d_out_count;
     fp.k_out = k_out;
 
-    int kHitBudget = 500;
-    if (const char* hb = getenv("B200ANN_HIT_BUDGET")) kHitBudget = std::max(100, atoi(hb));
+    const int kHitBudget = ix->gemm_hit_budget;
     auto gemm_launch = [&](long long begin, long long end, int seed_mode) -> int {
         GemmLaunch g{};
         g.q_shadow = ix->q_shadow.p;
@@ -529,7 +535,10 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
     //   seed   : over the first S rows only the best score of every 32-row group is kept (fixed slots, no atomics); the
     //            k-th best group maximum is a valid threshold, as tight as having seen ~S rows.  Needs S/32 >= 4k groups.
     //   chunks : then [0, c1), [c1, c2), ... sized so that each adds roughly kHitBudget candidates per query.
-    const long long seed_rows = std::min<long long>(ix->n / 256 * 256, (long long)kGemmPoolCap * 32);
+    // Seeding is an extra pass over its rows (the first chunk scores them again), so it is kept short: 65536 rows (2048
+    // group maxima, >= 8 groups per neighbour up to k = 256) measured 1.6 % faster than 131072 on the 10M x 200 batch.
+    long long seed_rows = std::min<long long>(ix->n / 256 * 256, std::min<long long>((long long)kGemmPoolCap * 32, std::max<long long>(65536, 256LL * k_eff)));
+    if (ix->gemm_seed_rows > 0) seed_rows = std::min<long long>(seed_rows, ix->gemm_seed_rows / 256 * 256);
     const bool use_seed = seed_rows >= 128LL * k_eff && seed_rows >= 4096;
     // a chunk `growth` times the rows seen so far adds about (growth - 1) * 1.9 * k candidates per query
     int growth = (int)std::min<double>(8.0, std::max<double>(2.0, 1.0 + kHitBudget / (1.9 * std::max(1, k_eff))));
@@ -539,6 +548,7 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
         if (rc2) return rc2;
         SelectParams sp = fp;
         sp.seed_count = (int)(seed_rows / 32);
+        sp.sort_cap = std::max(sp.sort_cap, sp.seed_count);   // every seed entry is loaded
         CUDA_TRY(launch_compact_pool(sp, b, st));
         ix->launches++;
         // a threshold learnt from S rows lets through about 2.2 * k / S of the rows (group loss 1.13 x margin ~1.9)
@@ -964,6 +974,28 @@ int ann_merge_topk_device(int32_t device, const int64_t* d_ids, const float* d_d
     return ANN_OK;
 }
 
+int ann_exchange_merge_device(int32_t device, const void* const* peer_local, void* const* peer_final, int32_t world, int32_t b,
+                              int32_t k, int32_t q_begin, int32_t q_count, void* stream) {
+    if (world < 1 || world > kMaxPeers) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_exchange_merge_device: world must be in [1, 16]");
+    if (b < 0 || q_begin < 0 || q_count < 0 || (long long)q_begin + q_count > b)
+        return fail(ANN_ERR_INVALID_ARGUMENT, "ann_exchange_merge_device: query range outside the batch");
+    if (k < 0) return fail(ANN_ERR_NEGATIVE_K, "ann_exchange_merge_device: k < 0");
+    if (!peer_local || !peer_final) return fail(ANN_ERR_NULL_POINTER, "ann_exchange_merge_device: NULL pointer table");
+    if (b == 0 || k == 0 || q_count == 0) return ANN_OK;
+    if ((long long)(world + 1) * k * 12 > 200 * 1024) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_exchange_merge_device: (world + 1) * k too large");
+    PeerBlocks pb{};
+    for (int s = 0; s < world; ++s) {
+        if (!peer_local[s] || !peer_final[s]) return fail(ANN_ERR_NULL_POINTER, "ann_exchange_merge_device: NULL block pointer");
+        pb.local[s] = static_cast<const unsigned char*>(peer_local[s]);
+        pb.final_[s] = static_cast<unsigned char*>(peer_final[s]);
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(launch_exchange_merge(pb, world, b, k, q_begin, q_count, (cudaStream_t)stream));
+    return ANN_OK;
+}
+
+size_t ann_result_block_bytes(int32_t b, int32_t k) { return (b < 0 || k < 0) ? 0 : result_block_bytes(b, k); }
+
 int ann_set_option(ann_index* ix, const char* name, int64_t value) {
     if (!ix || !name) return fail(ANN_ERR_NULL_POINTER, "ann_set_option: NULL argument");
     std::lock_guard<std::mutex> lk(ix->mu);
@@ -981,6 +1013,20 @@ int ann_set_option(ann_index* ix, const char* name, int64_t value) {
     }
     if (!strcmp(name, "device_fallback")) {
         ix->device_fallback = value != 0;
+        return ANN_OK;
+    }
+    if (!strcmp(name, "gemm_hit_budget")) {
+        if (value < 100 || value > kGemmPoolCap / 2) return fail(ANN_ERR_INVALID_ARGUMENT, "gemm_hit_budget must be in [100, 2048]");
+        ix->gemm_hit_budget = (int)value;
+        return ANN_OK;
+    }
+    if (!strcmp(name, "gemm_small_select")) {
+        ix->gemm_small_select = value ? 1 : 0;
+        return ANN_OK;
+    }
+    if (!strcmp(name, "gemm_seed_rows")) {
+        if (value < 0) return fail(ANN_ERR_INVALID_ARGUMENT, "gemm_seed_rows must be >= 0");
+        ix->gemm_seed_rows = value;
         return ANN_OK;
     }
     if (!strcmp(name, "gemm_epi_warps")) {

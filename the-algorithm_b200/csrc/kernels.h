@@ -74,6 +74,8 @@ struct SelectParams {
     int pub_stride, pub_count, j_pub;
     int k;
     int seed_count;         // > 0: the pool holds exactly this many seed entries (group maxima); derive tau, discard them
+    int sort_cap, exact_cap;  // shared-memory capacities (entries) of the approximate and exact stages; 0 = 4096 / 2048.
+                              // exact_cap must be a power of two; exceeding either flags the query for the exact fallback
     // exact rescoring inputs
     const float* rows;
     const int64_t* ids;
@@ -96,6 +98,18 @@ cudaError_t launch_fill_empty(int64_t* out_ids, float* out_dist, int32_t* out_co
 // ---------------------------------------------------------------- K5: shard merge
 cudaError_t launch_merge(const int64_t* ids, const float* dist, const int32_t* count, int shards, int b, int k,
                          int64_t* out_ids, float* out_dist, int32_t* out_count, cudaStream_t stream);
+
+// K5b: the same merge fused with the exchange.  A "result block" for (b, k) is one allocation laid out
+//   [ids: b*k int64][dist: b*k float][count: b int32]        (result_block_bytes)
+// `local[s]` is rank s's block of per-shard results and `final_[s]` its block for the merged answer, both mapped into this
+// process (peer memory over NVLink).  This rank merges the queries [q_begin, q_begin + q_count) and writes them to every final block.
+constexpr int kMaxPeers = 16;
+struct PeerBlocks {
+    const unsigned char* local[kMaxPeers];
+    unsigned char* final_[kMaxPeers];
+};
+inline size_t result_block_bytes(long long b, long long k) { return (size_t)(b * k * 12 + b * 4); }
+cudaError_t launch_exchange_merge(const PeerBlocks& pb, int world, int b, int k, int q_begin, int q_count, cudaStream_t stream);
 
 // ---------------------------------------------------------------- exact fallback (degenerate ties, NaN queries)
 struct FallbackParams {

@@ -16,8 +16,10 @@ namespace b200ann {
 namespace {
 
 constexpr int kSelThreads = 256;
-constexpr int kSortCap = 4096;    // approximate-stage sort capacity per query
-constexpr int kExactCap = 2048;   // survivors + specials rescored exactly (power of two)
+constexpr int kSortCap = 4096;    // default approximate-stage capacity per query (SelectParams::sort_cap overrides)
+constexpr int kExactCap = 2048;   // default survivors + specials rescored exactly (power of two; SelectParams::exact_cap)
+__host__ __device__ inline int sort_cap_of(const SelectParams& p) { return p.sort_cap > 0 ? p.sort_cap : kSortCap; }
+__host__ __device__ inline int exact_cap_of(const SelectParams& p) { return p.exact_cap > 0 ? p.exact_cap : kExactCap; }
 
 __device__ __forceinline__ bool pair_greater(uint32_t ka, long long ia, uint32_t kb, long long ib) {
     return ka > kb || (ka == kb && ia > ib);
@@ -124,6 +126,7 @@ __device__ uint32_t kth_key_radix(const entry_t* buf, int n, int k, uint32_t* hi
 // Everything with g <= *tau_out may still belong to the exact top-k.  Returns false on overflow.
 __device__ bool load_and_threshold(const SelectParams& p, int q, entry_t* buf, uint32_t* hist, int* n_out, float* tau_out) {
     __shared__ int n_s;
+    const int sort_cap = sort_cap_of(p);
     QueryState* qs = p.qstate + q;
     const float eps_abs = qs->eps_abs, eps_rel = qs->eps_rel;
     const int pool_n = p.seed_count > 0 ? min(p.seed_count, p.pool_cap) : min((int)qs->pool_count, p.pool_cap);
@@ -142,12 +145,12 @@ __device__ bool load_and_threshold(const SelectParams& p, int q, entry_t* buf, u
         const float ge = entry_g(e);
         if (ge <= tau && ge < kSpecialG) {   // special rows scored -1e38 by the tensor-core filter are handled separately
             int slot = atomicAdd(&n_s, 1);
-            if (slot < kSortCap) buf[slot] = e;
+            if (slot < sort_cap) buf[slot] = e;
         }
     }
     __syncthreads();
     const int n = n_s;
-    if (n > kSortCap) {
+    if (n > sort_cap) {
         if (threadIdx.x == 0) atomicOr(&qs->flags, kFlagSurvivorOverflow);
         return false;
     }
@@ -201,9 +204,10 @@ __global__ void __launch_bounds__(kSelThreads, 4) compact_pool_kernel(SelectPara
 // ---- finalize: survivors + specials -> exact distances -> (distance, id) order -> outputs -------------------
 __global__ void __launch_bounds__(kSelThreads, 4) finalize_kernel(SelectParams p) {
     extern __shared__ __align__(16) unsigned char sm[];
-    entry_t* buf = reinterpret_cast<entry_t*>(sm);                       // kSortCap entries
-    long long* cid = reinterpret_cast<long long*>(sm + kSortCap * 8);      // kExactCap ids
-    uint32_t* ckey = reinterpret_cast<uint32_t*>(sm + kSortCap * 8 + kExactCap * 8);  // kExactCap keys
+    const int sort_cap = sort_cap_of(p), exact_cap = exact_cap_of(p);
+    entry_t* buf = reinterpret_cast<entry_t*>(sm);                       // sort_cap entries
+    long long* cid = reinterpret_cast<long long*>(sm + (size_t)sort_cap * 8);      // exact_cap ids
+    uint32_t* ckey = reinterpret_cast<uint32_t*>(sm + (size_t)sort_cap * 8 + (size_t)exact_cap * 8);  // exact_cap keys
     __shared__ uint32_t hist[256];
     __shared__ int n_cand_s;
     const int q = blockIdx.x;
@@ -251,11 +255,11 @@ __global__ void __launch_bounds__(kSelThreads, 4) finalize_kernel(SelectParams p
             row = spec_rows[i - n];
         }
         const int slot = atomicAdd(&n_cand_s, 1);
-        if (slot < kExactCap) crow[slot] = row;
+        if (slot < exact_cap) crow[slot] = row;
     }
     __syncthreads();
     const int n_cand = n_cand_s;
-    if (n_cand > kExactCap) {
+    if (n_cand > exact_cap) {
         if (threadIdx.x == 0) atomicOr(&qs->flags, kFlagSurvivorOverflow);
         fail_fill();
         return;
@@ -263,7 +267,7 @@ __global__ void __launch_bounds__(kSelThreads, 4) finalize_kernel(SelectParams p
     {
         // the query as doubles (and its squared norm) once per CTA, in the shared memory the approximate entries occupied
         double* q64 = reinterpret_cast<double*>(buf);                                  // <= 8 KB (dim <= 1024)
-        uint32_t* okey = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(buf) + 8192);   // kExactCap keys
+        uint32_t* okey = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(buf) + 8192);   // exact_cap keys (sort_cap * 8 >= 8192 + exact_cap * 4)
         __shared__ double nb_s;
         const float* qv = p.queries + (size_t)q * p.q_pitch;
         for (int i = threadIdx.x; i < p.dim; i += blockDim.x) q64[i] = (double)qv[i];
@@ -357,8 +361,84 @@ __global__ void __launch_bounds__(kSelThreads) merge_topk_kernel(const int64_t* 
     if (threadIdx.x == 0 && out_count) out_count[q] = cnt;
 }
 
+// ---- K5b: shard merge fused with its exchange over NVLink peer memory ------------------------------------------
+// Every rank keeps its local top-k of the whole batch in a "result block" (ids | distances | counts, see kernels.h) that
+// its peers have mapped.  Rank r owns the queries [q_begin, q_begin + q_count): one CTA per query PULLS that query's k
+// entries from each of the `world` blocks (P2P loads), merges them, and PUSHES the merged row into every rank's final
+// block (P2P stores).  So the all-gather and the merge are one kernel, each rank moves and merges only 1/world of the
+// batch, and no rank ever holds the world * b * k gathered lists.
+// The lists arrive sorted by (distance key, id), so the merge is rank counting instead of a sort: the final position of
+// entry j of list s is j + the number of entries of every other list that precede it (two binary searches' worth of
+// shared-memory probes), ties between lists broken by shard index.  No barriers after the load.
+__global__ void __launch_bounds__(kSelThreads) exchange_merge_kernel(PeerBlocks pb, int world, int b, int k, int q_begin) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    long long* lid = reinterpret_cast<long long*>(sm);                         // [world][k]
+    long long* oid = lid + (size_t)world * k;                                  // [k] merged ids
+    uint32_t* lkey = reinterpret_cast<uint32_t*>(oid + k);                     // [world][k]
+    uint32_t* okey = lkey + (size_t)world * k;                                 // [k] merged keys
+    __shared__ int cnt_s[kMaxPeers];
+    const int q = q_begin + blockIdx.x;
+    const size_t dist_off = (size_t)b * k * 8, cnt_off = (size_t)b * k * 12;
+    if (threadIdx.x < world) {
+        const int c = *reinterpret_cast<const int32_t*>(pb.local[threadIdx.x] + cnt_off + (size_t)q * 4);
+        cnt_s[threadIdx.x] = min(max(c, 0), k);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < world * k; i += blockDim.x) {
+        const int s = i / k, j = i - s * k;
+        if (j < cnt_s[s]) {
+            lid[i] = *reinterpret_cast<const long long*>(pb.local[s] + ((size_t)q * k + j) * 8);
+            lkey[i] = float_order_key(*reinterpret_cast<const float*>(pb.local[s] + dist_off + ((size_t)q * k + j) * 4));
+        }
+    }
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        oid[j] = -1;
+        okey[j] = float_order_key(INFINITY);
+    }
+    __syncthreads();
+    int total = 0;
+    for (int s = 0; s < world; ++s) total += cnt_s[s];
+    for (int i = threadIdx.x; i < world * k; i += blockDim.x) {
+        const int s = i / k, j = i - s * k;
+        if (j >= cnt_s[s]) continue;
+        const uint32_t key = lkey[i];
+        const long long id = lid[i];
+        int rank = j;
+        for (int t = 0; t < world && rank < k; ++t) {
+            if (t == s) continue;
+            // entries of list t that sort before (key, id, s): strictly smaller pairs, and equal pairs when t < s
+            const uint32_t* tk = lkey + (size_t)t * k;
+            const long long* ti = lid + (size_t)t * k;
+            int lo = 0, hi = cnt_s[t];
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const uint32_t mk = tk[mid];
+                const long long mi = ti[mid];
+                const bool before = mk < key || (mk == key && (mi < id || (mi == id && t < s)));
+                if (before) lo = mid + 1;
+                else hi = mid;
+            }
+            rank += lo;
+        }
+        if (rank < k) {
+            oid[rank] = id;
+            okey[rank] = key;
+        }
+    }
+    __syncthreads();
+    const int cnt = min(k, total);
+    for (int i = threadIdx.x; i < world * k; i += blockDim.x) {
+        const int p = i / k, j = i - p * k;
+        unsigned char* f = pb.final_[p];
+        *reinterpret_cast<long long*>(f + ((size_t)q * k + j) * 8) = oid[j];
+        *reinterpret_cast<float*>(f + dist_off + ((size_t)q * k + j) * 4) = float_from_order_key(okey[j]);
+    }
+    if (threadIdx.x < world) *reinterpret_cast<int32_t*>(pb.final_[threadIdx.x] + cnt_off + (size_t)q * 4) = cnt;
+    __threadfence_system();   // the peers read these rows after the next cross-rank barrier
+}
+
 cudaError_t launch_compact_pool(const SelectParams& p, int b, cudaStream_t stream) {
-    size_t smem = (size_t)kSortCap * 8;
+    size_t smem = (size_t)sort_cap_of(p) * 8;
     cudaError_t e = cudaFuncSetAttribute(compact_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     compact_pool_kernel<<<b, kSelThreads, smem, stream>>>(p);
@@ -366,7 +446,8 @@ cudaError_t launch_compact_pool(const SelectParams& p, int b, cudaStream_t strea
 }
 
 cudaError_t launch_finalize(const SelectParams& p, int b, cudaStream_t stream) {
-    size_t smem = (size_t)kSortCap * 8 + (size_t)kExactCap * 12;
+    size_t smem = (size_t)sort_cap_of(p) * 8 + (size_t)exact_cap_of(p) * 12;
+    if ((size_t)sort_cap_of(p) * 8 < 8192 + (size_t)exact_cap_of(p) * 4) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     finalize_kernel<<<b, kSelThreads, smem, stream>>>(p);
@@ -391,6 +472,16 @@ cudaError_t launch_merge(const int64_t* ids, const float* dist, const int32_t* c
     cudaError_t e = cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     merge_topk_kernel<<<b, kSelThreads, smem, stream>>>(ids, dist, count, shards, b, k, n2, out_ids, out_dist, out_count);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_exchange_merge(const PeerBlocks& pb, int world, int b, int k, int q_begin, int q_count, cudaStream_t stream) {
+    if (q_count <= 0) return cudaSuccess;
+    const size_t smem = (size_t)(world + 1) * k * 12;
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    exchange_merge_kernel<<<q_count, kSelThreads, smem, stream>>>(pb, world, b, k, q_begin);
     return cudaGetLastError();
 }
 

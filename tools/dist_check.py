@@ -4,7 +4,9 @@
 
 Rows are sharded contiguously across ranks, queries replicated, each rank answers locally through the C ABI
 (ann_query_batch_device), the per-rank top-k are all-gathered over NCCL and merged by the K5 kernel
-(ann_merge_topk_device).  Every rank must hold the single-shard answer of the CPU oracle, bit for bit."""
+(ann_merge_topk_device) -- and, second route, exchanged and merged by the fused peer-memory kernel
+(ann_exchange_merge_device, ann/exchange.py).  Every rank must hold the single-shard answer of the CPU oracle, bit for
+bit, by both routes; the two routes are also timed (CUDA events, max over ranks)."""
 import os
 import sys
 from pathlib import Path
@@ -21,6 +23,8 @@ _pkg.load()
 import oracle  # noqa: E402
 from the_algorithm_b200.ann.brute_force import BruteForceIndex, merge_topk_device  # noqa: E402
 from the_algorithm_b200.ann.common import Cosine, FuturePool, InnerProduct, L2  # noqa: E402
+from the_algorithm_b200.ann.distributed import ShardedBruteForceIndex  # noqa: E402
+from the_algorithm_b200.ann.exchange import PeerExchange  # noqa: E402
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -54,12 +58,105 @@ for metric, n, d, b, k in ((InnerProduct, 200_003, 200, 300, 100), (Cosine, 50_0
     wi, wd, wc = oracle.query_canonical(metric.ordinal, corpus, ids, q, k)
     ok = bool((mi.cpu().numpy() == wi).all() and (md.cpu().numpy().view(np.uint32) == wd.view(np.uint32)).all()
               and (mc.cpu().numpy() == wc).all())
-    t = torch.tensor([1 if ok else 0], device=dev)
+    # second route: the shard's results land in a peer-mapped block; one fused kernel exchanges and merges
+    px = PeerExchange(b, k, dev)
+    ok2 = True
+    for rep in range(3):   # repeated: the barriers must also protect block reuse
+        ix.query_batch_device(qd, k, *px.local.tensors, st)
+        fi, fd, fc = px.exchange_merge(st)
+        torch.cuda.synchronize()
+        ok2 &= bool((fi.cpu().numpy() == wi).all() and (fd.cpu().numpy().view(np.uint32) == wd.view(np.uint32)).all()
+                    and (fc.cpu().numpy() == wc).all())
+    ix.raise_pending_error()
+    # third: the host class that bench.py uses (route picked automatically; must be the fused one on this box)
+    sx = ShardedBruteForceIndex(ix, device=dev)
+    for rep in range(2):
+        si, sd, sc = sx.batch_query_device(qd, k, st)
+        torch.cuda.synchronize()
+        ok2 &= bool((si.cpu().numpy() == wi).all() and (sd.cpu().numpy().view(np.uint32) == wd.view(np.uint32)).all()
+                    and (sc.cpu().numpy() == wc).all())
+    ok2 &= sx.route == "fused"
+    del sx
+
+    def timed(fn, reps=20):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        tt = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    def route_nccl():
+        dist.all_gather_into_tensor(g_ids, oi)
+        dist.all_gather_into_tensor(g_dist, od)
+        dist.all_gather_into_tensor(g_cnt, oc)
+        merge_topk_device(g_ids, g_dist, g_cnt, k, st)
+
+    ms_nccl = timed(route_nccl)
+    ms_fused = timed(lambda: px.exchange_merge(st))
+    t = torch.tensor([1 if ok else 0, 1 if ok2 else 0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"{metric.name} n={n} d={d} b={b} k={k} world={world}: identical_to_single_shard_oracle={bool(t.item())}", flush=True)
-    ok_all &= bool(t.item())
+        print(f"{metric.name} n={n} d={d} b={b} k={k} world={world}: identical_to_single_shard_oracle={bool(t[0].item())} "
+              f"fused_exchange_merge_identical={bool(t[1].item())} all_gather+merge={ms_nccl * 1e3:.1f}us fused={ms_fused * 1e3:.1f}us",
+              flush=True)
+    ok_all &= bool(t[0].item()) and bool(t[1].item())
+    del px
     ix.close()
+# ---- the two merge routes at the headline result shape (4096 queries x top-100), synthetic sorted lists ----
+b, k = 4096, 100
+px = PeerExchange(b, k, dev)
+gen = torch.Generator(device=dev)
+gen.manual_seed(100 + rank)
+px.local.dist.copy_(torch.sort(torch.randn((b, k), generator=gen, device=dev), dim=1).values)
+px.local.ids.copy_(torch.randint(0, 1 << 40, (b, k), generator=gen, device=dev))
+px.local.count.fill_(k)
+g_ids = torch.empty((world, b, k), dtype=torch.int64, device=dev)
+g_dist = torch.empty((world, b, k), dtype=torch.float32, device=dev)
+g_cnt = torch.empty((world, b), dtype=torch.int32, device=dev)
+st = torch.cuda.current_stream().cuda_stream
+
+
+def route_nccl_big():
+    dist.all_gather_into_tensor(g_ids, px.local.ids)
+    dist.all_gather_into_tensor(g_dist, px.local.dist)
+    dist.all_gather_into_tensor(g_cnt, px.local.count)
+    return merge_topk_device(g_ids, g_dist, g_cnt, k, st)
+
+
+def timed_big(fn, reps=50):
+    for _ in range(5):
+        fn()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    tt = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    return float(tt.item())
+
+
+mi, md, mc = route_nccl_big()
+fi, fd, fc = px.exchange_merge(st)
+torch.cuda.synchronize()
+same = bool(torch.equal(mi, fi) and torch.equal(md.view(torch.int32), fd.view(torch.int32)) and torch.equal(mc, fc))
+tt = torch.tensor([1 if same else 0], device=dev)
+dist.all_reduce(tt, op=dist.ReduceOp.MIN)
+ms_a, ms_f = timed_big(route_nccl_big), timed_big(lambda: px.exchange_merge(st))
+if rank == 0:
+    print(f"b={b} k={k} world={world}: routes_identical={bool(tt.item())} all_gather+merge={ms_a * 1e3:.1f}us "
+          f"fused_exchange_merge={ms_f * 1e3:.1f}us", flush=True)
+ok_all &= bool(tt.item())
+del px
 dist.destroy_process_group()
 if rank == 0:
     print("DIST_OK", ok_all, flush=True)
