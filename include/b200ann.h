@@ -124,6 +124,17 @@ ANN_API int ann_exchange_merge_device(int32_t device, const void *const *peer_lo
                                       int32_t b, int32_t k, int32_t q_begin, int32_t q_count, void *stream);
 ANN_API size_t ann_result_block_bytes(int32_t b, int32_t k);
 
+/* KnnHelper.findNearestNeighbours (ann/src/main/scala/com/twitter/ann/scalding/offline/KnnHelper.scala:168-215, 248-347):
+ * the exact k nearest corpus rows of every query, host buffers in and out -- the offline all-pairs job behind
+ * KnnTruthSetGenerator.  The corpus is cut into tiles of corpus_tile_rows rows that fit the device (<= 0: as many as fit;
+ * one tile = one index = one of the reference's "search groups"), queries stream through in tiles of query_tile (<= 0: 4096)
+ * with the H2D copy of the next tile and the D2H copy of the previous one overlapped with the kernels of the current one, and
+ * per-corpus-tile lists are merged on the device in canonical (distance, id) order, so the answer equals one index over the
+ * whole corpus.  cfg gives metric / dim / device / flags.  out_ids / out_dist are [nq][k], out_count [nq] (may be NULL). */
+ANN_API int ann_knn_join(const ann_config *cfg, const int64_t *corpus_ids, const float *corpus_rows, int64_t n,
+                         const float *queries, int64_t nq, int32_t k, int64_t corpus_tile_rows, int32_t query_tile,
+                         int64_t *out_ids, float *out_dist, int32_t *out_count);
+
 /* Tuning / introspection.
  * Options: "path" (0 auto, 1 streaming scan, 2 tensor-core GEMM filter, 3 exact fallback for every query), "gemm_min_batch", "gemm_cta_group" (1|2), "gemm_epi_warps" (0 auto, 8, 16),
  *          "gemm_hit_budget" (candidates one chunk may add per query, default 500), "gemm_seed_rows" (0 = default 65536),

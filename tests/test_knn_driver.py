@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 import oracle
+from oracle import oracle_np as onp
 from the_algorithm_b200.ann.knn import (java_float_to_string, load_truth_set, nearest_neighbors_to_string, recall,
                                         write_truth_set)
 
@@ -52,6 +53,58 @@ def test_find_nearest_neighbours_matches_oracle_and_round_trips(tmp_path):
     truth = load_truth_set(p)
     assert all(truth[int(qids[j])] == oi[j].tolist() for j in range(700))
     assert recall(truth[0], oi[0].tolist(), 10) == 1.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("metric_name", ["L2", "Cosine", "InnerProduct"])
+@pytest.mark.parametrize("corpus_tile,query_tile", [(0, 4096), (7000, 256), (2999, 100), (30_000, 33)])
+def test_native_knn_join_matches_oracle(metric_name, corpus_tile, query_tile):
+    """ann_knn_join (KnnHelper.findNearestNeighbours in one native call): one or several corpus tiles merged on the
+    device, ragged query tiles through the double-buffered pipeline -- always the single-index answer, bit for bit."""
+    from the_algorithm_b200.ann.common import Metric
+    from the_algorithm_b200.ann.knn import knn_join
+
+    metric = Metric.from_string(metric_name)
+    rng = np.random.default_rng(8)
+    corpus = (rng.standard_normal((20_001, 48)) / 7).astype(np.float32)
+    corpus[15_000:15_040] = corpus[:40]                      # exact ties across corpus tiles
+    ids = rng.permutation(20_001).astype(np.int64) * 7 - 3
+    q = rng.uniform(-1, 1, (777, 48)).astype(np.float32)
+    gi, gd, gc = knn_join(q, ids, corpus, metric, 25, query_tile=query_tile, corpus_tile_rows=corpus_tile)
+    oi, od, oc = oracle.query_canonical(metric.ordinal, corpus, ids, q, 25)
+    assert (gc == oc).all() and (gi == oi).all()
+    assert (gd.view(np.uint32) == od.view(np.uint32)).all()
+
+
+@pytest.mark.gpu
+def test_native_knn_join_edge_cases_and_flagged_queries():
+    """k > rows of a corpus tile, k = 0, empty corpus, and queries the bounded selector cannot answer (a NaN query; a
+    corpus of identical rows where everything ties): those tiles are redone through the exact fallback."""
+    from the_algorithm_b200 import _capi
+    from the_algorithm_b200.ann.common import InnerProduct, L2
+    from the_algorithm_b200.ann.knn import knn_join
+
+    rng = np.random.default_rng(9)
+    corpus = rng.standard_normal((1500, 16)).astype(np.float32)
+    ids = np.arange(1500, dtype=np.int64)[::-1].copy()
+    q = rng.standard_normal((50, 16)).astype(np.float32)
+    q[7, 3] = np.nan
+    for ct in (0, 400):                                       # 400 rows per corpus tile < k: short per-tile lists
+        gi, gd, gc = knn_join(q, ids, corpus, L2, 600, query_tile=16, corpus_tile_rows=ct)
+        oi, od, oc = oracle.query_canonical(oracle.L2, corpus, ids, q, 600)
+        assert (gc == oc).all() and (gi == oi).all()
+        assert (onp.float_order_key(gd) == onp.float_order_key(od)).all()
+    gi, gd, gc = knn_join(q, ids, corpus, L2, 0)
+    assert gi.shape == (50, 0) and gc.tolist() == [0] * 50
+    gi, gd, gc = knn_join(q, ids[:0], corpus[:0], L2, 5)
+    assert (gi == -1).all() and np.isinf(gd).all() and gc.tolist() == [0] * 50
+    same = np.ones((30_000, 8), np.float32)                   # every row ties: far more than the selector holds
+    sid = rng.permutation(30_000).astype(np.int64)
+    gi, gd, gc = knn_join(np.ones((3, 8), np.float32), sid, same, InnerProduct, 10, corpus_tile_rows=12_000)
+    assert gi.tolist() == [list(range(10))] * 3 and gd.tolist() == [[-7.0] * 10] * 3 and gc.tolist() == [10] * 3
+    with pytest.raises(_capi.AnnError) as e:
+        knn_join(q, ids, corpus, L2, -1)
+    assert e.value.code == _capi.ANN_ERR_NEGATIVE_K
 
 
 @pytest.mark.gpu

@@ -80,6 +80,32 @@ def find_nearest_neighbours(query_ids: Sequence, query_embeddings, index_ids, in
             index.close()
 
 
+def knn_join(query_embeddings, index_ids, index_embeddings, metric: Metric, num_neighbors: int, *, device: int = 0,
+             query_tile: int = 4096, corpus_tile_rows: int = 0, l2_squared: bool = False):
+    """`ann_knn_join`: the whole job in ONE native call -- corpus tiles that fit the device, query tiles streaming through
+    with copies overlapped with the kernels, per-corpus-tile lists merged on the device.  Returns (ids [nq,k] int64,
+    distances [nq,k] float32, counts [nq] int32) with `index_ids` as given (int64).  `find_nearest_neighbours` above is the
+    same computation driven tile by tile from Python through an index object."""
+    import ctypes
+
+    from .. import _capi
+
+    q = np.ascontiguousarray(query_embeddings, dtype=np.float32)
+    rows = np.ascontiguousarray(index_embeddings, dtype=np.float32)
+    ids = np.ascontiguousarray(index_ids, dtype=np.int64)
+    if q.ndim != 2 or rows.ndim != 2 or (rows.shape[0] and rows.shape[1] != q.shape[1]) or ids.shape != (rows.shape[0],):
+        raise ValueError("knn_join: queries [nq, d], rows [n, d], ids [n] expected")
+    nq, k = q.shape[0], int(num_neighbors)
+    out_ids = np.empty((nq, max(k, 0)), np.int64)
+    out_dist = np.empty((nq, max(k, 0)), np.float32)
+    out_cnt = np.zeros((nq,), np.int32)
+    cfg = _capi.AnnConfig(metric.ordinal, q.shape[1], 0, device, _capi.ANN_FLAG_L2_SQUARED if l2_squared else 0)
+    p = lambda a: ctypes.c_void_p(a.ctypes.data)   # noqa: E731
+    _capi.check(_capi.lib().ann_knn_join(ctypes.byref(cfg), p(ids), p(rows), rows.shape[0], p(q), nq, k, corpus_tile_rows,
+                                         query_tile, p(out_ids), p(out_dist), p(out_cnt)))
+    return out_ids, out_dist, out_cnt
+
+
 def write_truth_set(path, results: Iterable[Tuple[object, Sequence[Tuple[object, float]]]]) -> int:
     """One TSV line per query, KnnTruthSetGenerator's output (`TypedText.tsv(knnOutputPath)`, :58-70).  Returns the line count."""
     path = Path(path)

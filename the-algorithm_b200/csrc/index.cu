@@ -35,6 +35,13 @@ int fail(int code, const std::string& msg) {
     return code;
 }
 
+}  // namespace
+
+// for the other translation units of the library (knn_join.cu): record the message ann_last_error() returns
+int b200ann::report_error(int code, const char* msg) { return fail(code, msg ? msg : ""); }
+
+namespace {
+
 #define CUDA_TRY(expr)                                                                                         \
     do {                                                                                                       \
         cudaError_t _e = (expr);                                                                               \
@@ -488,8 +495,9 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
         // a chunk is sized to add about kHitBudget candidates per query, so its hit density is budget / rows; above
         // ~1.5e-4 hits per score the epilogue is the bottleneck and wants 16 warps (same-process A/B, tools/ab_options.py:
         // 2.82 -> 2.52 ms per 4096-query batch over 1.25M rows; neutral at 10M rows where sparse chunks dominate)
+        // With a single resident query tile (b <= 256) the launch is HBM bound and 8 warps measured 8 % faster.
         g.epi_warps = ix->gemm_epi_warps ? ix->gemm_epi_warps
-                                         : ((!seed_mode && (double)(end - begin) * 1.5e-4 < (double)kHitBudget) ? 16 : 8);
+                                         : ((!seed_mode && b > 256 && (double)(end - begin) * 1.5e-4 < (double)kHitBudget) ? 16 : 8);
         g.nb_stages = gemm_row_stages(ix->kp, ix->smem_optin);
         g.sm_count = ix->sm_count;
         g.qstate = qs_base;

@@ -99,6 +99,9 @@ cudaError_t launch_fill_empty(int64_t* out_ids, float* out_dist, int32_t* out_co
 cudaError_t launch_merge(const int64_t* ids, const float* dist, const int32_t* count, int shards, int b, int k,
                          int64_t* out_ids, float* out_dist, int32_t* out_count, cudaStream_t stream);
 
+// sets the thread-local message behind ann_last_error() and returns `code` (index.cu)
+int report_error(int code, const char* msg);
+
 // K5b: the same merge fused with the exchange.  A "result block" for (b, k) is one allocation laid out
 //   [ids: b*k int64][dist: b*k float][count: b int32]        (result_block_bytes)
 // `local[s]` is rank s's block of per-shard results and `final_[s]` its block for the merged answer, both mapped into this

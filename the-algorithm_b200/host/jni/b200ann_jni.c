@@ -51,6 +51,17 @@ NATIVE(jint, queryBatch)(JNIEnv *env, jobject self, jlong handle, jobject querie
                            (int64_t *)addr(env, out_ids), (float *)addr(env, out_dist), (int32_t *)addr(env, out_count));
 }
 
+/* KnnHelper.findNearestNeighbours in one native call (ann_knn_join): host buffers in, host buffers out */
+NATIVE(jint, knnJoin)(JNIEnv *env, jobject self, jint metric, jint dim, jint device, jint flags, jobject corpus_ids,
+                      jobject corpus_rows, jlong n, jobject queries, jlong nq, jint k, jlong corpus_tile_rows, jint query_tile,
+                      jobject out_ids, jobject out_dist, jobject out_count) {
+    (void)self;
+    ann_config cfg = {metric, dim, 0, device, (uint32_t)flags};
+    return ann_knn_join(&cfg, (const int64_t *)addr(env, corpus_ids), (const float *)addr(env, corpus_rows), n,
+                        (const float *)addr(env, queries), nq, k, corpus_tile_rows, query_tile, (int64_t *)addr(env, out_ids),
+                        (float *)addr(env, out_dist), (int32_t *)addr(env, out_count));
+}
+
 NATIVE(jstring, lastError)(JNIEnv *env, jobject self) {
     (void)self;
     return (*env)->NewStringUTF(env, ann_last_error());

@@ -30,6 +30,10 @@ object B200AnnNative {
   @native def size(handle: Long): Long
   @native def queryBatch(handle: Long, queries: ByteBuffer, b: Int, dim: Int, k: Int,
     outIds: ByteBuffer, outDist: ByteBuffer, outCount: ByteBuffer): Int
+  // KnnHelper.findNearestNeighbours (scalding/offline/KnnHelper.scala:168-215) as one native job: ann_knn_join
+  @native def knnJoin(metric: Int, dim: Int, device: Int, flags: Int, corpusIds: ByteBuffer, corpusRows: ByteBuffer, n: Long,
+    queries: ByteBuffer, nq: Long, k: Int, corpusTileRows: Long, queryTile: Int,
+    outIds: ByteBuffer, outDist: ByteBuffer, outCount: ByteBuffer): Int
   @native def lastError(): String
 }
 
