@@ -1,12 +1,12 @@
 """BASELINE.json configs 3 and 5 on one B200 (run under gpurun; writes JSON lines to gpurun_out/).
 
-    python tools/config_runs.py latency   [--rows 10000000 --dim 128 --metric L2 --queries 1000]
+    python tests/checks/config_runs.py latency   [--rows 10000000 --dim 128 --metric L2 --queries 1000]
         config 3: single-query top-100, one query per call through the HOST entry point (H2D + scan + finalize + D2H +
         synchronise inside every call); p50 / p90 / p99 latency and the algorithmic scan GB/s they imply.
-    python tools/config_runs.py streaming [--rows 6250000 --appends 125000 --append-batch 512 --query-batch 256]
+    python tests/checks/config_runs.py streaming [--rows 6250000 --appends 125000 --append-batch 512 --query-batch 256]
         config 5 (one rank's share of 50M rows + 1M appends over 8 ranks): batched appends interleaved with batched
         queries; append rows/s, query QPS and a visibility check (a row appended before a query is found by it).
-    python tools/config_runs.py knnjoin   [--rows 2000000 --dim 200 --metric InnerProduct --queries 65536]
+    python tests/checks/config_runs.py knnjoin   [--rows 2000000 --dim 200 --metric InnerProduct --queries 65536]
         the offline all-pairs job (KnnHelper.findNearestNeighbours): ann_knn_join (one native call, copies overlapped with
         the kernels) against the same job as a loop of blocking ann_query_batch calls; both from host buffers, results equal.
 """
@@ -21,7 +21,7 @@ from pathlib import Path
 import numpy as np
 import torch
 
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 import _pkg  # noqa: E402
 

@@ -1,7 +1,7 @@
 """Developer check for the tcgen05 GEMM-filter path (run under gpurun, each invocation wrapped in `timeout`).
 
-    python tools/dev_check_gemm.py parity <cta_group>        small/medium parity against the CPU oracle
-    python tools/dev_check_gemm.py time <cta_group> [n] [b]  timing at the headline shape (10M x 200, b = 4096)
+    python tests/checks/dev_check_gemm.py parity <cta_group>        small/medium parity against the CPU oracle
+    python tests/checks/dev_check_gemm.py time <cta_group> [n] [b]  timing at the headline shape (10M x 200, b = 4096)
 """
 from __future__ import annotations
 
@@ -12,7 +12,7 @@ from pathlib import Path
 
 import numpy as np
 
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 import _pkg  # noqa: E402
 

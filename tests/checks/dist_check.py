@@ -1,6 +1,6 @@
 """Multi-GPU parity check, run under torchrun on R GPUs of one box:
 
-    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/checks/dist_check.py
 
 Rows are sharded contiguously across ranks, queries replicated, each rank answers locally through the C ABI
 (ann_query_batch_device), the per-rank top-k are all-gathered over NCCL and merged by the K5 kernel
@@ -15,7 +15,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-ROOT = Path(__file__).resolve().parents[1]
+ROOT = Path(__file__).resolve().parents[2]
 sys.path.insert(0, str(ROOT))
 import _pkg  # noqa: E402
 

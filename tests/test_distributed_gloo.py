@@ -2,7 +2,7 @@
 sharding, round-robin batch routing, replicated queries, all-gather of each rank's local top-k in the [shards][b][k]
 layout, canonical merge -> identical to the single-shard answer.  The two DEVICE calls (the shard's query and the merge
 kernel) are oracle-backed test doubles here (no GPU); everything between them is the product's ShardedBruteForceIndex.
-On B200s the same class runs ann_query_batch_device + the fused exchange/merge kernel (tools/dist_check.py, bench.py)."""
+On B200s the same class runs ann_query_batch_device + the fused exchange/merge kernel (tests/checks/dist_check.py, bench.py)."""
 import os
 import socket
 

@@ -13,7 +13,7 @@ rank sees the same batch), each rank answers over its rows, and the per-rank top
 
 Both give every rank the complete merged batch, ordered by (Float.compare(distance), id): with globally unique ids that
 is bit for bit the single-shard answer (tests/test_distributed_gloo.py on CPU with test doubles for the two device
-calls; tools/dist_check.py and bench.py --gpus N on GPUs).
+calls; tests/checks/dist_check.py and bench.py --gpus N on GPUs).
 """
 from __future__ import annotations
 
