@@ -124,6 +124,28 @@ ANN_API int ann_exchange_merge_device(int32_t device, const void *const *peer_lo
                                       int32_t b, int32_t k, int32_t q_begin, int32_t q_count, void *stream);
 ANN_API size_t ann_result_block_bytes(int32_t b, int32_t k);
 
+/* The shard-side half of ComposedQueryable.queryWithDistance's fan-out (ShardApi.scala:72-79) when the shards are GPUs of
+ * one box: ann_query_batch_device split in two so that the shards can share what they learn before the expensive part.
+ *   ann_query_seed_device   prepares the batch, scores a small prefix of this shard's rows and publishes, per query, k
+ *                           witnessed upper bounds on the exact distance key into d_seed_keys[b*k] (uint32; 0xFFFFFFFF =
+ *                           no bound: shard too small, or a batch this shard answers with its streaming scan);
+ *   -- the caller makes every shard's published keys visible to every shard (cross-rank barrier; the key arrays live in
+ *      peer-mapped memory, peer_seed_keys[s] is shard s's array as seen from this process) --
+ *   ann_query_finish_device takes the k-th smallest bound over all `world` shards as the batch's global threshold (at
+ *                           least k rows of the whole index are at least that near, so nothing farther can be in the
+ *                           global top-k), scores the shard against it and writes this shard's candidates for the global
+ *                           top-k: out_count[q] may be smaller than k even when the shard holds more than k rows.
+ * Merged with ann_exchange_merge_device / ann_merge_topk_device the lists give exactly the single-index answer.  With 8
+ * shards a shard's threshold is as tight as if it had scored 8x the prefix, which removes most of its candidate handling.
+ * The two calls must be issued in this order with the same (b, dim, k) and the same stream; any other query, append or
+ * update on the handle in between makes the finish call fail with ANN_ERR_INVALID_ARGUMENT (the scratch is shared).
+ * world = 0 or peer_seed_keys = NULL: no sharing (the finish call then completes an ordinary local query). */
+ANN_API int ann_query_seed_device(ann_index *ix, const float *d_queries, int32_t b, int32_t dim, int32_t k,
+                                  uint32_t *d_seed_keys, void *stream);
+ANN_API int ann_query_finish_device(ann_index *ix, const float *d_queries, int32_t b, int32_t dim, int32_t k,
+                                    const uint32_t *const *peer_seed_keys, int32_t world, int64_t *d_out_ids,
+                                    float *d_out_dist, int32_t *d_out_count, void *stream);
+
 /* KnnHelper.findNearestNeighbours (ann/src/main/scala/com/twitter/ann/scalding/offline/KnnHelper.scala:168-215, 248-347):
  * the exact k nearest corpus rows of every query, host buffers in and out -- the offline all-pairs job behind
  * KnnTruthSetGenerator.  The corpus is cut into tiles of corpus_tile_rows rows that fit the device (<= 0: as many as fit;

@@ -30,7 +30,7 @@ ANN_FLAG_NO_SHADOW = 0x2
 # every symbol include/b200ann.h declares (tests/test_capi_symbols.py checks header <-> library <-> this list)
 SYMBOLS = (
     "ann_create", "ann_destroy", "ann_append_batch", "ann_append_batch_device", "ann_update_batch", "ann_read_rows", "ann_size", "ann_query_batch",
-    "ann_query_batch_device", "ann_merge_topk_device", "ann_exchange_merge_device", "ann_result_block_bytes", "ann_knn_join", "ann_set_option", "ann_get_stat", "ann_last_error", "ann_version",
+    "ann_query_batch_device", "ann_merge_topk_device", "ann_exchange_merge_device", "ann_result_block_bytes", "ann_query_seed_device", "ann_query_finish_device", "ann_knn_join", "ann_set_option", "ann_get_stat", "ann_last_error", "ann_version",
 )
 
 
@@ -80,6 +80,10 @@ def lib() -> ctypes.CDLL:
         L.ann_merge_topk_device.argtypes = [i32, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]
         L.ann_exchange_merge_device.restype = ctypes.c_int
         L.ann_exchange_merge_device.argtypes = [i32, ctypes.POINTER(vp), ctypes.POINTER(vp), i32, i32, i32, i32, i32, vp]
+        L.ann_query_seed_device.restype = ctypes.c_int
+        L.ann_query_seed_device.argtypes = [vp, vp, i32, i32, i32, vp, vp]
+        L.ann_query_finish_device.restype = ctypes.c_int
+        L.ann_query_finish_device.argtypes = [vp, vp, i32, i32, i32, ctypes.POINTER(vp), i32, vp, vp, vp, vp]
         L.ann_result_block_bytes.restype = ctypes.c_size_t
         L.ann_result_block_bytes.argtypes = [i32, i32]
         L.ann_knn_join.restype = ctypes.c_int

@@ -258,6 +258,27 @@ class BruteForceIndex(Appendable, Queryable):
                 ctypes.c_void_p(out_ids_t.data_ptr()), ctypes.c_void_p(out_dist_t.data_ptr()),
                 None if out_count_t is None else ctypes.c_void_p(out_count_t.data_ptr()), ctypes.c_void_p(stream)))
 
+    def query_seed_device(self, queries_t, k: int, seed_keys_t, stream: int = 0) -> None:
+        """First half of a sharded query (`ann_query_seed_device`): prepare the batch, score a prefix of this shard and
+        publish k bounds per query into `seed_keys_t` ([b, k] int32/uint32 CUDA tensor, normally peer-mapped memory)."""
+        with self._lock:
+            self.flush()
+            _capi.check(_capi.lib().ann_query_seed_device(
+                self._h, ctypes.c_void_p(queries_t.data_ptr()), int(queries_t.shape[0]), int(queries_t.shape[1]), int(k),
+                ctypes.c_void_p(seed_keys_t.data_ptr()), ctypes.c_void_p(stream)))
+
+    def query_finish_device(self, queries_t, k: int, peer_seed_key_ptrs, out_ids_t, out_dist_t, out_count_t, stream: int = 0) -> None:
+        """Second half (`ann_query_finish_device`): `peer_seed_key_ptrs` are the device addresses of every shard's published
+        key array as mapped into this process (own shard included); the shard is scored against the global threshold they
+        imply and its candidates for the global top-k are written to the outputs (count may be < k)."""
+        world = len(peer_seed_key_ptrs)
+        arr = (ctypes.c_void_p * max(world, 1))(*[int(p) for p in peer_seed_key_ptrs])
+        with self._lock:
+            _capi.check(_capi.lib().ann_query_finish_device(
+                self._h, ctypes.c_void_p(queries_t.data_ptr()), int(queries_t.shape[0]), int(queries_t.shape[1]), int(k),
+                arr if world else None, world, ctypes.c_void_p(out_ids_t.data_ptr()), ctypes.c_void_p(out_dist_t.data_ptr()),
+                None if out_count_t is None else ctypes.c_void_p(out_count_t.data_ptr()), ctypes.c_void_p(stream)))
+
     def raise_pending_error(self) -> None:
         v = ctypes.c_int64()
         _capi.check(_capi.lib().ann_get_stat(self._h, b"pending_error", ctypes.byref(v)))

@@ -150,6 +150,17 @@ struct ann_index {
     long long kernel_launches_timed = 0;
     long long last_candidates = 0;
     long long launches = 0, last_path = 0, exact_fallback_queries = 0;
+    long long last_gemm_chunks = 0;   // chunk launches (seed excluded) of the last tensor-core query
+
+    // two-phase sharded query (ann_query_seed_device -> ann_query_finish_device): what the first phase left behind
+    struct SeedSession {
+        bool open = false;        // a seed call is waiting for its finish call
+        bool gemm = false;        // the batch is on the tensor-core path (prep done, scratch in place)
+        bool seeded = false;      // ... and a seed launch ran: this shard's bounds are published
+        bool clobbered = false;   // another call touched the scratch or the rows in between
+        int b = 0, k = 0;
+        long long seed_rows = 0;
+    } sess;
 };
 
 namespace {
@@ -219,6 +230,7 @@ int grow(ann_index* ix, long long need, cudaStream_t st) {
 
 // rows/ids already on the device (or staged there); place them and run K1
 int append_device_core(ann_index* ix, const int64_t* d_ids, const float* d_rows, long long n_new, cudaStream_t st) {
+    if (ix->sess.open) ix->sess.clobbered = true;   // new rows may raise the error bounds a pending two-phase query was prepared with
     int rc = grow(ix, ix->n + n_new, st);
     if (rc) return rc;
     float* dst = ix->rows + (size_t)ix->n * ix->pitch;
@@ -420,8 +432,12 @@ int query_scan(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
 
 // K3 flow: geometric row chunks, each scored by the tensor-core filter against the thresholds learnt from the rows
 // before it; an approximate compaction between chunks; one exact finalize at the end.
+// mode 0: the whole flow.  mode 1 / 2: the two halves of a sharded query -- 1 = prepare + seed launch + publish this
+// shard's bounds into `seed_keys_out`; 2 = take the global threshold from every shard's bounds (`peers`), then chunks +
+// finalize on the scratch mode 1 left in place.
 int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b, int k_eff, int k_out, int64_t* d_out_ids,
-               float* d_out_dist, int32_t* d_out_count, cudaStream_t st) {
+               float* d_out_dist, int32_t* d_out_count, cudaStream_t st, int mode = 0, uint32_t* seed_keys_out = nullptr,
+               const PeerSeedKeys* peers = nullptr, int world = 1) {
     const int b_pad = (b + 127) / 128 * 128;
     CUDA_TRY(ix->q_padded.ensure((size_t)b * ix->pitch));
     const int qkp = (ix->kp + 63) / 64 * 64;
@@ -446,8 +462,10 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
     pp.pub_keys = nullptr;
     pp.pub_stride = 0;
     pp.bad_queries = &ix->scalars->bad_queries;
-    CUDA_TRY(launch_prep_queries(pp, st));
-    ix->launches++;
+    if (mode != 2) {
+        CUDA_TRY(launch_prep_queries(pp, st));
+        ix->launches++;
+    }
 
     SelectParams fp{};
     if (ix->gemm_small_select) {   // pools on this path hold a few hundred entries; overflow still falls back exactly
@@ -547,22 +565,50 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
     // group maxima, >= 8 groups per neighbour up to k = 256) measured 1.6 % faster than 131072 on the 10M x 200 batch.
     long long seed_rows = std::min<long long>(ix->n / 256 * 256, std::min<long long>((long long)kGemmPoolCap * 32, std::max<long long>(65536, 256LL * k_eff)));
     if (ix->gemm_seed_rows > 0) seed_rows = std::min<long long>(seed_rows, ix->gemm_seed_rows / 256 * 256);
-    const bool use_seed = seed_rows >= 128LL * k_eff && seed_rows >= 4096;
+    bool use_seed = seed_rows >= 128LL * k_eff && seed_rows >= 4096;
+    if (mode == 2) {   // what phase 1 decided and did
+        use_seed = ix->sess.seeded;
+        seed_rows = ix->sess.seed_rows;
+    }
     // a chunk `growth` times the rows seen so far adds about (growth - 1) * 1.9 * k candidates per query
     int growth = (int)std::min<double>(8.0, std::max<double>(2.0, 1.0 + kHitBudget / (1.9 * std::max(1, k_eff))));
     long long begin = 0, end;
+    ix->last_gemm_chunks = 0;
     if (use_seed) {
-        int rc2 = gemm_launch(0, seed_rows, 1);
-        if (rc2) return rc2;
-        SelectParams sp = fp;
-        sp.seed_count = (int)(seed_rows / 32);
-        sp.sort_cap = std::max(sp.sort_cap, sp.seed_count);   // every seed entry is loaded
-        CUDA_TRY(launch_compact_pool(sp, b, st));
-        ix->launches++;
+        double seen = (double)seed_rows;   // rows the threshold has been learnt from
+        if (mode != 2) {
+            int rc2 = gemm_launch(0, seed_rows, 1);
+            if (rc2) return rc2;
+            SelectParams sp = fp;
+            sp.seed_count = (int)(seed_rows / 32);
+            sp.sort_cap = std::max(sp.sort_cap, sp.seed_count);   // every seed entry is loaded
+            sp.seed_keys_out = mode == 1 ? seed_keys_out : nullptr;
+            CUDA_TRY(launch_compact_pool(sp, b, st));
+            ix->launches++;
+        }
+        if (mode == 1) {
+            ix->sess.seeded = true;
+            ix->sess.seed_rows = seed_rows;
+            return ANN_OK;
+        }
+        if (mode == 2 && peers && world > 1) {
+            // K5c: the k-th best of the union of all shards' published bounds replaces this shard's own seed threshold:
+            // as tight as one seed over world * seed_rows rows, for the price of one seed launch per shard
+            CUDA_TRY(launch_seed_merge(*peers, world, qs_base, b, k_eff, st));
+            ix->launches++;
+            seen *= world;
+        }
         // a threshold learnt from S rows lets through about 2.2 * k / S of the rows (group loss 1.13 x margin ~1.9)
-        end = std::min<long long>(ix->n, std::max<long long>(seed_rows, (long long)((double)kHitBudget * seed_rows / (2.2 * k_eff))));
+        end = std::min<long long>(ix->n, std::max<long long>(seed_rows, (long long)((double)kHitBudget * seen / (2.2 * k_eff))));
         end = (end + 255) / 256 * 256;
+        if (mode == 2 && ix->n - end < end / 4) end = ix->n;   // no sliver of a last chunk behind a shard-sized first one
         if (end > ix->n) end = ix->n;
+    } else if (mode == 1) {
+        // too few rows to seed from: nothing to publish, phase 2 runs the unseeded schedule
+        CUDA_TRY(cudaMemsetAsync(seed_keys_out, 0xFF, (size_t)b * k_out * sizeof(uint32_t), st));
+        ix->sess.seeded = false;
+        ix->sess.seed_rows = 0;
+        return ANN_OK;
     } else {
         // no seed: the first chunk is scored with tau = +inf (every row is a candidate), so it must fit the pool
         end = std::min<long long>(ix->n, kGemmPoolCap / 2);
@@ -570,6 +616,7 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
     for (;;) {
         int rc2 = gemm_launch(begin, end, 0);
         if (rc2) return rc2;
+        ix->last_gemm_chunks++;
         if (end >= ix->n) break;
         CUDA_TRY(launch_compact_pool(fp, b, st));
         ix->launches++;
@@ -828,6 +875,7 @@ int ann_update_batch(ann_index* ix, const int64_t* slots, const float* rows, int
     int rc = set_device(ix);
     if (rc) return rc;
     cudaStream_t st = ix->stream;
+    if (ix->sess.open) ix->sess.clobbered = true;   // published bounds may have been witnessed by rows that no longer exist
     CUDA_TRY(ix->upd_rows.ensure((size_t)n * ix->dim));
     CUDA_TRY(ix->upd_slots.ensure((size_t)n));
     CUDA_TRY(cudaMemcpyAsync(ix->upd_rows.p, rows, (size_t)n * ix->dim * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -918,7 +966,88 @@ int ann_query_batch_device(ann_index* ix, const float* d_queries, int32_t b, int
     int rc = set_device(ix);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;  // NULL = the legacy default stream
+    if (ix->sess.open) ix->sess.clobbered = true;   // the per-query scratch of a pending two-phase query is overwritten
     rc = query_core(ix, d_queries, b, k, d_out_ids, d_out_dist, d_out_count, st);
+    if (rc == ANN_OK && ix->device_fallback) rc = resolve_flagged(ix, d_queries, b, k, d_out_ids, d_out_dist, d_out_count, st);
+    return rc;
+}
+
+// ---- two-phase sharded query: seed (publish this shard's bounds) -> [caller: cross-shard barrier] -> finish ----
+int ann_query_seed_device(ann_index* ix, const float* d_queries, int32_t b, int32_t dim, int32_t k, uint32_t* d_seed_keys,
+                          void* stream) {
+    if (!ix) return fail(ANN_ERR_NULL_POINTER, "ann_query_seed_device: index is NULL");
+    if (b < 0) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_query_seed_device: b < 0");
+    if (k < 0) return fail(ANN_ERR_NEGATIVE_K, "ann_query_seed_device: k < 0");
+    if (dim != ix->dim) return fail(ANN_ERR_DIMENSION_MISMATCH, "ann_query_seed_device: query dimension != index dimension");
+    if (b > 0 && (!d_queries || (k > 0 && !d_seed_keys))) return fail(ANN_ERR_NULL_POINTER, "ann_query_seed_device: NULL buffer");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    int rc = set_device(ix);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    ix->sess = ann_index::SeedSession{};
+    ix->sess.open = true;
+    ix->sess.b = b;
+    ix->sess.k = k;
+    if (b == 0 || k == 0) return ANN_OK;
+    const int k_eff = (int)std::min<long long>(k, ix->n);
+    constexpr int kMaxGemmBatch = 16384;
+    const bool gemm = ix->n > 0 && k_eff <= kMaxK && ix->path_opt != 3 && ix->path_opt != 1 && b <= kMaxGemmBatch &&
+                      gemm_eligible(ix, b, k_eff) && (ix->path_opt == 2 || b >= ix->gemm_min_batch);
+    if (!gemm) {   // scan / exact paths keep their own thresholds: nothing to publish, the finish call runs the whole query
+        CUDA_TRY(cudaMemsetAsync(d_seed_keys, 0xFF, (size_t)b * k * sizeof(uint32_t), st));
+        return ANN_OK;
+    }
+    ix->sess.gemm = true;
+    CUDA_TRY(ix->qstate.ensure((size_t)b));
+    rc = query_gemm(ix, ix->qstate.p, d_queries, b, k_eff, k, nullptr, nullptr, nullptr, st, 1, d_seed_keys);
+    if (rc) ix->sess = ann_index::SeedSession{};
+    return rc;
+}
+
+int ann_query_finish_device(ann_index* ix, const float* d_queries, int32_t b, int32_t dim, int32_t k,
+                            const uint32_t* const* peer_seed_keys, int32_t world, int64_t* d_out_ids, float* d_out_dist,
+                            int32_t* d_out_count, void* stream) {
+    if (!ix) return fail(ANN_ERR_NULL_POINTER, "ann_query_finish_device: index is NULL");
+    if (b < 0) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_query_finish_device: b < 0");
+    if (k < 0) return fail(ANN_ERR_NEGATIVE_K, "ann_query_finish_device: k < 0");
+    if (dim != ix->dim) return fail(ANN_ERR_DIMENSION_MISMATCH, "ann_query_finish_device: query dimension != index dimension");
+    if (world < 0 || world > kMaxPeers) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_query_finish_device: world must be in [0, 16]");
+    if (b > 0 && (!d_queries || (k > 0 && (!d_out_ids || !d_out_dist))))
+        return fail(ANN_ERR_NULL_POINTER, "ann_query_finish_device: NULL buffer");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    int rc = set_device(ix);
+    if (rc) return rc;
+    const ann_index::SeedSession sess = ix->sess;
+    if (!sess.open || sess.b != b || sess.k != k)
+        return fail(ANN_ERR_INVALID_ARGUMENT, "ann_query_finish_device: no pending ann_query_seed_device call with this (b, k)");
+    if (sess.clobbered) {
+        ix->sess.open = false;
+        return fail(ANN_ERR_INVALID_ARGUMENT,
+                    "ann_query_finish_device: another query, append or update ran on this index between the seed and finish calls");
+    }
+    if (b == 0) {
+        ix->sess.open = false;
+        return ANN_OK;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!sess.gemm) {
+        ix->sess.open = false;
+        rc = query_core(ix, d_queries, b, k, d_out_ids, d_out_dist, d_out_count, st);
+    } else {
+        PeerSeedKeys pk{};
+        int w = 0;
+        if (peer_seed_keys)
+            for (int s2 = 0; s2 < world; ++s2) {
+                if (!peer_seed_keys[s2]) {
+                    ix->sess.open = false;
+                    return fail(ANN_ERR_NULL_POINTER, "ann_query_finish_device: NULL seed-key pointer");
+                }
+                pk.keys[w++] = peer_seed_keys[s2];
+            }
+        const int k_eff = (int)std::min<long long>(k, ix->n);
+        rc = query_gemm(ix, ix->qstate.p, d_queries, b, k_eff, k, d_out_ids, d_out_dist, d_out_count, st, 2, nullptr, &pk, w);
+        ix->sess.open = false;
+    }
     if (rc == ANN_OK && ix->device_fallback) rc = resolve_flagged(ix, d_queries, b, k, d_out_ids, d_out_dist, d_out_count, st);
     return rc;
 }
@@ -935,6 +1064,7 @@ int ann_query_batch(ann_index* ix, const float* queries, int32_t b, int32_t dim,
     int rc = set_device(ix);
     if (rc) return rc;
     cudaStream_t st = ix->stream;
+    if (ix->sess.open) ix->sess.clobbered = true;
     const size_t nk = (size_t)b * (size_t)std::max(k, 1);
     CUDA_TRY(ix->q_in.ensure((size_t)b * ix->dim));
     CUDA_TRY(ix->out_ids.ensure(nk));
@@ -1078,6 +1208,7 @@ int ann_get_stat(const ann_index* ix, const char* name, int64_t* value) {
     }
     if (!strcmp(name, "launches")) *value = ix->launches;
     else if (!strcmp(name, "last_path")) *value = ix->last_path;
+    else if (!strcmp(name, "last_gemm_chunks")) *value = ix->last_gemm_chunks;
     else if (!strcmp(name, "exact_fallback_queries")) *value = ix->exact_fallback_queries;
     else if (!strcmp(name, "n_special")) *value = (int64_t)ix->n_special;
     else if (!strcmp(name, "row_bytes")) *value = (int64_t)ix->n * ix->pitch * 4;

@@ -74,6 +74,8 @@ struct SelectParams {
     int pub_stride, pub_count, j_pub;
     int k;
     int seed_count;         // > 0: the pool holds exactly this many seed entries (group maxima); derive tau, discard them
+    uint32_t* seed_keys_out;  // with seed_count: also publish, per query, the k best group maxima as upper bounds on exact
+                              // badness (order keys of g + eps, [b][k], 0xFFFFFFFF padded) for the other shards (K5c)
     int sort_cap, exact_cap;  // shared-memory capacities (entries) of the approximate and exact stages; 0 = 4096 / 2048.
                               // exact_cap must be a power of two; exceeding either flags the query for the exact fallback
     // exact rescoring inputs
@@ -113,6 +115,15 @@ struct PeerBlocks {
 };
 inline size_t result_block_bytes(long long b, long long k) { return (size_t)(b * k * 12 + b * 4); }
 cudaError_t launch_exchange_merge(const PeerBlocks& pb, int world, int b, int k, int q_begin, int q_count, cudaStream_t stream);
+
+// K5c: threshold seeding shared between the shards of one index.  Every shard publishes, per query, k witnessed upper
+// bounds on exact badness (SelectParams::seed_keys_out); the k-th smallest over the union of all shards' bounds is a bound
+// on the GLOBAL k-th best, so a shard may discard everything above it (+ its own error margin) even where its own rows
+// alone would not justify that.  `keys[s]` is shard s's [b][k] key array mapped into this process (peer memory).
+struct PeerSeedKeys {
+    const uint32_t* keys[kMaxPeers];
+};
+cudaError_t launch_seed_merge(const PeerSeedKeys& pk, int world, QueryState* qstate, int b, int k, cudaStream_t stream);
 
 // ---------------------------------------------------------------- exact fallback (degenerate ties, NaN queries)
 struct FallbackParams {

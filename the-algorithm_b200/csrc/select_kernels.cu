@@ -25,6 +25,12 @@ __device__ __forceinline__ bool pair_greater(uint32_t ka, long long ia, uint32_t
     return ka > kb || (ka == kb && ia > ib);
 }
 
+// One side of the margin, rounded up: g + eps.  A witness row's exact badness is at most its approximate g + eps; a
+// candidate's exact badness is at least its approximate g - eps.  widen() is both sides at once.
+__device__ __forceinline__ float widen_half_up(float g, float eps_abs, float eps_rel) {
+    return __fadd_ru(g, __fadd_ru(eps_abs, __fmul_ru(eps_rel, fabsf(g))));
+}
+
 __device__ void bitonic_sort_pairs(uint32_t* key, long long* id, int n2) {
     for (int k = 2; k <= n2; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -124,7 +130,8 @@ __device__ uint32_t kth_key_radix(const entry_t* buf, int n, int k, uint32_t* hi
 // Shared front end of compaction and finalize: load the pool entries that pass the current threshold into `buf`
 // (unsorted), find the k-th best approximate badness with a radix select, tighten the threshold to k-th + margin.
 // Everything with g <= *tau_out may still belong to the exact top-k.  Returns false on overflow.
-__device__ bool load_and_threshold(const SelectParams& p, int q, entry_t* buf, uint32_t* hist, int* n_out, float* tau_out) {
+__device__ bool load_and_threshold(const SelectParams& p, int q, entry_t* buf, uint32_t* hist, int* n_out, float* tau_out,
+                                   uint32_t* kth_key_out = nullptr) {
     __shared__ int n_s;
     const int sort_cap = sort_cap_of(p);
     QueryState* qs = p.qstate + q;
@@ -154,9 +161,11 @@ __device__ bool load_and_threshold(const SelectParams& p, int q, entry_t* buf, u
         if (threadIdx.x == 0) atomicOr(&qs->flags, kFlagSurvivorOverflow);
         return false;
     }
+    if (kth_key_out) *kth_key_out = 0xFFFFFFFFu;
     if (n >= p.k && p.k > 0) {
         const uint32_t kk = kth_key_radix(buf, n, p.k, hist);
         tau = fminf(tau, widen(float_from_order_key(kk), eps_abs, eps_rel));
+        if (kth_key_out) *kth_key_out = kk;
     }
     *n_out = n;
     *tau_out = tau;
@@ -179,8 +188,36 @@ __global__ void __launch_bounds__(kSelThreads, 4) compact_pool_kernel(SelectPara
     }
     int n;
     float tau;
-    if (!load_and_threshold(p, q, buf, hist, &n, &tau)) return;
+    uint32_t kk;
+    if (!load_and_threshold(p, q, buf, hist, &n, &tau, &kk)) {
+        if (p.seed_count > 0 && p.seed_keys_out)
+            for (int j = threadIdx.x; j < p.k; j += blockDim.x) p.seed_keys_out[(size_t)q * p.k + j] = 0xFFFFFFFFu;
+        return;
+    }
     if (p.seed_count > 0) {   // seed entries carry no row: keep only the threshold
+        if (p.seed_keys_out) {
+            // K5c publish: the k best group maxima, each widened to an upper bound on the exact badness of a real row of
+            // this shard (distinct groups => distinct rows).  Order does not matter to the consumer; entries equal to the
+            // k-th key all publish the same value, so the tail is simply filled with it.
+            uint32_t* out = p.seed_keys_out + (size_t)q * p.k;
+            const float ea = qs->eps_abs, er = qs->eps_rel;
+            if (threadIdx.x == 0) n_keep = 0;
+            __syncthreads();
+            if (kk != 0xFFFFFFFFu) {
+                for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                    const uint32_t key = (uint32_t)(buf[i] >> 32);
+                    if (key < kk) {
+                        const int slot = atomicAdd(&n_keep, 1);     // fewer than k entries are strictly below the k-th key
+                        out[slot] = float_order_key(widen_half_up(float_from_order_key(key), ea, er));
+                    }
+                }
+                __syncthreads();
+                const uint32_t fill = float_order_key(widen_half_up(float_from_order_key(kk), ea, er));
+                for (int j = n_keep + threadIdx.x; j < p.k; j += blockDim.x) out[j] = fill;
+            } else {
+                for (int j = threadIdx.x; j < p.k; j += blockDim.x) out[j] = 0xFFFFFFFFu;   // fewer than k groups: no bound
+            }
+        }
         if (threadIdx.x == 0) {
             qs->pool_count = 0;
             qs->tau_key = float_order_key(tau);
@@ -435,6 +472,39 @@ __global__ void __launch_bounds__(kSelThreads) exchange_merge_kernel(PeerBlocks 
     }
     if (threadIdx.x < world) *reinterpret_cast<int32_t*>(pb.final_[threadIdx.x] + cnt_off + (size_t)q * 4) = cnt;
     __threadfence_system();   // the peers read these rows after the next cross-rank barrier
+}
+
+// ---- K5c: global threshold from every shard's published seed bounds -------------------------------------------------
+// One CTA per query: pull the k published bounds of each of the `world` shards (P2P loads, k*4 bytes each), take the
+// k-th smallest U of the union -- at least k distinct rows of the whole index have exact badness <= U, so the global
+// k-th best is <= U -- and tighten this shard's threshold to U + eps (this shard's own error margin for its candidates).
+__global__ void __launch_bounds__(kSelThreads) seed_merge_kernel(PeerSeedKeys pk, int world, QueryState* qstate, int k) {
+    extern __shared__ __align__(16) unsigned char sm[];
+    uint32_t* keys = reinterpret_cast<uint32_t*>(sm);   // [world][k]
+    const int q = blockIdx.x;
+    const int total = world * k;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int s = i / k, j = i - s * k;
+        keys[i] = __ldcg(pk.keys[s] + (size_t)q * k + j);
+    }
+    __syncthreads();
+    const uint32_t u = cta_kth_smallest_key(keys, total, k, nullptr);   // pads are 0xFFFFFFFF: fewer than k bounds => no bound
+    if (threadIdx.x == 0 && u < 0xFF800000u) {
+        QueryState* qs = qstate + q;
+        const float tau_g = widen_half_up(float_from_order_key(u), qs->eps_abs, qs->eps_rel);
+        const uint32_t tg = float_order_key(tau_g);
+        if (tg < qs->tau_key) qs->tau_key = tg;
+    }
+}
+
+cudaError_t launch_seed_merge(const PeerSeedKeys& pk, int world, QueryState* qstate, int b, int k, cudaStream_t stream) {
+    if (b <= 0 || k <= 0 || world <= 0) return cudaSuccess;
+    const size_t smem = (size_t)world * k * 4;
+    if (smem > 200 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(seed_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    seed_merge_kernel<<<b, kSelThreads, smem, stream>>>(pk, world, qstate, k);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_compact_pool(const SelectParams& p, int b, cudaStream_t stream) {
