@@ -134,7 +134,10 @@ ANN_API size_t ann_result_block_bytes(int32_t b, int32_t k);
  *   ann_query_finish_device takes the k-th smallest bound over all `world` shards as the batch's global threshold (at
  *                           least k rows of the whole index are at least that near, so nothing farther can be in the
  *                           global top-k), scores the shard against it and writes this shard's candidates for the global
- *                           top-k: out_count[q] may be smaller than k even when the shard holds more than k rows.
+ *                           top-k: every row of the shard that can belong to it, with exact distances, in canonical order.
+ *                           The list is NOT necessarily the shard's own exact top-k (rows beyond the global threshold may
+ *                           be missing while rows just inside its error margin are present) and out_count[q] may be
+ *                           smaller than k even when the shard holds more than k rows.
  * Merged with ann_exchange_merge_device / ann_merge_topk_device the lists give exactly the single-index answer.  With 8
  * shards a shard's threshold is as tight as if it had scored 8x the prefix, which removes most of its candidate handling.
  * The two calls must be issued in this order with the same (b, dim, k) and the same stream; any other query, append or

@@ -75,7 +75,16 @@ for metric, n, d, b, k in ((InnerProduct, 200_003, 200, 300, 100), (Cosine, 50_0
         torch.cuda.synchronize()
         ok2 &= bool((si.cpu().numpy() == wi).all() and (sd.cpu().numpy().view(np.uint32) == wd.view(np.uint32)).all()
                     and (sc.cpu().numpy() == wc).all())
-    ok2 &= sx.route == "fused"
+    ok2 &= sx.route == "fused" and sx.share_seeds
+    del sx
+    # fourth: the same class on the collective route (seed bounds all-gathered over NCCL, lists all-gathered, K5 merge)
+    sx = ShardedBruteForceIndex(ix, device=dev, route="allgather")
+    for rep in range(2):
+        si, sd, sc = sx.batch_query_device(qd, k, st)
+        torch.cuda.synchronize()
+        ok2 &= bool((si.cpu().numpy() == wi).all() and (sd.cpu().numpy().view(np.uint32) == wd.view(np.uint32)).all()
+                    and (sc.cpu().numpy() == wc).all())
+    ix.raise_pending_error()
     del sx
 
     def timed(fn, reps=20):

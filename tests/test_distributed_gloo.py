@@ -43,6 +43,50 @@ class _OracleShard:
         out_count.copy_(torch.from_numpy(lc))
 
 
+def _order_keys(d):
+    """Float.compare as unsigned keys (Metric.scala:17-36), vectorised: the domain the shards publish bounds in."""
+    bits = np.ascontiguousarray(d, np.float32).view(np.uint32)
+    keys = np.where(bits & 0x80000000, ~bits, bits | 0x80000000).astype(np.uint32)
+    return np.where(np.isnan(d), np.uint32(0xFFFFFFFF), keys)
+
+
+class _OracleShardTwoPhase(_OracleShard):
+    """Test double for the two-phase shard query (ann_query_seed_device / ann_query_finish_device): the seed call publishes
+    the k best exact distance keys of the shard's first PREFIX rows, the finish call returns the shard's top-k cut at the
+    k-th smallest key of ALL shards' published bounds -- lists shorter than k, exactly what the CUDA engine hands the merge."""
+    PREFIX = 200
+
+    def _all(self, d):
+        ids = np.concatenate(self.ids) if self.ids else np.zeros((0,), np.int64)
+        rows = np.concatenate(self.rows) if self.rows else np.zeros((0, d), np.float32)
+        return ids, rows
+
+    def query_seed_device(self, queries, k, seed_keys, stream=0):
+        ids, rows = self._all(queries.shape[1])
+        _, ld, lc = oracle.query_canonical(self.metric, rows[:self.PREFIX], ids[:self.PREFIX], queries.numpy(), k)
+        keys = _order_keys(ld)
+        keys[np.arange(k)[None, :] >= lc[:, None]] = 0xFFFFFFFF          # fewer than k rows in the prefix: no bound
+        seed_keys.copy_(torch.from_numpy(keys.view(np.int32)))
+        self.pending = (int(queries.shape[0]), k)
+
+    def query_finish_device(self, queries, k, peer_seed_key_ptrs, out_ids, out_dist, out_count, stream=0):
+        import ctypes
+        b = int(queries.shape[0])
+        assert self.pending == (b, k)
+        every = np.stack([np.frombuffer((ctypes.c_uint32 * (b * k)).from_address(int(p)), np.uint32).reshape(b, k)
+                          for p in peer_seed_key_ptrs])                   # [world, b, k]
+        bound = np.sort(every.transpose(1, 0, 2).reshape(b, -1), axis=1)[:, k - 1]   # k-th smallest of the union, per query
+        ids, rows = self._all(queries.shape[1])
+        li, ld, lc = oracle.query_canonical(self.metric, rows, ids, queries.numpy(), k)
+        keep = (_order_keys(ld) <= bound[:, None]) & (np.arange(k)[None, :] < lc[:, None])
+        lc = keep.sum(axis=1).astype(np.int32)                            # lists are sorted: the kept entries are a prefix
+        li[~keep], ld[~keep] = -1, np.inf
+        self.cut = int((lc < k).sum())
+        out_ids.copy_(torch.from_numpy(li))
+        out_dist.copy_(torch.from_numpy(ld))
+        out_count.copy_(torch.from_numpy(lc))
+
+
 def _oracle_merge(g_ids, g_dist, g_cnt, k, stream=0):
     """Test double for merge_topk_device: [S,b,k] -> [b,k] through oracle.merge."""
     b = g_ids.shape[1]
@@ -52,7 +96,7 @@ def _oracle_merge(g_ids, g_dist, g_cnt, k, stream=0):
     return torch.from_numpy(oi), torch.from_numpy(od), torch.from_numpy(oc)
 
 
-def _worker(rank, world, port, metric, n, d, b, k, routed, ret):
+def _worker(rank, world, port, metric, n, d, b, k, routed, ret, two_phase=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -65,7 +109,7 @@ def _worker(rank, world, port, metric, n, d, b, k, routed, ret):
         corpus[n // 2: n // 2 + 5] = corpus[:5]              # ties across the shard boundary
         ids = rng.permutation(n).astype(np.int64)
         q = rng.uniform(-1, 1, (b, d)).astype(np.float32)
-        sx = ShardedBruteForceIndex(_OracleShard(metric), merge=_oracle_merge)
+        sx = ShardedBruteForceIndex(_OracleShardTwoPhase(metric) if two_phase else _OracleShard(metric), merge=_oracle_merge)
         assert (sx.rank, sx.world, sx.route) == (rank, world, "allgather")
         if routed:                                            # streaming appends: batches of 100 rows, round-robin
             kept = 0
@@ -81,6 +125,10 @@ def _worker(rank, world, port, metric, n, d, b, k, routed, ret):
             wi, wd, wc = oracle.query_canonical(metric, corpus, ids, q, k)
             ok &= bool((oi.numpy() == wi).all() and (od.numpy().view(np.uint32) == wd.view(np.uint32)).all()
                        and (oc.numpy() == wc).all())
+        if two_phase:   # the global bound really shortened some per-shard lists (otherwise the test proves nothing new)
+            c = torch.tensor([sx.local.cut])
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+            ok &= int(c.item()) > 0
         t = torch.tensor([1 if ok else 0])
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         if rank == 0:
@@ -96,6 +144,21 @@ def test_two_rank_shard_merge_equals_single_shard(metric, routed):
     ret = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, metric, 1001, 24, 5, 16, routed, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert ret.get(timeout=5) == 1
+
+
+@pytest.mark.parametrize("metric", [oracle.L2, oracle.INNER_PRODUCT])
+def test_two_rank_shared_seed_thresholds_equal_single_shard(metric):
+    """The two-phase shard query: seeds published, all-gathered, every shard cut at the global bound, merged."""
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, metric, 1001, 24, 5, 16, False, ret, True)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:

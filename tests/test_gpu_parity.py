@@ -427,6 +427,145 @@ def test_fused_exchange_merge_kernel_matches_oracle_merge(world, b, k):
             assert (onp.float_order_key(od[qi]) == onp.float_order_key(ed)).all()
 
 
+def _two_phase(shards, q_t, k, stream):
+    """seed on every shard -> (same stream, so no barrier needed) -> finish on every shard against all published bounds"""
+    import torch
+
+    b = q_t.shape[0]
+    dev = q_t.device
+    keys = torch.empty((len(shards), b, k), dtype=torch.int32, device=dev)
+    g_ids = torch.empty((len(shards), b, k), dtype=torch.int64, device=dev)
+    g_dist = torch.empty((len(shards), b, k), dtype=torch.float32, device=dev)
+    g_cnt = torch.empty((len(shards), b), dtype=torch.int32, device=dev)
+    for s, ix in enumerate(shards):
+        ix.query_seed_device(q_t, k, keys[s], stream)
+    ptrs = [keys[s].data_ptr() for s in range(len(shards))]
+    for s, ix in enumerate(shards):
+        ix.query_finish_device(q_t, k, ptrs, g_ids[s], g_dist[s], g_cnt[s], stream)
+    return keys, g_ids, g_dist, g_cnt
+
+
+@pytest.mark.parametrize("mi", [0, 1, 2])
+@pytest.mark.parametrize("n_shards,n_per,b", [(2, 70_001, 130), (8, 160_000, 64)])
+def test_two_phase_sharded_query_shares_seed_thresholds(mi, n_shards, n_per, b):
+    """ann_query_seed_device / ann_query_finish_device over the shards of one index (all on one GPU here): every shard
+    publishes k bounds from its seed launch, every shard is scored against the k-th best bound of ALL shards, and the
+    merged lists equal the single-index oracle answer bit for bit although the per-shard lists are cut short."""
+    import torch
+
+    metric = metrics()[mi]
+    n, d, k = n_shards * n_per, 32, 100
+    corpus, ids, q = make(n, d, b, seed=500 + n_shards, dup=True)
+    pool = G["FuturePool"].immediate_pool()
+    shards = []
+    for s in range(n_shards):
+        ix = G["BruteForceIndex"].apply(metric, pool)
+        ix.append_batch(ids[s * n_per:(s + 1) * n_per], corpus[s * n_per:(s + 1) * n_per])
+        shards.append(ix)
+    dev = torch.device("cuda", 0)
+    q_t = torch.from_numpy(q).to(dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(2):   # the scratch and the key arrays are reused by the next batch
+        keys, g_ids, g_dist, g_cnt = _two_phase(shards, q_t, k, stream)
+        mi_, md_, mc_ = G["merge_topk_device"](g_ids, g_dist, g_cnt, k)
+        torch.cuda.synchronize()
+        for ix in shards:
+            ix.raise_pending_error()
+            assert ix.stat("last_path") == 2
+        oi, od, oc = oracle.query_canonical(metric.ordinal, corpus, ids, q, k)
+        assert (mc_.cpu().numpy() == oc).all()
+        assert (mi_.cpu().numpy() == oi).all()
+        assert (md_.cpu().numpy().view(np.uint32) == od.view(np.uint32)).all()
+    kk = keys.cpu().numpy().view(np.uint32)
+    assert (kk < 0xFF800000).all()                       # every shard seeded and published finite bounds
+    cnt = g_cnt.cpu().numpy()
+    assert (cnt <= k).all() and (cnt >= 0).all()
+    assert (cnt.sum(axis=0) >= k).all()                  # together the lists always cover the global top-k
+    # What one shard returns: real rows of ITS range with their exact distances, in canonical order, and among them every
+    # row of the shard that belongs to the global answer.  (Not necessarily the shard's own exact top-k: rows beyond the
+    # global bound may be missing while rows just inside its error margin are present.)
+    s0 = 0
+    li, ld, lc = oracle.query_canonical(metric.ordinal, corpus[:n_per], ids[:n_per], q, 4 * k)
+    gi0, gd0 = g_ids[s0].cpu().numpy(), g_dist[s0].cpu().numpy()
+    mine = set(ids[:n_per].tolist())
+    for qi in range(b):
+        c = cnt[s0, qi]
+        exact = dict(zip(li[qi, :lc[qi]].tolist(), ld[qi, :lc[qi]].view(np.uint32).tolist()))
+        got_ids = gi0[qi, :c].tolist()
+        assert len(set(got_ids)) == c and (gi0[qi, c:] == -1).all()
+        assert all(exact.get(i) == db for i, db in zip(got_ids, gd0[qi, :c].view(np.uint32).tolist()))
+        keys_q = list(zip(onp.float_order_key(gd0[qi, :c]).tolist(), got_ids))
+        assert keys_q == sorted(keys_q)
+        assert [i for i in oi[qi].tolist() if i in mine] == [i for i in got_ids if i in set(oi[qi].tolist())]
+    # sharing is worth something: one shard alone needs more chunk launches than with everyone's bounds
+    if n_shards == 8:
+        with_sharing = shards[0].stat("last_gemm_chunks")
+        o = [torch.empty((b, k), dtype=torch.int64, device=dev), torch.empty((b, k), dtype=torch.float32, device=dev),
+             torch.empty((b,), dtype=torch.int32, device=dev)]
+        shards[0].query_batch_device(q_t, k, *o, stream)
+        torch.cuda.synchronize()
+        assert with_sharing == 1 and shards[0].stat("last_gemm_chunks") == 2
+    for ix in shards:
+        ix.close()
+
+
+def test_two_phase_query_session_rules_and_unseeded_paths():
+    import torch
+
+    AnnError = G["_capi"].AnnError
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.current_stream().cuda_stream
+    pool = G["FuturePool"].immediate_pool()
+    k = 10
+    corpus, ids, q = make(3000, 24, 40, seed=77)
+    ix = G["BruteForceIndex"].apply(G["L2"], pool)
+    ix.append_batch(ids, corpus)
+    q_t = torch.from_numpy(q).to(dev)
+    outs = lambda b: (torch.empty((b, k), dtype=torch.int64, device=dev), torch.empty((b, k), dtype=torch.float32, device=dev),
+                      torch.empty((b,), dtype=torch.int32, device=dev))
+    keys = torch.zeros((40, k), dtype=torch.int32, device=dev)
+    want = oracle.query_canonical(0, corpus, ids, q, k)
+
+    def same(o, w, b=None):
+        torch.cuda.synchronize()
+        return all((x.cpu().numpy()[:b] == y[:b]).all() for x, y in zip(o, w))
+
+    # a shard too small to seed (3000 rows): nothing published, finish is the ordinary tensor-core query
+    o = outs(40)
+    ix.query_seed_device(q_t, k, keys, stream)
+    ix.query_finish_device(q_t, k, [keys.data_ptr()], *o, stream)
+    assert same(o, want) and (keys.cpu().numpy() == -1).all() and ix.stat("last_path") == 2
+    # a single query goes through the streaming scan: same contract
+    o = outs(1)
+    ix.query_seed_device(q_t[:1], k, keys, stream)
+    ix.query_finish_device(q_t[:1], k, [keys.data_ptr()], *o, stream)
+    assert same(o, want, 1) and ix.stat("last_path") == 1
+    # no sharing requested (world = 0)
+    o = outs(40)
+    ix.query_seed_device(q_t, k, keys, stream)
+    ix.query_finish_device(q_t, k, [], *o, stream)
+    assert same(o, want)
+    # finish without seed, with another shape, or after something else used the handle in between: refused
+    with pytest.raises(AnnError) as e:
+        ix.query_finish_device(q_t, k, [keys.data_ptr()], *o, stream)
+    assert e.value.code == G["_capi"].ANN_ERR_INVALID_ARGUMENT
+    ix.query_seed_device(q_t, k, keys, stream)
+    with pytest.raises(AnnError):
+        ix.query_finish_device(q_t[:7], k, [keys.data_ptr()], *outs(7), stream)
+    ix.query_seed_device(q_t, k, keys, stream)
+    ix.query_batch_device(q_t, k, *o, stream)
+    with pytest.raises(AnnError):
+        ix.query_finish_device(q_t, k, [keys.data_ptr()], *o, stream)
+    ix.query_seed_device(q_t, k, keys, stream)
+    ix.append_batch(ids[:5] + 10**6, corpus[:5])
+    with pytest.raises(AnnError):
+        ix.query_finish_device(q_t, k, [keys.data_ptr()], *o, stream)
+    # and the handle is still good afterwards
+    ix.query_seed_device(q_t, 0, keys, stream)
+    ix.query_finish_device(q_t, 0, [keys.data_ptr()], *o, stream)
+    ix.close()
+
+
 # ------------------------------------------------------------------------------------------------ full-size properties
 def test_full_size_properties_10m_rows():
     """At BASELINE's full size the oracle is too slow, so check size-independent properties on a 10M x 128 L2 index:

@@ -8,6 +8,10 @@ rank sees the same batch), each rank answers over its rows, and the per-rank top
   route "fused"     -- the default on GPUs that can map each other's memory: the shard's results land in a peer-mapped
                        result block and ONE kernel (`ann_exchange_merge_device`, ann/exchange.py) pulls this rank's slice
                        of the batch from every peer over NVLink, merges it and pushes the merged rows to every peer.
+                       With `share_seeds` (default) the local query is the two-phase one: every shard first publishes k
+                       bounds per query learnt from a short prefix of its rows (`ann_query_seed_device`), and after one
+                       barrier scores its rows against the k-th best bound of ALL shards (`ann_query_finish_device`) -- a
+                       threshold as tight as one shard would get from `world` times the prefix.
   route "allgather" -- `all_gather` of the three result arrays in the [shards][b][k] layout (NCCL; gloo on CPU) followed
                        by the merge kernel (`ann_merge_topk_device`) over the whole batch on every rank.
 
@@ -36,7 +40,8 @@ class ShardedBruteForceIndex:
     `query_batch_device(queries, k, out_ids, out_dist, out_count, stream)`); `merge` is the [S,b,k] merge used by the
     all-gather route (default: the CUDA merge kernel)."""
 
-    def __init__(self, local, group=None, route: str = "auto", merge: Optional[Callable] = None, device=None):
+    def __init__(self, local, group=None, route: str = "auto", merge: Optional[Callable] = None, device=None,
+                 share_seeds: bool = True):
         import torch
         import torch.distributed as dist
 
@@ -46,9 +51,11 @@ class ShardedBruteForceIndex:
         self.world = dist.get_world_size(self.group)
         self.device = torch.device(device) if device is not None else torch.device("cpu")
         self._merge = merge
+        self.share_seeds = share_seeds   # fused route: two-phase local query around a cross-shard threshold exchange
         self._px = {}          # (b, k) -> PeerExchange
         self._gather = {}      # (b, k) -> gathered buffers
         self._own = {}         # (b, k) -> this rank's result arrays (all-gather route)
+        self._seeds = {}       # (b, k) -> (this rank's published seed bounds, everyone's) (all-gather route)
         self._appended_batches = 0
         if route not in ("auto", "fused", "allgather"):
             raise ValueError(f"route must be auto, fused or allgather, not {route!r}")
@@ -93,7 +100,13 @@ class ShardedBruteForceIndex:
             except Exception as e:   # the ranks cannot map each other's memory: keep the collective route
                 self.route, self.route_note = "allgather", f"peer mapping unavailable: {type(e).__name__}: {e}"
             else:
-                self.local.query_batch_device(queries, k, px.local.ids, px.local.dist, px.local.count, stream)
+                if self.share_seeds and hasattr(self.local, "query_seed_device"):
+                    # the shards pool what a short prefix of each taught them: one global threshold instead of `world` local ones
+                    self.local.query_seed_device(queries, k, px.seed_keys, stream)
+                    px.seed_barrier()
+                    self.local.query_finish_device(queries, k, px.seed_ptrs, px.local.ids, px.local.dist, px.local.count, stream)
+                else:
+                    self.local.query_batch_device(queries, k, px.local.ids, px.local.dist, px.local.count, stream)
                 return px.exchange_merge(stream)
         key = (b, k)
         if key not in self._own:
@@ -104,7 +117,19 @@ class ShardedBruteForceIndex:
                                  torch.empty((self.world, b, k), dtype=torch.float32, device=dev),
                                  torch.empty((self.world, b), dtype=torch.int32, device=dev))
         own, gathered = self._own[key], self._gather[key]
-        self.local.query_batch_device(queries, k, own[0], own[1], own[2], stream)
+        if self.share_seeds and hasattr(self.local, "query_seed_device"):
+            if key not in self._seeds:
+                self._seeds[key] = (torch.empty((b, k), dtype=torch.int32, device=self.device),
+                                    torch.empty((self.world, b, k), dtype=torch.int32, device=self.device))
+            mine, every = self._seeds[key]
+            self.local.query_seed_device(queries, k, mine, stream)
+            if self.device.type == "cuda":
+                dist.all_gather_into_tensor(every, mine, group=self.group)
+            else:
+                dist.all_gather(list(every.unbind(0)), mine, group=self.group)
+            self.local.query_finish_device(queries, k, [every[s].data_ptr() for s in range(self.world)], own[0], own[1], own[2], stream)
+        else:
+            self.local.query_batch_device(queries, k, own[0], own[1], own[2], stream)
         for g, o in zip(gathered, own):
             if self.device.type == "cuda":
                 dist.all_gather_into_tensor(g, o, group=self.group)

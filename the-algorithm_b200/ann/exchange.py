@@ -11,6 +11,13 @@ merges 1/world of the batch; two stream-ordered cross-rank barriers bracket the 
     ix.query_batch_device(q, k, *px.local.tensors, stream)   # the shard's results land in the mapped block directly
     ids, dist, cnt = px.exchange_merge(stream)        # every rank ends up with the whole merged batch
 
+or, sharing the shards' threshold seeds first (`ann_query_seed_device` / `ann_query_finish_device`):
+
+    ix.query_seed_device(q, k, px.seed_keys, stream)  # this shard's k bounds per query, into its mapped key array
+    px.seed_barrier()
+    ix.query_finish_device(q, k, px.seed_ptrs, *px.local.tensors, stream)   # scored against the global threshold
+    ids, dist, cnt = px.exchange_merge(stream)
+
 Peer mapping uses torch's symmetric memory (cuMem allocations exchanged between the ranks of a process group), which is
 plumbing in the same sense as the NCCL communicator; the kernel and the layout are this repo's.  `PeerExchange` raises
 if the ranks cannot map each other (no P2P); callers then keep the all-gather + `merge_topk_device` route.
@@ -78,16 +85,25 @@ class PeerExchange:
         self.world = dist.get_world_size(self.group)
         nb = result_block_bytes(b, k)
         self._stride = (nb + 255) // 256 * 256
-        self._buf = symm_mem.empty(2 * self._stride, dtype=torch.uint8, device=self.device)
+        seed_bytes = (b * k * 4 + 255) // 256 * 256          # this rank's published seed bounds, [b][k] uint32
+        self._buf = symm_mem.empty(2 * self._stride + seed_bytes, dtype=torch.uint8, device=self.device)
         self._hdl = symm_mem.rendezvous(self._buf, self.group)
         ptrs: List[int] = [int(p) for p in self._hdl.buffer_ptrs]
         assert len(ptrs) == self.world and ptrs[self.rank] == self._buf.data_ptr()
         self._local_ptrs = ptrs
         self._final_ptrs = [p + self._stride for p in ptrs]
+        self.seed_ptrs = [p + 2 * self._stride for p in ptrs]
         self.local = ResultBlock(self._buf, b, k, 0)
         self.final = ResultBlock(self._buf, b, k, self._stride)
+        self.seed_keys = self._buf[2 * self._stride: 2 * self._stride + b * k * 4].view(torch.int32).view(b, k)
         self.q_begin, q_end = slice_of(self.rank, self.world, b)
         self.q_count = q_end - self.q_begin
+
+    def seed_barrier(self) -> None:
+        """Collective, between `query_seed_device` and `query_finish_device`: every rank's published bounds are complete.
+        No second barrier is needed before the next batch overwrites `seed_keys`: a rank gets there only through the
+        barriers of `exchange_merge`, which every peer enters after its own finish call has read the keys."""
+        self._hdl.barrier(channel=2)
 
     def exchange_merge(self, stream: int = 0):
         """Collective.  `local` must have been written on the CURRENT torch stream (== `stream`): the barriers are enqueued
