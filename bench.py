@@ -13,8 +13,10 @@ value   : whole-job queries/s with queries and outputs resident in HBM (CUDA eve
           barrier + synchronize on both sides, max over ranks)
 e2e     : the same through the host-buffer C-ABI call ann_query_batch (pinned host queries in, host results out,
           H2D / D2H inside the timed region)
-N > 1   : STRONG scaling on the same 10M-row corpus -- rows sharded contiguously across ranks, queries replicated,
-          one exchange step: the fused exchange+merge kernel over NVLink peer memory (each rank pulls, merges and
+N > 1   : STRONG scaling on the same 10M-row corpus -- rows sharded contiguously across ranks, queries replicated.
+          Every rank first publishes k bounds per query from a short seed launch over its shard; after one barrier each
+          rank filters its rows against the k-th best bound of ALL ranks (ann_query_seed_device / _finish_device), then
+          the exchange step: the fused exchange+merge kernel over NVLink peer memory (each rank pulls, merges and
           pushes 1/N of the batch; ann/exchange.py), or NCCL all-gather + merge kernel if peers cannot be mapped.
 roofline: dominant kernel = gemm_filter (tensor bound); achieved = 2*N_local*d*B flop / its CUDA-event time.
 cpu_baseline / --impl reference: the reference-faithful C restatement (oracle/oracle.c: linked list of heap rows,
@@ -59,11 +61,14 @@ def parse():
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 streaming scan, 2 tensor-core GEMM filter")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-queries", type=int, default=0, help="queries in the CPU sample (0 = one per host thread)")
+    ap.add_argument("--no-share-seeds", action="store_true",
+                    help="N > 1: every rank filters against its own thresholds only (A/B of the shared seed bounds)")
     return ap.parse_args()
 
 
 def config_dict(a, n_gpus, route=""):
-    how = {"fused": "one fused exchange+merge kernel over NVLink peer memory (each rank merges 1/N of the batch)",
+    how = {"fused": "shared seed thresholds (every rank filters against the k-th best bound of all ranks' seed launches), then "
+                    "one fused exchange+merge kernel over NVLink peer memory (each rank merges 1/N of the batch)",
            "allgather": "NCCL all-gather of local top-k + merge kernel"}.get(route or "fused", route)
     return {
         "workload": f"configs[1]: exact {a.metric} top-{a.k} over {a.rows}x{a.dim} fp32 corpus, query batch {a.batch}",
@@ -245,7 +250,7 @@ def run_ours(a):
     out_dist = torch.empty((b, k), dtype=torch.float32, device=dev)
     out_cnt = torch.empty((b,), dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream()
-    sx = ShardedBruteForceIndex(ix, device=dev) if world > 1 else None
+    sx = ShardedBruteForceIndex(ix, device=dev, share_seeds=not a.no_share_seeds) if world > 1 else None
 
     def step_device(queries):
         if world == 1:
