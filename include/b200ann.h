@@ -160,6 +160,19 @@ ANN_API int ann_knn_join(const ann_config *cfg, const int64_t *corpus_ids, const
                          const float *queries, int64_t nq, int32_t k, int64_t corpus_tile_rows, int32_t query_tile,
                          int64_t *out_ids, float *out_dist, int32_t *out_count);
 
+/* The Metric trait itself (Metric.scala:76-86) for plain vector pairs, host buffers: out[i] = metric.distance(a_i, b_i) for
+ * the n rows of a[n*dim] and b[n*dim] -- L2 (Metric.scala:89-94), Cosine (:120-125), InnerProduct (:153-158), computed on the
+ * device with exactly the arithmetic the query path returns (DESIGN.md conventions C1-C4; flags: ANN_FLAG_L2_SQUARED).
+ * `absoluteDistance` (:82-86) is the same number for these three metrics. */
+ANN_API int ann_distance_pairs(int32_t metric, uint32_t flags, int32_t dim, const float *a, const float *b, int64_t n,
+                               float *out, int32_t device);
+
+/* MetricUtil.norm (Metric.scala:285-289): out = rows with every row scaled to unit L2 norm (convention C8: squared norm
+ * accumulated in fp64 in index order, fp64 divide, one rounding to fp32; a zero row becomes NaN).  This is the step the
+ * reference's HNSW / Faiss backends apply before treating Cosine as InnerProduct (DistanceFunctionGenerator.scala:11-15,
+ * Hnsw.scala:149-155, QueryableIndexAdapter.scala:43-50); the brute-force index does NOT need it (norms are kept per row). */
+ANN_API int ann_normalize_rows(int32_t dim, const float *rows, int64_t n, float *out, int32_t device);
+
 /* Tuning / introspection.
  * Options: "path" (0 auto, 1 streaming scan, 2 tensor-core GEMM filter, 3 exact fallback for every query), "gemm_min_batch", "gemm_cta_group" (1|2), "gemm_epi_warps" (0 auto, 8, 16),
  *          "gemm_hit_budget" (candidates one chunk may add per query, default 500), "gemm_seed_rows" (0 = default 65536),

@@ -50,6 +50,8 @@ def lib() -> ctypes.CDLL:
         cp = ctypes.POINTER(ctypes.c_int32)
         L.oracle_distance.restype = ctypes.c_float
         L.oracle_distance.argtypes = [ctypes.c_int, fp, fp, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.oracle_normalize.restype = None
+        L.oracle_normalize.argtypes = [fp, ctypes.c_int, fp]
         L.oracle_float_order_key.restype = ctypes.c_uint32
         L.oracle_float_order_key.argtypes = [ctypes.c_float]
         L.oracle_query_canonical.restype = ctypes.c_int
@@ -90,6 +92,16 @@ def distance(metric: int, row, query, accum: int = 0, l2_squared: int = 0) -> np
     r, rp = _f(row)
     q, qp = _f(query)
     return np.float32(lib().oracle_distance(metric, rp, qp, r.shape[-1], accum, l2_squared))
+
+
+def normalize(rows) -> np.ndarray:
+    """MetricUtil.norm (Metric.scala:285-289) under convention C8, row by row."""
+    r, _ = _f(np.atleast_2d(rows))
+    out = np.empty_like(r)
+    fp = ctypes.POINTER(ctypes.c_float)
+    for i in range(r.shape[0]):
+        lib().oracle_normalize(r[i].ctypes.data_as(fp), r.shape[1], out[i].ctypes.data_as(fp))
+    return out
 
 
 def query_canonical(metric: int, corpus, ids, queries, k: int, accum: int = 0, l2_squared: int = 0,

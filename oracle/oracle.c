@@ -164,6 +164,17 @@ float oracle_distance(int metric, const float *row, const float *query, int d, i
     return distance(metric, row, query, d, accum, l2_squared);
 }
 
+/* MetricUtil.norm (Metric.scala:285-289) -> EmbeddingMath.Float.normalize (unshipped): L2-normalise a vector, the step
+ * HNSW / Faiss use to turn Cosine into InnerProduct (DistanceFunctionGenerator.scala:11-15; Hnsw.scala:149-155).
+ * Convention C8 (unpinned like C1-C4): the squared norm accumulates in fp64 in index order, each element is divided in
+ * fp64 by sqrt(norm2) and rounded once to fp32.  A zero vector gives 0/0 = NaN in every element. */
+void oracle_normalize(const float *v, int d, float *out) {
+    double n2 = 0.0;
+    for (int i = 0; i < d; ++i) n2 = n2 + (double)v[i] * (double)v[i];
+    double nrm = sqrt(n2);
+    for (int i = 0; i < d; ++i) out[i] = (float)((double)v[i] / nrm);
+}
+
 /* ------------------------------------------------------------------------------------------ */
 typedef struct {
     int64_t id;

@@ -55,6 +55,15 @@ def distances(metric: int, corpus: np.ndarray, query: np.ndarray, l2_squared: bo
         return (np.float32(1.0) - cs.astype(np.float32)).astype(np.float32)
 
 
+def normalize(rows) -> np.ndarray:
+    """MetricUtil.norm (Metric.scala:285-289), convention C8: fp64 sequential squared norm, fp64 divide, one rounding."""
+    a = np.atleast_2d(np.ascontiguousarray(rows, dtype=np.float32))
+    a64 = a.astype(np.float64)
+    n2 = _seq_sum_f64(lambda i: a64[:, i] * a64[:, i], a.shape[0], a.shape[1])
+    with np.errstate(all="ignore"):
+        return (a64 / np.sqrt(n2)[:, None]).astype(np.float32)
+
+
 def query_canonical(metric: int, corpus, ids, queries, k: int, l2_squared: bool = False):
     corpus = np.ascontiguousarray(corpus, dtype=np.float32)
     queries = np.atleast_2d(np.ascontiguousarray(queries, dtype=np.float32))

@@ -566,6 +566,63 @@ def test_two_phase_query_session_rules_and_unseeded_paths():
     ix.close()
 
 
+@pytest.mark.parametrize("mi", [0, 1, 2])
+@pytest.mark.parametrize("d", [1, 3, 200, 1024])
+def test_metric_distance_pairs_match_oracle(mi, d):
+    """Metric.distance for plain pairs (ann_distance_pairs, Metric.scala:76-158) against oracle.distance, bit for bit,
+    special values included; and equal to what a query over the same rows returns."""
+    metric = metrics()[mi]
+    rng = np.random.default_rng(900 + d)
+    n = 257
+    a = (rng.standard_normal((n, d)) * 3).astype(np.float32)
+    b = rng.uniform(-1, 1, (n, d)).astype(np.float32)
+    a[0], b[1] = 0.0, 0.0                       # zero vectors (Cosine: 0/0 -> NaN)
+    a[2, 0], b[3, -1] = np.nan, np.inf          # non-finite entries
+    a[4] = b[4]                                 # identical vectors
+    a[5], b[5] = 1e-30, 1e-30                   # tiny magnitudes
+    a[6], b[6] = 3e18, 3e18                     # products overflow fp32 but not fp64
+    got = metric.distances(a, b)
+    want = np.array([oracle.distance(metric.ordinal, a[i], b[i]) for i in range(n)], np.float32)
+    assert (onp.float_order_key(got) == onp.float_order_key(want)).all()
+    fin = np.isfinite(want)
+    assert (got[fin].view(np.uint32) == want[fin].view(np.uint32)).all()
+    one = metric.distance(a[10], b[10])
+    assert isinstance(one, metric.distance_class) and np.float32(one.distance) == want[10]
+    assert np.float32(metric.absolute_distance(a[10], b[10])) == want[10]
+    if metric.name == "L2":
+        sq = metric.distances(a[7:40], b[7:40], l2_squared=True)
+        wsq = np.array([oracle.distance(0, a[i], b[i], l2_squared=1) for i in range(7, 40)], np.float32)
+        assert (sq.view(np.uint32) == wsq.view(np.uint32)).all()
+    ix = G["BruteForceIndex"].apply(metric, G["FuturePool"].immediate_pool())
+    ix.append_batch(np.arange(16, dtype=np.int64), a[16:32])
+    gi, gd, _ = ix.batch_query_with_distance(b[20:21], 16)
+    ix.close()
+    pair = metric.distances(a[16:32], np.repeat(b[20:21], 16, axis=0))
+    assert (gd[0][np.argsort(gi[0])].view(np.uint32) == pair.view(np.uint32)).all()
+
+
+def test_metric_util_norm_matches_oracle_and_errors():
+    MetricUtil = __import__("the_algorithm_b200.ann.common", fromlist=["MetricUtil"]).MetricUtil
+    AnnError = G["_capi"].AnnError
+    rng = np.random.default_rng(31)
+    for d in (1, 7, 200, 1024):
+        rows = (rng.standard_normal((300, d)) * 20).astype(np.float32)
+        rows[3] = 0.0
+        rows[5, 0] = np.inf
+        got = MetricUtil.norm(rows)
+        want = oracle.normalize(rows)
+        assert (onp.float_order_key(got) == onp.float_order_key(want)).all()
+        assert (MetricUtil.norm(rows[7]).view(np.uint32) == want[7].view(np.uint32)).all()    # single vector in, single out
+    assert G["L2"].distances(np.zeros((0, 5), np.float32), np.zeros((0, 5), np.float32)).shape == (0,)
+    with pytest.raises(AnnError) as e:
+        G["L2"].distances(np.zeros((2, 5), np.float32), np.zeros((2, 6), np.float32))
+    assert e.value.code == G["_capi"].ANN_ERR_DIMENSION_MISMATCH
+    with pytest.raises(AnnError):
+        G["L2"].distances(np.zeros((2, 2000), np.float32), np.zeros((2, 2000), np.float32))
+    with pytest.raises(AnnError):
+        G["L2"].distances(np.zeros((2, 5), np.float32), np.zeros((2, 5), np.float32), device=99)
+
+
 # ------------------------------------------------------------------------------------------------ full-size properties
 def test_full_size_properties_10m_rows():
     """At BASELINE's full size the oracle is too slow, so check size-independent properties on a 10M x 128 L2 index:

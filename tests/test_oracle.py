@@ -48,6 +48,26 @@ def test_kat_rounding_points():
     assert oracle.distance(IP, a, b, accum=1) == np.float32(1.0)   # 1 - 0
 
 
+def test_kat_normalize():
+    """MetricUtil.norm (Metric.scala:285-289) under convention C8; hand-computed answers."""
+    out = oracle.normalize([[3.0, 4.0], [0.0, -2.0], [1.0, 1.0], [0.0, 0.0]])
+    assert (out[0] == np.array([0.6, 0.8], np.float32)).all()                     # fp32(3/5), fp32(4/5)
+    assert (out[1] == np.array([0.0, -1.0], np.float32)).all() and not np.signbit(out[1][0])
+    assert (out[2] == np.float32(1.0 / math.sqrt(2.0))).all()                      # fp32(1 / sqrt(2)) from the fp64 quotient
+    assert np.isnan(out[3]).all()                                                  # zero vector: 0/0
+    rng = np.random.default_rng(5)
+    rows = rng.standard_normal((64, 37)).astype(np.float32) * 50
+    got = oracle.normalize(rows)
+    assert (got.view(np.uint32) == onp.normalize(rows).view(np.uint32)).all()      # C and numpy restatements agree bit for bit
+    assert np.allclose(np.linalg.norm(got.astype(np.float64), axis=1), 1.0, atol=1e-6)
+    # Cosine(a, b) == InnerProduct(norm(a), norm(b)) up to the roundings of the normalised copies -- the identity the
+    # reference's HNSW / Faiss backends rely on (DistanceFunctionGenerator.scala:11-15)
+    for i in range(0, 60, 2):
+        c = oracle.distance(COS, rows[i], rows[i + 1])
+        ip = oracle.distance(IP, got[i], got[i + 1])
+        assert abs(float(c) - float(ip)) <= 1e-6
+
+
 def test_float_compare_total_order():
     vals = np.array([np.nan, np.inf, 1.0, 0.0, -0.0, -1.0, -np.inf], dtype=np.float32)
     keys = [oracle.lib().oracle_float_order_key(float(v)) for v in vals]

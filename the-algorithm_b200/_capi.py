@@ -30,7 +30,7 @@ ANN_FLAG_NO_SHADOW = 0x2
 # every symbol include/b200ann.h declares (tests/test_capi_symbols.py checks header <-> library <-> this list)
 SYMBOLS = (
     "ann_create", "ann_destroy", "ann_append_batch", "ann_append_batch_device", "ann_update_batch", "ann_read_rows", "ann_size", "ann_query_batch",
-    "ann_query_batch_device", "ann_merge_topk_device", "ann_exchange_merge_device", "ann_result_block_bytes", "ann_query_seed_device", "ann_query_finish_device", "ann_knn_join", "ann_set_option", "ann_get_stat", "ann_last_error", "ann_version",
+    "ann_query_batch_device", "ann_merge_topk_device", "ann_exchange_merge_device", "ann_result_block_bytes", "ann_query_seed_device", "ann_query_finish_device", "ann_knn_join", "ann_distance_pairs", "ann_normalize_rows", "ann_set_option", "ann_get_stat", "ann_last_error", "ann_version",
 )
 
 
@@ -88,6 +88,10 @@ def lib() -> ctypes.CDLL:
         L.ann_result_block_bytes.argtypes = [i32, i32]
         L.ann_knn_join.restype = ctypes.c_int
         L.ann_knn_join.argtypes = [ctypes.POINTER(AnnConfig), vp, vp, i64, vp, i64, i32, i64, i32, vp, vp, vp]
+        L.ann_distance_pairs.restype = ctypes.c_int
+        L.ann_distance_pairs.argtypes = [i32, ctypes.c_uint32, i32, vp, vp, i64, vp, i32]
+        L.ann_normalize_rows.restype = ctypes.c_int
+        L.ann_normalize_rows.argtypes = [i32, vp, i64, vp, i32]
         L.ann_set_option.restype = ctypes.c_int
         L.ann_set_option.argtypes = [vp, ctypes.c_char_p, i64]
         L.ann_get_stat.restype = ctypes.c_int

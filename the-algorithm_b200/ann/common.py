@@ -111,18 +111,23 @@ class Metric:
     fromAbsoluteDistance = from_absolute_distance
 
     def distance(self, embedding1, embedding2, device: int = 0) -> Distance:
-        """metric.distance(embedding1, embedding2).  Computed by the GPU engine itself (a one-row index and a
-        k=1 query), so the value is bit-identical to what queries return; there is no host arithmetic."""
-        from .brute_force import BruteForceIndex
+        """metric.distance(embedding1, embedding2) (Metric.scala:76-86).  Computed on the device (`ann_distance_pairs`)
+        with the arithmetic of the query path, so the value is bit-identical to what queries return; there is no host
+        arithmetic."""
+        return self.from_absolute_distance(self.distances(np.reshape(embedding1, (1, -1)), np.reshape(embedding2, (1, -1)), device)[0])
 
-        e1 = np.ascontiguousarray(embedding1, dtype=np.float32).reshape(1, -1)
-        ix = BruteForceIndex.apply(self, FuturePool.immediate_pool(), device=device)
-        try:
-            ix.append_batch(np.zeros(1, dtype=np.int64), e1)
-            _, dist, _ = ix.batch_query_with_distance(np.ascontiguousarray(embedding2, dtype=np.float32).reshape(1, -1), 1)
-            return self.from_absolute_distance(dist[0, 0])
-        finally:
-            ix.close()
+    def distances(self, embeddings1, embeddings2, device: int = 0, l2_squared: bool = False) -> np.ndarray:
+        """`distance` for n pairs at once: rows of two [n, dim] arrays -> float32 [n]."""
+        from .. import _capi
+
+        a = np.ascontiguousarray(embeddings1, dtype=np.float32)
+        b = np.ascontiguousarray(embeddings2, dtype=np.float32)
+        if a.ndim != 2 or a.shape != b.shape:
+            raise _capi.AnnError(_capi.ANN_ERR_DIMENSION_MISMATCH, f"embeddings differ in shape: {a.shape} vs {b.shape}")
+        out = np.empty((a.shape[0],), dtype=np.float32)
+        _capi.check(_capi.lib().ann_distance_pairs(self.ordinal, _capi.ANN_FLAG_L2_SQUARED if l2_squared else 0, a.shape[1],
+                                                   a.ctypes.data, b.ctypes.data, a.shape[0], out.ctypes.data, device))
+        return out
 
     def absolute_distance(self, embedding1, embedding2, device: int = 0) -> float:
         return self.distance(embedding1, embedding2, device).distance
@@ -157,6 +162,22 @@ class _Cosine(Metric):
 
 class _InnerProduct(Metric):
     name, ordinal, distance_class = "InnerProduct", 2, InnerProductDistance
+
+
+class MetricUtil:
+    """object MetricUtil (Metric.scala:263-290): only `norm` has callers outside Metric itself."""
+
+    @staticmethod
+    def norm(embedding, device: int = 0) -> np.ndarray:
+        """MetricUtil.norm (Metric.scala:285-289): the embedding(s) scaled to unit L2 norm, on the device
+        (`ann_normalize_rows`).  Accepts one vector or an [n, dim] array."""
+        from .. import _capi
+
+        e = np.ascontiguousarray(embedding, dtype=np.float32)
+        rows = e.reshape(1, -1) if e.ndim == 1 else e
+        out = np.empty_like(rows)
+        _capi.check(_capi.lib().ann_normalize_rows(rows.shape[1], rows.ctypes.data, rows.shape[0], out.ctypes.data, device))
+        return out.reshape(e.shape)
 
 
 L2 = _L2()
