@@ -18,6 +18,10 @@ int main() {
         if (res.size() != 2 || res[0].neighbor != 9 || res[0].distance.distance != -1.0f || res[1].neighbor != 7) return 12;
         auto only = ix.query({1.0f, 0.0f}, 0).get();
         if (!only.empty()) return 13;
+        if (distance(Metric::L2, {0.0f, 0.0f}, {3.0f, 4.0f}).distance != 5.0f) return 15;           // Metric.scala:89-94
+        if (distance(Metric::InnerProduct, {1.0f, 2.0f, 3.0f}, {4.0f, 5.0f, 6.0f}).distance != -31.0f) return 16;
+        auto unit = norm({3.0f, 4.0f});                                                               // Metric.scala:285-289
+        if (unit.size() != 2 || unit[0] != 0.6f || unit[1] != 0.8f) return 17;
         std::printf("gpu ok\n");
         return 0;
     } catch (const AnnError& e) {

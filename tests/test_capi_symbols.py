@@ -61,6 +61,14 @@ def test_argument_validation_without_gpu(built_lib):
     assert L.ann_query_batch(None, None, 1, 1, 1, None, None, None) == _capi.ANN_ERR_NULL_POINTER
     assert L.ann_merge_topk_device(0, None, None, None, 0, 1, 1, None, None, None, None) == _capi.ANN_ERR_INVALID_ARGUMENT
     assert L.ann_merge_topk_device(0, None, None, None, 2, 1, -1, None, None, None, None) == _capi.ANN_ERR_NEGATIVE_K
+    assert L.ann_query_seed_device(None, None, 1, 1, 1, None, None) == _capi.ANN_ERR_NULL_POINTER
+    assert L.ann_query_finish_device(None, None, 1, 1, 1, None, 0, None, None, None, None) == _capi.ANN_ERR_NULL_POINTER
+    assert L.ann_distance_pairs(9, 0, 4, None, None, 1, None, 0) == _capi.ANN_ERR_INVALID_ARGUMENT
+    assert L.ann_distance_pairs(0, 0, 4000, None, None, 1, None, 0) == _capi.ANN_ERR_INVALID_ARGUMENT
+    assert L.ann_distance_pairs(0, 0, 4, None, None, 1, None, 0) == _capi.ANN_ERR_NULL_POINTER
+    assert L.ann_distance_pairs(0, 0, 4, None, None, 0, None, 0) == _capi.ANN_OK          # nothing to do
+    assert L.ann_normalize_rows(0, None, 1, None, 0) == _capi.ANN_ERR_INVALID_ARGUMENT
+    assert L.ann_normalize_rows(4, None, 1, None, 0) == _capi.ANN_ERR_NULL_POINTER
     L.ann_destroy(None)  # ignored
 
 
@@ -85,6 +93,14 @@ def test_no_cpu_fallback_when_device_missing(built_lib):
     ix = BruteForceIndex(InnerProduct, FuturePool.immediate_pool())
     with pytest.raises(_capi.AnnError):
         ix.append_batch([1], np.ones((1, 16), np.float32))
+    # the Metric trait's own entry points compute on the device too: no host arithmetic stands in for them
+    from the_algorithm_b200.ann.common import MetricUtil
+
+    with pytest.raises(_capi.AnnError) as e:
+        InnerProduct.distance(np.ones(16, np.float32), np.ones(16, np.float32))
+    assert e.value.code in (_capi.ANN_ERR_NO_DEVICE, _capi.ANN_ERR_CUDA)
+    with pytest.raises(_capi.AnnError):
+        MetricUtil.norm(np.ones(16, np.float32))
 
 
 def test_product_never_imports_oracle():

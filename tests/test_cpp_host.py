@@ -46,7 +46,10 @@ def test_scala_binding_names_every_abi_entry_point_it_uses():
     scala = (ROOT / "the-algorithm_b200" / "host" / "scala" / "GpuBruteForceIndex.scala").read_text()
     jni = (ROOT / "the-algorithm_b200" / "host" / "jni" / "b200ann_jni.c").read_text()
     for native, abi in (("create", "ann_create"), ("destroy", "ann_destroy"), ("appendBatch", "ann_append_batch"),
-                        ("size", "ann_size"), ("queryBatch", "ann_query_batch"), ("lastError", "ann_last_error")):
+                        ("size", "ann_size"), ("queryBatch", "ann_query_batch"), ("lastError", "ann_last_error"),
+                        ("knnJoin", "ann_knn_join"), ("distancePairs", "ann_distance_pairs"),
+                        ("normalizeRows", "ann_normalize_rows"), ("querySeedDevice", "ann_query_seed_device"),
+                        ("queryFinishDevice", "ann_query_finish_device")):
         assert f"def {native}(" in scala and abi in jni
     for trait in ("extends Appendable[T, BruteForceRuntimeParams.type, D]", "with Queryable[T, BruteForceRuntimeParams.type, D]"):
         assert trait in scala

@@ -77,6 +77,23 @@ inline void check(int rc) {
     if (rc != ANN_OK) throw AnnError(rc, ann_last_error());
 }
 
+// Metric.distance(embedding1, embedding2) -- Metric.scala:76-86 (L2 :89-94, Cosine :120-125, InnerProduct :153-158) -- on the
+// device, with the arithmetic of the query path (ann_distance_pairs).  `absoluteDistance` is the same number here.
+inline Distance distance(Metric metric, const std::vector<float>& embedding1, const std::vector<float>& embedding2, int device = 0) {
+    if (embedding1.size() != embedding2.size()) throw AnnError(ANN_ERR_DIMENSION_MISMATCH, "embeddings differ in dimension");
+    float out = 0.f;
+    check(ann_distance_pairs(static_cast<int32_t>(metric), 0u, static_cast<int32_t>(embedding1.size()), embedding1.data(),
+                             embedding2.data(), 1, &out, device));
+    return Distance{out};
+}
+
+// MetricUtil.norm -- Metric.scala:285-289 -- the embedding scaled to unit L2 norm (ann_normalize_rows)
+inline std::vector<float> norm(const std::vector<float>& embedding, int device = 0) {
+    std::vector<float> out(embedding.size());
+    check(ann_normalize_rows(static_cast<int32_t>(embedding.size()), embedding.data(), 1, out.data(), device));
+    return out;
+}
+
 template <typename T>
 class Queryable {
 public:

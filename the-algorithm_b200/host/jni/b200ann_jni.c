@@ -62,6 +62,38 @@ NATIVE(jint, knnJoin)(JNIEnv *env, jobject self, jint metric, jint dim, jint dev
                         (float *)addr(env, out_dist), (int32_t *)addr(env, out_count));
 }
 
+/* Metric.distance for n plain pairs / MetricUtil.norm (Metric.scala:76-86, 285-289): host buffers, computed on the device */
+NATIVE(jint, distancePairs)(JNIEnv *env, jobject self, jint metric, jint flags, jint dim, jobject a, jobject b, jlong n,
+                            jobject out, jint device) {
+    (void)self;
+    return ann_distance_pairs(metric, (uint32_t)flags, dim, (const float *)addr(env, a), (const float *)addr(env, b), n,
+                              (float *)addr(env, out), device);
+}
+
+NATIVE(jint, normalizeRows)(JNIEnv *env, jobject self, jint dim, jobject rows, jlong n, jobject out, jint device) {
+    (void)self;
+    return ann_normalize_rows(dim, (const float *)addr(env, rows), n, (float *)addr(env, out), device);
+}
+
+/* The shard-side query in two halves (ann_query_seed_device / ann_query_finish_device).  Device addresses travel as
+ * longs: the query batch, the key arrays and the result block live in device memory the host mapped across its GPUs
+ * (CUDA IPC); peerSeedKeys is a direct buffer holding `world` 64-bit device addresses. */
+NATIVE(jint, querySeedDevice)(JNIEnv *env, jobject self, jlong handle, jlong d_queries, jint b, jint dim, jint k,
+                              jlong d_seed_keys, jlong stream) {
+    (void)env; (void)self;
+    return ann_query_seed_device((ann_index *)(intptr_t)handle, (const float *)(intptr_t)d_queries, b, dim, k,
+                                 (uint32_t *)(intptr_t)d_seed_keys, (void *)(intptr_t)stream);
+}
+
+NATIVE(jint, queryFinishDevice)(JNIEnv *env, jobject self, jlong handle, jlong d_queries, jint b, jint dim, jint k,
+                                jobject peer_seed_keys, jint world, jlong d_out_ids, jlong d_out_dist, jlong d_out_count,
+                                jlong stream) {
+    (void)self;
+    return ann_query_finish_device((ann_index *)(intptr_t)handle, (const float *)(intptr_t)d_queries, b, dim, k,
+                                   (const uint32_t *const *)addr(env, peer_seed_keys), world, (int64_t *)(intptr_t)d_out_ids,
+                                   (float *)(intptr_t)d_out_dist, (int32_t *)(intptr_t)d_out_count, (void *)(intptr_t)stream);
+}
+
 NATIVE(jstring, lastError)(JNIEnv *env, jobject self) {
     (void)self;
     return (*env)->NewStringUTF(env, ann_last_error());

@@ -34,6 +34,15 @@ object B200AnnNative {
   @native def knnJoin(metric: Int, dim: Int, device: Int, flags: Int, corpusIds: ByteBuffer, corpusRows: ByteBuffer, n: Long,
     queries: ByteBuffer, nq: Long, k: Int, corpusTileRows: Long, queryTile: Int,
     outIds: ByteBuffer, outDist: ByteBuffer, outCount: ByteBuffer): Int
+  // Metric.distance for n pairs / MetricUtil.norm (common/Metric.scala:76-86, 285-289) on the device, query-path arithmetic
+  @native def distancePairs(metric: Int, flags: Int, dim: Int, a: ByteBuffer, b: ByteBuffer, n: Long, out: ByteBuffer,
+    device: Int): Int
+  @native def normalizeRows(dim: Int, rows: ByteBuffer, n: Long, out: ByteBuffer, device: Int): Int
+  // one shard's half of ComposedQueryable's fan-out (common/ShardApi.scala:72-79) when the shards are GPUs of one box:
+  // publish bounds -> [cross-GPU barrier] -> score against the global bound (ann_query_seed_device / _finish_device)
+  @native def querySeedDevice(handle: Long, dQueries: Long, b: Int, dim: Int, k: Int, dSeedKeys: Long, stream: Long): Int
+  @native def queryFinishDevice(handle: Long, dQueries: Long, b: Int, dim: Int, k: Int, peerSeedKeys: ByteBuffer, world: Int,
+    dOutIds: Long, dOutDist: Long, dOutCount: Long, stream: Long): Int
   @native def lastError(): String
 }
 
