@@ -17,6 +17,7 @@ namespace {
 
 constexpr int kSelThreads = 256;
 constexpr int kSortCap = 4096;    // default approximate-stage capacity per query (SelectParams::sort_cap overrides)
+constexpr int kRankSortMax = 384; // up to this many exact candidates are ordered by rank counting, more by the bitonic network
 constexpr int kExactCap = 2048;   // default survivors + specials rescored exactly (power of two; SelectParams::exact_cap)
 __host__ __device__ inline int sort_cap_of(const SelectParams& p) { return p.sort_cap > 0 ? p.sort_cap : kSortCap; }
 __host__ __device__ inline int exact_cap_of(const SelectParams& p) { return p.exact_cap > 0 ? p.exact_cap : kExactCap; }
@@ -239,6 +240,7 @@ __global__ void __launch_bounds__(kSelThreads, 4) compact_pool_kernel(SelectPara
 }
 
 // ---- finalize: survivors + specials -> exact distances -> (distance, id) order -> outputs -------------------
+template <int METRIC>
 __global__ void __launch_bounds__(kSelThreads, 4) finalize_kernel(SelectParams p) {
     extern __shared__ __align__(16) unsigned char sm[];
     const int sort_cap = sort_cap_of(p), exact_cap = exact_cap_of(p);
@@ -302,6 +304,19 @@ __global__ void __launch_bounds__(kSelThreads, 4) finalize_kernel(SelectParams p
         return;
     }
     {
+        // The candidate rows are scattered over the whole matrix and every rescoring thread walks its row front to back, so
+        // without help each 64-byte step of that walk is a fresh DRAM miss (13 dependent misses per 800-byte row).  Ask for
+        // every line of every candidate row (and its id) up front: all the misses of the CTA are then in flight together,
+        // and the walks below run out of L2.
+        const int row_bytes = p.dim * 4;
+        const int lines = (row_bytes + 127) / 128 + 1;          // rows are not 128-byte aligned: one more line may be touched
+        for (int i = threadIdx.x; i < n_cand * lines; i += blockDim.x) {
+            const int c = i / lines, j = i - c * lines;
+            const char* base = reinterpret_cast<const char*>(p.rows + (size_t)crow[c] * p.pitch);
+            const char* at = base + min(j * 128, row_bytes - 4);
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(at));
+            if (j == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.ids + crow[c]));
+        }
         // the query as doubles (and its squared norm) once per CTA, in the shared memory the approximate entries occupied
         double* q64 = reinterpret_cast<double*>(buf);                                  // <= 8 KB (dim <= 1024)
         uint32_t* okey = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(buf) + 8192);   // exact_cap keys (sort_cap * 8 >= 8192 + exact_cap * 4)
@@ -309,18 +324,51 @@ __global__ void __launch_bounds__(kSelThreads, 4) finalize_kernel(SelectParams p
         const float* qv = p.queries + (size_t)q * p.q_pitch;
         for (int i = threadIdx.x; i < p.dim; i += blockDim.x) q64[i] = (double)qv[i];
         __syncthreads();
-        if (threadIdx.x == 0) nb_s = (p.metric == kMetricCosine) ? exact_query_norm2(q64, p.dim) : 0.0;
+        if (threadIdx.x == 0) nb_s = (METRIC == kMetricCosine) ? exact_query_norm2(q64, p.dim) : 0.0;
         __syncthreads();
         const ExactQuery eq{q64, nb_s};
         // one thread per candidate row, all candidates in parallel; several CTAs per SM overlap each other's
         // dependent-miss chains (the kernel is latency bound, so occupancy -- not per-thread ILP -- is what pays)
         for (int c = threadIdx.x; c < n_cand; c += blockDim.x) {
             const uint32_t row = crow[c];
-            const float dist = exact_distance_rows(p.metric, p.rows + (size_t)row * p.pitch, eq, p.dim, p.l2_squared);
+            const float dist = exact_distance_rows<true, METRIC>(METRIC, p.rows + (size_t)row * p.pitch, eq, p.dim, p.l2_squared);
             cid[c] = p.ids[row];
             okey[c] = float_order_key(dist);
         }
         __syncthreads();
+        if (n_cand <= kRankSortMax) {
+            // Few candidates (the normal case: ~2k): order them by rank counting instead of a bitonic network -- the output
+            // position of a candidate is the number of candidates that precede it under (distance key, id, slot), one pass
+            // of broadcast shared-memory reads and no barriers, against 36 barrier-separated stages for 256 elements.
+            const int cnt = min(p.k, n_cand);
+            for (int c = threadIdx.x; c < n_cand; c += blockDim.x) {
+                const uint32_t key = okey[c];
+                const long long id = cid[c];
+                int rank = 0, equal = 0;
+                for (int j = 0; j < n_cand; ++j) {       // keys only: two predicated adds per broadcast load
+                    const uint32_t kj = okey[j];
+                    rank += kj < key ? 1 : 0;
+                    equal += kj == key ? 1 : 0;
+                }
+                if (equal > 1) {                         // exact distance ties (itself included): order those by (id, slot)
+                    for (int j = 0; j < n_cand; ++j) {
+                        if (okey[j] != key) continue;
+                        const long long ij = cid[j];
+                        rank += (ij < id || (ij == id && j < c)) ? 1 : 0;
+                    }
+                }
+                if (rank < cnt) {
+                    oid[rank] = id;
+                    od[rank] = float_from_order_key(key);
+                }
+            }
+            for (int j = cnt + threadIdx.x; j < p.k_out; j += blockDim.x) {
+                oid[j] = -1;
+                od[j] = INFINITY;
+            }
+            if (threadIdx.x == 0 && p.out_count) p.out_count[q] = cnt;
+            return;
+        }
         for (int i = threadIdx.x; i < n_cand; i += blockDim.x) ckey[i] = okey[i];
         __syncthreads();
     }
@@ -518,9 +566,11 @@ cudaError_t launch_compact_pool(const SelectParams& p, int b, cudaStream_t strea
 cudaError_t launch_finalize(const SelectParams& p, int b, cudaStream_t stream) {
     size_t smem = (size_t)sort_cap_of(p) * 8 + (size_t)exact_cap_of(p) * 12;
     if ((size_t)sort_cap_of(p) * 8 < 8192 + (size_t)exact_cap_of(p) * 4) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    void (*fn)(SelectParams) = p.metric == kMetricL2 ? finalize_kernel<kMetricL2>
+                               : p.metric == kMetricCosine ? finalize_kernel<kMetricCosine> : finalize_kernel<kMetricIP>;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    finalize_kernel<<<b, kSelThreads, smem, stream>>>(p);
+    fn<<<b, kSelThreads, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
