@@ -43,7 +43,35 @@ def case(name, metric, n, d, b, k, seed, special=False, dup=False, scale=1.0):
     print(name, corpus.shape, q.shape, k)
 
 
+def metric_case():
+    """Metric.distance for plain pairs and MetricUtil.norm (Metric.scala:76-158, 285-289): one fixture for the direct
+    entry points (ann_distance_pairs / ann_normalize_rows), special values included."""
+    rng = np.random.default_rng(777)
+    n, d = 96, 37
+    a = (rng.standard_normal((n, d)) * 3).astype(np.float32)
+    b = rng.uniform(-1, 1, (n, d)).astype(np.float32)
+    a[0], b[1] = 0.0, 0.0
+    a[2, 0], b[3, -1] = np.nan, np.inf
+    a[4] = b[4]
+    a[5], b[5] = 1e-30, 1e-30
+    a[6], b[6] = 3e18, 3e18
+    a[7] = -0.0
+    out = {"a": a, "b": b}
+    for m, mn in ((oracle.L2, "l2"), (oracle.COSINE, "cosine"), (oracle.INNER_PRODUCT, "ip")):
+        dist = np.array([oracle.distance(m, a[i], b[i]) for i in range(n)], np.float32)
+        twin = np.array([onp.distances(m, a[i:i + 1], b[i])[0] for i in range(n)], np.float32)
+        assert (onp.float_order_key(dist) == onp.float_order_key(twin)).all(), mn
+        out[f"dist_{mn}"] = dist
+    out["dist_l2_squared"] = np.array([oracle.distance(oracle.L2, a[i], b[i], l2_squared=1) for i in range(n)], np.float32)
+    out["norm_a"] = oracle.normalize(a)
+    assert (onp.float_order_key(out["norm_a"]) == onp.float_order_key(onp.normalize(a))).all()
+    (OUT / "metric").mkdir(exist_ok=True)
+    np.savez_compressed(OUT / "metric" / "pairs.npz", **out)
+    print("metric/pairs", a.shape)
+
+
 if __name__ == "__main__":
+    metric_case()
     for m, mn in ((oracle.L2, "l2"), (oracle.COSINE, "cosine"), (oracle.INNER_PRODUCT, "ip")):
         case(f"{mn}_small", m, 300, 24, 6, 10, seed=100 + m)
         case(f"{mn}_k_gt_n", m, 40, 8, 3, 64, seed=200 + m)

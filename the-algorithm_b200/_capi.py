@@ -10,7 +10,7 @@ from pathlib import Path
 _HERE = Path(__file__).resolve().parent
 import os
 
-# B200ANN_LIB lets a developer A/B two builds of the same ABI in one process environment (tools/ab_build.sh)
+# B200ANN_LIB lets a developer A/B two builds of the same ABI (point it at the other libb200ann.so)
 LIB_PATH = Path(os.environ["B200ANN_LIB"]) if os.environ.get("B200ANN_LIB") else _HERE / "lib" / "libb200ann.so"
 
 ANN_OK = 0

@@ -509,8 +509,6 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
         g.cta_group = ix->gemm_cta_group;
         g.seed_mode = seed_mode;
         // a chunk is sized to add about kHitBudget candidates per query, so its hit density is budget / rows; above
-        // ~1.5e-4 hits per score the epilogue is the bottleneck and wants 16 warps (measured crossover, 10M x 200)
-        // a chunk is sized to add about kHitBudget candidates per query, so its hit density is budget / rows; above
         // ~1.5e-4 hits per score the epilogue is the bottleneck and wants 16 warps (same-process A/B, tools/ab_options.py:
         // 2.82 -> 2.52 ms per 4096-query batch over 1.25M rows; neutral at 10M rows where sparse chunks dominate)
         // With a single resident query tile (b <= 256) the launch is HBM bound and 8 warps measured 8 % faster.
