@@ -192,7 +192,8 @@ def run_reference(a):
     line = {
         "impl": "reference", "metric": metric_name(a), "value": res["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32 (fp64 accumulate)", "data": "synthetic", "config": config_dict(a, a.gpus),
+        "vs_baseline": None, "dtype": "f64", "dtype_detail": "fp32 embeddings, fp64 accumulation, one rounding to fp32",
+        "data": "synthetic", "config": config_dict(a, a.gpus),
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -337,12 +338,13 @@ def run_ours(a):
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
     except Exception:
         pass
-    traffic = None
+    traffic, traffic_detail = None, None
     try:   # DRAM bytes of the same kernel from the committed ncu --set full capture of this command (profiles/)
         tj = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())
         if (n, d, b, k, world, a.metric) == (10_000_000, 200, 4096, 100, 1, "InnerProduct"):
-            traffic = {"dram_bytes_per_step": tj["gemm_filter_dram_bytes_per_step"],
-                       "algorithmic_shadow_bytes_per_step": tj["algorithmic_shadow_bytes_per_step"], "source": tj["source"]}
+            traffic = float(tj["gemm_filter_dram_bytes_per_step"])     # dram read + write, summed over the step's launches
+            traffic_detail = {"unit": "bytes per step (the kernel's 6 launches of one batch), like `achieved`",
+                              "operand_bytes_per_step": tj["algorithmic_shadow_bytes_per_step"], "source": tj["source"]}
     except Exception:
         pass
     if last_path == 2:
@@ -353,7 +355,7 @@ def run_ours(a):
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
                     if peaks else "fallback 1.4 PFLOP/s sustained",
-                    "traffic": traffic, "kernel_ms_per_step": kernel_us / 1e3 / a.steps,
+                    "traffic": traffic, "traffic_detail": traffic_detail, "kernel_ms_per_step": kernel_us / 1e3 / a.steps,
                     "launches_per_step": kernel_n / a.steps,
                     "algorithmic_flops_per_step": flops_step}
     else:
@@ -397,8 +399,9 @@ def run_ours(a):
         line = {
             "metric": metric_name(a), "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "bf16 filter (tcgen05, fp32 accumulate) + exact fp64-accumulated fp32 distances" if last_path == 2
-                     else "f32 scan + exact fp64-accumulated fp32 distances",
+            "dtype": "bf16" if last_path == 2 else "f32",
+            "dtype_detail": ("bf16 candidate filter on tcgen05 (fp32 accumulate)" if last_path == 2 else "f32 streaming scan")
+                            + " + exact rescoring of the survivors: fp64 accumulation, one rounding to fp32 (bit-identical to the oracle)",
             "data": "synthetic", "config": config_dict(a, n_gpus, sx.route if sx else ""),
             "e2e": {"value": b / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": b * d * 4,
                     "d2h_bytes_per_step": b * k * 12 + b * 4, "ms_per_step": e2e_ms,
