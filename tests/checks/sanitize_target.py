@@ -1,6 +1,7 @@
 """Tiny target for `compute-sanitizer --tool memcheck` (run under gpurun, wrapped in `timeout`): every kernel of the library on
 small shapes -- append / update, prep, streaming scan, tensor-core filter (cta_group 1 and 2, seed + chunks + resident-query
-mode), compaction, finalize, exact fallback, merge.  Exits non-zero if a result differs from the CPU oracle."""
+mode), compaction, finalize, exact fallback, merge, the two-phase shard query (seed publish + seed merge, 70k-row shards), the
+fused exchange/merge kernel and the plain-pair metric kernels.  Exits non-zero if a result differs from the CPU oracle."""
 import sys
 from pathlib import Path
 
@@ -49,5 +50,54 @@ for metric in (InnerProduct, Cosine, L2):
     for s in shards:
         s.close()
     ix.close()
+# ---- two-phase shard query (K5c), fused exchange/merge (K5b) and the metric kernels, on shapes with ragged tails ----
+import torch  # noqa: E402
+
+from the_algorithm_b200.ann.common import MetricUtil  # noqa: E402
+from the_algorithm_b200.ann.exchange import ResultBlock, exchange_merge_blocks, result_block_bytes, slice_of  # noqa: E402
+
+dev = torch.device("cuda", 0)
+st = torch.cuda.current_stream().cuda_stream
+n_per, d, b, k = 70_003, 24, 37, 33
+corpus = (rng.standard_normal((3 * n_per, d)) / 5).astype(np.float32)
+ids = rng.permutation(3 * n_per).astype(np.int64)
+q = rng.uniform(-1, 1, (b, d)).astype(np.float32)
+q_t = torch.from_numpy(q).to(dev)
+for metric in (InnerProduct, Cosine, L2):
+    shards = []
+    for s_ in range(3):
+        ix = BruteForceIndex.apply(metric, FuturePool.immediate_pool())
+        ix.append_batch(ids[s_ * n_per:(s_ + 1) * n_per], corpus[s_ * n_per:(s_ + 1) * n_per])
+        shards.append(ix)
+    keys = torch.empty((3, b, k), dtype=torch.int32, device=dev)
+    nb = result_block_bytes(b, k)
+    off = (nb + 255) // 256 * 256
+    bufs = [torch.zeros(2 * off, dtype=torch.uint8, device=dev) for _ in range(3)]
+    locs = [ResultBlock(bufs[s_], b, k, 0) for s_ in range(3)]
+    fins = [ResultBlock(bufs[s_], b, k, off) for s_ in range(3)]
+    for s_, ix in enumerate(shards):
+        ix.query_seed_device(q_t, k, keys[s_], st)
+    for s_, ix in enumerate(shards):
+        ix.query_finish_device(q_t, k, [keys[j].data_ptr() for j in range(3)], *locs[s_].tensors, st)
+    for r in range(3):
+        q0, q1 = slice_of(r, 3, b)
+        exchange_merge_blocks([x.ptr for x in locs], [x.ptr for x in fins], b, k, q0, q1 - q0, 0, st)
+    torch.cuda.synchronize()
+    want = oracle.query_canonical(metric.ordinal, corpus, ids, q, k)
+    good = all(bool((f.ids.cpu().numpy() == want[0]).all() and (f.dist.cpu().numpy().view(np.uint32) == want[1].view(np.uint32)).all())
+               for f in fins)
+    print(metric.name, "two-phase shards + fused exchange ok", good, flush=True)
+    ok &= good
+    a_, b_ = corpus[:1001], corpus[1001:2002]
+    pd = metric.distances(a_, b_)
+    wd = np.array([oracle.distance(metric.ordinal, a_[i], b_[i]) for i in range(len(a_))], np.float32)
+    good = bool((pd.view(np.uint32) == wd.view(np.uint32)).all())
+    print(metric.name, "distance pairs ok", good, flush=True)
+    ok &= good
+    for ix in shards:
+        ix.close()
+good = bool((MetricUtil.norm(corpus[:1001]).view(np.uint32) == oracle.normalize(corpus[:1001]).view(np.uint32)).all())
+print("normalize ok", good, flush=True)
+ok &= good
 print("SANITIZE_TARGET_OK", ok)
 sys.exit(0 if ok else 1)
