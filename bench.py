@@ -61,17 +61,40 @@ def parse():
     ap.add_argument("--path", type=int, default=0, help="0 auto, 1 streaming scan, 2 tensor-core GEMM filter")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-queries", type=int, default=0, help="queries in the CPU sample (0 = one per host thread)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra block (single-query scan, configs[2], configs[3])")
+    ap.add_argument("--lat-queries", type=int, default=400, help="sequential single queries in each latency run of the extra block")
+    ap.add_argument("--config4-rows", type=int, default=100_000_000,
+                    help="total rows of the configs[3] sub-run (Cosine, batch 1024), sharded over the ranks; 0 = skip")
+    ap.add_argument("--one-round", action="store_true",
+                    help="N > 1: seed round only (A/B of the second cross-shard round that shares the k best bounds)")
     ap.add_argument("--no-share-seeds", action="store_true",
                     help="N > 1: every rank filters against its own thresholds only (A/B of the shared seed bounds)")
     return ap.parse_args()
 
 
+def workload_name(a) -> str:
+    """Which BASELINE.json config the arguments are (by shape), or "custom"."""
+    shape = (a.rows, a.dim, a.batch, a.k, a.metric)
+    if shape == (10_000_000, 200, 4096, 100, "InnerProduct"):
+        tag = "configs[1]"
+    elif shape == (10_000_000, 128, 1, 100, "L2"):
+        tag = "configs[2]"
+    elif shape == (100_000_000, 200, 1024, 100, "Cosine"):
+        tag = "configs[3]"
+    elif shape == (100_000, 200, 1000, 100, "Cosine"):
+        tag = "configs[0]"
+    else:
+        tag = "custom (not a BASELINE.json config)"
+    return f"{tag}: exact {a.metric} top-{a.k} over {a.rows}x{a.dim} fp32 corpus, query batch {a.batch}"
+
+
 def config_dict(a, n_gpus, route=""):
-    how = {"fused": "shared seed thresholds (every rank filters against the k-th best bound of all ranks' seed launches), then "
-                    "one fused exchange+merge kernel over NVLink peer memory (each rank merges 1/N of the batch)",
+    how = {"fused": "three-phase sharded query: shared seed thresholds, tensor-core filter, the k best bounds of every rank shared "
+                    "after the last chunk so that each rank rescores only its share of the global survivors; then each rank "
+                    "pulls and merges ITS 1/N slice of the batch over NVLink peer memory (answer stays partitioned, no push)",
            "allgather": "NCCL all-gather of local top-k + merge kernel"}.get(route or "fused", route)
     return {
-        "workload": f"configs[1]: exact {a.metric} top-{a.k} over {a.rows}x{a.dim} fp32 corpus, query batch {a.batch}",
+        "workload": workload_name(a),
         "rows": a.rows, "dim": a.dim, "batch": a.batch, "k": a.k, "distance": a.metric,
         "sharding": "single GPU" if n_gpus == 1 else f"rows sharded contiguously over {n_gpus} ranks, queries replicated, " + how,
         "l2_flush": "none needed: every step streams the corpus shadow (>= 4 GB per 10M rows) through a 126 MB L2",
@@ -124,7 +147,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------- CPU baseline
-def cpu_baseline_run(corpus_np, ids_np, queries_np, metric_ord: int, k: int, steps: int, warmup: int):
+def cpu_baseline_run(corpus_np, ids_np, queries_np, metric_ord: int, k: int, steps: int, warmup: int, keep: bool = False):
     """Times the reference-faithful restatement (oracle.FaithfulIndex) with one whole query per host thread."""
     import oracle
 
@@ -139,7 +162,7 @@ def cpu_baseline_run(corpus_np, ids_np, queries_np, metric_ord: int, k: int, ste
     per_step = []
     for s in range(warmup + steps):
         t0 = time.time()
-        ix.query(queries_np, k, nthreads=cores)
+        answers = ix.query(queries_np, k, nthreads=cores)
         dt = time.time() - t0
         if s >= warmup:
             per_step.append(dt)
@@ -148,7 +171,7 @@ def cpu_baseline_run(corpus_np, ids_np, queries_np, metric_ord: int, k: int, ste
     return {"value": nq * len(per_step) / tot, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{nq} queries per step x {len(per_step)} step(s) against the full {corpus_np.shape[0]}x{corpus_np.shape[1]} "
                       f"corpus, one query per thread; linked-list build {build_s:.1f}s not timed",
-            "ms_per_step": 1000.0 * tot / len(per_step)}
+            "ms_per_step": 1000.0 * tot / len(per_step), "answers": answers if keep else None}
 
 
 def gen_host_data(a, device_ok: bool):
@@ -204,6 +227,50 @@ def run_reference(a):
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
+def result_digest(ids_np, dist_np, cnt_np) -> str:
+    """sha256 over the whole batch's neighbour ids, distance bits and counts: equal digests = bit-identical answers."""
+    import hashlib
+
+    import numpy as np
+
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(ids_np, dtype=np.int64).tobytes())
+    h.update(np.ascontiguousarray(dist_np, dtype=np.float32).view(np.uint32).tobytes())
+    h.update(np.ascontiguousarray(cnt_np, dtype=np.int32).tobytes())
+    return h.hexdigest()[:32]
+
+
+def parity_against(got, want, tie_tolerant=False):
+    """Compare GPU rows with oracle rows for the same queries.  `tie_tolerant`: ids may be permuted inside a run of exactly
+    equal distances (the reference's heap order is history-dependent there), and the last run may differ in
+    membership when the tie straddles rank k."""
+    import numpy as np
+
+    gi, gd, gc = got
+    wi, wd, wc = want
+    dist_ok = bool((gd.view(np.uint32) == wd.view(np.uint32)).all()) and bool((gc == wc).all())
+    ids_ok = bool((gi == wi).all())
+    tie_positions = 0
+    if tie_tolerant and not ids_ok and dist_ok:
+        ok = True
+        for r in range(gi.shape[0]):
+            n = int(gc[r])
+            j = 0
+            while j < n:
+                e = j
+                while e + 1 < n and gd[r, e + 1].view(np.uint32) == gd[r, j].view(np.uint32):
+                    e += 1
+                if not (gi[r, j:e + 1] == wi[r, j:e + 1]).all():
+                    tie_positions += e + 1 - j
+                    if e - j == 0 and e != n - 1:       # a difference outside any tie run
+                        ok = False
+                    elif e != n - 1 and sorted(gi[r, j:e + 1].tolist()) != sorted(wi[r, j:e + 1].tolist()):
+                        ok = False
+                j = e + 1
+        return dist_ok, ok, tie_positions
+    return dist_ok, ids_ok, tie_positions
+
+
 def run_ours(a):
     import numpy as np
     import torch
@@ -225,44 +292,19 @@ def run_ours(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n_gpus = world
-
-    metric = Metric.from_string(a.metric)
-    n, d, b, k = a.rows, a.dim, a.batch, a.k
-    lo, hi = shard_range(n, world, rank)
-    n_local = hi - lo
-
-    # ---- build the shard (not timed): same generator stream on every rank, each keeps its own row range ----
-    ix = BruteForceIndex(metric, FuturePool.immediate_pool(), device=local_rank, capacity_hint=n_local)
-    g = torch.Generator(device=dev)
-    g.manual_seed(0x5EED0001)
-    for c0 in range(0, n, 1_000_000):
-        m = min(1_000_000, n - c0)
-        rows = torch.randn((m, d), generator=g, device=dev) / d ** 0.5
-        s, e = max(c0, lo), min(c0 + m, hi)
-        if s < e:
-            ix.append_batch_device(torch.arange(s, e, device=dev, dtype=torch.int64), rows[s - c0:e - c0].contiguous())
-    del rows
-    g.manual_seed(0x5EED0002)
-    q_dev = (torch.rand((b, d), generator=g, device=dev) * 2 - 1).contiguous()
-    if a.path:
-        ix.set_option("path", a.path)
-
-    out_ids = torch.empty((b, k), dtype=torch.int64, device=dev)
-    out_dist = torch.empty((b, k), dtype=torch.float32, device=dev)
-    out_cnt = torch.empty((b,), dtype=torch.int32, device=dev)
     stream = torch.cuda.current_stream()
-    sx = ShardedBruteForceIndex(ix, device=dev, share_seeds=not a.no_share_seeds) if world > 1 else None
-
-    def step_device(queries):
-        if world == 1:
-            ix.query_batch_device(queries, k, out_ids, out_dist, out_cnt, stream.cuda_stream)
-            return out_ids, out_dist, out_cnt
-        return sx.batch_query_device(queries, k, stream.cuda_stream)   # local query + exchange + merge, on every rank
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     def timed(fn, steps):
         barrier()
@@ -272,12 +314,54 @@ def run_ours(a):
             fn()
         e1.record(stream)
         barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    def build_shard(metric, n, d, seed):
+        """This rank's contiguous row range of the n x d corpus; every rank draws the same generator stream."""
+        lo, hi = shard_range(n, world, rank)
+        ix_ = BruteForceIndex(metric, FuturePool.immediate_pool(), device=local_rank, capacity_hint=hi - lo)
+        g_ = torch.Generator(device=dev)
+        g_.manual_seed(seed)
+        for c0 in range(0, n, 1_000_000):
+            m = min(1_000_000, n - c0)
+            rows = torch.randn((m, d), generator=g_, device=dev) / d ** 0.5
+            s_, e_ = max(c0, lo), min(c0 + m, hi)
+            if s_ < e_:
+                ix_.append_batch_device(torch.arange(s_, e_, device=dev, dtype=torch.int64), rows[s_ - c0:e_ - c0].contiguous())
+            del rows
+        return ix_, hi - lo
+
+    def gather_rows(t_ids, t_dist, t_cnt):
+        """Whole-batch answer on rank 0 (numpy) from every rank's slice -- outside every timed region."""
+        part = (t_ids.cpu().numpy(), t_dist.cpu().numpy(), t_cnt.cpu().numpy())
+        if world == 1:
+            return part
+        parts = [None] * world
+        dist.all_gather_object(parts, part)
+        return tuple(np.concatenate([p_[j] for p_ in parts]) for j in range(3))
+
+    metric = Metric.from_string(a.metric)
+    n, d, b, k = a.rows, a.dim, a.batch, a.k
+
+    # ---- build the shard (not timed) ----
+    ix, n_local = build_shard(metric, n, d, 0x5EED0001)
+    g = torch.Generator(device=dev)
+    g.manual_seed(0x5EED0002)
+    q_dev = (torch.rand((b, d), generator=g, device=dev) * 2 - 1).contiguous()
+    if a.path:
+        ix.set_option("path", a.path)
+
+    out_ids = torch.empty((b, k), dtype=torch.int64, device=dev)
+    out_dist = torch.empty((b, k), dtype=torch.float32, device=dev)
+    out_cnt = torch.empty((b,), dtype=torch.int32, device=dev)
+    sx = ShardedBruteForceIndex(ix, device=dev, share_seeds=not a.no_share_seeds, two_round=not a.one_round) if world > 1 else None
+
+    def step_device(queries):
+        if world == 1:
+            ix.query_batch_device(queries, k, out_ids, out_dist, out_cnt, stream.cuda_stream)
+            return out_ids, out_dist, out_cnt
+        # local three-phase query + pull/merge of THIS rank's 1/N slice of the batch (the answer stays partitioned)
+        return sx.batch_query_device(queries, k, stream.cuda_stream, deliver="slice")
 
     # ---- warm-up, then the device-resident measurement ----
     for _ in range(max(a.warmup, 3)):
@@ -301,15 +385,17 @@ def run_ours(a):
 
     # ---- end to end through the host-buffer C-ABI call: pinned queries in, host results out ----
     q_pin = q_dev.cpu().pin_memory()
-    h_ids = torch.empty((b, k), dtype=torch.int64).pin_memory()
-    h_dist = torch.empty((b, k), dtype=torch.float32).pin_memory()
-    h_cnt = torch.empty((b,), dtype=torch.int32).pin_memory()
+    q0, q1 = (0, b) if world == 1 else sx.slice_range(b)
+    h_ids = torch.empty((q1 - q0, k), dtype=torch.int64).pin_memory()
+    h_dist = torch.empty((q1 - q0, k), dtype=torch.float32).pin_memory()
+    h_cnt = torch.empty((q1 - q0,), dtype=torch.int32).pin_memory()
     q_np = q_pin.numpy()
     out_np = (h_ids.numpy(), h_dist.numpy(), h_cnt.numpy())      # pinned result buffers handed to the C ABI
 
     def step_e2e():
         if world == 1:
             return ix.batch_query_with_distance(q_np, k, out=out_np)   # ann_query_batch: H2D, query path, D2H inside the call
+        # N ranks: every rank needs the whole query batch (rows are sharded, queries replicated) and keeps its slice of the answer
         qd = q_pin.to(dev, non_blocking=True)
         oi, od, oc = step_device(qd)
         h_ids.copy_(oi, non_blocking=True)
@@ -325,12 +411,13 @@ def run_ours(a):
     for _ in range(a.steps):
         step_e2e()
     barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / a.steps
-    if world > 1:
-        t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / a.steps)
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- the answer itself: digest of the whole batch (must be the same at every N), no flagged rows ----
+    full = gather_rows(torch.from_numpy(out_np[0]), torch.from_numpy(out_np[1]), torch.from_numpy(out_np[2]))
+    digest = result_digest(*full)
+    flagged_rows = int((full[2] < 0).sum())
 
     # ---- roofline of the dominant kernel (CUDA events around each launch, on the launching stream) ----
     peaks = {}
@@ -340,10 +427,10 @@ def run_ours(a):
         pass
     traffic, traffic_detail = None, None
     try:   # DRAM bytes of the same kernel from the committed ncu --set full capture of this command (profiles/)
-        tj = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())
+        tj = json.loads(next(p_ for p_ in (ROOT / "profiles" / "traffic.json", ROOT / "profiles" / "r01_traffic.json") if p_.exists()).read_text())
         if (n, d, b, k, world, a.metric) == (10_000_000, 200, 4096, 100, 1, "InnerProduct"):
             traffic = float(tj["gemm_filter_dram_bytes_per_step"])     # dram read + write, summed over the step's launches
-            traffic_detail = {"unit": "bytes per step (the kernel's 6 launches of one batch), like `achieved`",
+            traffic_detail = {"unit": "bytes per step (the kernel's launches of one batch), like `achieved`",
                               "operand_bytes_per_step": tj["algorithmic_shadow_bytes_per_step"], "source": tj["source"]}
     except Exception:
         pass
@@ -355,6 +442,7 @@ def run_ours(a):
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak) if achieved else None,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
                     if peaks else "fallback 1.4 PFLOP/s sustained",
+                    "frac_of_burst": (achieved / float(peaks["bf16_tflops"])) if achieved and peaks.get("bf16_tflops") else None,
                     "traffic": traffic, "traffic_detail": traffic_detail, "kernel_ms_per_step": kernel_us / 1e3 / a.steps,
                     "launches_per_step": kernel_n / a.steps,
                     "algorithmic_flops_per_step": flops_step}
@@ -367,8 +455,95 @@ def run_ours(a):
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
                     "kernel_ms_per_step": kernel_us / 1e3 / a.steps, "launches_per_step": kernel_n / a.steps}
 
-    # ---- CPU baseline on the host cores (rank 0, N = 1 only; bounded sample) ----
-    cpu = None
+    # ---- extra, same process: the HBM-bound single-query scan on this corpus, config 3 and config 4 ----
+    extra = {}
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+
+    def latency_run(index, queries_np, nq_lat, scan_bytes_per_query):
+        """Sequential single queries through the host call (H2D + kernels + D2H per call): p50 / p99, and the kernel-only
+        scan bandwidth from the CUDA events around the scan launches."""
+        index.set_option("path", 1)
+        for i in range(5):
+            index.batch_query_with_distance(queries_np[i:i + 1], k)
+        index.set_option("timing", 1)
+        lat = []
+        for i in range(nq_lat):
+            t_ = time.perf_counter()
+            index.batch_query_with_distance(queries_np[i % len(queries_np)][None, :], k)
+            lat.append((time.perf_counter() - t_) * 1e3)
+        kus = index.stat("kernel_us")
+        index.set_option("timing", 0)
+        index.set_option("path", 0)
+        lat.sort()
+        p50, p99 = lat[len(lat) // 2], lat[min(len(lat) - 1, int(len(lat) * 0.99))]
+        gbs_kernel = scan_bytes_per_query * nq_lat / (kus * 1e-6) / 1e9 if kus else None
+        return {"queries": nq_lat, "p50_ms": p50, "p99_ms": p99, "qps_single_stream": 1e3 / (sum(lat) / len(lat)),
+                "scan_GBps_kernel": gbs_kernel, "scan_GBps_per_host_call_p50": scan_bytes_per_query / (p50 * 1e-3) / 1e9,
+                "hbm_peak_GBps": hbm_peak, "frac_of_hbm_peak_kernel": gbs_kernel / hbm_peak if gbs_kernel else None,
+                "frac_of_hbm_peak_per_host_call_p50": scan_bytes_per_query / (p50 * 1e-3) / 1e9 / hbm_peak,
+                "algorithmic_bytes_per_query": scan_bytes_per_query}
+
+    if not a.no_extra and world == 1 and last_path == 2:
+        try:   # BASELINE.json's metric: "scan GB/s vs HBM peak" -- B = 1 on the headline corpus, fp32 rows streamed from HBM
+            r_ = latency_run(ix, q_np, a.lat_queries, float(n) * d * 4 + (float(n) * 4 if a.metric == "Cosine" else 0.0))
+            r_["workload"] = f"single-query {a.metric} top-{k} over {n}x{d} fp32 (streaming scan), sequential host calls"
+            extra["scan"] = r_
+        except Exception as e:
+            extra["scan"] = {"error": repr(e)}
+    ix_closed = False
+    if not a.no_extra and world == 1:
+        try:   # configs[2]: single-query L2 top-100 over 10M x 128, batch 1, p50/p99 latency
+            ix3, _ = build_shard(Metric.from_string("L2"), 10_000_000, 128, 0x5EED0003)
+            g.manual_seed(0x5EED0004)
+            q3 = (torch.rand((256, 128), generator=g, device=dev) * 2 - 1).cpu().numpy()
+            r_ = latency_run(ix3, q3, a.lat_queries, 10_000_000.0 * 128 * 4)
+            r_["workload"] = "configs[2]: single-query L2 top-100 over 10000000x128 fp32, batch 1, sequential host calls"
+            i3, d3, c3 = ix3.batch_query_with_distance(q3[:64], k)
+            r_["result_digest"] = result_digest(i3, d3, c3)
+            extra["config3"] = r_
+            ix3.close()
+        except Exception as e:
+            extra["config3"] = {"error": repr(e)}
+    if not a.no_extra and a.config4_rows > 0:
+        try:   # configs[3]: Cosine top-100 over 100M x 200 row-sharded over the N ranks, batch 1024
+            ix.close()
+            ix_closed = True
+            torch.cuda.empty_cache()
+            n4, b4 = a.config4_rows, 1024
+            ix4, n4_local = build_shard(Metric.from_string("Cosine"), n4, d, 0x5EED0005)
+            g.manual_seed(0x5EED0006)
+            q4 = (torch.rand((b4, d), generator=g, device=dev) * 2 - 1).contiguous()
+            o4 = (torch.empty((b4, k), dtype=torch.int64, device=dev), torch.empty((b4, k), dtype=torch.float32, device=dev),
+                  torch.empty((b4,), dtype=torch.int32, device=dev))
+            sx4 = ShardedBruteForceIndex(ix4, device=dev, share_seeds=not a.no_share_seeds, two_round=not a.one_round) if world > 1 else None
+
+            def step4():
+                if world == 1:
+                    ix4.query_batch_device(q4, k, o4[0], o4[1], o4[2], stream.cuda_stream)
+                    return o4
+                return sx4.batch_query_device(q4, k, stream.cuda_stream, deliver="slice")
+
+            for _ in range(3):
+                r4 = step4()
+            barrier()
+            ix4.raise_pending_error()
+            ix4.set_option("timing", 1)
+            steps4 = max(3, min(a.steps, 10))
+            ms4 = timed(step4, steps4) / steps4
+            kus4 = ix4.stat("kernel_us")
+            ix4.set_option("timing", 0)
+            full4 = gather_rows(*r4)
+            tf4 = 2.0 * n4_local * d * b4 * steps4 / (kus4 * 1e-6) / 1e12 if kus4 else None
+            extra["config4"] = {"workload": f"configs[3]: Cosine top-{k} over {n4}x{d} fp32 row-sharded over {world} rank(s), batch {b4}",
+                                "value": b4 / (ms4 * 1e-3), "unit": UNIT, "ms_per_step": ms4, "steps": steps4, "n_gpus": world,
+                                "rows_per_rank": n4_local, "kernel_TFLOPs_per_rank": tf4,
+                                "result_digest": result_digest(*full4), "flagged_rows": int((full4[2] < 0).sum())}
+            ix4.close()
+        except Exception as e:
+            extra["config4"] = {"error": repr(e)}
+
+    # ---- CPU baseline on the host cores (rank 0, N = 1 only; bounded sample) + parity of the sample ----
+    cpu, parity = None, None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         try:
             import oracle
@@ -376,25 +551,40 @@ def run_ours(a):
             cores = oracle.max_threads()
             nq = a.cpu_queries or cores
             parts = []
-            # the device-resident corpus itself, copied back: the CPU arm sees exactly the rows the GPU scanned
+            # the device-resident corpus itself, regenerated from the same stream: the CPU arm sees exactly the rows the GPU scanned
             g.manual_seed(0x5EED0001)
             for c0 in range(0, n, 1_000_000):
                 m = min(1_000_000, n - c0)
                 parts.append((torch.randn((m, d), generator=g, device=dev) / d ** 0.5).cpu())
             corpus_np = torch.cat(parts).numpy()
             del parts
-            r = cpu_baseline_run(corpus_np, np.arange(n, dtype=np.int64), q_np[:nq], METRIC_BY_NAME[a.metric], k, 1, 0)
+            mo = METRIC_BY_NAME[a.metric]
+            r = cpu_baseline_run(corpus_np, np.arange(n, dtype=np.int64), q_np[:nq], mo, k, 1, 0, keep=True)
             cpu = {kk: r[kk] for kk in ("value", "unit", "cores", "kind", "sample")}
-            # separately labelled "fair CPU" figure: contiguous rows, unrolled fp32 loop, all threads --
+            # parity of the sample: the CPU arm's own answers for these queries against the GPU batch's rows (outside every
+            # timed region).  Two oracles: canonical (distance, id) order -- must match bit for bit -- and the reference-
+            # faithful heap order, which may permute ids only inside runs of exactly equal distances.
+            got = (full[0][:nq], full[1][:nq], full[2][:nq])
+            canon = oracle.query_canonical(mo, corpus_np, None, q_np[:nq], k, nthreads=cores)
+            d_ok, i_ok, _ = parity_against(got, canon)
+            fd_ok, fi_ok, ties = parity_against(got, r["answers"], tie_tolerant=True)
+            parity = {"queries": nq, "against": "oracle/oracle.c on the full corpus: canonical (C5) order and the reference-faithful "
+                                                "linked-list + PriorityQueue restatement (the timed cpu_baseline run itself)",
+                      "ids_identical": i_ok, "dist_bits_identical": d_ok, "faithful_dist_bits_identical": fd_ok,
+                      "faithful_ids_identical_off_exact_ties": fi_ok, "faithful_tie_positions": ties}
+            # separately labelled "fair CPU" figure: query-blocked, row-parallel, SIMD, -O3 -ffast-math (oracle/fast_cpu.c) --
             # so that the ratio is not only against the reference's pointer-chasing layout.  Timed only, never a parity oracle.
-            nq2 = min(a.batch, 4 * cores)
+            nq2 = min(a.batch, 256)
             t0 = time.time()
-            oracle.query_fast_cpu(METRIC_BY_NAME[a.metric], corpus_np, None, q_np[:nq2], k, nthreads=cores)
-            cpu["fair_contiguous_fp32"] = {"value": nq2 / (time.time() - t0), "unit": UNIT, "cores": cores, "queries": nq2}
+            oracle.query_blocked_cpu(mo, corpus_np, None, q_np[:nq2], k, nthreads=cores)
+            cpu["fair_blocked_simd_fp32"] = {"value": nq2 / (time.time() - t0), "unit": UNIT, "cores": cores, "queries": nq2,
+                                             "what": "oracle/fast_cpu.c: 16-query blocks x 64-row tiles, threads split the rows, "
+                                                     "gcc -O3 -ffast-math with AVX-512/AVX2 clones"}
             del corpus_np
         except Exception as e:  # the baseline is a report, never a reason to lose the measurement
             cpu = {"value": None, "unit": UNIT, "cores": None, "kind": "port", "sample": f"failed: {e!r}"}
 
+    rc = 0
     if rank == 0:
         line = {
             "metric": metric_name(a), "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": a.steps, "warmup": max(a.warmup, 3),
@@ -403,17 +593,27 @@ def run_ours(a):
             "dtype_detail": ("bf16 candidate filter on tcgen05 (fp32 accumulate)" if last_path == 2 else "f32 streaming scan")
                             + " + exact rescoring of the survivors: fp64 accumulation, one rounding to fp32 (bit-identical to the oracle)",
             "data": "synthetic", "config": config_dict(a, n_gpus, sx.route if sx else ""),
-            "e2e": {"value": b / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": b * d * 4,
+            "e2e": {"value": b / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": b * d * 4 * world,
                     "d2h_bytes_per_step": b * k * 12 + b * 4, "ms_per_step": e2e_ms,
-                    "api": "ann_query_batch (host buffers)" if world == 1 else "pinned H2D + ann_query_batch_device + exchange/merge + D2H"},
+                    "api": "ann_query_batch (host buffers)" if world == 1 else
+                           "per rank: pinned H2D of the batch + three-phase sharded query + slice merge + D2H of the rank's 1/N slice"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "path": {1: "scan", 2: "gemm"}.get(last_path, str(last_path)),
+            "result_digest": digest, "flagged_rows": flagged_rows, "parity_sample": parity, "extra": extra,
         }
         print(json.dumps(line), flush=True)
-    ix.close()
+        if flagged_rows:
+            print("bench.py: the timed batch contains flagged (invalid) rows", file=sys.stderr)
+            rc = 3
+        if parity and not (parity["ids_identical"] and parity["dist_bits_identical"] and parity["faithful_dist_bits_identical"]
+                           and parity["faithful_ids_identical_off_exact_ties"]):
+            print("bench.py: PARITY MISMATCH between the GPU batch and the CPU oracle sample", file=sys.stderr)
+            rc = 4
+    if not ix_closed:
+        ix.close()
     if world > 1:
         dist.destroy_process_group()
-    return 0
+    return rc
 
 
 def main():

@@ -60,6 +60,12 @@ typedef enum ann_status {
 /* flags for ann_config.flags */
 #define ANN_FLAG_L2_SQUARED 0x1u /* return squared L2 (Faiss METRIC_L2 style, QueryableIndexAdapter.scala:174) */
 #define ANN_FLAG_NO_SHADOW 0x2u  /* do not keep the bf16 shadow matrix: batched tensor-core path disabled */
+/* Accumulator convention of the returned distances.  The reference's arithmetic (EmbeddingMath.Float) is unshipped;
+ * MetricUtil.dot is typed Float with no cast (Metric.scala:264-269) while l2distance / cosineSimilarity return Double
+ * (:271-283).  Default (flag clear): sums accumulate in fp64 in index order and round once to fp32 (oracle accum=0).
+ * With this flag every sum accumulates sequentially in fp32 with individually rounded operations (oracle accum=1), so the
+ * neighbour ids match a reference whose EmbeddingMath accumulates in Float.  Selection stays exact under either. */
+#define ANN_FLAG_ACCUM_F32 0x4u
 
 typedef struct ann_config {
     int32_t metric;        /* ann_metric                                                          */
@@ -148,6 +154,56 @@ ANN_API int ann_query_seed_device(ann_index *ix, const float *d_queries, int32_t
 ANN_API int ann_query_finish_device(ann_index *ix, const float *d_queries, int32_t b, int32_t dim, int32_t k,
                                     const uint32_t *const *peer_seed_keys, int32_t world, int64_t *d_out_ids,
                                     float *d_out_dist, int32_t *d_out_count, void *stream);
+
+/* The same sharded query with a SECOND cross-shard round, so that the exact rescoring also shrinks with the shard count.
+ * A shard's own k-th best (of 1/R of the rows) is far looser than the global k-th, so with ann_query_finish_device every
+ * shard still rescores ~2k survivors per query.  Split once more:
+ *   ann_query_seed_device     as above;                                         -- barrier --
+ *   ann_query_filter_device   global seed threshold, tensor-core chunks, last compaction; publishes this shard's k best
+ *                             approximate scores, each widened to an upper bound on the exact distance key of its row,
+ *                             into d_kth_keys[b*k] (0xFFFFFFFF = no bound);      -- barrier --
+ *   ann_query_rescore_device  takes the k-th smallest of all shards' bounds as the global cut, rescores only the rows of
+ *                             this shard under it (about 2k/R per query) exactly and writes them in canonical order.
+ * Same session rules as above (same (b, dim, k) and stream, nothing else on the handle in between).  A query the bounded
+ * selector cannot answer on some shard is reported with out_count[q] = -1 (the row is invalid, not empty); the merges
+ * below propagate the -1, so every consumer sees it and can re-ask with "device_fallback" = 1. */
+ANN_API int ann_query_filter_device(ann_index *ix, const float *d_queries, int32_t b, int32_t dim, int32_t k,
+                                    const uint32_t *const *peer_seed_keys, int32_t world, uint32_t *d_kth_keys,
+                                    void *stream);
+ANN_API int ann_query_rescore_device(ann_index *ix, const float *d_queries, int32_t b, int32_t dim, int32_t k,
+                                     const uint32_t *const *peer_kth_keys, int32_t world, int64_t *d_out_ids,
+                                     float *d_out_dist, int32_t *d_out_count, void *stream);
+
+/* Pull-only form of ann_exchange_merge_device: merge this rank's slice [q_begin, q_begin + q_count) of the batch from all
+ * `world` local result blocks (P2P loads) into plain arrays on this device -- d_out_ids / d_out_dist [q_count*k],
+ * d_out_count [q_count] (may be NULL).  The merged answer stays partitioned across the ranks: nothing is pushed, and no
+ * barrier is needed after the kernel (only before it, so that every local block is complete). */
+ANN_API int ann_exchange_merge_slice_device(int32_t device, const void *const *peer_local, int32_t world, int32_t b,
+                                            int32_t k, int32_t q_begin, int32_t q_count, int64_t *d_out_ids,
+                                            float *d_out_dist, int32_t *d_out_count, void *stream);
+
+/* ---- one process, several GPUs: ShardedAppendable + ComposedQueryable as ONE handle (ShardApi.scala:34-48, 58-87) --------
+ * The form a single-JVM host calls.  ann_sharded_create builds one shard per listed device (device_ids == NULL: devices
+ * 0..n_devices-1; cfg->device is ignored, cfg->capacity_hint is the total over all shards; a device may be listed more
+ * than once, which puts several shards on it) and enables peer access between them.  ann_sharded_append_batch cuts a batch into n_devices contiguous parts, part s to shard s, copied in parallel
+ * (ids == NULL => insertion index of the composed index).  ann_sharded_query_batch answers b host queries into host
+ * buffers: every device runs the three-phase sharded query above on its own stream from its own host thread, ordered
+ * across devices by CUDA events, then merges and returns its 1/n_devices slice of the batch.  The result is bit for bit
+ * the single-index answer (globally unique ids).  Flagged queries are re-answered with every shard's exact fallback. */
+typedef struct ann_sharded_index ann_sharded_index;
+ANN_API int ann_sharded_create(const ann_config *cfg, const int32_t *device_ids, int32_t n_devices,
+                               ann_sharded_index **out);
+ANN_API void ann_sharded_destroy(ann_sharded_index *sx);
+ANN_API int ann_sharded_append_batch(ann_sharded_index *sx, const int64_t *ids, const float *rows, int64_t n);
+ANN_API int ann_sharded_size(const ann_sharded_index *sx, int64_t *n);
+ANN_API int ann_sharded_query_batch(ann_sharded_index *sx, const float *queries, int32_t b, int32_t dim, int32_t k,
+                                    int64_t *out_ids, float *out_dist, int32_t *out_count);
+/* Borrow shard `shard` (owned by the composed handle) and its row count. */
+ANN_API int ann_sharded_shard(ann_sharded_index *sx, int32_t shard, ann_index **out, int64_t *rows);
+/* "two_round" (1 = seed + k-best rounds, default; 0 = seed round only); any other name is applied to every shard.
+ * Stats: "shards", "peer_access", "fallback_batches", "queries"; any other name is summed over the shards. */
+ANN_API int ann_sharded_set_option(ann_sharded_index *sx, const char *name, int64_t value);
+ANN_API int ann_sharded_get_stat(const ann_sharded_index *sx, const char *name, int64_t *value);
 
 /* KnnHelper.findNearestNeighbours (ann/src/main/scala/com/twitter/ann/scalding/offline/KnnHelper.scala:168-215, 248-347):
  * the exact k nearest corpus rows of every query, host buffers in and out -- the offline all-pairs job behind

@@ -24,9 +24,13 @@ L2, COSINE, INNER_PRODUCT = 0, 1, 2
 METRIC_BY_NAME = {"L2": L2, "Cosine": COSINE, "InnerProduct": INNER_PRODUCT}
 
 
+_FAST_PATH = _HERE / "_build" / "libfastcpu.so"
+
+
 def build(force: bool = False) -> Path:
-    src = _HERE / "oracle.c"
-    if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < src.stat().st_mtime:
+    stale = any(not lib_.exists() or lib_.stat().st_mtime < (_HERE / src).stat().st_mtime
+                for lib_, src in ((_LIB_PATH, "oracle.c"), (_FAST_PATH, "fast_cpu.c")))
+    if force or stale:
         subprocess.run(["make", "-C", str(_HERE), "-s", "all"], check=True)
     return _LIB_PATH
 
@@ -123,6 +127,35 @@ def query_canonical(metric: int, corpus, ids, queries, k: int, accum: int = 0, l
                                  out_dist.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
                                  out_cnt.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), accum, l2_squared, nthreads)
     return out_ids, out_dist, out_cnt
+
+
+_fast = None
+
+
+def query_blocked_cpu(metric: int, corpus, ids, queries, k: int, nthreads: int = 0):
+    """The "fair CPU" figure (oracle/fast_cpu.c): query-blocked, row-parallel, SIMD, -O3 -ffast-math.  TIMED ONLY: fp32
+    lane-parallel sums, so ids can differ from the oracle where distances are within fp32 noise of each other."""
+    global _fast
+    if _fast is None:
+        if not _FAST_PATH.exists():
+            build()
+        _fast = ctypes.CDLL(str(_FAST_PATH))
+        _fast.fastcpu_query.restype = ctypes.c_int
+        _fast.fastcpu_query.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int64), ctypes.c_int64,
+                                        ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.c_int, ctypes.c_int,
+                                        ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_float), ctypes.c_int]
+    c, cp_ = _f(corpus)
+    q, qp = _f(np.atleast_2d(queries))
+    n, d = c.shape
+    b = q.shape[0]
+    ip_ = None
+    if ids is not None:
+        i, ip_ = _i(ids)
+    out_ids = np.full((b, k), -1, dtype=np.int64)
+    out_dist = np.full((b, k), np.inf, dtype=np.float32)
+    _fast.fastcpu_query(metric, cp_, ip_, n, d, qp, b, k, out_ids.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                        out_dist.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), nthreads)
+    return out_ids, out_dist
 
 
 def query_fast_cpu(metric: int, corpus, ids, queries, k: int, nthreads: int = 0):

@@ -1,0 +1,234 @@
+"""Round-2 GPU parity tests (through the C ABI, against the CPU oracle on the same seeded inputs):
+the fp32 accumulator convention (ANN_FLAG_ACCUM_F32 = oracle accum=1), the headline shape of BASELINE.json configs[1]
+against the oracle on sampled queries, k beyond 4096 on the exact fallback, an empty shard under ComposedQueryable."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import oracle_np as onp
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5  # BASELINE.json north_star: distances within 1e-5 relative error in fp32
+
+
+def _imports():
+    from the_algorithm_b200 import _capi
+    from the_algorithm_b200.ann.brute_force import BruteForceIndex
+    from the_algorithm_b200.ann.common import (ComposedQueryable, Cosine, EntityEmbedding, FuturePool, InnerProduct, L2,
+                                               RandomShardFunction, ShardedAppendable)
+    return locals()
+
+
+G = None
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _g():
+    global G
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    G = _imports()
+    yield
+
+
+def metrics():
+    return [G["InnerProduct"], G["Cosine"], G["L2"]]
+
+
+def make(n, d, b, seed, dup=False):
+    rng = np.random.default_rng(seed)
+    corpus = (rng.standard_normal((n, d)) / np.sqrt(d)).astype(np.float32)
+    if dup and n >= 100:
+        m = n // 100 + 1
+        corpus[n // 2: n // 2 + m] = corpus[:m]
+    q = rng.uniform(-1, 1, (b, d)).astype(np.float32)
+    ids = rng.permutation(n).astype(np.int64) * 13 - 17
+    return corpus, ids, q
+
+
+def same(got, want):
+    gi, gd, gc = got
+    oi, od, oc = want
+    assert (gc == oc).all()
+    assert (gi == oi).all(), f"ids differ at {np.argwhere(gi != oi)[:4].tolist()}"
+    assert (onp.float_order_key(gd) == onp.float_order_key(od)).all()
+
+
+# ------------------------------------------------------------------------------------------------ accumulator convention
+@pytest.mark.parametrize("mi", [0, 1, 2])
+@pytest.mark.parametrize("path,n,d,b,k", [(1, 20_000, 200, 9, 100), (2, 50_000, 200, 300, 100), (2, 33_333, 128, 257, 100),
+                                          (1, 3000, 37, 4, 7), (2, 20_000, 72, 64, 17), (3, 5000, 24, 3, 40)])
+def test_fp32_accumulator_convention_matches_oracle_accum1(mi, path, n, d, b, k):
+    """ANN_FLAG_ACCUM_F32: ids and distance bits equal the oracle's sequential-fp32 arithmetic (Metric.scala:264-269 types
+    `dot` as Float) on the scan, the tensor-core filter and the exact fallback."""
+    m = metrics()[mi]
+    corpus, ids, q = make(n, d, b, seed=n + d + b + 1, dup=(n == 33_333))
+    ix = G["BruteForceIndex"].apply(m, G["FuturePool"].immediate_pool(), accum_f32=True)
+    ix.append_batch(ids, corpus)
+    ix.set_option("path", path)
+    got = ix.batch_query_with_distance(q, k)
+    assert ix.stat("last_path") == path
+    ix.close()
+    same(got, oracle.query_canonical(m.ordinal, corpus, ids, q, k, accum=1))
+
+
+def test_fp32_and_fp64_conventions_differ_only_where_the_oracles_differ():
+    """Both conventions on the same data: each equals its own oracle, and where the two oracles agree so do the indexes."""
+    corpus, ids, q = make(20_000, 200, 64, seed=99)
+    m = G["InnerProduct"]
+    res = {}
+    for acc in (False, True):
+        ix = G["BruteForceIndex"].apply(m, G["FuturePool"].immediate_pool(), accum_f32=acc)
+        ix.append_batch(ids, corpus)
+        res[acc] = ix.batch_query_with_distance(q, 100)
+        ix.close()
+    o64 = oracle.query_canonical(m.ordinal, corpus, ids, q, 100, accum=0)
+    o32 = oracle.query_canonical(m.ordinal, corpus, ids, q, 100, accum=1)
+    same(res[False], o64)
+    same(res[True], o32)
+    fin = np.isfinite(o64[1])
+    assert np.all(np.abs(res[True][1][fin] - o64[1][fin]) <= REL_TOL * np.maximum(np.abs(o64[1][fin]), 1e-30))
+
+
+@pytest.mark.parametrize("mi", [0, 1, 2])
+def test_metric_pairs_fp32_convention(mi):
+    m = metrics()[mi]
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((300, 200)).astype(np.float32)
+    b = rng.standard_normal((300, 200)).astype(np.float32)
+    got = m.distances(a, b, accum_f32=True)
+    want = np.array([oracle.distance(m.ordinal, a[i], b[i], accum=1) for i in range(300)], np.float32)
+    assert (got.view(np.uint32) == want.view(np.uint32)).all()
+
+
+# ------------------------------------------------------------------------------------------------ large k on the fallback
+@pytest.mark.parametrize("k", [5000, 16384])
+def test_exact_fallback_k_beyond_4096(k):
+    """k in (4096, 16384] needs 96-192 KB of dynamic shared memory in the fallback's sort kernel (opt-in attribute)."""
+    corpus, ids, q = make(20_000, 16, 2, seed=k)
+    m = G["L2"]
+    ix = G["BruteForceIndex"].apply(m, G["FuturePool"].immediate_pool())
+    ix.append_batch(ids, corpus)
+    got = ix.batch_query_with_distance(q, k)
+    assert ix.stat("last_path") == 3
+    ix.close()
+    same(got, oracle.query_canonical(m.ordinal, corpus, ids, q, k))
+
+
+# ------------------------------------------------------------------------------------------------ composed, empty shard
+def test_composed_queryable_tolerates_an_empty_shard():
+    """ShardedAppendable with RandomShardFunction leaves shards empty early on; the reference's ComposedQueryable just gets
+    an empty list from them (ShardApi.scala:72-86)."""
+    m = G["Cosine"]
+    corpus, ids, q = make(3000, 32, 5, seed=8)
+    shards = [G["BruteForceIndex"](m, G["FuturePool"].immediate_pool()) for _ in range(3)]
+    shards[0].append_batch(ids[:1700], corpus[:1700])
+    shards[2].append_batch(ids[1700:], corpus[1700:])           # shard 1 stays empty (NULL handle)
+    cq = G["ComposedQueryable"](shards)
+    got = cq.batch_query_with_distance(q, 20)
+    same(got, oracle.query_canonical(m.ordinal, corpus, ids, q, 20))
+    assert [n.neighbor for n in cq.query_with_distance(q[0], 20).result()] == got[0][0].tolist()
+    for s in shards:
+        s.close()
+
+
+# ------------------------------------------------------------------------------------------------ headline shape vs oracle
+def test_config2_shape_sampled_queries_match_oracle():
+    """BASELINE.json configs[1] at full size -- InnerProduct top-100 over 10M x 200, batch 4096 on the tensor-core path --
+    compared with the canonical oracle on 12 sampled queries of that batch (multi-threaded oracle, seconds)."""
+    import torch
+
+    dev = torch.device("cuda", 0)
+    n, d, b, k = 10_000_000, 200, 4096, 100
+    g = torch.Generator(device=dev)
+    g.manual_seed(0x5EED0001)
+    ix = G["BruteForceIndex"](G["InnerProduct"], G["FuturePool"].immediate_pool(), capacity_hint=n)
+    host = np.empty((n, d), dtype=np.float32)
+    for c0 in range(0, n, 1_000_000):
+        rows = torch.randn((1_000_000, d), generator=g, device=dev) / d ** 0.5
+        ix.append_batch_device(torch.arange(c0, c0 + 1_000_000, device=dev, dtype=torch.int64), rows)
+        host[c0:c0 + 1_000_000] = rows.cpu().numpy()
+    g.manual_seed(0x5EED0002)
+    q = (torch.rand((b, d), generator=g, device=dev) * 2 - 1).cpu().numpy()
+    gi, gd, gc = ix.batch_query_with_distance(q, k)
+    assert ix.stat("last_path") == 2
+    ix.close()
+    sample = np.linspace(0, b - 1, 12).astype(np.int64)
+    oi, od, oc = oracle.query_canonical(2, host, None, q[sample], k)
+    same((gi[sample], gd[sample], gc[sample]), (oi, od, oc))
+    keys = onp.float_order_key(gd).astype(np.int64)
+    assert ((keys[:, 1:] > keys[:, :-1]) | ((keys[:, 1:] == keys[:, :-1]) & (gi[:, 1:] > gi[:, :-1]))).all()
+
+
+# ------------------------------------------------------------------------------------------------ one process, R shards
+def _devices(shards):
+    import torch
+
+    n = torch.cuda.device_count()
+    return [s % n for s in range(shards)]       # one GPU: every shard on it (same code path, events instead of NVLink)
+
+
+@pytest.mark.parametrize("two_round", [1, 0])
+@pytest.mark.parametrize("mi", [0, 1, 2])
+@pytest.mark.parametrize("shards,n,d,b,k", [(2, 70_001, 200, 130, 100), (3, 50_000, 64, 40, 10), (8, 400_000, 128, 64, 100),
+                                            (4, 9000, 32, 7, 100), (2, 150, 16, 5, 100)])
+def test_in_process_sharded_handle_equals_single_index(two_round, mi, shards, n, d, b, k):
+    """ann_sharded_* (one process, R shards, CUDA events between the phases): bit for bit the single-index oracle answer."""
+    from the_algorithm_b200.ann.sharded import GpuShardedBruteForceIndex
+
+    m = metrics()[mi]
+    corpus, ids, q = make(n, d, b, seed=n + shards, dup=True)
+    sx = GpuShardedBruteForceIndex(m, G["FuturePool"].immediate_pool(), dim=d, devices=_devices(shards))
+    sx.set_option("two_round", two_round)
+    half = n // 2
+    sx.append_batch(ids[:half], corpus[:half])         # two appends: every shard holds two non-adjacent row ranges
+    sx.append_batch(ids[half:], corpus[half:])
+    assert sx.size() == n and sum(sx.shard_sizes()) == n and max(sx.shard_sizes()) - min(sx.shard_sizes()) <= 2
+    want = oracle.query_canonical(m.ordinal, corpus, ids, q, k)
+    for rep in range(2):                                # repeated: buffers and events are reused
+        same(sx.batch_query_with_distance(q, k), want)
+    assert sx.stat("fallback_batches") == 0
+    assert [x.neighbor for x in sx.query_with_distance(q[0], 5).result()] == want[0][0, :5].tolist()
+    sx.close()
+
+
+@pytest.mark.parametrize("mi", [0, 1, 2])
+def test_in_process_sharded_handle_answers_degenerate_batches_exactly(mi):
+    """A NaN query and thousands of identical rows flag the bounded selectors of some shards: the handle must notice (count
+    = -1 travels through the merge) and answer the batch again through the exact fallback -- never a silently short list."""
+    from the_algorithm_b200.ann.sharded import GpuShardedBruteForceIndex
+
+    m = metrics()[mi]
+    corpus, ids, q = make(40_000, 48, 12, seed=77)
+    corpus[5000:12000] = corpus[17]                     # 7000 exact duplicates: far more ties than any pool holds
+    q[3] = corpus[17] * 3.0                             # ... and a query they are all nearest to
+    q[7, 5] = np.nan
+    sx = GpuShardedBruteForceIndex(m, G["FuturePool"].immediate_pool(), dim=48, devices=_devices(3))
+    sx.append_batch(ids, corpus)
+    got = sx.batch_query_with_distance(q, 100)
+    assert sx.stat("fallback_batches") == 1
+    same(got, oracle.query_canonical(m.ordinal, corpus, ids, q, 100))
+    sx.close()
+
+
+def test_in_process_sharded_handle_errors_and_empty():
+    from the_algorithm_b200.ann.sharded import GpuShardedBruteForceIndex
+
+    AnnError = G["_capi"].AnnError
+    sx = GpuShardedBruteForceIndex(G["L2"], G["FuturePool"].immediate_pool(), dim=8, devices=_devices(2))
+    gi, gd, gc = sx.batch_query_with_distance(np.zeros((3, 8), np.float32), 5)      # empty index: empty lists
+    assert (gc == 0).all() and (gi == -1).all() and np.isinf(gd).all()
+    with pytest.raises(AnnError) as e:
+        sx.batch_query_with_distance(np.zeros((3, 9), np.float32), 5)
+    assert e.value.code == G["_capi"].ANN_ERR_DIMENSION_MISMATCH
+    with pytest.raises(AnnError):
+        sx.append_batch(None, np.zeros((3, 9), np.float32))
+    sx.append_batch(None, np.arange(24, dtype=np.float32).reshape(3, 8))            # ids default to the composed insertion index
+    gi, gd, gc = sx.batch_query_with_distance(np.zeros((1, 8), np.float32), 5)
+    assert gc[0] == 3 and gi[0, :3].tolist() == [0, 1, 2]
+    assert sx.batch_query_with_distance(np.zeros((2, 8), np.float32), 0)[2].tolist() == [0, 0]
+    sx.close()
+    with pytest.raises(AnnError):
+        GpuShardedBruteForceIndex(G["L2"], G["FuturePool"].immediate_pool(), dim=8, devices=[99])

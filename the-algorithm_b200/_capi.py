@@ -26,11 +26,15 @@ ANN_ERR_UNKNOWN_OPTION = -9
 
 ANN_FLAG_L2_SQUARED = 0x1
 ANN_FLAG_NO_SHADOW = 0x2
+ANN_FLAG_ACCUM_F32 = 0x4
 
 # every symbol include/b200ann.h declares (tests/test_capi_symbols.py checks header <-> library <-> this list)
 SYMBOLS = (
     "ann_create", "ann_destroy", "ann_append_batch", "ann_append_batch_device", "ann_update_batch", "ann_read_rows", "ann_size", "ann_query_batch",
-    "ann_query_batch_device", "ann_merge_topk_device", "ann_exchange_merge_device", "ann_result_block_bytes", "ann_query_seed_device", "ann_query_finish_device", "ann_knn_join", "ann_distance_pairs", "ann_normalize_rows", "ann_set_option", "ann_get_stat", "ann_last_error", "ann_version",
+    "ann_query_batch_device", "ann_merge_topk_device", "ann_exchange_merge_device", "ann_result_block_bytes", "ann_query_seed_device", "ann_query_finish_device",
+    "ann_query_filter_device", "ann_query_rescore_device", "ann_exchange_merge_slice_device",
+    "ann_sharded_create", "ann_sharded_destroy", "ann_sharded_append_batch", "ann_sharded_size", "ann_sharded_query_batch",
+    "ann_sharded_shard", "ann_sharded_set_option", "ann_sharded_get_stat", "ann_knn_join", "ann_distance_pairs", "ann_normalize_rows", "ann_set_option", "ann_get_stat", "ann_last_error", "ann_version",
 )
 
 
@@ -84,6 +88,28 @@ def lib() -> ctypes.CDLL:
         L.ann_query_seed_device.argtypes = [vp, vp, i32, i32, i32, vp, vp]
         L.ann_query_finish_device.restype = ctypes.c_int
         L.ann_query_finish_device.argtypes = [vp, vp, i32, i32, i32, ctypes.POINTER(vp), i32, vp, vp, vp, vp]
+        L.ann_query_filter_device.restype = ctypes.c_int
+        L.ann_query_filter_device.argtypes = [vp, vp, i32, i32, i32, ctypes.POINTER(vp), i32, vp, vp]
+        L.ann_query_rescore_device.restype = ctypes.c_int
+        L.ann_query_rescore_device.argtypes = [vp, vp, i32, i32, i32, ctypes.POINTER(vp), i32, vp, vp, vp, vp]
+        L.ann_exchange_merge_slice_device.restype = ctypes.c_int
+        L.ann_exchange_merge_slice_device.argtypes = [i32, ctypes.POINTER(vp), i32, i32, i32, i32, i32, vp, vp, vp, vp]
+        L.ann_sharded_create.restype = ctypes.c_int
+        L.ann_sharded_create.argtypes = [ctypes.POINTER(AnnConfig), ctypes.POINTER(i32), i32, ctypes.POINTER(vp)]
+        L.ann_sharded_destroy.restype = None
+        L.ann_sharded_destroy.argtypes = [vp]
+        L.ann_sharded_append_batch.restype = ctypes.c_int
+        L.ann_sharded_append_batch.argtypes = [vp, vp, vp, i64]
+        L.ann_sharded_size.restype = ctypes.c_int
+        L.ann_sharded_size.argtypes = [vp, ctypes.POINTER(i64)]
+        L.ann_sharded_query_batch.restype = ctypes.c_int
+        L.ann_sharded_query_batch.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp]
+        L.ann_sharded_shard.restype = ctypes.c_int
+        L.ann_sharded_shard.argtypes = [vp, i32, ctypes.POINTER(vp), ctypes.POINTER(i64)]
+        L.ann_sharded_set_option.restype = ctypes.c_int
+        L.ann_sharded_set_option.argtypes = [vp, ctypes.c_char_p, i64]
+        L.ann_sharded_get_stat.restype = ctypes.c_int
+        L.ann_sharded_get_stat.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(i64)]
         L.ann_result_block_bytes.restype = ctypes.c_size_t
         L.ann_result_block_bytes.argtypes = [i32, i32]
         L.ann_knn_join.restype = ctypes.c_int

@@ -46,14 +46,18 @@ class BruteForceIndex(Appendable, Queryable):
     _PENDING_FLUSH = 4096
 
     def __init__(self, metric: Metric, future_pool: FuturePool, device: int = 0, capacity_hint: int = 0,
-                 l2_squared: bool = False, shadow: bool = True):
+                 l2_squared: bool = False, shadow: bool = True, accum_f32: bool = False):
         self.metric = metric
         self.future_pool = future_pool
         self.device = device
         self.dim: Optional[int] = None
         self._h = ctypes.c_void_p()
+        # accum_f32: distances follow the sequential-fp32 accumulator convention (ANN_FLAG_ACCUM_F32, include/b200ann.h)
         self._cfg = dict(capacity_hint=capacity_hint, flags=(_capi.ANN_FLAG_L2_SQUARED if l2_squared else 0) |
-                         (0 if shadow else _capi.ANN_FLAG_NO_SHADOW))
+                         (0 if shadow else _capi.ANN_FLAG_NO_SHADOW) | (_capi.ANN_FLAG_ACCUM_F32 if accum_f32 else 0))
+        self._slots = None
+        self._slots_version = -1
+        self._version = 0          # bumped by every successful append: the id -> slot map is rebuilt when it lags
         self._lock = threading.RLock()
         self._pending_ids: List = []
         self._pending_rows: List[np.ndarray] = []
@@ -65,8 +69,9 @@ class BruteForceIndex(Appendable, Queryable):
     # ---- construction -------------------------------------------------------------------------------------
     @staticmethod
     def apply(metric: Metric, future_pool: FuturePool, initial_embeddings: Iterable[EntityEmbedding] = (), *,
-              device: int = 0, capacity_hint: int = 0, l2_squared: bool = False, shadow: bool = True) -> "BruteForceIndex":
-        ix = BruteForceIndex(metric, future_pool, device, capacity_hint, l2_squared, shadow)
+              device: int = 0, capacity_hint: int = 0, l2_squared: bool = False, shadow: bool = True,
+              accum_f32: bool = False) -> "BruteForceIndex":
+        ix = BruteForceIndex(metric, future_pool, device, capacity_hint, l2_squared, shadow, accum_f32)
         ids, rows = [], []
         for e in initial_embeddings:
             ids.append(e.id)
@@ -114,31 +119,27 @@ class BruteForceIndex(Appendable, Queryable):
             if not self._pending_rows:
                 return
             ids, rows = self._pending_ids, self._pending_rows
-            self._pending_ids, self._pending_rows = [], []
             dims = {r.shape[-1] for r in rows}
-            if len(dims) != 1:
+            if len(dims) != 1:   # nothing is dropped: the rows stay buffered, every later flush reports the same error
                 raise _capi.AnnError(_capi.ANN_ERR_DIMENSION_MISMATCH, "appended embeddings differ in dimension")
-            self.append_batch(ids, np.stack(rows))
+            self.append_batch(ids, np.stack(rows))      # raises before the buffers are released
+            self._pending_ids, self._pending_rows = [], []
 
-    def _device_ids(self, ids, n: int) -> np.ndarray:
+    def _device_ids(self, ids, n: int):
+        """Device ids of a batch + the entries its success adds to the host id table (committed by the caller only after
+        the C call succeeded, so a failed append cannot desynchronise slot and id)."""
         if ids is None:
             dev = np.arange(self._n, self._n + n, dtype=np.int64)
-            if self._id_table is not None:
-                self._id_table.extend(dev.tolist())
-            return dev
+            return dev, (dev.tolist() if self._id_table is not None else None)
         if isinstance(ids, np.ndarray) and ids.dtype.kind in "iu" and self._id_table is None:
-            return np.ascontiguousarray(ids, dtype=np.int64)
+            return np.ascontiguousarray(ids, dtype=np.int64), None
         ids = list(ids)
         if self._id_table is None and all(isinstance(i, (int, np.integer)) and _I64_MIN <= int(i) <= _I64_MAX for i in ids):
-            return np.asarray(ids, dtype=np.int64)
+            return np.asarray(ids, dtype=np.int64), None
         # generic T: slot table.  Ties then break by insertion slot (documented in DESIGN.md).
-        if self._id_table is None:
-            if self._n:
-                raise TypeError("cannot mix native int64 ids with generic ids in one index")
-            self._id_table = []
-            self.native_ids = False
-        self._id_table.extend(ids)
-        return np.arange(self._n, self._n + n, dtype=np.int64)
+        if self._id_table is None and self._n:
+            raise TypeError("cannot mix native int64 ids with generic ids in one index")
+        return np.arange(self._n, self._n + n, dtype=np.int64), ids
 
     def append_batch(self, ids, rows) -> None:
         rows = np.ascontiguousarray(rows, dtype=np.float32)
@@ -149,11 +150,17 @@ class BruteForceIndex(Appendable, Queryable):
             if n == 0:
                 return
             self._ensure(rows.shape[1])
-            dev_ids = self._device_ids(ids, n)
-            if dev_ids.shape[0] != n:
+            dev_ids, table_add = self._device_ids(ids, n)
+            if dev_ids.shape[0] != n or (table_add is not None and len(table_add) != n):
                 raise ValueError("ids and rows differ in length")
             _capi.check(_capi.lib().ann_append_batch(self._h, _ptr(dev_ids), _ptr(rows), n))
+            if table_add is not None:
+                if self._id_table is None:
+                    self._id_table = []
+                    self.native_ids = False
+                self._id_table.extend(table_add)
             self._n += n
+            self._version += 1
 
     def append_batch_device(self, ids_t, rows_t, stream: int = 0) -> None:
         """rows_t: CUDA float32 [n, dim] tensor, ids_t: CUDA int64 [n] tensor (or None) on this index's device."""
@@ -168,16 +175,21 @@ class BruteForceIndex(Appendable, Queryable):
                 self._h, None if ids_t is None else ctypes.c_void_p(ids_t.data_ptr()), ctypes.c_void_p(rows_t.data_ptr()),
                 n, ctypes.c_void_p(stream)))
             self._n += n
+            self._version += 1
 
     # ---- Updatable (Api.scala:148-150) ---------------------------------------------------------------------------
     def _slot_map(self):
-        """id -> insertion slot, built on first use from the ids stored on the device (later appends keep it current)."""
-        if getattr(self, "_slots", None) is None or len(self._slots) != self._n:
+        """id -> insertion slot of the FIRST row carrying that id, rebuilt whenever rows were appended since it was built."""
+        if self._slots is None or self._slots_version != self._version:
             if self._id_table is not None:
-                self._slots = {i: s for s, i in enumerate(self._id_table)}
+                it = self._id_table
             else:
                 ids, _ = self.read_rows(0, self._n) if self._n else (np.zeros(0, np.int64), None)
-                self._slots = {int(i): s for s, i in enumerate(ids)}
+                it = (int(i) for i in ids)
+            slots = {}
+            for s, i in enumerate(it):
+                slots.setdefault(i, s)
+            self._slots, self._slots_version = slots, self._version
         return self._slots
 
     def update_batch(self, ids, rows) -> None:
@@ -188,17 +200,18 @@ class BruteForceIndex(Appendable, Queryable):
             self.flush()
             smap = self._slot_map() if self._n else {}
             ids = list(ids)
-            known = [j for j, i in enumerate(ids) if (i if self._id_table is not None else int(i)) in smap]
-            fresh = [j for j in range(len(ids)) if j not in set(known)]
+            key = (lambda i: i) if self._id_table is not None else int
+            known = [j for j, i in enumerate(ids) if key(i) in smap]
+            known_set = set(known)
+            fresh = [j for j in range(len(ids)) if j not in known_set]
             if known:
-                slots = np.asarray([smap[ids[j] if self._id_table is not None else int(ids[j])] for j in known], dtype=np.int64)
+                slots = np.asarray([smap[key(ids[j])] for j in known], dtype=np.int64)
                 sub = np.ascontiguousarray(rows[known])
                 if sub.shape[1] != self.dim:
                     raise _capi.AnnError(_capi.ANN_ERR_DIMENSION_MISMATCH, "embedding dimension != index dimension")
                 _capi.check(_capi.lib().ann_update_batch(self._h, _ptr(slots), _ptr(sub), len(known)))
             if fresh:
                 self.append_batch([ids[j] for j in fresh], rows[fresh])
-                self._slots = None
 
     def update(self, entity: EntityEmbedding) -> Future:
         return self.future_pool(lambda: self.update_batch([entity.id], np.asarray(entity.embedding, np.float32).reshape(1, -1)))
@@ -253,6 +266,12 @@ class BruteForceIndex(Appendable, Queryable):
         Call raise_pending_error() after the stream has been synchronised."""
         with self._lock:
             self.flush()
+            if not self._h:   # nothing appended yet: an empty list per query (BruteForceIndex.scala:76-89), as on the host path
+                out_ids_t.fill_(-1)
+                out_dist_t.fill_(float("inf"))
+                if out_count_t is not None:
+                    out_count_t.zero_()
+                return
             _capi.check(_capi.lib().ann_query_batch_device(
                 self._h, ctypes.c_void_p(queries_t.data_ptr()), int(queries_t.shape[0]), int(queries_t.shape[1]), int(k),
                 ctypes.c_void_p(out_ids_t.data_ptr()), ctypes.c_void_p(out_dist_t.data_ptr()),
@@ -279,7 +298,30 @@ class BruteForceIndex(Appendable, Queryable):
                 arr if world else None, world, ctypes.c_void_p(out_ids_t.data_ptr()), ctypes.c_void_p(out_dist_t.data_ptr()),
                 None if out_count_t is None else ctypes.c_void_p(out_count_t.data_ptr()), ctypes.c_void_p(stream)))
 
+    def query_filter_device(self, queries_t, k: int, peer_seed_key_ptrs, kth_keys_t, stream: int = 0) -> None:
+        """Middle phase of the three-phase sharded query (`ann_query_filter_device`): global seed threshold, tensor-core
+        chunks, last compaction; publishes this shard's k best bounds per query into `kth_keys_t` ([b, k] CUDA tensor)."""
+        world = len(peer_seed_key_ptrs)
+        arr = (ctypes.c_void_p * max(world, 1))(*[int(p) for p in peer_seed_key_ptrs])
+        with self._lock:
+            _capi.check(_capi.lib().ann_query_filter_device(
+                self._h, ctypes.c_void_p(queries_t.data_ptr()), int(queries_t.shape[0]), int(queries_t.shape[1]), int(k),
+                arr if world else None, world, ctypes.c_void_p(kth_keys_t.data_ptr()), ctypes.c_void_p(stream)))
+
+    def query_rescore_device(self, queries_t, k: int, peer_kth_key_ptrs, out_ids_t, out_dist_t, out_count_t, stream: int = 0) -> None:
+        """Last phase (`ann_query_rescore_device`): exact rescoring of this shard's rows under the k-th best bound of ALL
+        shards; writes this shard's candidates for the global top-k (count may be < k; -1 = flagged, row invalid)."""
+        world = len(peer_kth_key_ptrs)
+        arr = (ctypes.c_void_p * max(world, 1))(*[int(p) for p in peer_kth_key_ptrs])
+        with self._lock:
+            _capi.check(_capi.lib().ann_query_rescore_device(
+                self._h, ctypes.c_void_p(queries_t.data_ptr()), int(queries_t.shape[0]), int(queries_t.shape[1]), int(k),
+                arr if world else None, world, ctypes.c_void_p(out_ids_t.data_ptr()), ctypes.c_void_p(out_dist_t.data_ptr()),
+                None if out_count_t is None else ctypes.c_void_p(out_count_t.data_ptr()), ctypes.c_void_p(stream)))
+
     def raise_pending_error(self) -> None:
+        if not self._h:
+            return
         v = ctypes.c_int64()
         _capi.check(_capi.lib().ann_get_stat(self._h, b"pending_error", ctypes.byref(v)))
 

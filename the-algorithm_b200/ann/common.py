@@ -116,8 +116,9 @@ class Metric:
         arithmetic."""
         return self.from_absolute_distance(self.distances(np.reshape(embedding1, (1, -1)), np.reshape(embedding2, (1, -1)), device)[0])
 
-    def distances(self, embeddings1, embeddings2, device: int = 0, l2_squared: bool = False) -> np.ndarray:
-        """`distance` for n pairs at once: rows of two [n, dim] arrays -> float32 [n]."""
+    def distances(self, embeddings1, embeddings2, device: int = 0, l2_squared: bool = False, accum_f32: bool = False) -> np.ndarray:
+        """`distance` for n pairs at once: rows of two [n, dim] arrays -> float32 [n].  `accum_f32` selects the
+        sequential-fp32 accumulator convention (ANN_FLAG_ACCUM_F32)."""
         from .. import _capi
 
         a = np.ascontiguousarray(embeddings1, dtype=np.float32)
@@ -125,7 +126,8 @@ class Metric:
         if a.ndim != 2 or a.shape != b.shape:
             raise _capi.AnnError(_capi.ANN_ERR_DIMENSION_MISMATCH, f"embeddings differ in shape: {a.shape} vs {b.shape}")
         out = np.empty((a.shape[0],), dtype=np.float32)
-        _capi.check(_capi.lib().ann_distance_pairs(self.ordinal, _capi.ANN_FLAG_L2_SQUARED if l2_squared else 0, a.shape[1],
+        _capi.check(_capi.lib().ann_distance_pairs(self.ordinal, (_capi.ANN_FLAG_L2_SQUARED if l2_squared else 0) |
+                                                   (_capi.ANN_FLAG_ACCUM_F32 if accum_f32 else 0), a.shape[1],
                                                    a.ctypes.data, b.ctypes.data, a.shape[0], out.ctypes.data, device))
         return out
 
@@ -423,10 +425,12 @@ class ComposedQueryable(Queryable):
         dev = torch.device("cuda", self.indices[0].device)
         dq = torch.from_numpy(q).to(dev)
         s = len(self.indices)
-        ids = torch.empty((s, b, max(k, 1)), dtype=torch.int64, device=dev)
-        dist = torch.empty((s, b, max(k, 1)), dtype=torch.float32, device=dev)
+        ids = torch.full((s, b, max(k, 1)), -1, dtype=torch.int64, device=dev)
+        dist = torch.full((s, b, max(k, 1)), float("inf"), dtype=torch.float32, device=dev)
         cnt = torch.zeros((s, b), dtype=torch.int32, device=dev)
         for j, ix in enumerate(self.indices):
+            if ix.size() == 0:   # an empty shard contributes an empty list (RandomShardFunction leaves shards empty early on)
+                continue
             ix.query_batch_device(dq, k, ids[j], dist[j], cnt[j])
         oi, od, oc = merge_topk_device(ids, dist, cnt, k)
         torch.cuda.synchronize(dev)

@@ -11,7 +11,11 @@ rank sees the same batch), each rank answers over its rows, and the per-rank top
                        With `share_seeds` (default) the local query is the two-phase one: every shard first publishes k
                        bounds per query learnt from a short prefix of its rows (`ann_query_seed_device`), and after one
                        barrier scores its rows against the k-th best bound of ALL shards (`ann_query_finish_device`) -- a
-                       threshold as tight as one shard would get from `world` times the prefix.
+                       threshold as tight as one shard would get from `world` times the prefix.  With `two_round`
+                       (default) a second exchange follows the last chunk (`ann_query_filter_device` publishes every shard's
+                       k best bounds, `ann_query_rescore_device` rescores only what the k-th best bound of ALL shards lets
+                       through), so the exact rescoring shrinks with the shard count too; and with deliver="slice" the
+                       merged answer stays partitioned: rank r receives only its 1/world slice, nothing is pushed.
   route "allgather" -- `all_gather` of the three result arrays in the [shards][b][k] layout (NCCL; gloo on CPU) followed
                        by the merge kernel (`ann_merge_topk_device`) over the whole batch on every rank.
 
@@ -41,7 +45,7 @@ class ShardedBruteForceIndex:
     all-gather route (default: the CUDA merge kernel)."""
 
     def __init__(self, local, group=None, route: str = "auto", merge: Optional[Callable] = None, device=None,
-                 share_seeds: bool = True):
+                 share_seeds: bool = True, two_round: bool = True):
         import torch
         import torch.distributed as dist
 
@@ -52,6 +56,7 @@ class ShardedBruteForceIndex:
         self.device = torch.device(device) if device is not None else torch.device("cpu")
         self._merge = merge
         self.share_seeds = share_seeds   # fused route: two-phase local query around a cross-shard threshold exchange
+        self.two_round = two_round       # ... plus a second exchange of the k best bounds after the last chunk (three phases)
         self._px = {}          # (b, k) -> PeerExchange
         self._gather = {}      # (b, k) -> gathered buffers
         self._own = {}         # (b, k) -> this rank's result arrays (all-gather route)
@@ -87,27 +92,82 @@ class ShardedBruteForceIndex:
             self._px[key] = PeerExchange(b, k, self.device, self.group)
         return self._px[key]
 
-    def batch_query_device(self, queries, k: int, stream: int = 0):
-        """Collective: every rank passes the same [b, dim] batch (on its own device) and receives the merged
-        (ids [b,k], dist [b,k], count [b]).  The returned tensors are reused by the next call with the same (b, k)."""
+    def batch_query_device(self, queries, k: int, stream: int = 0, deliver: str = "all", exact: bool = False):
+        """Collective: every rank passes the same [b, dim] batch (on its own device).
+
+        deliver="all"   -> every rank receives the whole merged batch (ids [b,k], dist [b,k], count [b]);
+        deliver="slice" -> every rank receives only ITS rows [q_begin, q_begin + q_count) of the merged batch (fused route;
+                           `slice_range(b)` gives the range): the answer stays partitioned, nothing is pushed between ranks
+                           after the merge and the step ends without a trailing barrier.
+        The call is asynchronous on `stream` and the returned tensors are reused by the next call with the same (b, k).
+        CONTRACT for degenerate inputs: a query that some shard's bounded selector could not answer (thousands of exact
+        ties inside the margin, a NaN / zero-norm Cosine query, pool overflow) comes back with count = -1 -- the row is
+        INVALID, never silently incomplete.  `batch_query` (the synchronous form) re-answers such batches with
+        `exact=True`, which switches every shard to its exact fallback; asynchronous callers check `count < 0` themselves
+        after synchronising."""
         import torch
         import torch.distributed as dist
 
         b = int(queries.shape[0])
+        if deliver not in ("all", "slice"):
+            raise ValueError("deliver must be 'all' or 'slice'")
+        if exact and hasattr(self.local, "set_option"):
+            self.local.set_option("device_fallback", 1)
+        try:
+            return self._batch_query_device(queries, k, stream, deliver, exact, b, torch, dist)
+        finally:
+            if exact and hasattr(self.local, "set_option"):
+                self.local.set_option("device_fallback", 0)
+
+    def slice_range(self, b: int) -> Tuple[int, int]:
+        """Rows of a b-query batch that `deliver="slice"` returns on this rank."""
+        from .exchange import slice_of
+
+        return slice_of(self.rank, self.world, b)
+
+    def batch_query(self, queries, k: int, stream: int = 0):
+        """Synchronous, always-exact form: the whole merged batch on every rank as (ids, dist, count) CUDA tensors.  Batches
+        in which any rank saw a flagged query are answered again through every shard's exact fallback (collective: all
+        ranks take the same decision because they all hold the same merged counts)."""
+        import torch
+
+        ids, dist_, cnt = self.batch_query_device(queries, k, stream, deliver="all")
+        if self.device.type == "cuda":
+            torch.cuda.current_stream(self.device).synchronize()
+        if bool((cnt < 0).any()):
+            if hasattr(self.local, "raise_pending_error"):
+                try:
+                    self.local.raise_pending_error()      # clears the sticky device word of the first attempt
+                except Exception:
+                    pass
+            ids, dist_, cnt = self.batch_query_device(queries, k, stream, deliver="all", exact=True)
+            if self.device.type == "cuda":
+                torch.cuda.current_stream(self.device).synchronize()
+        return ids, dist_, cnt
+
+    def _batch_query_device(self, queries, k, stream, deliver, exact, b, torch, dist):
         if self.route == "fused":
             try:
                 px = self._exchange_for(b, k)
             except Exception as e:   # the ranks cannot map each other's memory: keep the collective route
                 self.route, self.route_note = "allgather", f"peer mapping unavailable: {type(e).__name__}: {e}"
             else:
-                if self.share_seeds and hasattr(self.local, "query_seed_device"):
+                if exact or not (self.share_seeds and hasattr(self.local, "query_seed_device")):
+                    self.local.query_batch_device(queries, k, px.local.ids, px.local.dist, px.local.count, stream)
+                elif self.two_round and hasattr(self.local, "query_filter_device"):
+                    # three phases around two small exchanges: seed bounds, then the k best bounds after the last chunk, so
+                    # that every shard rescores only its share of the global survivors
+                    self.local.query_seed_device(queries, k, px.seed_keys, stream)
+                    px.seed_barrier()
+                    self.local.query_filter_device(queries, k, px.seed_ptrs, px.kth_keys, stream)
+                    px.kth_barrier()
+                    self.local.query_rescore_device(queries, k, px.kth_ptrs, px.local.ids, px.local.dist, px.local.count, stream)
+                else:
                     # the shards pool what a short prefix of each taught them: one global threshold instead of `world` local ones
                     self.local.query_seed_device(queries, k, px.seed_keys, stream)
                     px.seed_barrier()
                     self.local.query_finish_device(queries, k, px.seed_ptrs, px.local.ids, px.local.dist, px.local.count, stream)
-                else:
-                    self.local.query_batch_device(queries, k, px.local.ids, px.local.dist, px.local.count, stream)
-                return px.exchange_merge(stream)
+                return px.merge_slice(stream) if deliver == "slice" else px.exchange_merge(stream)
         key = (b, k)
         if key not in self._own:
             dev = self.device
@@ -117,7 +177,7 @@ class ShardedBruteForceIndex:
                                  torch.empty((self.world, b, k), dtype=torch.float32, device=dev),
                                  torch.empty((self.world, b), dtype=torch.int32, device=dev))
         own, gathered = self._own[key], self._gather[key]
-        if self.share_seeds and hasattr(self.local, "query_seed_device"):
+        if not exact and self.share_seeds and hasattr(self.local, "query_seed_device"):
             if key not in self._seeds:
                 self._seeds[key] = (torch.empty((b, k), dtype=torch.int32, device=self.device),
                                     torch.empty((self.world, b, k), dtype=torch.int32, device=self.device))
@@ -138,4 +198,8 @@ class ShardedBruteForceIndex:
         merge = self._merge
         if merge is None:
             from .brute_force import merge_topk_device as merge
-        return merge(gathered[0], gathered[1], gathered[2], k, stream)
+        out = merge(gathered[0], gathered[1], gathered[2], k, stream)
+        if deliver == "slice":
+            q0, q1 = self.slice_range(b)
+            return out[0][q0:q1], out[1][q0:q1], out[2][q0:q1]
+        return out

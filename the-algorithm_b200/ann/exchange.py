@@ -65,6 +65,16 @@ def exchange_merge_blocks(local_ptrs: Sequence[int], final_ptrs: Sequence[int], 
                                                       ctypes.c_void_p(stream)))
 
 
+def exchange_merge_slice(local_ptrs: Sequence[int], b: int, k: int, q_begin: int, q_count: int, out_ids_t, out_dist_t, out_count_t,
+                         device: int, stream: int = 0) -> None:
+    """`ann_exchange_merge_slice_device`: pull + merge this rank's slice into plain [q_count, k] CUDA tensors (no push)."""
+    world = len(local_ptrs)
+    arr = ctypes.c_void_p * world
+    _capi.check(_capi.lib().ann_exchange_merge_slice_device(
+        device, arr(*local_ptrs), world, b, k, q_begin, q_count, ctypes.c_void_p(out_ids_t.data_ptr()),
+        ctypes.c_void_p(out_dist_t.data_ptr()), ctypes.c_void_p(out_count_t.data_ptr()), ctypes.c_void_p(stream)))
+
+
 def slice_of(rank: int, world: int, b: int) -> Tuple[int, int]:
     """The queries rank `rank` merges: [rank*b/world, (rank+1)*b/world) -- together the slices tile the batch."""
     return rank * b // world, (rank + 1) * b // world
@@ -86,7 +96,8 @@ class PeerExchange:
         nb = result_block_bytes(b, k)
         self._stride = (nb + 255) // 256 * 256
         seed_bytes = (b * k * 4 + 255) // 256 * 256          # this rank's published seed bounds, [b][k] uint32
-        self._buf = symm_mem.empty(2 * self._stride + seed_bytes, dtype=torch.uint8, device=self.device)
+        # layout: [local block][final block][seed bounds][k-best bounds of the second round]
+        self._buf = symm_mem.empty(2 * self._stride + 2 * seed_bytes, dtype=torch.uint8, device=self.device)
         self._hdl = symm_mem.rendezvous(self._buf, self.group)
         ptrs: List[int] = [int(p) for p in self._hdl.buffer_ptrs]
         assert len(ptrs) == self.world and ptrs[self.rank] == self._buf.data_ptr()
@@ -96,8 +107,30 @@ class PeerExchange:
         self.local = ResultBlock(self._buf, b, k, 0)
         self.final = ResultBlock(self._buf, b, k, self._stride)
         self.seed_keys = self._buf[2 * self._stride: 2 * self._stride + b * k * 4].view(torch.int32).view(b, k)
+        self.kth_ptrs = [p + 2 * self._stride + seed_bytes for p in ptrs]
+        o2 = 2 * self._stride + seed_bytes
+        self.kth_keys = self._buf[o2: o2 + b * k * 4].view(torch.int32).view(b, k)
         self.q_begin, q_end = slice_of(self.rank, self.world, b)
         self.q_count = q_end - self.q_begin
+        qn = max(self.q_count, 1)
+        self.slice_ids = torch.empty((qn, k), dtype=torch.int64, device=self.device)[: self.q_count]
+        self.slice_dist = torch.empty((qn, k), dtype=torch.float32, device=self.device)[: self.q_count]
+        self.slice_count = torch.empty((qn,), dtype=torch.int32, device=self.device)[: self.q_count]
+
+    def kth_barrier(self) -> None:
+        """Collective, between `query_filter_device` and `query_rescore_device`: every rank's k-best bounds are complete."""
+        self._hdl.barrier(channel=3)
+
+    def merge_slice(self, stream: int = 0):
+        """Collective.  One barrier (every rank's local block is complete), then this rank pulls and merges ITS slice of
+        the batch into its own (slice_ids, slice_dist, slice_count) -- rows [q_begin, q_begin + q_count) of the answer.
+        Nothing is pushed and no barrier follows: a peer overwrites the block this kernel reads only after the barriers of
+        the next batch, which this rank enters after the kernel (stream order)."""
+        self._hdl.barrier(channel=0)
+        if self.q_count:
+            exchange_merge_slice(self._local_ptrs, self.b, self.k, self.q_begin, self.q_count, self.slice_ids, self.slice_dist,
+                                 self.slice_count, self.device.index or 0, stream)
+        return self.slice_ids, self.slice_dist, self.slice_count
 
     def seed_barrier(self) -> None:
         """Collective, between `query_seed_device` and `query_finish_device`: every rank's published bounds are complete.

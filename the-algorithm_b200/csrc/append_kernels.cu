@@ -179,6 +179,15 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(PrepParams p, int b_p
                     eps_rel = t22;
                 }
             }
+            if (p.accum_f32) {
+                // ANN_FLAG_ACCUM_F32: the value the answer is ordered by is itself a sequential fp32 sum, up to
+                // gamma32 * sum|terms| away from the real distance; that error joins the filter's own on the badness scale.
+                const float g32 = 1.05f * (float)(p.dim + 4) * u24;
+                if (p.metric == kMetricIP) eps_abs += g32 * amax * nb;
+                else if (p.metric == kMetricCosine) eps_abs += (2.f * g32 + 4.f * u24) * nb;
+                else if (p.path == 1) eps_rel += g32;                       // scan: g = sum (a-b)^2, a sum of non-negative terms
+                else eps_abs += 0.5f * g32 * (amax + nb) * (amax + nb) * 1.0001f;   // gemm: g = (L2^2 - |b|^2) / 2
+            }
             QueryState st;
             st.eps_abs = eps_abs + tiny;
             st.eps_rel = eps_rel;

@@ -139,6 +139,49 @@ __device__ __forceinline__ float exact_distance_rows(int metric_rt, const float*
     return __fsub_rn(1.0f, __double2float_rn(cs));
 }
 
+// ---- the other accumulator convention (ANN_FLAG_ACCUM_F32): MetricUtil.dot is typed Float with no cast at its call site
+// (Metric.scala:264-269), so the unshipped EmbeddingMath.Float.dotProduct most plausibly accumulates in fp32.  Operation
+// for operation the oracle's distance_f32 (oracle/oracle.c, accum=1): sequential fp32 accumulation in index order with
+// individually rounded mul / add (no contraction), correctly rounded sqrt / div, `1 - x` in fp32.  `qf` is the query in
+// fp32 (shared memory), `nbf` its sequential fp32 squared norm.
+__device__ __forceinline__ float exact_query_norm2_f32(const float* qf, int d) {
+    float nb = 0.f;
+    for (int i = 0; i < d; ++i) nb = __fadd_rn(nb, __fmul_rn(qf[i], qf[i]));
+    return nb;
+}
+
+template <bool kGlobal = true, int METRIC = -1>
+__device__ __forceinline__ float exact_distance_rows_f32(int metric_rt, const float* __restrict__ a, const float* qf, float nbf, int d,
+                                                         int l2_squared) {
+    const int metric = METRIC >= 0 ? METRIC : metric_rt;
+    const float4* a4 = reinterpret_cast<const float4*>(a);
+    auto ld = [&](int i) -> float4 { return kGlobal ? __ldg(a4 + i) : a4[i]; };
+    const int n4 = (d + 3) >> 2;
+    float s0 = 0.f, s1 = 0.f;
+    auto step = [&](float x, float y) {
+        if (metric == kMetricL2) {
+            const float df = __fsub_rn(x, y);
+            s0 = __fadd_rn(s0, __fmul_rn(df, df));
+        } else {
+            s0 = __fadd_rn(s0, __fmul_rn(x, y));
+            if (metric == kMetricCosine) s1 = __fadd_rn(s1, __fmul_rn(x, x));
+        }
+    };
+    float4 cur = n4 > 0 ? ld(0) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < n4; ++j) {
+        const float4 nxt = (j + 1 < n4) ? ld(j + 1) : cur;
+        const int i = j << 2;
+        step(cur.x, qf[i]);
+        if (i + 1 < d) step(cur.y, qf[i + 1]);
+        if (i + 2 < d) step(cur.z, qf[i + 2]);
+        if (i + 3 < d) step(cur.w, qf[i + 3]);
+        cur = nxt;
+    }
+    if (metric == kMetricL2) return l2_squared ? s0 : __fsqrt_rn(s0);
+    if (metric == kMetricIP) return __fsub_rn(1.0f, s0);
+    return __fsub_rn(1.0f, __fdiv_rn(s0, __fmul_rn(__fsqrt_rn(s1), __fsqrt_rn(nbf))));
+}
+
 // ---- mbarrier / bulk-copy PTX (Hopper+; the only async-copy path used by the scan) -----------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

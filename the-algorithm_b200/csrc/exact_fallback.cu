@@ -31,17 +31,30 @@ struct SelectState {
 
 __device__ __forceinline__ unsigned long long id_key(long long id) { return (unsigned long long)id ^ 0x8000000000000000ull; }
 
+template <bool ACC32>
 __global__ void __launch_bounds__(256) exact_all_kernel(const float* __restrict__ rows, long long n, int pitch, int dim, int metric,
                                                         int l2_squared, const float* __restrict__ query, uint32_t* __restrict__ dkey) {
     extern __shared__ double q64[];
+    float* q32 = reinterpret_cast<float*>(q64);
     __shared__ double nb_s;
-    for (int i = threadIdx.x; i < dim; i += blockDim.x) q64[i] = (double)query[i];
+    __shared__ float nbf_s;
+    for (int i = threadIdx.x; i < dim; i += blockDim.x) {
+        if (ACC32) q32[i] = query[i];
+        else q64[i] = (double)query[i];
+    }
     __syncthreads();
-    if (threadIdx.x == 0) nb_s = (metric == kMetricCosine) ? exact_query_norm2(q64, dim) : 0.0;
+    if (threadIdx.x == 0) {
+        if (ACC32) nbf_s = (metric == kMetricCosine) ? exact_query_norm2_f32(q32, dim) : 0.f;
+        else nb_s = (metric == kMetricCosine) ? exact_query_norm2(q64, dim) : 0.0;
+    }
     __syncthreads();
-    const ExactQuery eq{q64, nb_s};
-    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x)
-        dkey[r] = float_order_key(exact_distance_rows(metric, rows + (size_t)r * pitch, eq, dim, l2_squared));
+    const ExactQuery eq{q64, ACC32 ? 0.0 : nb_s};
+    const float nbf = ACC32 ? nbf_s : 0.f;
+    for (long long r = blockIdx.x * (long long)blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+        const float* rp = rows + (size_t)r * pitch;
+        dkey[r] = float_order_key(ACC32 ? exact_distance_rows_f32(metric, rp, q32, nbf, dim, l2_squared)
+                                        : exact_distance_rows(metric, rp, eq, dim, l2_squared));
+    }
 }
 
 __global__ void init_state_kernel(SelectState* st, uint32_t k) {
@@ -199,7 +212,10 @@ cudaError_t launch_exact_fallback(const FallbackParams& p, cudaStream_t stream, 
     off += (size_t)2 * p.k * 8;
     uint32_t* lkey = reinterpret_cast<uint32_t*>(base + off);
     const int grid = (int)std::min<long long>((p.n_rows + 255) / 256, 148 * 8);
-    exact_all_kernel<<<grid, 256, p.dim * sizeof(double), stream>>>(p.rows, p.n_rows, p.pitch, p.dim, p.metric, p.l2_squared, p.query, dkey);
+    if (p.accum_f32)
+        exact_all_kernel<true><<<grid, 256, p.dim * sizeof(double), stream>>>(p.rows, p.n_rows, p.pitch, p.dim, p.metric, p.l2_squared, p.query, dkey);
+    else
+        exact_all_kernel<false><<<grid, 256, p.dim * sizeof(double), stream>>>(p.rows, p.n_rows, p.pitch, p.dim, p.metric, p.l2_squared, p.query, dkey);
     init_state_kernel<<<1, 256, 0, stream>>>(st, (uint32_t)p.k);
     for (int pass = 0; pass < 12; ++pass) {
         radix_hist_kernel<<<grid, 256, 0, stream>>>(dkey, p.ids, p.n_rows, st, pass);
@@ -208,6 +224,10 @@ cudaError_t launch_exact_fallback(const FallbackParams& p, cudaStream_t stream, 
     collect_kernel<<<grid, 256, 0, stream>>>(dkey, p.ids, p.n_rows, st, (uint32_t)p.k, lkey, lid);
     int n2 = 2;
     while (n2 < p.k) n2 <<= 1;
+    {   // k in (4096, 16384] needs 96..192 KB of dynamic shared memory: opt in like every other large-smem kernel
+        cudaError_t e = cudaFuncSetAttribute(fallback_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)n2 * 12));
+        if (e != cudaSuccess) return e;
+    }
     fallback_sort_kernel<<<1, 512, (size_t)n2 * 12, stream>>>(st, (uint32_t)p.k, lkey, lid, p.out_ids, p.out_dist, p.out_count, p.k_out);
     if (launches) *launches += 28;
     return cudaGetLastError();

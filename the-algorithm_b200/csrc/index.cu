@@ -108,7 +108,7 @@ __global__ void collect_flags_kernel(const QueryState* qs, int b, DeviceScalars*
 struct ann_index {
     ann_config cfg{};
     int dim = 0, pitch = 0, kp = 0, metric = 0;
-    bool l2_squared = false, use_shadow = true;
+    bool l2_squared = false, use_shadow = true, accum_f32 = false;
     int device = 0, sm_count = 0;
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;
@@ -158,6 +158,7 @@ struct ann_index {
         bool gemm = false;        // the batch is on the tensor-core path (prep done, scratch in place)
         bool seeded = false;      // ... and a seed launch ran: this shard's bounds are published
         bool clobbered = false;   // another call touched the scratch or the rows in between
+        bool filtered = false;    // ann_query_filter_device ran: only ann_query_rescore_device may follow
         int b = 0, k = 0;
         long long seed_rows = 0;
     } sess;
@@ -362,6 +363,7 @@ int query_scan(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
     pp.max_norm_bits = &ix->scalars->max_norm_bits;
     pp.max_resid_bits = &ix->scalars->max_resid_bits;
     pp.path = 1;
+    pp.accum_f32 = ix->accum_f32 ? 1 : 0;
     pp.pub_keys = ix->pub_keys.p;
     pp.pub_stride = kPubStride;
     pp.bad_queries = &ix->scalars->bad_queries;
@@ -413,6 +415,7 @@ int query_scan(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
         fp.pitch = ix->pitch;
         fp.metric = ix->metric;
         fp.l2_squared = ix->l2_squared ? 1 : 0;
+        fp.accum_f32 = ix->accum_f32 ? 1 : 0;
         fp.queries = ix->q_padded.p + (size_t)g0 * ix->pitch;
         fp.q_pitch = ix->pitch;
         fp.out_ids = d_out_ids + (size_t)g0 * k_out;
@@ -435,6 +438,9 @@ int query_scan(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
 // mode 0: the whole flow.  mode 1 / 2: the two halves of a sharded query -- 1 = prepare + seed launch + publish this
 // shard's bounds into `seed_keys_out`; 2 = take the global threshold from every shard's bounds (`peers`), then chunks +
 // finalize on the scratch mode 1 left in place.
+// mode 3 / 4 split mode 2 once more around a SECOND cross-shard round: 3 = thresholds + chunks + last compaction, which
+// publishes this shard's k best approximate bounds into `seed_keys_out`; 4 = exact finalize against the k-th best bound of
+// all shards (`peers`), so that every shard rescores only its share of the global survivors.
 int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b, int k_eff, int k_out, int64_t* d_out_ids,
                float* d_out_dist, int32_t* d_out_count, cudaStream_t st, int mode = 0, uint32_t* seed_keys_out = nullptr,
                const PeerSeedKeys* peers = nullptr, int world = 1) {
@@ -459,10 +465,11 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
     pp.max_norm_bits = &ix->scalars->max_norm_bits;
     pp.max_resid_bits = &ix->scalars->max_resid_bits;
     pp.path = 2;
+    pp.accum_f32 = ix->accum_f32 ? 1 : 0;
     pp.pub_keys = nullptr;
     pp.pub_stride = 0;
     pp.bad_queries = &ix->scalars->bad_queries;
-    if (mode != 2) {
+    if (mode < 2) {
         CUDA_TRY(launch_prep_queries(pp, st));
         ix->launches++;
     }
@@ -487,6 +494,7 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
     fp.pitch = ix->pitch;
     fp.metric = ix->metric;
     fp.l2_squared = ix->l2_squared ? 1 : 0;
+    fp.accum_f32 = ix->accum_f32 ? 1 : 0;
     fp.queries = ix->q_padded.p;
     fp.q_pitch = ix->pitch;
     fp.out_ids = d_out_ids;
@@ -494,6 +502,19 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
     fp.out_count = d_out_count;
     fp.k_out = k_out;
 
+    if (mode == 4) {
+        if (peers && world > 1) {
+            fp.peer_keys = *peers;
+            fp.peer_world = world;
+        }
+        CUDA_TRY(launch_finalize(fp, b, st));
+        ix->launches++;
+        collect_flags_kernel<<<std::min(64, (b + 255) / 256), 256, 0, st>>>(qs_base, b, ix->scalars);
+        CUDA_TRY(cudaGetLastError());
+        ix->launches++;
+        ix->last_path = 2;
+        return ANN_OK;
+    }
     const int kHitBudget = ix->gemm_hit_budget;
     auto gemm_launch = [&](long long begin, long long end, int seed_mode) -> int {
         GemmLaunch g{};
@@ -564,7 +585,7 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
     long long seed_rows = std::min<long long>(ix->n / 256 * 256, std::min<long long>((long long)kGemmPoolCap * 32, std::max<long long>(65536, 256LL * k_eff)));
     if (ix->gemm_seed_rows > 0) seed_rows = std::min<long long>(seed_rows, ix->gemm_seed_rows / 256 * 256);
     bool use_seed = seed_rows >= 128LL * k_eff && seed_rows >= 4096;
-    if (mode == 2) {   // what phase 1 decided and did
+    if (mode >= 2) {   // what phase 1 decided and did
         use_seed = ix->sess.seeded;
         seed_rows = ix->sess.seed_rows;
     }
@@ -574,7 +595,7 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
     ix->last_gemm_chunks = 0;
     if (use_seed) {
         double seen = (double)seed_rows;   // rows the threshold has been learnt from
-        if (mode != 2) {
+        if (mode < 2) {
             int rc2 = gemm_launch(0, seed_rows, 1);
             if (rc2) return rc2;
             SelectParams sp = fp;
@@ -589,7 +610,7 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
             ix->sess.seed_rows = seed_rows;
             return ANN_OK;
         }
-        if (mode == 2 && peers && world > 1) {
+        if (mode >= 2 && peers && world > 1) {
             // K5c: the k-th best of the union of all shards' published bounds replaces this shard's own seed threshold:
             // as tight as one seed over world * seed_rows rows, for the price of one seed launch per shard
             CUDA_TRY(launch_seed_merge(*peers, world, qs_base, b, k_eff, st));
@@ -599,7 +620,7 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
         // a threshold learnt from S rows lets through about 2.2 * k / S of the rows (group loss 1.13 x margin ~1.9)
         end = std::min<long long>(ix->n, std::max<long long>(seed_rows, (long long)((double)kHitBudget * seen / (2.2 * k_eff))));
         end = (end + 255) / 256 * 256;
-        if (mode == 2 && ix->n - end < end / 4) end = ix->n;   // no sliver of a last chunk behind a shard-sized first one
+        if (mode >= 2 && ix->n - end < end / 4) end = ix->n;   // no sliver of a last chunk behind a shard-sized first one
         if (end > ix->n) end = ix->n;
     } else if (mode == 1) {
         // too few rows to seed from: nothing to publish, phase 2 runs the unseeded schedule
@@ -620,6 +641,13 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
         ix->launches++;
         begin = end;
         end = std::min<long long>(ix->n, end * growth);
+    }
+    if (mode == 3) {   // last compaction + publish; the exact finalize follows the second cross-shard round (mode 4)
+        SelectParams sp = fp;
+        sp.seed_keys_out = seed_keys_out;
+        CUDA_TRY(launch_compact_pool(sp, b, st));
+        ix->launches++;
+        return ANN_OK;
     }
     CUDA_TRY(launch_finalize(fp, b, st));
     ix->launches++;
@@ -662,6 +690,7 @@ int query_core(ann_index* ix, const float* d_queries, int b, int k, int64_t* d_o
             fp.dim = ix->dim;
             fp.metric = ix->metric;
             fp.l2_squared = ix->l2_squared ? 1 : 0;
+            fp.accum_f32 = ix->accum_f32 ? 1 : 0;
             fp.query = d_queries + (size_t)q * ix->dim;
             fp.scratch = ix->fb_scratch.p;
             fp.k = k_eff;
@@ -729,6 +758,7 @@ int resolve_flagged(ann_index* ix, const float* d_queries, int b, int k, int64_t
         fp.dim = ix->dim;
         fp.metric = ix->metric;
         fp.l2_squared = ix->l2_squared ? 1 : 0;
+        fp.accum_f32 = ix->accum_f32 ? 1 : 0;
         fp.query = d_queries + (size_t)q * ix->dim;
         fp.scratch = ix->fb_scratch.p;
         fp.k = k_eff;
@@ -799,6 +829,7 @@ int ann_create(const ann_config* cfg, ann_index** out) {
     ix->metric = cfg->metric;
     ix->pitch = (cfg->dim + 3) / 4 * 4;
     ix->l2_squared = (cfg->flags & ANN_FLAG_L2_SQUARED) != 0;
+    ix->accum_f32 = (cfg->flags & ANN_FLAG_ACCUM_F32) != 0;
     ix->use_shadow = (cfg->flags & ANN_FLAG_NO_SHADOW) == 0;
     ix->kp = (cfg->dim + (cfg->metric == kMetricL2 ? 3 : 1) + 7) / 8 * 8;   // + augmented columns (common.cuh, append_kernels.cu)
     ix->device = cfg->device;
@@ -1016,7 +1047,7 @@ int ann_query_finish_device(ann_index* ix, const float* d_queries, int32_t b, in
     int rc = set_device(ix);
     if (rc) return rc;
     const ann_index::SeedSession sess = ix->sess;
-    if (!sess.open || sess.b != b || sess.k != k)
+    if (!sess.open || sess.b != b || sess.k != k || sess.filtered)
         return fail(ANN_ERR_INVALID_ARGUMENT, "ann_query_finish_device: no pending ann_query_seed_device call with this (b, k)");
     if (sess.clobbered) {
         ix->sess.open = false;
@@ -1048,6 +1079,119 @@ int ann_query_finish_device(ann_index* ix, const float* d_queries, int32_t b, in
     }
     if (rc == ANN_OK && ix->device_fallback) rc = resolve_flagged(ix, d_queries, b, k, d_out_ids, d_out_dist, d_out_count, st);
     return rc;
+}
+
+// ---- three-phase sharded query: seed -> [barrier] -> filter (publishes the k best bounds) -> [barrier] -> rescore ----
+namespace {
+int check_session(ann_index* ix, const char* who, int32_t b, int32_t dim, int32_t k, int32_t world, bool want_filtered) {
+    char msg[256];
+    if (b < 0) { snprintf(msg, sizeof(msg), "%s: b < 0", who); return fail(ANN_ERR_INVALID_ARGUMENT, msg); }
+    if (k < 0) { snprintf(msg, sizeof(msg), "%s: k < 0", who); return fail(ANN_ERR_NEGATIVE_K, msg); }
+    if (dim != ix->dim) { snprintf(msg, sizeof(msg), "%s: query dimension != index dimension", who); return fail(ANN_ERR_DIMENSION_MISMATCH, msg); }
+    if (world < 0 || world > kMaxPeers) { snprintf(msg, sizeof(msg), "%s: world must be in [0, 16]", who); return fail(ANN_ERR_INVALID_ARGUMENT, msg); }
+    const ann_index::SeedSession& sess = ix->sess;
+    if (!sess.open || sess.b != b || sess.k != k || sess.filtered != want_filtered) {
+        snprintf(msg, sizeof(msg), "%s: out of sequence (expected ann_query_seed_device -> ann_query_filter_device -> "
+                 "ann_query_rescore_device with the same (b, k))", who);
+        return fail(ANN_ERR_INVALID_ARGUMENT, msg);
+    }
+    if (sess.clobbered) {
+        ix->sess.open = false;
+        snprintf(msg, sizeof(msg), "%s: another query, append or update ran on this index since ann_query_seed_device", who);
+        return fail(ANN_ERR_INVALID_ARGUMENT, msg);
+    }
+    return ANN_OK;
+}
+}  // namespace
+
+int ann_query_filter_device(ann_index* ix, const float* d_queries, int32_t b, int32_t dim, int32_t k,
+                            const uint32_t* const* peer_seed_keys, int32_t world, uint32_t* d_kth_keys, void* stream) {
+    if (!ix) return fail(ANN_ERR_NULL_POINTER, "ann_query_filter_device: index is NULL");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    int rc = check_session(ix, "ann_query_filter_device", b, dim, k, world, false);
+    if (rc) return rc;
+    if (b > 0 && (!d_queries || (k > 0 && !d_kth_keys))) {
+        ix->sess.open = false;
+        return fail(ANN_ERR_NULL_POINTER, "ann_query_filter_device: NULL buffer");
+    }
+    rc = set_device(ix);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    ix->sess.filtered = true;
+    if (b == 0 || k == 0) return ANN_OK;
+    if (!ix->sess.gemm) {   // scan / exact paths: nothing to publish, the rescore call answers the whole local query
+        CUDA_TRY(cudaMemsetAsync(d_kth_keys, 0xFF, (size_t)b * k * sizeof(uint32_t), st));
+        return ANN_OK;
+    }
+    PeerSeedKeys pk{};
+    int w = 0;
+    if (peer_seed_keys)
+        for (int s2 = 0; s2 < world; ++s2) {
+            if (!peer_seed_keys[s2]) {
+                ix->sess.open = false;
+                return fail(ANN_ERR_NULL_POINTER, "ann_query_filter_device: NULL seed-key pointer");
+            }
+            pk.keys[w++] = peer_seed_keys[s2];
+        }
+    const int k_eff = (int)std::min<long long>(k, ix->n);
+    if (k_eff < k) CUDA_TRY(cudaMemsetAsync(d_kth_keys, 0xFF, (size_t)b * k * sizeof(uint32_t), st));   // pitch k, k_eff bounds per row
+    rc = query_gemm(ix, ix->qstate.p, d_queries, b, k_eff, k, nullptr, nullptr, nullptr, st, 3, d_kth_keys, &pk, w);
+    if (rc) ix->sess.open = false;
+    return rc;
+}
+
+int ann_query_rescore_device(ann_index* ix, const float* d_queries, int32_t b, int32_t dim, int32_t k,
+                             const uint32_t* const* peer_kth_keys, int32_t world, int64_t* d_out_ids, float* d_out_dist,
+                             int32_t* d_out_count, void* stream) {
+    if (!ix) return fail(ANN_ERR_NULL_POINTER, "ann_query_rescore_device: index is NULL");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    int rc = check_session(ix, "ann_query_rescore_device", b, dim, k, world, true);
+    if (rc) return rc;
+    const bool gemm = ix->sess.gemm;
+    ix->sess.open = false;
+    if (b == 0) return ANN_OK;
+    if (!d_queries || (k > 0 && (!d_out_ids || !d_out_dist))) return fail(ANN_ERR_NULL_POINTER, "ann_query_rescore_device: NULL buffer");
+    rc = set_device(ix);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!gemm) {
+        rc = query_core(ix, d_queries, b, k, d_out_ids, d_out_dist, d_out_count, st);
+    } else {
+        PeerSeedKeys pk{};
+        int w = 0;
+        if (peer_kth_keys)
+            for (int s2 = 0; s2 < world; ++s2) {
+                if (!peer_kth_keys[s2]) return fail(ANN_ERR_NULL_POINTER, "ann_query_rescore_device: NULL key pointer");
+                pk.keys[w++] = peer_kth_keys[s2];
+            }
+        const int k_eff = (int)std::min<long long>(k, ix->n);
+        // the published arrays have pitch k; with k_eff < k (shard smaller than k) every row of the shard is a candidate anyway
+        rc = query_gemm(ix, ix->qstate.p, d_queries, b, k_eff, k, d_out_ids, d_out_dist, d_out_count, st, 4, nullptr,
+                        k_eff == k ? &pk : nullptr, k_eff == k ? w : 0);
+    }
+    if (rc == ANN_OK && ix->device_fallback) rc = resolve_flagged(ix, d_queries, b, k, d_out_ids, d_out_dist, d_out_count, st);
+    return rc;
+}
+
+int ann_exchange_merge_slice_device(int32_t device, const void* const* peer_local, int32_t world, int32_t b, int32_t k,
+                                    int32_t q_begin, int32_t q_count, int64_t* d_out_ids, float* d_out_dist, int32_t* d_out_count,
+                                    void* stream) {
+    if (world < 1 || world > kMaxPeers) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_exchange_merge_slice_device: world must be in [1, 16]");
+    if (b < 0 || q_begin < 0 || q_count < 0 || (long long)q_begin + q_count > b)
+        return fail(ANN_ERR_INVALID_ARGUMENT, "ann_exchange_merge_slice_device: query range outside the batch");
+    if (k < 0) return fail(ANN_ERR_NEGATIVE_K, "ann_exchange_merge_slice_device: k < 0");
+    if (!peer_local) return fail(ANN_ERR_NULL_POINTER, "ann_exchange_merge_slice_device: NULL pointer table");
+    if (b == 0 || k == 0 || q_count == 0) return ANN_OK;
+    if (!d_out_ids || !d_out_dist) return fail(ANN_ERR_NULL_POINTER, "ann_exchange_merge_slice_device: NULL output buffer");
+    if ((long long)(world + 1) * k * 12 > 200 * 1024) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_exchange_merge_slice_device: (world + 1) * k too large");
+    PeerBlocks pb{};
+    for (int s = 0; s < world; ++s) {
+        if (!peer_local[s]) return fail(ANN_ERR_NULL_POINTER, "ann_exchange_merge_slice_device: NULL block pointer");
+        pb.local[s] = static_cast<const unsigned char*>(peer_local[s]);
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(launch_exchange_merge(pb, world, b, k, q_begin, q_count, (cudaStream_t)stream, d_out_ids, d_out_dist, d_out_count));
+    return ANN_OK;
 }
 
 int ann_query_batch(ann_index* ix, const float* queries, int32_t b, int32_t dim, int32_t k, int64_t* out_ids, float* out_dist,

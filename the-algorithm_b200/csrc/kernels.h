@@ -36,6 +36,7 @@ struct PrepParams {
     const uint32_t* max_norm_bits;
     const uint32_t* max_resid_bits;
     int path;               // 1 = scan (fp32 error model), 2 = gemm (bf16 error model)
+    int accum_f32;          // the exact distances are fp32-accumulated: their own rounding error joins the margins
     uint32_t* pub_keys;     // [b][pub_stride] reset to 0xFFFFFFFF (scan path) or nullptr
     int pub_stride;
     unsigned long long* bad_queries;  // count of queries with non-finite entries / zero norm under Cosine
@@ -63,6 +64,11 @@ size_t scan_smem_bytes(int qb, int pitch, int warps, int cap);
 cudaError_t launch_scan(const ScanParams& p, int qb, int grid, size_t smem, cudaStream_t stream);
 
 // ---------------------------------------------------------------- selection: compaction + exact finalize
+constexpr int kMaxPeers = 16;
+// `keys[s]` is shard s's published [b][k] bound array mapped into this process (peer memory over NVLink)
+struct PeerSeedKeys {
+    const uint32_t* keys[kMaxPeers];
+};
 struct SelectParams {
     QueryState* qstate;     // [b]
     entry_t* pool;          // [b][pool_cap]
@@ -75,7 +81,10 @@ struct SelectParams {
     int k;
     int seed_count;         // > 0: the pool holds exactly this many seed entries (group maxima); derive tau, discard them
     uint32_t* seed_keys_out;  // with seed_count: also publish, per query, the k best group maxima as upper bounds on exact
-                              // badness (order keys of g + eps, [b][k], 0xFFFFFFFF padded) for the other shards (K5c)
+                              // badness (order keys of g + eps, [b][k], 0xFFFFFFFF padded) for the other shards (K5c);
+                              // without seed_count (compaction after the last chunk): the k best pool entries, likewise
+    PeerSeedKeys peer_keys;   // finalize: every shard's bounds published after the last chunk (second cross-shard round)
+    int peer_world;           // number of valid peer_keys entries; 0 = single shard, no global bound
     int sort_cap, exact_cap;  // shared-memory capacities (entries) of the approximate and exact stages; 0 = 4096 / 2048.
                               // exact_cap must be a power of two; exceeding either flags the query for the exact fallback
     // exact rescoring inputs
@@ -83,6 +92,7 @@ struct SelectParams {
     const int64_t* ids;
     long long n_rows;
     int dim, pitch, metric, l2_squared;
+    int accum_f32;          // ANN_FLAG_ACCUM_F32: exact distances accumulate sequentially in fp32 (oracle accum=1)
     const float* queries;   // [b][q_pitch] fp32
     int q_pitch;
     int64_t* out_ids;       // [b][k_out]
@@ -108,21 +118,19 @@ int report_error(int code, const char* msg);
 //   [ids: b*k int64][dist: b*k float][count: b int32]        (result_block_bytes)
 // `local[s]` is rank s's block of per-shard results and `final_[s]` its block for the merged answer, both mapped into this
 // process (peer memory over NVLink).  This rank merges the queries [q_begin, q_begin + q_count) and writes them to every final block.
-constexpr int kMaxPeers = 16;
 struct PeerBlocks {
     const unsigned char* local[kMaxPeers];
     unsigned char* final_[kMaxPeers];
 };
 inline size_t result_block_bytes(long long b, long long k) { return (size_t)(b * k * 12 + b * 4); }
-cudaError_t launch_exchange_merge(const PeerBlocks& pb, int world, int b, int k, int q_begin, int q_count, cudaStream_t stream);
+// slice_ids != nullptr: pull-only delivery into plain [q_count][k] arrays of this rank (final_ is not touched)
+cudaError_t launch_exchange_merge(const PeerBlocks& pb, int world, int b, int k, int q_begin, int q_count, cudaStream_t stream,
+                                  int64_t* slice_ids = nullptr, float* slice_dist = nullptr, int32_t* slice_count = nullptr);
 
 // K5c: threshold seeding shared between the shards of one index.  Every shard publishes, per query, k witnessed upper
 // bounds on exact badness (SelectParams::seed_keys_out); the k-th smallest over the union of all shards' bounds is a bound
 // on the GLOBAL k-th best, so a shard may discard everything above it (+ its own error margin) even where its own rows
 // alone would not justify that.  `keys[s]` is shard s's [b][k] key array mapped into this process (peer memory).
-struct PeerSeedKeys {
-    const uint32_t* keys[kMaxPeers];
-};
 cudaError_t launch_seed_merge(const PeerSeedKeys& pk, int world, QueryState* qstate, int b, int k, cudaStream_t stream);
 
 // ---------------------------------------------------------------- exact fallback (degenerate ties, NaN queries)
@@ -130,7 +138,7 @@ struct FallbackParams {
     const float* rows;
     const int64_t* ids;
     long long n_rows;
-    int pitch, dim, metric, l2_squared;
+    int pitch, dim, metric, l2_squared, accum_f32;
     const float* query;     // [dim] fp32 on the device
     void* scratch;          // fallback_scratch_bytes(n_rows, k)
     int k, k_out;           // k = min(requested k, n_rows)

@@ -24,7 +24,24 @@ namespace {
 constexpr int kWarpsPerCta = 8;
 
 // distance(a, b) with the index's conventions; a and b in shared memory
-__device__ float pair_distance(int metric, const float* a, const float* b, int d, int l2_squared) {
+__device__ float pair_distance(int metric, const float* a, const float* b, int d, int l2_squared, int accum_f32) {
+    if (accum_f32) {   // ANN_FLAG_ACCUM_F32: the oracle's distance_f32, operation for operation (b is a plain fp32 vector here)
+        const float nb = metric == kMetricCosine ? exact_query_norm2_f32(b, d) : 0.f;
+        // a lives in shared memory as dim floats; the float4 walk of the index kernels wants 16-byte alignment, so go scalar
+        float s0 = 0.f, s1 = 0.f;
+        for (int i = 0; i < d; ++i) {
+            if (metric == kMetricL2) {
+                const float df = __fsub_rn(a[i], b[i]);
+                s0 = __fadd_rn(s0, __fmul_rn(df, df));
+            } else {
+                s0 = __fadd_rn(s0, __fmul_rn(a[i], b[i]));
+                if (metric == kMetricCosine) s1 = __fadd_rn(s1, __fmul_rn(a[i], a[i]));
+            }
+        }
+        if (metric == kMetricL2) return l2_squared ? s0 : __fsqrt_rn(s0);
+        if (metric == kMetricIP) return __fsub_rn(1.0f, s0);
+        return __fsub_rn(1.0f, __fdiv_rn(s0, __fmul_rn(__fsqrt_rn(s1), __fsqrt_rn(nb))));
+    }
     if (metric == kMetricL2) {
         double acc = 0.0;
         for (int i = 0; i < d; ++i) {
@@ -43,8 +60,8 @@ __device__ float pair_distance(int metric, const float* a, const float* b, int d
     return __fsub_rn(1.0f, __double2float_rn(cs));
 }
 
-__global__ void __launch_bounds__(32 * kWarpsPerCta) distance_pairs_kernel(int metric, int l2_squared, int dim, const float* a,
-                                                                           const float* b, long long n, float* out) {
+__global__ void __launch_bounds__(32 * kWarpsPerCta) distance_pairs_kernel(int metric, int l2_squared, int accum_f32, int dim,
+                                                                           const float* a, const float* b, long long n, float* out) {
     extern __shared__ float sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* sa = sm + (size_t)warp * 2 * dim;
@@ -55,7 +72,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) distance_pairs_kernel(int m
             sb[i] = b[(size_t)p * dim + i];
         }
         __syncwarp();
-        if (lane == 0) out[p] = pair_distance(metric, sa, sb, dim, l2_squared);
+        if (lane == 0) out[p] = pair_distance(metric, sa, sb, dim, l2_squared, accum_f32);
         __syncwarp();
     }
 }
@@ -139,7 +156,7 @@ int ann_distance_pairs(int32_t metric, uint32_t flags, int32_t dim, const float*
     METRIC_TRY(cudaMemcpy(st.p[1], b, bytes, cudaMemcpyHostToDevice));
     const size_t smem = (size_t)kWarpsPerCta * 2 * dim * sizeof(float);
     METRIC_TRY(cudaFuncSetAttribute(distance_pairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    distance_pairs_kernel<<<grid_for(n), 32 * kWarpsPerCta, smem>>>(metric, (flags & ANN_FLAG_L2_SQUARED) ? 1 : 0, dim, st.p[0], st.p[1],
+    distance_pairs_kernel<<<grid_for(n), 32 * kWarpsPerCta, smem>>>(metric, (flags & ANN_FLAG_L2_SQUARED) ? 1 : 0, (flags & ANN_FLAG_ACCUM_F32) ? 1 : 0, dim, st.p[0], st.p[1],
                                                                    (long long)n, st.p[2]);
     METRIC_TRY(cudaGetLastError());
     METRIC_TRY(cudaMemcpy(out, st.p[2], (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));

@@ -145,6 +145,19 @@ __device__ bool load_and_threshold(const SelectParams& p, int q, entry_t* buf, u
         uint32_t gk = cta_kth_smallest_key(p.pub_keys + (size_t)q * p.pub_stride, p.pub_count, p.j_pub, nullptr);
         if (gk < 0xFF800000u) tau = fminf(tau, widen(float_from_order_key(gk), eps_abs, eps_rel));
     }
+    if (p.peer_world > 0 && p.k > 0) {
+        // k-th smallest of the union of every shard's published bounds (P2P loads, k*4 bytes per shard): at least k distinct
+        // rows of the whole index have exact badness <= U, so nothing above U + eps (this shard's margin) can be in the answer
+        const int total = p.peer_world * p.k;     // <= sort_cap (checked by the launcher)
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const int s = i / p.k, j = i - s * p.k;
+            buf[i] = (entry_t)__ldcg(p.peer_keys.keys[s] + (size_t)q * p.k + j) << 32;
+        }
+        __syncthreads();
+        const uint32_t u = kth_key_radix(buf, total, p.k, hist);
+        if (u < 0xFF800000u) tau = fminf(tau, widen_half_up(float_from_order_key(u), eps_abs, eps_rel));
+        __syncthreads();
+    }
     if (threadIdx.x == 0) n_s = 0;
     __syncthreads();
     const entry_t* pool = p.pool + (size_t)q * p.pool_cap;
@@ -183,16 +196,20 @@ __global__ void __launch_bounds__(kSelThreads, 4) compact_pool_kernel(SelectPara
     __shared__ int n_keep;
     const int q = blockIdx.x;
     QueryState* qs = p.qstate + q;
+    auto publish_nothing = [&]() {   // a flagged query publishes "no bound" (never stale keys of an earlier batch)
+        if (p.seed_keys_out)
+            for (int j = threadIdx.x; j < p.k; j += blockDim.x) p.seed_keys_out[(size_t)q * p.k + j] = 0xFFFFFFFFu;
+    };
     if (p.seed_count == 0 && qs->pool_count > (uint32_t)p.pool_cap) {
         if (threadIdx.x == 0) atomicOr(&qs->flags, kFlagPoolOverflow);
+        publish_nothing();
         return;
     }
     int n;
     float tau;
     uint32_t kk;
     if (!load_and_threshold(p, q, buf, hist, &n, &tau, &kk)) {
-        if (p.seed_count > 0 && p.seed_keys_out)
-            for (int j = threadIdx.x; j < p.k; j += blockDim.x) p.seed_keys_out[(size_t)q * p.k + j] = 0xFFFFFFFFu;
+        publish_nothing();
         return;
     }
     if (p.seed_count > 0) {   // seed entries carry no row: keep only the threshold
@@ -237,10 +254,34 @@ __global__ void __launch_bounds__(kSelThreads, 4) compact_pool_kernel(SelectPara
         qs->pool_count = n_keep;
         qs->tau_key = float_order_key(tau);
     }
+    if (p.seed_keys_out) {
+        // Second cross-shard round (sharded query, after the last chunk): publish this shard's k best approximate keys,
+        // each widened to an upper bound on the exact badness of the row that produced it.  The k-th smallest over all
+        // shards' arrays bounds the GLOBAL k-th best, which lets every shard rescore only its share of the ~2k global
+        // survivors instead of its own ~2k (the local k-th of 1/R of the rows is far looser than the global one).
+        uint32_t* out = p.seed_keys_out + (size_t)q * p.k;
+        const float ea = qs->eps_abs, er = qs->eps_rel;
+        __shared__ int n_pub;
+        if (threadIdx.x == 0) n_pub = 0;
+        __syncthreads();
+        if (kk != 0xFFFFFFFFu) {   // n >= k: entries strictly below the k-th key, then the k-th key itself as often as needed
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const uint32_t key = (uint32_t)(buf[i] >> 32);
+                if (key < kk) out[atomicAdd(&n_pub, 1)] = float_order_key(widen_half_up(float_from_order_key(key), ea, er));
+            }
+            __syncthreads();
+            const uint32_t fill = float_order_key(widen_half_up(float_from_order_key(kk), ea, er));
+            for (int j = n_pub + threadIdx.x; j < p.k; j += blockDim.x) out[j] = fill;
+        } else {                   // fewer than k candidates under the threshold: every one is a witness, the rest is "no bound"
+            for (int i = threadIdx.x; i < n; i += blockDim.x)
+                out[i] = float_order_key(widen_half_up(entry_g(buf[i]), ea, er));
+            for (int j = n + threadIdx.x; j < p.k; j += blockDim.x) out[j] = 0xFFFFFFFFu;
+        }
+    }
 }
 
 // ---- finalize: survivors + specials -> exact distances -> (distance, id) order -> outputs -------------------
-template <int METRIC>
+template <int METRIC, bool ACC32>
 __global__ void __launch_bounds__(kSelThreads, 4) finalize_kernel(SelectParams p) {
     extern __shared__ __align__(16) unsigned char sm[];
     const int sort_cap = sort_cap_of(p), exact_cap = exact_cap_of(p);
@@ -259,7 +300,7 @@ __global__ void __launch_bounds__(kSelThreads, 4) finalize_kernel(SelectParams p
             oid[j] = -1;
             od[j] = INFINITY;
         }
-        if (threadIdx.x == 0 && p.out_count) p.out_count[q] = 0;
+        if (threadIdx.x == 0 && p.out_count) p.out_count[q] = -1;   // flagged: the row is INVALID (not an empty list)
     };
 
     if (qs->pool_count > (uint32_t)p.pool_cap) {
@@ -321,17 +362,28 @@ __global__ void __launch_bounds__(kSelThreads, 4) finalize_kernel(SelectParams p
         double* q64 = reinterpret_cast<double*>(buf);                                  // <= 8 KB (dim <= 1024)
         uint32_t* okey = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(buf) + 8192);   // exact_cap keys (sort_cap * 8 >= 8192 + exact_cap * 4)
         __shared__ double nb_s;
+        __shared__ float nbf_s;
+        float* q32 = reinterpret_cast<float*>(buf);      // ANN_FLAG_ACCUM_F32: the query stays fp32 (same region)
         const float* qv = p.queries + (size_t)q * p.q_pitch;
-        for (int i = threadIdx.x; i < p.dim; i += blockDim.x) q64[i] = (double)qv[i];
+        for (int i = threadIdx.x; i < p.dim; i += blockDim.x) {
+            if (ACC32) q32[i] = qv[i];
+            else q64[i] = (double)qv[i];
+        }
         __syncthreads();
-        if (threadIdx.x == 0) nb_s = (METRIC == kMetricCosine) ? exact_query_norm2(q64, p.dim) : 0.0;
+        if (threadIdx.x == 0) {
+            if (ACC32) nbf_s = (METRIC == kMetricCosine) ? exact_query_norm2_f32(q32, p.dim) : 0.f;
+            else nb_s = (METRIC == kMetricCosine) ? exact_query_norm2(q64, p.dim) : 0.0;
+        }
         __syncthreads();
-        const ExactQuery eq{q64, nb_s};
+        const ExactQuery eq{q64, ACC32 ? 0.0 : nb_s};
+        const float nbf = ACC32 ? nbf_s : 0.f;
         // one thread per candidate row, all candidates in parallel; several CTAs per SM overlap each other's
         // dependent-miss chains (the kernel is latency bound, so occupancy -- not per-thread ILP -- is what pays)
         for (int c = threadIdx.x; c < n_cand; c += blockDim.x) {
             const uint32_t row = crow[c];
-            const float dist = exact_distance_rows<true, METRIC>(METRIC, p.rows + (size_t)row * p.pitch, eq, p.dim, p.l2_squared);
+            const float* rp = p.rows + (size_t)row * p.pitch;
+            const float dist = ACC32 ? exact_distance_rows_f32<true, METRIC>(METRIC, rp, q32, nbf, p.dim, p.l2_squared)
+                                     : exact_distance_rows<true, METRIC>(METRIC, rp, eq, p.dim, p.l2_squared);
             cid[c] = p.ids[row];
             okey[c] = float_order_key(dist);
         }
@@ -414,8 +466,13 @@ __global__ void __launch_bounds__(kSelThreads) merge_topk_kernel(const int64_t* 
     __shared__ int total_s;
     if (threadIdx.x == 0) {
         int t = 0;
-        for (int s = 0; s < shards; ++s) t += min(max(count[(size_t)s * b + q], 0), k);
-        total_s = t;
+        bool flagged = false;   // a shard could not answer this query with its bounded selector (count = -1): the merged row
+        for (int s = 0; s < shards; ++s) {   // is invalid too and says so, instead of silently missing that shard's rows
+            const int c = count[(size_t)s * b + q];
+            flagged = flagged || c < 0;
+            t += min(max(c, 0), k);
+        }
+        total_s = flagged ? -1 : t;
     }
     for (int i = threadIdx.x; i < n2; i += blockDim.x) {
         int s = i / k, j = i - s * k;
@@ -432,7 +489,7 @@ __global__ void __launch_bounds__(kSelThreads) merge_topk_kernel(const int64_t* 
     __syncthreads();
     // NaN distances share the pad key; order them before pads by id (pads carry INT64_MAX).
     bitonic_sort_pairs(ckey, cid, n2);
-    const int cnt = min(k, total_s);
+    const int cnt = total_s < 0 ? -1 : min(k, total_s);
     for (int j = threadIdx.x; j < k; j += blockDim.x) {
         size_t off = (size_t)q * k + j;
         if (j < cnt) {
@@ -455,17 +512,26 @@ __global__ void __launch_bounds__(kSelThreads) merge_topk_kernel(const int64_t* 
 // The lists arrive sorted by (distance key, id), so the merge is rank counting instead of a sort: the final position of
 // entry j of list s is j + the number of entries of every other list that precede it (two binary searches' worth of
 // shared-memory probes), ties between lists broken by shard index.  No barriers after the load.
-__global__ void __launch_bounds__(kSelThreads) exchange_merge_kernel(PeerBlocks pb, int world, int b, int k, int q_begin) {
+// Two delivery modes: push (slice_ids == nullptr) writes the merged rows of this rank's slice into EVERY rank's final
+// block; pull-only (slice_ids != nullptr) writes them to plain [q_count][k] arrays on this rank -- the answer stays
+// partitioned across the ranks, nothing is pushed and no barrier is needed after the kernel.
+// A row some shard flagged (count < 0: its bounded selector could not answer it) is delivered as count = -1.
+__global__ void __launch_bounds__(kSelThreads) exchange_merge_kernel(PeerBlocks pb, int world, int b, int k, int q_begin,
+                                                                     int64_t* slice_ids, float* slice_dist, int32_t* slice_count) {
     extern __shared__ __align__(16) unsigned char sm[];
     long long* lid = reinterpret_cast<long long*>(sm);                         // [world][k]
     long long* oid = lid + (size_t)world * k;                                  // [k] merged ids
     uint32_t* lkey = reinterpret_cast<uint32_t*>(oid + k);                     // [world][k]
     uint32_t* okey = lkey + (size_t)world * k;                                 // [k] merged keys
     __shared__ int cnt_s[kMaxPeers];
+    __shared__ int flagged_s;
     const int q = q_begin + blockIdx.x;
     const size_t dist_off = (size_t)b * k * 8, cnt_off = (size_t)b * k * 12;
+    if (threadIdx.x == 0) flagged_s = 0;
+    __syncthreads();
     if (threadIdx.x < world) {
         const int c = *reinterpret_cast<const int32_t*>(pb.local[threadIdx.x] + cnt_off + (size_t)q * 4);
+        if (c < 0) flagged_s = 1;
         cnt_s[threadIdx.x] = min(max(c, 0), k);
     }
     __syncthreads();
@@ -511,12 +577,23 @@ __global__ void __launch_bounds__(kSelThreads) exchange_merge_kernel(PeerBlocks 
         }
     }
     __syncthreads();
-    const int cnt = min(k, total);
+    const int cnt = flagged_s ? -1 : min(k, total);
+    if (slice_ids) {
+        const size_t row = (size_t)blockIdx.x * k;
+        for (int j = threadIdx.x; j < k; j += blockDim.x) {
+            const bool ok = j < cnt;
+            slice_ids[row + j] = ok ? oid[j] : -1;
+            slice_dist[row + j] = ok ? float_from_order_key(okey[j]) : INFINITY;
+        }
+        if (threadIdx.x == 0 && slice_count) slice_count[blockIdx.x] = cnt;
+        return;
+    }
     for (int i = threadIdx.x; i < world * k; i += blockDim.x) {
         const int p = i / k, j = i - p * k;
+        const bool ok = j < cnt;
         unsigned char* f = pb.final_[p];
-        *reinterpret_cast<long long*>(f + ((size_t)q * k + j) * 8) = oid[j];
-        *reinterpret_cast<float*>(f + dist_off + ((size_t)q * k + j) * 4) = float_from_order_key(okey[j]);
+        *reinterpret_cast<long long*>(f + ((size_t)q * k + j) * 8) = ok ? oid[j] : -1;
+        *reinterpret_cast<float*>(f + dist_off + ((size_t)q * k + j) * 4) = ok ? float_from_order_key(okey[j]) : INFINITY;
     }
     if (threadIdx.x < world) *reinterpret_cast<int32_t*>(pb.final_[threadIdx.x] + cnt_off + (size_t)q * 4) = cnt;
     __threadfence_system();   // the peers read these rows after the next cross-rank barrier
@@ -566,8 +643,14 @@ cudaError_t launch_compact_pool(const SelectParams& p, int b, cudaStream_t strea
 cudaError_t launch_finalize(const SelectParams& p, int b, cudaStream_t stream) {
     size_t smem = (size_t)sort_cap_of(p) * 8 + (size_t)exact_cap_of(p) * 12;
     if ((size_t)sort_cap_of(p) * 8 < 8192 + (size_t)exact_cap_of(p) * 4) return cudaErrorInvalidValue;
-    void (*fn)(SelectParams) = p.metric == kMetricL2 ? finalize_kernel<kMetricL2>
-                               : p.metric == kMetricCosine ? finalize_kernel<kMetricCosine> : finalize_kernel<kMetricIP>;
+    if (p.peer_world < 0 || p.peer_world > kMaxPeers || (long long)p.peer_world * p.k > sort_cap_of(p)) return cudaErrorInvalidValue;
+    void (*fn)(SelectParams);
+    if (p.accum_f32)
+        fn = p.metric == kMetricL2 ? finalize_kernel<kMetricL2, true>
+             : p.metric == kMetricCosine ? finalize_kernel<kMetricCosine, true> : finalize_kernel<kMetricIP, true>;
+    else
+        fn = p.metric == kMetricL2 ? finalize_kernel<kMetricL2, false>
+             : p.metric == kMetricCosine ? finalize_kernel<kMetricCosine, false> : finalize_kernel<kMetricIP, false>;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     fn<<<b, kSelThreads, smem, stream>>>(p);
@@ -595,13 +678,14 @@ cudaError_t launch_merge(const int64_t* ids, const float* dist, const int32_t* c
     return cudaGetLastError();
 }
 
-cudaError_t launch_exchange_merge(const PeerBlocks& pb, int world, int b, int k, int q_begin, int q_count, cudaStream_t stream) {
+cudaError_t launch_exchange_merge(const PeerBlocks& pb, int world, int b, int k, int q_begin, int q_count, cudaStream_t stream,
+                                  int64_t* slice_ids, float* slice_dist, int32_t* slice_count) {
     if (q_count <= 0) return cudaSuccess;
     const size_t smem = (size_t)(world + 1) * k * 12;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(exchange_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    exchange_merge_kernel<<<q_count, kSelThreads, smem, stream>>>(pb, world, b, k, q_begin);
+    exchange_merge_kernel<<<q_count, kSelThreads, smem, stream>>>(pb, world, b, k, q_begin, slice_ids, slice_dist, slice_count);
     return cudaGetLastError();
 }
 
