@@ -205,6 +205,39 @@ ANN_API int ann_sharded_shard(ann_sharded_index *sx, int32_t shard, ann_index **
 ANN_API int ann_sharded_set_option(ann_sharded_index *sx, const char *name, int64_t value);
 ANN_API int ann_sharded_get_stat(const ann_sharded_index *sx, const char *name, int64_t *value);
 
+/* ---- the reference's on-disk format (csrc/persist.cu) -------------------------------------------------------------------
+ * SerializableBruteForceIndex.toDirectory (BruteForceIndex.scala:142-161) / BruteForceDeserialization.fromDirectory
+ * (BruteForceDeserialization.scala:42-63): one file `BruteForceFileData` holding back-to-back TBinaryProtocol encodings of
+ * PersistedEmbedding {1: binary id, 2: embedding.Embedding} (serialization.thrift:7-10; ThriftIteratorIO.scala:14-56) until
+ * end of file; sharded indexes are `shard_<i>/` sub-directories (ShardedSerialization.scala:9-11,28-66).  A `_SUCCESS`
+ * marker is added (IndexOutputFile.scala:29,58-62).
+ *   id_format : how Injection[T, Array[Byte]] encodes the id (AnnInjections.scala:8-12) -- Long = 8 bytes big-endian, Int = 4;
+ *               ANN_ID_AUTO accepts either when reading and writes Long.
+ *   layout    : which member of the tensor union carries the floats when WRITING (the inner embedding.thrift is not in the
+ *               open-source tree; the assumption is stated in csrc/persist.cu).  The reader accepts all three.
+ * ann_load_directory: cfg gives metric / device / flags / capacity_hint; cfg->dim may be 0 (taken from the first record).
+ * A truncated trailing record ends the stream silently, like the reference's END_OF_FILE handling. */
+#define ANN_ID_AUTO 0
+#define ANN_ID_INT64_BE 1
+#define ANN_ID_INT32_BE 2
+#define ANN_LAYOUT_FLOAT_TENSOR 0  /* Embedding{1: GeneralTensor{5: FloatTensor{1: list<double>}}}  (default) */
+#define ANN_LAYOUT_DOUBLE_TENSOR 1 /* Embedding{1: GeneralTensor{6: DoubleTensor{1: list<double>}}}            */
+#define ANN_LAYOUT_RAW_FLOAT 2     /* Embedding{1: GeneralTensor{1: RawTypedTensor{1: FLOAT, 2: LE float32 bytes}}} */
+ANN_API int ann_save_directory(ann_index *ix, const char *directory, int32_t id_format, int32_t layout);
+ANN_API int ann_load_directory(const ann_config *cfg, const char *directory, int32_t id_format, ann_index **out);
+ANN_API int ann_sharded_save_directory(ann_sharded_index *sx, const char *directory, int32_t id_format, int32_t layout);
+/* Loads `shard_<i>/` sub-directories (or a plain index directory) into a composed handle over the listed devices; rows are
+ * re-dealt over the devices, so the directory may have been written with any number of shards. */
+ANN_API int ann_sharded_load_directory(const ann_config *cfg, const char *directory, int32_t id_format,
+                                       const int32_t *device_ids, int32_t n_devices, ann_sharded_index **out);
+/* The record codec alone (host code, no device): encode one PersistedEmbedding into `out` (returns its size in bytes, also
+ * when out == NULL or too small; -1 on bad arguments), decode the record at the head of `bytes` (*consumed = 0 at end of
+ * stream; row may be NULL to learn *dim first). */
+ANN_API int64_t ann_persisted_embedding_encode(int64_t id, int32_t id_format, const float *row, int32_t dim, int32_t layout,
+                                               unsigned char *out, int64_t capacity);
+ANN_API int ann_persisted_embedding_decode(const unsigned char *bytes, int64_t len, int32_t id_format, int64_t *id,
+                                           float *row, int32_t row_capacity, int32_t *dim, int64_t *consumed);
+
 /* KnnHelper.findNearestNeighbours (ann/src/main/scala/com/twitter/ann/scalding/offline/KnnHelper.scala:168-215, 248-347):
  * the exact k nearest corpus rows of every query, host buffers in and out -- the offline all-pairs job behind
  * KnnTruthSetGenerator.  The corpus is cut into tiles of corpus_tile_rows rows that fit the device (<= 0: as many as fit;
@@ -235,7 +268,7 @@ ANN_API int ann_normalize_rows(int32_t dim, const float *rows, int64_t n, float 
  *          "timing" (1 = bracket every scan / GEMM-filter launch with CUDA events on its stream),
  *          "device_fallback" (1 = ann_query_batch_device synchronises its stream and re-answers flagged queries with the
  *          exact fallback, like the host entry point always does; 0 = stay asynchronous and report them, default).
- * Stats:   "launches" (kernels launched so far), "last_path", "shadow_bytes", "row_bytes", "n_special", "capacity",
+ * Stats:   "launches" (kernels launched so far), "last_path", "shadow_bytes", "row_bytes", "n_special", "capacity", "dim",
  *          "sm_count", "kernel_us" / "kernel_launches_timed" (accumulated since "timing" was set; synchronises),
  *          "pending_error" (synchronises the device and returns the sticky selector-overflow status, if any). */
 ANN_API int ann_set_option(ann_index *ix, const char *name, int64_t value);

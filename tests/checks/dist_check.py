@@ -75,8 +75,55 @@ for metric, n, d, b, k in ((InnerProduct, 200_003, 200, 300, 100), (Cosine, 50_0
         torch.cuda.synchronize()
         ok2 &= bool((si.cpu().numpy() == wi).all() and (sd.cpu().numpy().view(np.uint32) == wd.view(np.uint32)).all()
                     and (sc.cpu().numpy() == wc).all())
-    ok2 &= sx.route == "fused" and sx.share_seeds
+    ok2 &= sx.route == "fused" and sx.share_seeds and sx.two_round
+    # ... and its slice delivery: every rank receives only its rows of the merged batch, nothing is pushed
+    q0, q1 = sx.slice_range(b)
+    for rep in range(3):
+        si, sd, sc = sx.batch_query_device(qd, k, st, deliver="slice")
+        torch.cuda.synchronize()
+        ok2 &= bool(si.shape[0] == q1 - q0 and (si.cpu().numpy() == wi[q0:q1]).all()
+                    and (sd.cpu().numpy().view(np.uint32) == wd[q0:q1].view(np.uint32)).all() and (sc.cpu().numpy() == wc[q0:q1]).all())
     del sx
+    # the same with the seed round only (A/B of the second cross-shard round)
+    sx = ShardedBruteForceIndex(ix, device=dev, two_round=False)
+    for rep in range(2):
+        si, sd, sc = sx.batch_query_device(qd, k, st)
+        torch.cuda.synchronize()
+        ok2 &= bool((si.cpu().numpy() == wi).all() and (sd.cpu().numpy().view(np.uint32) == wd.view(np.uint32)).all()
+                    and (sc.cpu().numpy() == wc).all())
+    del sx
+    # degenerate batch: a NaN query and a query nearest to thousands of identical rows flag some shard's bounded selector.
+    # The asynchronous call must say so (count = -1 on every rank), the synchronous one must answer exactly.
+    if metric is InnerProduct:
+        corpus2 = corpus.copy()
+        corpus2[lo + 100: lo + 100 + min(7000, hi - lo - 100)] = corpus2[3]      # every shard holds thousands of duplicates
+        q2 = q.copy()
+        q2[1] = corpus2[3] * 4.0
+        q2[2, 7] = np.nan
+        ixd = BruteForceIndex.apply(metric, FuturePool.immediate_pool(), device=local)
+        ixd.append_batch(ids[lo:hi], corpus2[lo:hi])
+        full2 = np.empty_like(corpus)
+        parts = [None] * world
+        dist.all_gather_object(parts, corpus2[lo:hi])
+        full2 = np.concatenate(parts)
+        w2 = oracle.query_canonical(metric.ordinal, full2, ids, q2, k)
+        qd2 = torch.from_numpy(q2).to(dev)
+        sxd = ShardedBruteForceIndex(ixd, device=dev)
+        ai, ad, ac = sxd.batch_query_device(qd2, k, st)
+        torch.cuda.synchronize()
+        flagged = ac.cpu().numpy() < 0
+        ok2 &= bool(flagged[1] and flagged[2])
+        good = ~flagged
+        ok2 &= bool((ai.cpu().numpy()[good] == w2[0][good]).all())
+        try:
+            ixd.raise_pending_error()
+        except Exception:
+            pass
+        bi, bd, bc = sxd.batch_query(qd2, k, st)
+        ok2 &= bool((bi.cpu().numpy() == w2[0]).all() and (bd.cpu().numpy().view(np.uint32) == w2[1].view(np.uint32)).all()
+                    and (bc.cpu().numpy() == w2[2]).all())
+        del sxd
+        ixd.close()
     # fourth: the same class on the collective route (seed bounds all-gathered over NCCL, lists all-gathered, K5 merge)
     sx = ShardedBruteForceIndex(ix, device=dev, route="allgather")
     for rep in range(2):

@@ -232,3 +232,59 @@ def test_in_process_sharded_handle_errors_and_empty():
     sx.close()
     with pytest.raises(AnnError):
         GpuShardedBruteForceIndex(G["L2"], G["FuturePool"].immediate_pool(), dim=8, devices=[99])
+
+
+# ------------------------------------------------------------------------------------------------ the reference's on-disk format
+@pytest.mark.parametrize("layout", [0, 2])
+def test_thrift_directory_round_trip(tmp_path, layout):
+    """ann_save_directory / ann_load_directory: BruteForceFileData as a TBinaryProtocol PersistedEmbedding stream
+    (BruteForceIndex.scala:142-161, ThriftIteratorIO.scala:14-56), `_SUCCESS`, reloaded index answers identically."""
+    import struct
+
+    from the_algorithm_b200.ann.brute_force import SerializableBruteForceIndex
+
+    m = G["Cosine"]
+    corpus, ids, q = make(5000, 24, 6, seed=3)
+    ix = G["BruteForceIndex"].apply(m, G["FuturePool"].immediate_pool())
+    ix.append_batch(ids, corpus)
+    SerializableBruteForceIndex.to_directory(ix, tmp_path / "idx", layout=layout)
+    data = (tmp_path / "idx" / "BruteForceFileData").read_bytes()
+    assert (tmp_path / "idx" / "_SUCCESS").exists()
+    assert data[:7] == bytes([11, 0, 1, 0, 0, 0, 8]) and struct.unpack(">q", data[7:15])[0] == ids[0]     # first record's id, big-endian Long
+    if layout == 0:
+        assert len(data) == 5000 * (3 + 4 + 8 + 3 + 3 + 3 + 3 + 1 + 4 + 24 * 8 + 4)
+    ix2 = SerializableBruteForceIndex.from_directory(tmp_path / "idx", m, G["FuturePool"].immediate_pool())
+    assert ix2.size() == 5000 and ix2.dim == 24
+    same(ix2.batch_query_with_distance(q, 50), ix.batch_query_with_distance(q, 50))
+    same(ix2.batch_query_with_distance(q, 50), oracle.query_canonical(m.ordinal, corpus, ids, q, 50))
+    ri, rr = ix2.read_rows(0, 5000)
+    assert (ri == ids).all() and (rr.view(np.uint32) == corpus.view(np.uint32)).all()        # insertion order and bits preserved
+    # a truncated trailing record is the end of the stream (ThriftIteratorIO.scala:42-49)
+    (tmp_path / "cut").mkdir()
+    (tmp_path / "cut" / "BruteForceFileData").write_bytes(data[: len(data) // 2 + 11])
+    ix3 = SerializableBruteForceIndex.from_directory(tmp_path / "cut", m, G["FuturePool"].immediate_pool())
+    assert 0 < ix3.size() <= 2501
+    for i in (ix, ix2, ix3):
+        i.close()
+
+
+def test_sharded_directory_layout_and_reload_with_another_shard_count(tmp_path):
+    """ShardedSerialization: `shard_<i>/BruteForceFileData` (ShardedSerialization.scala:28-38); ComposedQueryableDeserialization
+    reads whatever shard directories exist (:49-66) -- here 3 written, reloaded over 2 shards, and one shard alone."""
+    from the_algorithm_b200.ann.brute_force import SerializableBruteForceIndex
+    from the_algorithm_b200.ann.sharded import GpuShardedBruteForceIndex
+
+    m = G["L2"]
+    corpus, ids, q = make(9000, 16, 5, seed=4)
+    sx = GpuShardedBruteForceIndex(m, G["FuturePool"].immediate_pool(), dim=16, devices=_devices(3))
+    sx.append_batch(ids, corpus)
+    sx.to_directory(tmp_path / "sh")
+    assert sorted(p.name for p in (tmp_path / "sh").iterdir()) == ["_SUCCESS", "shard_0", "shard_1", "shard_2"]
+    want = oracle.query_canonical(m.ordinal, corpus, ids, q, 30)
+    sx2 = GpuShardedBruteForceIndex.from_directory(tmp_path / "sh", m, G["FuturePool"].immediate_pool(), devices=_devices(2))
+    assert sx2.size() == 9000 and sx2.dim == 16
+    same(sx2.batch_query_with_distance(q, 30), want)
+    one = SerializableBruteForceIndex.from_directory(tmp_path / "sh" / "shard_1", m, G["FuturePool"].immediate_pool())
+    assert one.size() == 3000 and (one.read_rows(0, 3000)[0] == ids[3000:6000]).all()
+    for i in (sx, sx2, one):
+        i.close()

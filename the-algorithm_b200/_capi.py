@@ -27,6 +27,8 @@ ANN_ERR_UNKNOWN_OPTION = -9
 ANN_FLAG_L2_SQUARED = 0x1
 ANN_FLAG_NO_SHADOW = 0x2
 ANN_FLAG_ACCUM_F32 = 0x4
+ANN_ID_AUTO, ANN_ID_INT64_BE, ANN_ID_INT32_BE = 0, 1, 2
+ANN_LAYOUT_FLOAT_TENSOR, ANN_LAYOUT_DOUBLE_TENSOR, ANN_LAYOUT_RAW_FLOAT = 0, 1, 2
 
 # every symbol include/b200ann.h declares (tests/test_capi_symbols.py checks header <-> library <-> this list)
 SYMBOLS = (
@@ -34,7 +36,9 @@ SYMBOLS = (
     "ann_query_batch_device", "ann_merge_topk_device", "ann_exchange_merge_device", "ann_result_block_bytes", "ann_query_seed_device", "ann_query_finish_device",
     "ann_query_filter_device", "ann_query_rescore_device", "ann_exchange_merge_slice_device",
     "ann_sharded_create", "ann_sharded_destroy", "ann_sharded_append_batch", "ann_sharded_size", "ann_sharded_query_batch",
-    "ann_sharded_shard", "ann_sharded_set_option", "ann_sharded_get_stat", "ann_knn_join", "ann_distance_pairs", "ann_normalize_rows", "ann_set_option", "ann_get_stat", "ann_last_error", "ann_version",
+    "ann_sharded_shard", "ann_sharded_set_option", "ann_sharded_get_stat",
+    "ann_save_directory", "ann_load_directory", "ann_sharded_save_directory", "ann_sharded_load_directory",
+    "ann_persisted_embedding_encode", "ann_persisted_embedding_decode", "ann_knn_join", "ann_distance_pairs", "ann_normalize_rows", "ann_set_option", "ann_get_stat", "ann_last_error", "ann_version",
 )
 
 
@@ -110,6 +114,18 @@ def lib() -> ctypes.CDLL:
         L.ann_sharded_set_option.argtypes = [vp, ctypes.c_char_p, i64]
         L.ann_sharded_get_stat.restype = ctypes.c_int
         L.ann_sharded_get_stat.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(i64)]
+        L.ann_save_directory.restype = ctypes.c_int
+        L.ann_save_directory.argtypes = [vp, ctypes.c_char_p, i32, i32]
+        L.ann_load_directory.restype = ctypes.c_int
+        L.ann_load_directory.argtypes = [ctypes.POINTER(AnnConfig), ctypes.c_char_p, i32, ctypes.POINTER(vp)]
+        L.ann_sharded_save_directory.restype = ctypes.c_int
+        L.ann_sharded_save_directory.argtypes = [vp, ctypes.c_char_p, i32, i32]
+        L.ann_sharded_load_directory.restype = ctypes.c_int
+        L.ann_sharded_load_directory.argtypes = [ctypes.POINTER(AnnConfig), ctypes.c_char_p, i32, ctypes.POINTER(i32), i32, ctypes.POINTER(vp)]
+        L.ann_persisted_embedding_encode.restype = ctypes.c_int64
+        L.ann_persisted_embedding_encode.argtypes = [i64, i32, vp, i32, i32, vp, i64]
+        L.ann_persisted_embedding_decode.restype = ctypes.c_int
+        L.ann_persisted_embedding_decode.argtypes = [vp, i64, i32, ctypes.POINTER(i64), vp, i32, ctypes.POINTER(i32), ctypes.POINTER(i64)]
         L.ann_result_block_bytes.restype = ctypes.c_size_t
         L.ann_result_block_bytes.argtypes = [i32, i32]
         L.ann_knn_join.restype = ctypes.c_int

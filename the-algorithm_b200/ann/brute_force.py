@@ -391,19 +391,23 @@ _MAGIC = b"B200ANN\x01"
 class SerializableBruteForceIndex:
     """Mirror of SerializableBruteForceIndex / BruteForceDeserialization (BruteForceIndex.scala:94-162;
     BruteForceDeserialization.scala:18-64): one data file `BruteForceFileData` inside a directory, `_SUCCESS` marker
-    (common/IndexOutputFile.scala:60).
+    (common/IndexOutputFile.scala:29,58-62).
 
-    The reference streams TBinaryProtocol `PersistedEmbedding{1: binary id, 2: embedding.Embedding}` structs with no header
-    (ThriftIteratorIO.scala:14-22); the inner `embedding.Embedding` thrift struct is not in the open-source tree, so byte
-    compatibility cannot be pinned.  This is the native raw format instead (little endian):
+    fmt="thrift" (default) is the reference's own format, written and read natively (`ann_save_directory` /
+    `ann_load_directory`, csrc/persist.cu): back-to-back TBinaryProtocol `PersistedEmbedding{1: binary id, 2:
+    embedding.Embedding}` structs with no header (ThriftIteratorIO.scala:14-22), ids as big-endian Long
+    (AnnInjections.scala:8).  The inner `embedding.Embedding` thrift struct is not in the open-source tree; the assumed
+    layout is stated in persist.cu and switchable with `layout` (the reader accepts every variant).
+    fmt="raw" is the compact native layout kept from round 1 (little endian):
         magic "B200ANN\x01" | int32 metric ordinal | int32 dim | int64 n | int64 ids[n] | float32 rows[n][dim]
-    Only native int64 ids are persisted."""
+    `from_directory` recognises either by the magic.  Only native int64 ids are persisted."""
 
     DataFileName = BruteForceIndex.DataFileName
     SuccessMarker = "_SUCCESS"
 
     @staticmethod
-    def to_directory(index: BruteForceIndex, directory, chunk_rows: int = 1 << 20) -> None:
+    def to_directory(index: BruteForceIndex, directory, chunk_rows: int = 1 << 20, fmt: str = "thrift",
+                     id_format: int = _capi.ANN_ID_INT64_BE, layout: int = _capi.ANN_LAYOUT_FLOAT_TENSOR) -> None:
         import os
         from pathlib import Path
 
@@ -412,6 +416,15 @@ class SerializableBruteForceIndex:
         d = Path(directory)
         d.mkdir(parents=True, exist_ok=True)
         n = index.size()
+        if fmt == "thrift":
+            if not index._h:
+                (d / SerializableBruteForceIndex.DataFileName).write_bytes(b"")   # an empty stream is an empty index
+                (d / SerializableBruteForceIndex.SuccessMarker).write_bytes(b"")
+                return
+            _capi.check(_capi.lib().ann_save_directory(index._h, os.fsencode(str(d)), id_format, layout))
+            return
+        if fmt != "raw":
+            raise ValueError("fmt must be 'thrift' or 'raw'")
         dim = index.dim or 0
         with open(d / SerializableBruteForceIndex.DataFileName, "wb") as f:
             f.write(_MAGIC)
@@ -429,14 +442,26 @@ class SerializableBruteForceIndex:
 
     @staticmethod
     def from_directory(directory, metric: Metric, future_pool: FuturePool, *, device: int = 0,
-                       chunk_rows: int = 1 << 20) -> BruteForceIndex:
+                       chunk_rows: int = 1 << 20, dim: int = 0, id_format: int = _capi.ANN_ID_AUTO) -> BruteForceIndex:
+        import os
         from pathlib import Path
 
         d = Path(directory)
         with open(d / SerializableBruteForceIndex.DataFileName, "rb") as f:
-            if f.read(8) != _MAGIC:
-                raise ValueError("not a b200ann BruteForceFileData file")
-            ordinal, dim = np.frombuffer(f.read(8), dtype="<i4")
+            head = f.read(8)
+        if head != _MAGIC:      # the reference's thrift stream, decoded natively
+            index = BruteForceIndex(metric, future_pool, device=device)
+            cfg = _capi.AnnConfig(metric.ordinal, int(dim), 0, device, index._cfg["flags"])
+            h = ctypes.c_void_p()
+            _capi.check(_capi.lib().ann_load_directory(ctypes.byref(cfg), os.fsencode(str(d)), id_format, ctypes.byref(h)))
+            index._h = h
+            index.dim = index.stat("dim")
+            index._n = index.size()
+            index._version += 1
+            return index
+        with open(d / SerializableBruteForceIndex.DataFileName, "rb") as f:
+            f.read(8)
+            ordinal, dim_ = np.frombuffer(f.read(8), dtype="<i4")
             (n,) = np.frombuffer(f.read(8), dtype="<i8")
             if int(ordinal) != metric.ordinal:
                 raise ValueError(f"index was written with metric ordinal {ordinal}, asked to load as {metric}")
@@ -444,7 +469,7 @@ class SerializableBruteForceIndex:
             index = BruteForceIndex(metric, future_pool, device=device, capacity_hint=int(n))
             for s in range(0, int(n), chunk_rows):
                 m = min(chunk_rows, int(n) - s)
-                rows = np.frombuffer(f.read(m * int(dim) * 4), dtype="<f4").reshape(m, int(dim))
+                rows = np.frombuffer(f.read(m * int(dim_) * 4), dtype="<f4").reshape(m, int(dim_))
                 index.append_batch(ids[s:s + m], rows)
         return index
 

@@ -102,6 +102,34 @@ class GpuShardedBruteForceIndex(Appendable, Queryable):
             return [n.neighbor for n in self.query_with_distance(embedding, num_of_neighbors, runtime_params).result()]
         return self.future_pool(run)
 
+    # ---- ShardedSerialization / ComposedQueryableDeserialization (ShardedSerialization.scala:17-66) ---------------
+    def to_directory(self, directory, id_format: int = _capi.ANN_ID_INT64_BE, layout: int = _capi.ANN_LAYOUT_FLOAT_TENSOR) -> None:
+        """`shard_<i>/BruteForceFileData` per shard, the reference's thrift stream (csrc/persist.cu), plus `_SUCCESS`."""
+        import os
+
+        _capi.check(_capi.lib().ann_sharded_save_directory(self._h, os.fsencode(str(directory)), id_format, layout))
+
+    toDirectory = to_directory
+
+    @classmethod
+    def from_directory(cls, directory, metric: Metric, future_pool: FuturePool, devices: Sequence[int], dim: int = 0,
+                       id_format: int = _capi.ANN_ID_AUTO) -> "GpuShardedBruteForceIndex":
+        """Loads `shard_<i>/` directories written with ANY number of shards (or one unsharded index directory) into a
+        composed handle over `devices`; rows are re-dealt over the devices."""
+        import os
+
+        self = cls.__new__(cls)
+        self.metric, self.future_pool, self.devices = metric, future_pool, list(devices)
+        cfg = _capi.AnnConfig(metric.ordinal, int(dim), 0, 0, 0)
+        arr = (ctypes.c_int32 * len(self.devices))(*self.devices)
+        self._h = ctypes.c_void_p()
+        _capi.check(_capi.lib().ann_sharded_load_directory(ctypes.byref(cfg), os.fsencode(str(directory)), id_format, arr,
+                                                           len(self.devices), ctypes.byref(self._h)))
+        self.dim = self.stat("dim") // max(len(self.devices), 1)     # "dim" is summed over the shards like every per-shard stat
+        return self
+
+    fromDirectory = from_directory
+
     def set_option(self, name: str, value: int) -> None:
         _capi.check(_capi.lib().ann_sharded_set_option(self._h, name.encode(), int(value)))
 

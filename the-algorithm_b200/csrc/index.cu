@@ -1356,6 +1356,7 @@ int ann_get_stat(const ann_index* ix, const char* name, int64_t* value) {
     else if (!strcmp(name, "row_bytes")) *value = (int64_t)ix->n * ix->pitch * 4;
     else if (!strcmp(name, "shadow_bytes")) *value = ix->shadow ? (int64_t)ix->n * ix->kp * 2 : 0;
     else if (!strcmp(name, "capacity")) *value = ix->cap;
+    else if (!strcmp(name, "dim")) *value = ix->dim;
     else if (!strcmp(name, "sm_count")) *value = ix->sm_count;
     else return fail(ANN_ERR_UNKNOWN_OPTION, std::string("unknown stat: ") + name);
     return ANN_OK;
