@@ -20,8 +20,11 @@
  *     out_count[q] = min(max(k,0), size) valid entries; unused slots hold id = -1, distance = +inf.
  *   - there is no CPU fallback: every compute entry point fails with ANN_ERR_NO_DEVICE / ANN_ERR_CUDA
  *     when no sm_100 device is usable.
- *   - a handle may be used from several threads; calls on one handle are serialised internally.  A query
- *     observes every append whose call returned before the query was issued.
+ *   - a handle may be used from several threads.  Appends copy and prepare their rows without blocking queries (the
+ *     storage grows in place: virtual ranges reserved once, physical memory mapped behind the rows) and publish the new row
+ *     count at the end; queries on one handle share its scratch and run one device batch at a time, and concurrent small
+ *     host queries are combined into one device batch.  A query observes every append whose call returned before the
+ *     query was issued; appends in flight may or may not be visible (as with the reference's ConcurrentLinkedQueue).
  */
 #ifndef B200ANN_H_
 #define B200ANN_H_
@@ -262,14 +265,31 @@ ANN_API int ann_distance_pairs(int32_t metric, uint32_t flags, int32_t dim, cons
  * Hnsw.scala:149-155, QueryableIndexAdapter.scala:43-50); the brute-force index does NOT need it (norms are kept per row). */
 ANN_API int ann_normalize_rows(int32_t dim, const float *rows, int64_t n, float *out, int32_t device);
 
+/* Concurrent single-vector load against one handle, measured inside the library -- the C-ABI counterpart of the reference's
+ * load generator (service/loadtest/AnnLoadTestWorker.scala:92-115; latency percentiles in microseconds and achieved rate as
+ * LoadTestRecorder.scala:114-187 reports them).  `threads` host threads each issue `calls_per_thread` one-vector
+ * ann_query_batch calls over queries[nq*dim] (what QueryIndexThriftController.scala:39-90 does per RPC); with expect_ids
+ * ([nq*k], may be NULL) every answer is compared and mismatches counted.  Concurrent small calls on one handle are combined
+ * into device batches by the library's micro-batcher (options "coalesce_max_batch", "coalesce_small_b"). */
+typedef struct ann_load_stats {
+    double qps, avg_us, p50_us, p90_us, p99_us, wall_seconds;
+    int64_t calls, device_batches, mismatches;
+} ann_load_stats;
+ANN_API int ann_loadtest(ann_index *ix, const float *queries, int32_t nq, int32_t dim, int32_t k, int32_t threads,
+                         int32_t calls_per_thread, const int64_t *expect_ids, ann_load_stats *out);
+
 /* Tuning / introspection.
  * Options: "path" (0 auto, 1 streaming scan, 2 tensor-core GEMM filter, 3 exact fallback for every query), "gemm_min_batch", "gemm_cta_group" (1|2), "gemm_epi_warps" (0 auto, 8, 16),
  *          "gemm_hit_budget" (candidates one chunk may add per query, default 500), "gemm_seed_rows" (0 = default 65536),
  *          "timing" (1 = bracket every scan / GEMM-filter launch with CUDA events on its stream),
+ *          "coalesce_max_batch" (queries per merged device call of the host entry point's micro-batcher, default 2048; 0 = off),
+ *          "coalesce_small_b" (host calls with at most this many queries are combined with concurrent ones, default 32),
  *          "device_fallback" (1 = ann_query_batch_device synchronises its stream and re-answers flagged queries with the
  *          exact fallback, like the host entry point always does; 0 = stay asynchronous and report them, default).
  * Stats:   "launches" (kernels launched so far), "last_path", "shadow_bytes", "row_bytes", "n_special", "capacity", "dim",
  *          "sm_count", "kernel_us" / "kernel_launches_timed" (accumulated since "timing" was set; synchronises),
+ *          "coalesced_batches" / "coalesced_calls" (device batches the micro-batcher ran / host calls it served),
+ *          "mapped_bytes" (physical memory mapped behind the index arrays), "max_rows" (rows the reserved address range holds),
  *          "pending_error" (synchronises the device and returns the sticky selector-overflow status, if any). */
 ANN_API int ann_set_option(ann_index *ix, const char *name, int64_t value);
 ANN_API int ann_get_stat(const ann_index *ix, const char *name, int64_t *value);

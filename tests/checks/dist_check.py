@@ -112,16 +112,23 @@ for metric, n, d, b, k in ((InnerProduct, 200_003, 200, 300, 100), (Cosine, 50_0
         ai, ad, ac = sxd.batch_query_device(qd2, k, st)
         torch.cuda.synchronize()
         flagged = ac.cpu().numpy() < 0
-        ok2 &= bool(flagged[1] and flagged[2])
+        c1 = bool(flagged[1] and flagged[2])
         good = ~flagged
-        ok2 &= bool((ai.cpu().numpy()[good] == w2[0][good]).all())
+        c2 = bool((ai.cpu().numpy()[good] == w2[0][good]).all())
+        ok2 &= c1 and c2
         try:
             ixd.raise_pending_error()
         except Exception:
             pass
         bi, bd, bc = sxd.batch_query(qd2, k, st)
-        ok2 &= bool((bi.cpu().numpy() == w2[0]).all() and (bd.cpu().numpy().view(np.uint32) == w2[1].view(np.uint32)).all()
-                    and (bc.cpu().numpy() == w2[2]).all())
+        from oracle import oracle_np as onp   # NaN distances compare by order key (every NaN is the same Float.compare value)
+        c3 = bool((bi.cpu().numpy() == w2[0]).all() and (onp.float_order_key(bd.cpu().numpy()) == onp.float_order_key(w2[1])).all()
+                  and (bc.cpu().numpy() == w2[2]).all())
+        ok2 &= c3
+        if not (c1 and c2 and c3):
+            bad_rows = np.argwhere((bi.cpu().numpy() != w2[0]).any(axis=1)).ravel().tolist()
+            print(f"[rank {rank}] degenerate batch: flagged_as_expected={c1} ({int(flagged.sum())} flagged: {np.argwhere(flagged).ravel().tolist()[:8]}) "
+                  f"unflagged_rows_exact={c2} sync_exact={c3} bad_rows={bad_rows[:8]} counts={bc.cpu().numpy()[bad_rows[:8]].tolist()}", flush=True)
         del sxd
         ixd.close()
     # fourth: the same class on the collective route (seed bounds all-gathered over NCCL, lists all-gathered, K5 merge)

@@ -288,3 +288,81 @@ def test_sharded_directory_layout_and_reload_with_another_shard_count(tmp_path):
     assert one.size() == 3000 and (one.read_rows(0, 3000)[0] == ids[3000:6000]).all()
     for i in (sx, sx2, one):
         i.close()
+
+
+# ------------------------------------------------------------------------------------------------ micro-batcher, locking, storage
+def test_concurrent_single_vector_calls_are_coalesced_and_exact():
+    """64 native host threads issue one-vector ann_query_batch calls on one handle (what a thread-pooled query server does,
+    QueryIndexThriftController.scala:39-90): every answer equals the batched answer and the oracle, and the library ran far
+    fewer device batches than calls."""
+    m = G["InnerProduct"]
+    corpus, ids, q = make(300_000, 64, 256, seed=21)
+    ix = G["BruteForceIndex"].apply(m, G["FuturePool"].immediate_pool())
+    ix.append_batch(ids, corpus)
+    want = oracle.query_canonical(m.ordinal, corpus, ids, q, 20)
+    same(ix.batch_query_with_distance(q, 20), want)
+    st = ix.loadtest(q, 20, threads=64, calls_per_thread=40, expect_ids=want[0])
+    assert st["calls"] == 64 * 40 and st["mismatches"] == 0
+    assert st["device_batches"] < st["calls"] / 4, st
+    # switched off, every call is its own device batch -- and still exact
+    ix.set_option("coalesce_max_batch", 0)
+    st0 = ix.loadtest(q, 20, threads=8, calls_per_thread=10, expect_ids=want[0])
+    assert st0["mismatches"] == 0 and st0["device_batches"] == 0
+    ix.set_option("coalesce_max_batch", 2048)
+    # Python threads through the same entry point (ctypes releases the GIL), mixed k values in flight at once
+    from concurrent.futures import ThreadPoolExecutor
+
+    def one(i):
+        k = 20 if i % 3 else 7
+        gi, gd, gc = ix.batch_query_with_distance(q[i % 256][None, :], k)
+        return i, k, gi[0]
+
+    w7 = oracle.query_canonical(m.ordinal, corpus, ids, q, 7)[0]
+    with ThreadPoolExecutor(32) as ex:
+        for i, k, gi in ex.map(one, range(600)):
+            assert (gi == (want[0] if k == 20 else w7)[i % 256]).all()
+    ix.close()
+
+
+def test_appends_run_while_queries_run_and_storage_grows_in_place():
+    """Appendable / Queryable from FuturePool threads (BruteForceIndex.scala:49,71).  The storage grows without copies
+    (virtual ranges + mapped chunks): an index created with capacity_hint = 0 takes 600k rows in 150 batches while 8 threads
+    query it; every answer must be the exact top-k of SOME prefix of the appended rows, and the final state equals the oracle."""
+    import threading
+
+    m = G["L2"]
+    n, d, k = 600_000, 32, 10
+    corpus, ids, q = make(n, d, 16, seed=31)
+    ix = G["BruteForceIndex"](m, G["FuturePool"].immediate_pool(), capacity_hint=0)
+    first = 4000
+    ix.append_batch(ids[:first], corpus[:first])
+    stop = threading.Event()
+    errors, seen_sizes = [], []
+
+    def querier(t):
+        try:
+            while not stop.is_set():
+                gi, gd, gc = ix.batch_query_with_distance(q[t:t + 2], k)
+                assert (gc == k).all()
+                keys = onp.float_order_key(gd).astype(np.int64)
+                assert (keys[:, 1:] >= keys[:, :-1]).all()
+                seen_sizes.append(ix.size())
+        except Exception as e:       # noqa: BLE001
+            errors.append(e)
+
+    th = [threading.Thread(target=querier, args=(t,)) for t in range(8)]
+    for t_ in th:
+        t_.start()
+    step = (n - first) // 149
+    for s in range(first, n, step):
+        ix.append_batch(ids[s:s + step], corpus[s:s + step])
+    stop.set()
+    for t_ in th:
+        t_.join()
+    assert not errors, errors[:1]
+    assert ix.size() == n and len(set(seen_sizes)) > 3          # queries really interleaved with the appends
+    assert ix.stat("mapped_bytes") < 1.6 * n * (d * 4 + 8 + 4 + 40 * 2) + (256 << 20)   # in place: no doubled footprint
+    same(ix.batch_query_with_distance(q, k), oracle.query_canonical(m.ordinal, corpus, ids, q, k))
+    ri, rr = ix.read_rows(0, n)
+    assert (ri == ids).all() and (rr.view(np.uint32) == corpus.view(np.uint32)).all()
+    ix.close()

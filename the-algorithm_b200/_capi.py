@@ -38,13 +38,19 @@ SYMBOLS = (
     "ann_sharded_create", "ann_sharded_destroy", "ann_sharded_append_batch", "ann_sharded_size", "ann_sharded_query_batch",
     "ann_sharded_shard", "ann_sharded_set_option", "ann_sharded_get_stat",
     "ann_save_directory", "ann_load_directory", "ann_sharded_save_directory", "ann_sharded_load_directory",
-    "ann_persisted_embedding_encode", "ann_persisted_embedding_decode", "ann_knn_join", "ann_distance_pairs", "ann_normalize_rows", "ann_set_option", "ann_get_stat", "ann_last_error", "ann_version",
+    "ann_persisted_embedding_encode", "ann_persisted_embedding_decode", "ann_loadtest", "ann_knn_join", "ann_distance_pairs", "ann_normalize_rows", "ann_set_option", "ann_get_stat", "ann_last_error", "ann_version",
 )
 
 
 class AnnConfig(ctypes.Structure):
     _fields_ = [("metric", ctypes.c_int32), ("dim", ctypes.c_int32), ("capacity_hint", ctypes.c_int64),
                 ("device", ctypes.c_int32), ("flags", ctypes.c_uint32)]
+
+
+class AnnLoadStats(ctypes.Structure):
+    _fields_ = [("qps", ctypes.c_double), ("avg_us", ctypes.c_double), ("p50_us", ctypes.c_double), ("p90_us", ctypes.c_double),
+                ("p99_us", ctypes.c_double), ("wall_seconds", ctypes.c_double), ("calls", ctypes.c_int64),
+                ("device_batches", ctypes.c_int64), ("mismatches", ctypes.c_int64)]
 
 
 class AnnError(RuntimeError):
@@ -126,6 +132,8 @@ def lib() -> ctypes.CDLL:
         L.ann_persisted_embedding_encode.argtypes = [i64, i32, vp, i32, i32, vp, i64]
         L.ann_persisted_embedding_decode.restype = ctypes.c_int
         L.ann_persisted_embedding_decode.argtypes = [vp, i64, i32, ctypes.POINTER(i64), vp, i32, ctypes.POINTER(i32), ctypes.POINTER(i64)]
+        L.ann_loadtest.restype = ctypes.c_int
+        L.ann_loadtest.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp, ctypes.POINTER(AnnLoadStats)]
         L.ann_result_block_bytes.restype = ctypes.c_size_t
         L.ann_result_block_bytes.argtypes = [i32, i32]
         L.ann_knn_join.restype = ctypes.c_int

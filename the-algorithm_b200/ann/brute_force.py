@@ -354,6 +354,18 @@ class BruteForceIndex(Appendable, Queryable):
                 _capi.check(_capi.lib().ann_read_rows(self._h, start, n, _ptr(ids), _ptr(rows)))
             return ids, rows
 
+    def loadtest(self, queries, k: int, threads: int, calls_per_thread: int, expect_ids=None) -> dict:
+        """`ann_loadtest`: `threads` native host threads issue one-vector queries concurrently (the reference's load
+        generator, service/loadtest/AnnLoadTestWorker.scala:92-115); returns rate and latency percentiles in microseconds."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        exp = None if expect_ids is None else np.ascontiguousarray(expect_ids, dtype=np.int64)
+        st = _capi.AnnLoadStats()
+        with self._lock:
+            self.flush()
+        _capi.check(_capi.lib().ann_loadtest(self._h, _ptr(q), q.shape[0], q.shape[1], int(k), int(threads), int(calls_per_thread),
+                                             _ptr(exp), ctypes.byref(st)))
+        return {f: getattr(st, f) for f, _ in _capi.AnnLoadStats._fields_}
+
     # ---- tuning / introspection ------------------------------------------------------------------------------
     def set_option(self, name: str, value: int) -> None:
         _capi.check(_capi.lib().ann_set_option(self._h, name.encode(), int(value)))

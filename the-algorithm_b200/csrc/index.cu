@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
@@ -21,8 +22,12 @@
 #include <utility>
 #include <vector>
 
+#include <condition_variable>
+#include <deque>
+
 #include "../../include/b200ann.h"
 #include "kernels.h"
+#include "vmm.hpp"
 
 using namespace b200ann;
 
@@ -112,9 +117,18 @@ struct ann_index {
     int device = 0, sm_count = 0;
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;
-    std::mutex mu;
+    // Locking.  `mu` guards the published row count and the per-query scratch: a query holds it while it runs.  `append_mu`
+    // serialises appends among themselves; an append copies its rows and runs K1 on `append_stream` WITHOUT `mu` -- it only
+    // writes rows beyond the published count, and the storage below never moves (vmm.hpp) -- and takes `mu` just to publish.
+    // So appends do not wait for running queries and queries do not wait for running appends (BruteForceIndex.scala:48-52,
+    // 66-71: both are lock-free on a ConcurrentLinkedQueue).  In-place updates take both.
+    std::mutex mu, append_mu;
+    cudaStream_t append_stream = nullptr;
+    DeviceScalars* h_scalars = nullptr;   // pinned host mirror of the scalars' header (read back with the append's own sync)
 
-    long long cap = 0, n = 0;
+    long long cap = 0, n = 0, max_rows = 0;
+    // storage: virtual ranges reserved once, physical memory mapped behind the rows as they arrive (grows in place)
+    VmArray vm_rows, vm_ids, vm_inv, vm_norm, vm_shadow;
     float* rows = nullptr;
     int64_t* ids = nullptr;
     float* inv_norm = nullptr;
@@ -122,6 +136,20 @@ struct ann_index {
     __nv_bfloat16* shadow = nullptr;
     DeviceScalars* scalars = nullptr;
     unsigned long long n_special = 0;
+
+    // micro-batcher of the host entry point (see Coalescer below)
+    struct PendingQuery;
+    struct Coalescer {
+        std::mutex mu;
+        std::deque<PendingQuery*> pending;
+        bool leader_active = false;
+        int max_batch = 2048;   // queries per merged device call; 0 switches coalescing off
+        int small_b = 32;       // calls with at most this many queries are coalesced
+        float* pin_q = nullptr;               // pinned staging of the merged batch
+        unsigned char* pin_res = nullptr;
+        size_t cap_q = 0, cap_res = 0;
+        long long batches = 0, merged_calls = 0;
+    } co;
 
     // scratch
     DevBuf<float> q_in, q_padded, out_dist;
@@ -149,7 +177,8 @@ struct ann_index {
     double kernel_ms_total = 0.0;
     long long kernel_launches_timed = 0;
     long long last_candidates = 0;
-    long long launches = 0, last_path = 0, exact_fallback_queries = 0;
+    std::atomic<long long> launches{0};
+    long long last_path = 0, exact_fallback_queries = 0;
     long long last_gemm_chunks = 0;   // chunk launches (seed excluded) of the last tensor-core query
 
     // two-phase sharded query (ann_query_seed_device -> ann_query_finish_device): what the first phase left behind
@@ -171,67 +200,46 @@ int set_device(const ann_index* ix) {
     return ANN_OK;
 }
 
+// Map enough physical memory behind every array for `need` rows.  Nothing is copied and no pointer changes; fresh chunks
+// are zeroed on `st` (pad columns of `rows` and tile tails of every array must read as 0).
 int grow(ann_index* ix, long long need, cudaStream_t st) {
     if (need <= ix->cap) return ANN_OK;
-    long long ncap = std::max<long long>({need, ix->cap * 2, 1024});
-    ncap = (ncap + 127) / 128 * 128;
-    float* nrows = nullptr;
-    int64_t* nids = nullptr;
-    float *ninv = nullptr, *nnorm = nullptr;
-    __nv_bfloat16* nsh = nullptr;
-    // allocate everything first; on any failure release what was obtained and leave the index untouched
-    cudaError_t e = cudaMalloc(&nrows, (size_t)ncap * ix->pitch * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc(&nids, (size_t)ncap * sizeof(int64_t));
-    if (e == cudaSuccess) e = cudaMalloc(&nnorm, (size_t)ncap * sizeof(float));
-    if (e == cudaSuccess && ix->metric == kMetricCosine) e = cudaMalloc(&ninv, (size_t)ncap * sizeof(float));
-    if (e == cudaSuccess && ix->use_shadow) e = cudaMalloc(&nsh, (size_t)ncap * ix->kp * sizeof(__nv_bfloat16));
-    auto copy_all = [&]() -> cudaError_t {
-        cudaError_t c = cudaSuccess;
-        if (ix->n > 0) {
-            c = cudaMemcpyAsync(nrows, ix->rows, (size_t)ix->n * ix->pitch * sizeof(float), cudaMemcpyDeviceToDevice, st);
-            if (c == cudaSuccess) c = cudaMemcpyAsync(nids, ix->ids, (size_t)ix->n * sizeof(int64_t), cudaMemcpyDeviceToDevice, st);
-            if (c == cudaSuccess) c = cudaMemcpyAsync(nnorm, ix->row_norm, (size_t)ix->n * sizeof(float), cudaMemcpyDeviceToDevice, st);
-            if (c == cudaSuccess && ninv) c = cudaMemcpyAsync(ninv, ix->inv_norm, (size_t)ix->n * sizeof(float), cudaMemcpyDeviceToDevice, st);
-            if (c == cudaSuccess && nsh)
-                c = cudaMemcpyAsync(nsh, ix->shadow, (size_t)ix->n * ix->kp * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice, st);
-        }
-        // zero the tail: pad columns of `rows` and the whole shadow tail must read as 0
-        if (c == cudaSuccess)
-            c = cudaMemsetAsync(nrows + (size_t)ix->n * ix->pitch, 0, (size_t)(ncap - ix->n) * ix->pitch * sizeof(float), st);
-        if (c == cudaSuccess && nsh)
-            c = cudaMemsetAsync(nsh + (size_t)ix->n * ix->kp, 0, (size_t)(ncap - ix->n) * ix->kp * sizeof(__nv_bfloat16), st);
-        if (c == cudaSuccess) c = cudaStreamSynchronize(st);
-        return c;
-    };
-    if (e == cudaSuccess) e = copy_all();
-    if (e != cudaSuccess) {
-        cudaFree(nrows);
-        cudaFree(nids);
-        cudaFree(nnorm);
-        cudaFree(ninv);
-        cudaFree(nsh);
-        (void)cudaGetLastError();
-        char msg[256];
-        snprintf(msg, sizeof(msg), "growing the index to %lld rows failed: %s", ncap, cudaGetErrorString(e));
-        return fail(e == cudaErrorMemoryAllocation ? ANN_ERR_OUT_OF_MEMORY : ANN_ERR_CUDA, msg);
+    if (need > ix->max_rows) {
+        char msg[200];
+        snprintf(msg, sizeof(msg), "the index is limited to %lld rows on this device (address range reserved at creation)", ix->max_rows);
+        return fail(ANN_ERR_OUT_OF_MEMORY, msg);
     }
-    cudaFree(ix->rows);
-    cudaFree(ix->ids);
-    cudaFree(ix->row_norm);
-    cudaFree(ix->inv_norm);
-    cudaFree(ix->shadow);
-    ix->rows = nrows;
-    ix->ids = nids;
-    ix->row_norm = nnorm;
-    ix->inv_norm = ninv;
-    ix->shadow = nsh;
-    ix->cap = ncap;
+    const long long target = (need + 127) / 128 * 128;
+    struct Arr {
+        VmArray* vm;
+        size_t row_bytes;
+    } arrs[5] = {{&ix->vm_rows, (size_t)ix->pitch * sizeof(float)},
+                 {&ix->vm_ids, sizeof(int64_t)},
+                 {&ix->vm_norm, sizeof(float)},
+                 {ix->metric == kMetricCosine ? &ix->vm_inv : nullptr, sizeof(float)},
+                 {ix->use_shadow ? &ix->vm_shadow : nullptr, (size_t)ix->kp * sizeof(__nv_bfloat16)}};
+    long long ncap = ix->max_rows;
+    for (const Arr& a : arrs) {
+        if (!a.vm) continue;
+        size_t off = 0, len = 0;
+        cudaError_t e = a.vm->ensure((size_t)target * a.row_bytes, &off, &len);
+        if (e == cudaSuccess && len) e = cudaMemsetAsync(static_cast<char*>(a.vm->ptr()) + off, 0, len, st);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            char msg[256];
+            snprintf(msg, sizeof(msg), "growing the index to %lld rows failed: %s", target,
+                     e == cudaErrorMemoryAllocation ? "out of device memory" : cudaGetErrorString(e));
+            return fail(e == cudaErrorMemoryAllocation ? ANN_ERR_OUT_OF_MEMORY : ANN_ERR_CUDA, msg);
+        }
+        ncap = std::min<long long>(ncap, (long long)(a.vm->mapped / a.row_bytes));
+    }
+    ix->cap = ncap / 128 * 128;
     return ANN_OK;
 }
 
 // rows/ids already on the device (or staged there); place them and run K1
+// Caller holds append_mu (not mu): only rows beyond the published count are written.
 int append_device_core(ann_index* ix, const int64_t* d_ids, const float* d_rows, long long n_new, cudaStream_t st) {
-    if (ix->sess.open) ix->sess.clobbered = true;   // new rows may raise the error bounds a pending two-phase query was prepared with
     int rc = grow(ix, ix->n + n_new, st);
     if (rc) return rc;
     float* dst = ix->rows + (size_t)ix->n * ix->pitch;
@@ -698,7 +706,11 @@ int query_core(ann_index* ix, const float* d_queries, int b, int k, int64_t* d_o
             fp.out_ids = d_out_ids + (size_t)q * k;
             fp.out_dist = d_out_dist + (size_t)q * k;
             fp.out_count = d_out_count ? d_out_count + q : nullptr;
-            CUDA_TRY(launch_exact_fallback(fp, st, &ix->launches));
+            {
+                long long fl = 0;
+                CUDA_TRY(launch_exact_fallback(fp, st, &fl));
+                ix->launches += fl;
+            }
         }
         ix->last_path = 3;
         return ANN_OK;
@@ -766,7 +778,11 @@ int resolve_flagged(ann_index* ix, const float* d_queries, int b, int k, int64_t
         fp.out_ids = d_out_ids + (size_t)q * k;
         fp.out_dist = d_out_dist + (size_t)q * k;
         fp.out_count = d_out_count ? d_out_count + q : nullptr;
-        CUDA_TRY(launch_exact_fallback(fp, st, &ix->launches));
+        {
+                long long fl = 0;
+                CUDA_TRY(launch_exact_fallback(fp, st, &fl));
+                ix->launches += fl;
+            }
         ix->exact_fallback_queries++;
     }
     CUDA_TRY(cudaMemsetAsync(&ix->scalars->error_flags, 0, sizeof(uint32_t), st));
@@ -840,12 +856,46 @@ int ann_create(const ann_config* cfg, ann_index** out) {
         return rc;
     };
     if (cudaSetDevice(ix->device) != cudaSuccess) return cleanup(fail(ANN_ERR_CUDA, "cudaSetDevice failed"));
-    if (cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking) != cudaSuccess)
+    if (cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ix->append_stream, cudaStreamNonBlocking) != cudaSuccess)
         return cleanup(fail(ANN_ERR_CUDA, "cudaStreamCreate failed"));
     if (cudaMalloc(&ix->scalars, sizeof(DeviceScalars)) != cudaSuccess)
         return cleanup(fail(ANN_ERR_OUT_OF_MEMORY, "cudaMalloc failed"));
+    if (cudaHostAlloc(&ix->h_scalars, sizeof(DeviceScalars), cudaHostAllocDefault) != cudaSuccess)
+        return cleanup(fail(ANN_ERR_OUT_OF_MEMORY, "cudaHostAlloc failed"));
+    memset(ix->h_scalars, 0, sizeof(DeviceScalars));
     if (cudaMemsetAsync(ix->scalars, 0, sizeof(DeviceScalars), ix->stream) != cudaSuccess)
         return cleanup(fail(ANN_ERR_CUDA, "cudaMemset failed"));
+    // Address ranges for the whole life of the index: as many rows as could ever fit the device (192 GB of fp32 rows, local
+    // row numbers are 32 bit), halved until the reservation succeeds.  Physical memory follows the rows (grow()).
+    if (!vm_api().ok) return cleanup(fail(ANN_ERR_CUDA, "ann_create: the driver's virtual memory management API is unavailable"));
+    {
+        const size_t row_bytes = (size_t)ix->pitch * sizeof(float);
+        long long mr = (long long)std::min<unsigned long long>(0x7FFFFF80ull, (192ull << 30) / row_bytes) / 128 * 128;
+        const long long floor_rows = std::max<long long>((cfg->capacity_hint + 127) / 128 * 128, 1 << 20);
+        for (;;) {
+            mr = std::max(mr, floor_rows);
+            bool ok = ix->vm_rows.reserve((size_t)mr * row_bytes, ix->device) == cudaSuccess &&
+                      ix->vm_ids.reserve((size_t)mr * sizeof(int64_t), ix->device) == cudaSuccess &&
+                      ix->vm_norm.reserve((size_t)mr * sizeof(float), ix->device) == cudaSuccess &&
+                      (ix->metric != kMetricCosine || ix->vm_inv.reserve((size_t)mr * sizeof(float), ix->device) == cudaSuccess) &&
+                      (!ix->use_shadow || ix->vm_shadow.reserve((size_t)mr * ix->kp * sizeof(__nv_bfloat16), ix->device) == cudaSuccess);
+            if (ok) break;
+            ix->vm_rows.release();
+            ix->vm_ids.release();
+            ix->vm_norm.release();
+            ix->vm_inv.release();
+            ix->vm_shadow.release();
+            if (mr <= floor_rows) return cleanup(fail(ANN_ERR_OUT_OF_MEMORY, "ann_create: cannot reserve the index's address range"));
+            mr /= 2;
+        }
+        ix->max_rows = mr;
+        ix->rows = static_cast<float*>(ix->vm_rows.ptr());
+        ix->ids = static_cast<int64_t*>(ix->vm_ids.ptr());
+        ix->row_norm = static_cast<float*>(ix->vm_norm.ptr());
+        ix->inv_norm = ix->metric == kMetricCosine ? static_cast<float*>(ix->vm_inv.ptr()) : nullptr;
+        ix->shadow = ix->use_shadow ? static_cast<__nv_bfloat16*>(ix->vm_shadow.ptr()) : nullptr;
+    }
     if (cfg->capacity_hint > 0) {
         int rc = grow(ix, cfg->capacity_hint, ix->stream);
         if (rc) return cleanup(rc);
@@ -858,13 +908,17 @@ int ann_create(const ann_config* cfg, ann_index** out) {
 void ann_destroy(ann_index* ix) {
     if (!ix) return;
     cudaSetDevice(ix->device);
-    if (ix->stream) cudaStreamSynchronize(ix->stream);
-    cudaFree(ix->rows);
-    cudaFree(ix->ids);
-    cudaFree(ix->inv_norm);
-    cudaFree(ix->row_norm);
-    cudaFree(ix->shadow);
+    cudaDeviceSynchronize();   // nothing may still read the ranges that are about to be unmapped
+    ix->vm_rows.release();
+    ix->vm_ids.release();
+    ix->vm_norm.release();
+    ix->vm_inv.release();
+    ix->vm_shadow.release();
     cudaFree(ix->scalars);
+    if (ix->h_scalars) cudaFreeHost(ix->h_scalars);
+    if (ix->co.pin_q) cudaFreeHost(ix->co.pin_q);
+    if (ix->co.pin_res) cudaFreeHost(ix->co.pin_res);
+    if (ix->append_stream) cudaStreamDestroy(ix->append_stream);
     ix->q_in.release();
     ix->q_padded.release();
     ix->out_dist.release();
@@ -898,6 +952,7 @@ int ann_update_batch(ann_index* ix, const int64_t* slots, const float* rows, int
     if (n < 0) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_update_batch: n < 0");
     if (n == 0) return ANN_OK;
     if (!slots || !rows) return fail(ANN_ERR_NULL_POINTER, "ann_update_batch: NULL buffer");
+    std::lock_guard<std::mutex> alk(ix->append_mu);   // rewrites published rows: excludes appends AND queries
     std::lock_guard<std::mutex> lk(ix->mu);
     for (int64_t i = 0; i < n; ++i)
         if (slots[i] < 0 || slots[i] >= ix->n) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_update_batch: slot outside [0, size)");
@@ -949,20 +1004,33 @@ int ann_read_rows(ann_index* ix, int64_t start, int64_t n, int64_t* out_ids, flo
     return ANN_OK;
 }
 
+namespace {
+// Shared tail of both append entry points.  Caller holds append_mu.  One synchronisation: the copy of the caller's rows,
+// K1 and the read-back of the special-row census complete together; then the new row count is published under `mu`.
+int append_and_publish(ann_index* ix, const int64_t* ids, const float* rows, int64_t n, cudaStream_t st) {
+    int rc = append_device_core(ix, ids, rows, n, st);
+    if (rc) return rc;
+    // the special-row census decides which query kernels are legal, so it travels back with the same synchronisation
+    CUDA_TRY(cudaMemcpyAsync(ix->h_scalars, ix->scalars, kScalarsHeader, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    std::lock_guard<std::mutex> lk(ix->mu);
+    if (ix->sess.open) ix->sess.clobbered = true;   // new rows may raise the error bounds a pending sharded query was prepared with
+    ix->n += n;
+    ix->n_special = ix->h_scalars->n_special;
+    return ANN_OK;
+}
+}  // namespace
+
 int ann_append_batch(ann_index* ix, const int64_t* ids, const float* rows, int64_t n) {
     if (!ix) return fail(ANN_ERR_NULL_POINTER, "ann_append_batch: index is NULL");
     if (n < 0) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_append_batch: n < 0");
     if (n == 0) return ANN_OK;
     if (!rows) return fail(ANN_ERR_NULL_POINTER, "ann_append_batch: rows is NULL");
-    std::lock_guard<std::mutex> lk(ix->mu);
+    std::lock_guard<std::mutex> alk(ix->append_mu);
     int rc = set_device(ix);
     if (rc) return rc;
     // host pointers go straight into place (cudaMemcpyDefault): no staging copy of the batch
-    rc = append_device_core(ix, ids, rows, n, ix->stream);
-    if (rc) return rc;
-    CUDA_TRY(cudaStreamSynchronize(ix->stream));
-    ix->n += n;
-    return check_device_flags(ix, ix->stream);
+    return append_and_publish(ix, ids, rows, n, ix->append_stream);
 }
 
 int ann_append_batch_device(ann_index* ix, const int64_t* d_ids, const float* d_rows, int64_t n, void* stream) {
@@ -970,16 +1038,11 @@ int ann_append_batch_device(ann_index* ix, const int64_t* d_ids, const float* d_
     if (n < 0) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_append_batch_device: n < 0");
     if (n == 0) return ANN_OK;
     if (!d_rows) return fail(ANN_ERR_NULL_POINTER, "ann_append_batch_device: rows is NULL");
-    std::lock_guard<std::mutex> lk(ix->mu);
+    std::lock_guard<std::mutex> alk(ix->append_mu);
     int rc = set_device(ix);
     if (rc) return rc;
-    cudaStream_t st = (cudaStream_t)stream;  // NULL = the legacy default stream, as everywhere in CUDA
-    rc = append_device_core(ix, d_ids, d_rows, n, st);
-    if (rc) return rc;
-    // the special-row census decides which query kernels are legal, so it must be current
-    CUDA_TRY(cudaStreamSynchronize(st));
-    ix->n += n;
-    return check_device_flags(ix, st);
+    // NULL = the legacy default stream, as everywhere in CUDA
+    return append_and_publish(ix, d_ids, d_rows, n, (cudaStream_t)stream);
 }
 
 int ann_query_batch_device(ann_index* ix, const float* d_queries, int32_t b, int32_t dim, int32_t k, int64_t* d_out_ids,
@@ -1194,14 +1257,10 @@ int ann_exchange_merge_slice_device(int32_t device, const void* const* peer_loca
     return ANN_OK;
 }
 
-int ann_query_batch(ann_index* ix, const float* queries, int32_t b, int32_t dim, int32_t k, int64_t* out_ids, float* out_dist,
-                    int32_t* out_count) {
-    if (!ix) return fail(ANN_ERR_NULL_POINTER, "ann_query_batch: index is NULL");
-    if (b < 0) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_query_batch: b < 0");
-    if (k < 0) return fail(ANN_ERR_NEGATIVE_K, "ann_query_batch: k < 0");
-    if (dim != ix->dim) return fail(ANN_ERR_DIMENSION_MISMATCH, "ann_query_batch: query dimension != index dimension");
-    if (b == 0) return ANN_OK;
-    if (!queries || (k > 0 && (!out_ids || !out_dist))) return fail(ANN_ERR_NULL_POINTER, "ann_query_batch: NULL buffer");
+namespace {
+
+// The host-buffer query: H2D, query path, D2H, exact fallback for flagged queries.  Takes `mu`.
+int query_host(ann_index* ix, const float* queries, int32_t b, int32_t k, int64_t* out_ids, float* out_dist, int32_t* out_count) {
     std::lock_guard<std::mutex> lk(ix->mu);
     int rc = set_device(ix);
     if (rc) return rc;
@@ -1229,7 +1288,6 @@ int ann_query_batch(ann_index* ix, const float* queries, int32_t b, int32_t dim,
     };
     rc = copy_out();
     if (rc) return rc;
-    ix->n_special = hs.n_special;
     if (hs.error_flags) {   // rare: some queries were flagged by the bounded selector -> exact fallback, then copy again
         bool ran = false;
         rc = resolve_flagged(ix, ix->q_in.p, b, k, ix->out_ids.p, ix->out_dist.p, ix->out_count.p, st, &hs, &ran);
@@ -1239,6 +1297,152 @@ int ann_query_batch(ann_index* ix, const float* queries, int32_t b, int32_t dim,
         if (hs.error_flags) return check_device_flags(ix, st);
     }
     return ANN_OK;
+}
+
+}  // namespace
+
+// One waiting host call of the micro-batcher.
+struct ann_index::PendingQuery {
+    const float* q;
+    int b, k;
+    int64_t* ids;
+    float* dist;
+    int32_t* cnt;
+    int rc = ANN_OK;
+    std::string err;
+    bool done = false, promoted = false;
+    std::condition_variable cv;
+};
+
+namespace {
+
+// Online callers issue ONE vector per call from many threads (QueryIndexThriftController.scala:39-90 runs each RPC's query on
+// a FuturePool thread, UnsafeQueryIndexServer.scala:26-32,64-68), and a device call costs about a millisecond of corpus
+// streaming whatever its batch size.  So concurrent small calls on one handle are combined: the first caller to arrive while
+// no merged call is running becomes the leader, takes every waiting call with its k (up to max_batch queries), packs the
+// queries into pinned staging, runs ONE device batch (tensor-core path from 2 queries up), scatters the rows back and wakes
+// the others; whatever arrived meanwhile forms the next merged call, led by the first of them.  No timer: a lone caller
+// runs at once, and under load the batch size adapts to the arrival rate.  Results are identical to separate calls (every
+// query is answered exactly, independently of its batch).
+int query_coalesced(ann_index* ix, const float* queries, int32_t b, int32_t k, int64_t* out_ids, float* out_dist, int32_t* out_count) {
+    ann_index::Coalescer& co = ix->co;
+    ann_index::PendingQuery me;
+    me.q = queries;
+    me.b = b;
+    me.k = k;
+    me.ids = out_ids;
+    me.dist = out_dist;
+    me.cnt = out_count;
+    std::vector<ann_index::PendingQuery*> batch;
+    {
+        std::unique_lock<std::mutex> lk(co.mu);
+        co.pending.push_back(&me);
+        if (co.leader_active) {
+            me.cv.wait(lk, [&] { return me.done || me.promoted; });
+            if (me.done) {
+                if (me.rc) return fail(me.rc, me.err);
+                return ANN_OK;
+            }
+        }
+        co.leader_active = true;
+        // my batch: me, then every waiting call with my k in arrival order while the merged batch stays within max_batch
+        co.pending.erase(std::find(co.pending.begin(), co.pending.end(), &me));
+        batch.push_back(&me);
+        int taken = b;
+        for (auto it = co.pending.begin(); it != co.pending.end();) {
+            if ((*it)->k == k && taken + (*it)->b <= co.max_batch) {
+                taken += (*it)->b;
+                batch.push_back(*it);
+                it = co.pending.erase(it);
+            } else {
+                ++it;
+            }
+        }
+    }
+    int total = 0;
+    for (auto* r : batch) total += r->b;
+    int rc = ANN_OK;
+    std::string err;
+    if (batch.size() == 1) {
+        rc = query_host(ix, queries, b, k, out_ids, out_dist, out_count);
+        if (rc) err = g_last_error;
+    } else {
+        // pinned staging: [queries total*dim] and [ids total*k | dist total*k | count total]
+        const size_t qb = (size_t)total * ix->dim * sizeof(float), rb = (size_t)total * k * 12 + (size_t)total * 4;
+        cudaSetDevice(ix->device);
+        if (qb > co.cap_q) {
+            if (co.pin_q) cudaFreeHost(co.pin_q);
+            co.pin_q = nullptr;
+            co.cap_q = 0;
+            if (cudaHostAlloc(&co.pin_q, std::max(qb, (size_t)1 << 20), cudaHostAllocDefault) == cudaSuccess) co.cap_q = std::max(qb, (size_t)1 << 20);
+        }
+        if (rb > co.cap_res) {
+            if (co.pin_res) cudaFreeHost(co.pin_res);
+            co.pin_res = nullptr;
+            co.cap_res = 0;
+            if (cudaHostAlloc(&co.pin_res, std::max(rb, (size_t)1 << 20), cudaHostAllocDefault) == cudaSuccess) co.cap_res = std::max(rb, (size_t)1 << 20);
+        }
+        if (co.cap_q < qb || co.cap_res < rb) {
+            (void)cudaGetLastError();
+            rc = ANN_ERR_OUT_OF_MEMORY;
+            err = "micro-batcher: pinned staging allocation failed";
+        } else {
+            size_t off = 0;
+            for (auto* r : batch) {
+                memcpy(co.pin_q + off, r->q, (size_t)r->b * ix->dim * sizeof(float));
+                off += (size_t)r->b * ix->dim;
+            }
+            int64_t* s_ids = reinterpret_cast<int64_t*>(co.pin_res);
+            float* s_dist = reinterpret_cast<float*>(co.pin_res + (size_t)total * k * 8);
+            int32_t* s_cnt = reinterpret_cast<int32_t*>(co.pin_res + (size_t)total * k * 12);
+            rc = query_host(ix, co.pin_q, total, k, s_ids, s_dist, s_cnt);
+            if (rc) err = g_last_error;
+            else {
+                size_t row = 0;
+                for (auto* r : batch) {
+                    memcpy(r->ids, s_ids + row * k, (size_t)r->b * k * sizeof(int64_t));
+                    memcpy(r->dist, s_dist + row * k, (size_t)r->b * k * sizeof(float));
+                    if (r->cnt) memcpy(r->cnt, s_cnt + row, (size_t)r->b * sizeof(int32_t));
+                    row += (size_t)r->b;
+                }
+            }
+        }
+    }
+    {
+        std::lock_guard<std::mutex> lk(co.mu);
+        co.batches++;
+        co.merged_calls += (long long)batch.size();
+        for (auto* r : batch) {
+            if (r == &me) continue;
+            r->rc = rc;
+            r->err = err;
+            r->done = true;
+            r->cv.notify_one();
+        }
+        if (!co.pending.empty()) {   // hand the lead to the first call that arrived meanwhile
+            co.pending.front()->promoted = true;
+            co.pending.front()->cv.notify_one();
+        } else {
+            co.leader_active = false;
+        }
+    }
+    if (rc) return fail(rc, err);
+    return ANN_OK;
+}
+
+}  // namespace
+
+int ann_query_batch(ann_index* ix, const float* queries, int32_t b, int32_t dim, int32_t k, int64_t* out_ids, float* out_dist,
+                    int32_t* out_count) {
+    if (!ix) return fail(ANN_ERR_NULL_POINTER, "ann_query_batch: index is NULL");
+    if (b < 0) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_query_batch: b < 0");
+    if (k < 0) return fail(ANN_ERR_NEGATIVE_K, "ann_query_batch: k < 0");
+    if (dim != ix->dim) return fail(ANN_ERR_DIMENSION_MISMATCH, "ann_query_batch: query dimension != index dimension");
+    if (b == 0) return ANN_OK;
+    if (!queries || (k > 0 && (!out_ids || !out_dist))) return fail(ANN_ERR_NULL_POINTER, "ann_query_batch: NULL buffer");
+    if (k > 0 && ix->co.max_batch > 0 && b <= ix->co.small_b && b <= ix->co.max_batch)
+        return query_coalesced(ix, queries, b, k, out_ids, out_dist, out_count);
+    return query_host(ix, queries, b, k, out_ids, out_dist, out_count);
 }
 
 int ann_merge_topk_device(int32_t device, const int64_t* d_ids, const float* d_dist, const int32_t* d_count, int32_t shards,
@@ -1319,6 +1523,18 @@ int ann_set_option(ann_index* ix, const char* name, int64_t value) {
         ix->gemm_cta_group = (int)value;
         return ANN_OK;
     }
+    if (!strcmp(name, "coalesce_max_batch")) {   // 0 = every host call runs on its own
+        if (value < 0 || value > 16384) return fail(ANN_ERR_INVALID_ARGUMENT, "coalesce_max_batch must be in [0, 16384]");
+        std::lock_guard<std::mutex> clk(ix->co.mu);
+        ix->co.max_batch = (int)value;
+        return ANN_OK;
+    }
+    if (!strcmp(name, "coalesce_small_b")) {
+        if (value < 1) return fail(ANN_ERR_INVALID_ARGUMENT, "coalesce_small_b must be >= 1");
+        std::lock_guard<std::mutex> clk(ix->co.mu);
+        ix->co.small_b = (int)value;
+        return ANN_OK;
+    }
     if (!strcmp(name, "gemm_min_batch")) {
         if (value < 1) return fail(ANN_ERR_INVALID_ARGUMENT, "gemm_min_batch must be >= 1");
         ix->gemm_min_batch = (int)value;
@@ -1348,7 +1564,7 @@ int ann_get_stat(const ann_index* ix, const char* name, int64_t* value) {
         *value = !strcmp(name, "kernel_us") ? (int64_t)(m->kernel_ms_total * 1000.0) : m->kernel_launches_timed;
         return ANN_OK;
     }
-    if (!strcmp(name, "launches")) *value = ix->launches;
+    if (!strcmp(name, "launches")) *value = ix->launches.load();
     else if (!strcmp(name, "last_path")) *value = ix->last_path;
     else if (!strcmp(name, "last_gemm_chunks")) *value = ix->last_gemm_chunks;
     else if (!strcmp(name, "exact_fallback_queries")) *value = ix->exact_fallback_queries;
@@ -1357,6 +1573,10 @@ int ann_get_stat(const ann_index* ix, const char* name, int64_t* value) {
     else if (!strcmp(name, "shadow_bytes")) *value = ix->shadow ? (int64_t)ix->n * ix->kp * 2 : 0;
     else if (!strcmp(name, "capacity")) *value = ix->cap;
     else if (!strcmp(name, "dim")) *value = ix->dim;
+    else if (!strcmp(name, "coalesced_batches")) *value = ix->co.batches;
+    else if (!strcmp(name, "coalesced_calls")) *value = ix->co.merged_calls;
+    else if (!strcmp(name, "mapped_bytes")) *value = (int64_t)(ix->vm_rows.mapped + ix->vm_ids.mapped + ix->vm_norm.mapped + ix->vm_inv.mapped + ix->vm_shadow.mapped);
+    else if (!strcmp(name, "max_rows")) *value = ix->max_rows;
     else if (!strcmp(name, "sm_count")) *value = ix->sm_count;
     else return fail(ANN_ERR_UNKNOWN_OPTION, std::string("unknown stat: ") + name);
     return ANN_OK;
