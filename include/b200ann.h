@@ -69,6 +69,13 @@ typedef enum ann_status {
  * With this flag every sum accumulates sequentially in fp32 with individually rounded operations (oracle accum=1), so the
  * neighbour ids match a reference whose EmbeddingMath accumulates in Float.  Selection stays exact under either. */
 #define ANN_FLAG_ACCUM_F32 0x4u
+/* Cosine as normalised InnerProduct, the way the reference's HNSW / Faiss backends answer Cosine
+ * (hnsw/DistanceFunctionGenerator.scala:11-30; Hnsw.scala:149-155; faiss/QueryableIndexAdapter.scala:43-50): every appended
+ * row is stored as MetricUtil.norm(row) (Metric.scala:285-289) and every query is normalised the same way, so the distance
+ * is 1 - q^.a^ with InnerProduct's arithmetic and a scan reads neither norms nor inv-norms.  Needs metric = Cosine.
+ * ann_read_rows returns the stored (unit) rows.  Distances agree with the default Cosine arithmetic to ~1e-7 but are
+ * not bit-identical to it; the matching oracle is InnerProduct over oracle-normalised inputs. */
+#define ANN_FLAG_COSINE_UNIT_ROWS 0x8u
 
 typedef struct ann_config {
     int32_t metric;        /* ann_metric                                                          */

@@ -366,3 +366,28 @@ def test_appends_run_while_queries_run_and_storage_grows_in_place():
     ri, rr = ix.read_rows(0, n)
     assert (ri == ids).all() and (rr.view(np.uint32) == corpus.view(np.uint32)).all()
     ix.close()
+
+
+# ------------------------------------------------------------------------------------------------ Cosine over unit rows
+@pytest.mark.parametrize("path,n,d,b,k", [(1, 20_000, 200, 5, 100), (2, 50_000, 200, 200, 100), (3, 4000, 24, 3, 30)])
+def test_cosine_unit_rows_is_inner_product_over_normalised_vectors(path, n, d, b, k):
+    """ANN_FLAG_COSINE_UNIT_ROWS: rows stored as MetricUtil.norm(row), queries normalised, answered with InnerProduct's
+    arithmetic -- how the reference's HNSW / Faiss backends do Cosine (DistanceFunctionGenerator.scala:11-30).  Oracle:
+    InnerProduct over oracle-normalised corpus and queries, bit for bit; and within 1e-5 of the default Cosine arithmetic."""
+    corpus, ids, q = make(n, d, b, seed=n + path)
+    corpus[7] = 0.0                                                  # a zero row normalises to NaN: ordered last
+    ix = G["BruteForceIndex"].apply(G["Cosine"], G["FuturePool"].immediate_pool(), cosine_unit_rows=True)
+    ix.append_batch(ids, corpus)
+    ix.set_option("path", path)
+    got = ix.batch_query_with_distance(q, k)
+    assert ix.stat("last_path") == path
+    un, uq = oracle.normalize(corpus), oracle.normalize(q)
+    same(got, oracle.query_canonical(oracle.INNER_PRODUCT, un, ids, uq, k))
+    ri, rr = ix.read_rows(0, 64)
+    assert (onp.float_order_key(rr) == onp.float_order_key(un[:64])).all()     # the stored rows ARE the unit rows
+    ref = oracle.query_canonical(oracle.COSINE, corpus, ids, q, k)
+    fin = np.isfinite(ref[1]) & np.isfinite(got[1])
+    assert np.all(np.abs(got[1][fin] - ref[1][fin]) <= 1e-5 * np.maximum(np.abs(ref[1][fin]), 1e-3))
+    ix.close()
+    with pytest.raises(G["_capi"].AnnError):
+        G["BruteForceIndex"].apply(G["L2"], G["FuturePool"].immediate_pool(), cosine_unit_rows=True).append_batch(ids[:4], corpus[:4])

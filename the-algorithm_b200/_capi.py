@@ -27,6 +27,7 @@ ANN_ERR_UNKNOWN_OPTION = -9
 ANN_FLAG_L2_SQUARED = 0x1
 ANN_FLAG_NO_SHADOW = 0x2
 ANN_FLAG_ACCUM_F32 = 0x4
+ANN_FLAG_COSINE_UNIT_ROWS = 0x8
 ANN_ID_AUTO, ANN_ID_INT64_BE, ANN_ID_INT32_BE = 0, 1, 2
 ANN_LAYOUT_FLOAT_TENSOR, ANN_LAYOUT_DOUBLE_TENSOR, ANN_LAYOUT_RAW_FLOAT = 0, 1, 2
 

@@ -46,7 +46,7 @@ class BruteForceIndex(Appendable, Queryable):
     _PENDING_FLUSH = 4096
 
     def __init__(self, metric: Metric, future_pool: FuturePool, device: int = 0, capacity_hint: int = 0,
-                 l2_squared: bool = False, shadow: bool = True, accum_f32: bool = False):
+                 l2_squared: bool = False, shadow: bool = True, accum_f32: bool = False, cosine_unit_rows: bool = False):
         self.metric = metric
         self.future_pool = future_pool
         self.device = device
@@ -54,7 +54,8 @@ class BruteForceIndex(Appendable, Queryable):
         self._h = ctypes.c_void_p()
         # accum_f32: distances follow the sequential-fp32 accumulator convention (ANN_FLAG_ACCUM_F32, include/b200ann.h)
         self._cfg = dict(capacity_hint=capacity_hint, flags=(_capi.ANN_FLAG_L2_SQUARED if l2_squared else 0) |
-                         (0 if shadow else _capi.ANN_FLAG_NO_SHADOW) | (_capi.ANN_FLAG_ACCUM_F32 if accum_f32 else 0))
+                         (0 if shadow else _capi.ANN_FLAG_NO_SHADOW) | (_capi.ANN_FLAG_ACCUM_F32 if accum_f32 else 0) |
+                         (_capi.ANN_FLAG_COSINE_UNIT_ROWS if cosine_unit_rows else 0))
         self._slots = None
         self._slots_version = -1
         self._version = 0          # bumped by every successful append: the id -> slot map is rebuilt when it lags
@@ -70,8 +71,8 @@ class BruteForceIndex(Appendable, Queryable):
     @staticmethod
     def apply(metric: Metric, future_pool: FuturePool, initial_embeddings: Iterable[EntityEmbedding] = (), *,
               device: int = 0, capacity_hint: int = 0, l2_squared: bool = False, shadow: bool = True,
-              accum_f32: bool = False) -> "BruteForceIndex":
-        ix = BruteForceIndex(metric, future_pool, device, capacity_hint, l2_squared, shadow, accum_f32)
+              accum_f32: bool = False, cosine_unit_rows: bool = False) -> "BruteForceIndex":
+        ix = BruteForceIndex(metric, future_pool, device, capacity_hint, l2_squared, shadow, accum_f32, cosine_unit_rows)
         ids, rows = [], []
         for e in initial_embeddings:
             ids.append(e.id)

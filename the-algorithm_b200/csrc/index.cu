@@ -114,6 +114,7 @@ struct ann_index {
     ann_config cfg{};
     int dim = 0, pitch = 0, kp = 0, metric = 0;
     bool l2_squared = false, use_shadow = true, accum_f32 = false;
+    bool unit_rows = false;   // ANN_FLAG_COSINE_UNIT_ROWS: rows stored normalised, Cosine answered as InnerProduct over unit vectors
     int device = 0, sm_count = 0;
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;
@@ -152,7 +153,7 @@ struct ann_index {
     } co;
 
     // scratch
-    DevBuf<float> q_in, q_padded, out_dist;
+    DevBuf<float> q_in, q_padded, out_dist, q_unit;
     DevBuf<__nv_bfloat16> q_shadow;
     DevBuf<QueryState> qstate;
     DevBuf<entry_t> pool;
@@ -255,6 +256,10 @@ int append_device_core(ann_index* ix, const int64_t* d_ids, const float* d_rows,
         int blocks = (int)std::min<long long>((n_new + 255) / 256, 1024);
         iota_ids_kernel<<<blocks, 256, 0, st>>>(ix->ids, ix->n, n_new);
         CUDA_TRY(cudaGetLastError());
+        ix->launches++;
+    }
+    if (ix->unit_rows) {   // stored form = MetricUtil.norm(row) (convention C8); K1 below then sees unit rows
+        CUDA_TRY(launch_normalize_rows_device(ix->rows, ix->n, n_new, ix->dim, ix->pitch, nullptr, st));
         ix->launches++;
     }
     AppendParams ap{};
@@ -672,6 +677,16 @@ bool gemm_eligible(const ann_index* ix, int b, int k_eff) {
            gemm_row_stages(ix->kp, ix->smem_optin) > 0;
 }
 
+// ANN_FLAG_COSINE_UNIT_ROWS: the query is normalised too (MetricUtil.norm, C8) and the index answers 1 - q^.a^ as InnerProduct
+int unit_queries(ann_index* ix, const float** d_queries, int b, cudaStream_t st) {
+    if (!ix->unit_rows || b == 0 || !*d_queries) return ANN_OK;
+    CUDA_TRY(ix->q_unit.ensure((size_t)b * ix->dim));
+    CUDA_TRY(launch_normalize_rows_device(const_cast<float*>(*d_queries), 0, b, ix->dim, ix->dim, ix->q_unit.p, st));
+    ix->launches++;
+    *d_queries = ix->q_unit.p;
+    return ANN_OK;
+}
+
 int query_core(ann_index* ix, const float* d_queries, int b, int k, int64_t* d_out_ids, float* d_out_dist,
                int32_t* d_out_count, cudaStream_t st) {
     if (b == 0) return ANN_OK;
@@ -846,8 +861,19 @@ int ann_create(const ann_config* cfg, ann_index** out) {
     ix->pitch = (cfg->dim + 3) / 4 * 4;
     ix->l2_squared = (cfg->flags & ANN_FLAG_L2_SQUARED) != 0;
     ix->accum_f32 = (cfg->flags & ANN_FLAG_ACCUM_F32) != 0;
+    if (cfg->flags & ANN_FLAG_COSINE_UNIT_ROWS) {
+        // Cosine the way the reference's HNSW / Faiss backends do it (DistanceFunctionGenerator.scala:11-30, Hnsw.scala:149-155,
+        // QueryableIndexAdapter.scala:43-50): normalise once at append, then every scan is a plain inner product -- no norm
+        // array, no per-row inv_norm read.  Internally the index IS an InnerProduct index over unit rows.
+        if (cfg->metric != kMetricCosine) {
+            delete ix;
+            return fail(ANN_ERR_INVALID_ARGUMENT, "ann_create: ANN_FLAG_COSINE_UNIT_ROWS needs metric = Cosine");
+        }
+        ix->unit_rows = true;
+        ix->metric = kMetricIP;
+    }
     ix->use_shadow = (cfg->flags & ANN_FLAG_NO_SHADOW) == 0;
-    ix->kp = (cfg->dim + (cfg->metric == kMetricL2 ? 3 : 1) + 7) / 8 * 8;   // + augmented columns (common.cuh, append_kernels.cu)
+    ix->kp = (cfg->dim + (ix->metric == kMetricL2 ? 3 : 1) + 7) / 8 * 8;   // + augmented columns (common.cuh, append_kernels.cu)
     ix->device = cfg->device;
     ix->sm_count = prop.multiProcessorCount;
     ix->smem_optin = prop.sharedMemPerBlockOptin;
@@ -886,7 +912,7 @@ int ann_create(const ann_config* cfg, ann_index** out) {
             ix->vm_norm.release();
             ix->vm_inv.release();
             ix->vm_shadow.release();
-            if (mr <= floor_rows) return cleanup(fail(ANN_ERR_OUT_OF_MEMORY, "ann_create: cannot reserve the index's address range"));
+            if (mr <= floor_rows) return cleanup(fail(ANN_ERR_OUT_OF_MEMORY, "ann_create: reserving the address range for capacity_hint rows failed (more than the device can ever hold)"));
             mr /= 2;
         }
         ix->max_rows = mr;
@@ -920,6 +946,7 @@ void ann_destroy(ann_index* ix) {
     if (ix->co.pin_res) cudaFreeHost(ix->co.pin_res);
     if (ix->append_stream) cudaStreamDestroy(ix->append_stream);
     ix->q_in.release();
+    ix->q_unit.release();
     ix->q_padded.release();
     ix->out_dist.release();
     ix->q_shadow.release();
@@ -964,6 +991,10 @@ int ann_update_batch(ann_index* ix, const int64_t* slots, const float* rows, int
     CUDA_TRY(ix->upd_slots.ensure((size_t)n));
     CUDA_TRY(cudaMemcpyAsync(ix->upd_rows.p, rows, (size_t)n * ix->dim * sizeof(float), cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(ix->upd_slots.p, slots, (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, st));
+    if (ix->unit_rows) {
+        CUDA_TRY(launch_normalize_rows_device(ix->upd_rows.p, 0, n, ix->dim, ix->dim, nullptr, st));
+        ix->launches++;
+    }
     AppendParams ap{};
     ap.rows = ix->rows;
     ap.row0 = 0;
@@ -1059,6 +1090,8 @@ int ann_query_batch_device(ann_index* ix, const float* d_queries, int32_t b, int
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;  // NULL = the legacy default stream
     if (ix->sess.open) ix->sess.clobbered = true;   // the per-query scratch of a pending two-phase query is overwritten
+    rc = unit_queries(ix, &d_queries, b, st);
+    if (rc) return rc;
     rc = query_core(ix, d_queries, b, k, d_out_ids, d_out_dist, d_out_count, st);
     if (rc == ANN_OK && ix->device_fallback) rc = resolve_flagged(ix, d_queries, b, k, d_out_ids, d_out_dist, d_out_count, st);
     return rc;
@@ -1091,6 +1124,8 @@ int ann_query_seed_device(ann_index* ix, const float* d_queries, int32_t b, int3
     }
     ix->sess.gemm = true;
     CUDA_TRY(ix->qstate.ensure((size_t)b));
+    rc = unit_queries(ix, &d_queries, b, st);
+    if (rc) return rc;
     rc = query_gemm(ix, ix->qstate.p, d_queries, b, k_eff, k, nullptr, nullptr, nullptr, st, 1, d_seed_keys);
     if (rc) ix->sess = ann_index::SeedSession{};
     return rc;
@@ -1122,6 +1157,8 @@ int ann_query_finish_device(ann_index* ix, const float* d_queries, int32_t b, in
         return ANN_OK;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    rc = unit_queries(ix, &d_queries, b, st);
+    if (rc) return rc;
     if (!sess.gemm) {
         ix->sess.open = false;
         rc = query_core(ix, d_queries, b, k, d_out_ids, d_out_dist, d_out_count, st);
@@ -1217,6 +1254,8 @@ int ann_query_rescore_device(ann_index* ix, const float* d_queries, int32_t b, i
     rc = set_device(ix);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
+    rc = unit_queries(ix, &d_queries, b, st);
+    if (rc) return rc;
     if (!gemm) {
         rc = query_core(ix, d_queries, b, k, d_out_ids, d_out_dist, d_out_count, st);
     } else {
@@ -1272,7 +1311,10 @@ int query_host(ann_index* ix, const float* queries, int32_t b, int32_t k, int64_
     CUDA_TRY(ix->out_dist.ensure(nk));
     CUDA_TRY(ix->out_count.ensure((size_t)b));
     CUDA_TRY(cudaMemcpyAsync(ix->q_in.p, queries, (size_t)b * ix->dim * sizeof(float), cudaMemcpyHostToDevice, st));
-    rc = query_core(ix, ix->q_in.p, b, k, ix->out_ids.p, ix->out_dist.p, ix->out_count.p, st);
+    const float* d_q = ix->q_in.p;
+    rc = unit_queries(ix, &d_q, b, st);
+    if (rc) return rc;
+    rc = query_core(ix, d_q, b, k, ix->out_ids.p, ix->out_dist.p, ix->out_count.p, st);
     if (rc) return rc;
     // one round trip in the common case: results and the sticky flag word come back together
     DeviceScalars hs{};
@@ -1290,7 +1332,7 @@ int query_host(ann_index* ix, const float* queries, int32_t b, int32_t k, int64_
     if (rc) return rc;
     if (hs.error_flags) {   // rare: some queries were flagged by the bounded selector -> exact fallback, then copy again
         bool ran = false;
-        rc = resolve_flagged(ix, ix->q_in.p, b, k, ix->out_ids.p, ix->out_dist.p, ix->out_count.p, st, &hs, &ran);
+        rc = resolve_flagged(ix, d_q, b, k, ix->out_ids.p, ix->out_dist.p, ix->out_count.p, st, &hs, &ran);
         if (rc) return rc;
         rc = copy_out();
         if (rc) return rc;

@@ -25,6 +25,10 @@ struct AppendParams {
 };
 cudaError_t launch_append(const AppendParams& p, cudaStream_t stream);
 
+// MetricUtil.norm (Metric.scala:285-289, convention C8) on device rows: in place over rows [row0, row0+n) of a pitched matrix
+// (out == nullptr) or from a dense [n][dim] source into `out`.  metric_kernels.cu.
+cudaError_t launch_normalize_rows_device(float* rows, long long row0, long long n, int dim, int pitch, float* out, cudaStream_t stream);
+
 // ---------------------------------------------------------------- query preparation
 struct PrepParams {
     const float* queries;   // [b][dim]

@@ -94,6 +94,25 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) normalize_rows_kernel(int d
     }
 }
 
+// In place, rows of an index matrix (pitch >= dim): what ANN_FLAG_COSINE_UNIT_ROWS applies to every appended row.
+__global__ void __launch_bounds__(32 * kWarpsPerCta) normalize_inplace_kernel(float* rows, long long row0, long long n, int dim, int pitch) {
+    extern __shared__ float sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* sv = sm + (size_t)warp * dim;
+    for (long long r = (long long)blockIdx.x * kWarpsPerCta + warp; r < n; r += (long long)gridDim.x * kWarpsPerCta) {
+        float* a = rows + (size_t)(row0 + r) * pitch;
+        for (int i = lane; i < dim; i += 32) sv[i] = a[i];
+        __syncwarp();
+        double n2 = 0.0;
+        if (lane == 0)
+            for (int i = 0; i < dim; ++i) n2 = __fma_rn((double)sv[i], (double)sv[i], n2);
+        n2 = __shfl_sync(0xFFFFFFFFu, n2, 0);
+        const double nrm = __dsqrt_rn(n2);
+        for (int i = lane; i < dim; i += 32) a[i] = __double2float_rn(__ddiv_rn((double)sv[i], nrm));
+        __syncwarp();
+    }
+}
+
 struct Staging {
     float* p[3] = {nullptr, nullptr, nullptr};
     ~Staging() {
@@ -132,6 +151,17 @@ int pick_device(int device) {
 int grid_for(long long n) { return (int)std::min<long long>((n + kWarpsPerCta - 1) / kWarpsPerCta, 148LL * 8); }
 
 }  // namespace
+
+// MetricUtil.norm on device-resident rows (convention C8), in place (out == nullptr: rows [row0, row0+n) of a matrix with
+// `pitch`) or into a dense [n][dim] copy (`out`, source pitch = dim).
+cudaError_t launch_normalize_rows_device(float* rows, long long row0, long long n, int dim, int pitch, float* out, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    const size_t smem = (size_t)kWarpsPerCta * dim * sizeof(float);
+    if (out) normalize_rows_kernel<<<grid_for(n), 32 * kWarpsPerCta, smem, stream>>>(dim, rows + (size_t)row0 * dim, n, out);
+    else normalize_inplace_kernel<<<grid_for(n), 32 * kWarpsPerCta, smem, stream>>>(rows, row0, n, dim, pitch);
+    return cudaGetLastError();
+}
+
 }  // namespace b200ann
 
 using namespace b200ann;
