@@ -383,6 +383,20 @@ def run_ours(a):
     ms_step = ms_total / a.steps
     value = b / (ms_step * 1e-3)
 
+    # ---- where a step goes: CUDA events around EVERY kernel of the query path (a separate short loop: the extra event
+    # records cost a little, so this is not the timed region above); rank 0's view
+    bsteps = 5
+    ix.set_option("timing", 2)
+    ms_b = timed(lambda: step_device(q_dev), bsteps) / bsteps
+    breakdown = {"ms_per_step_with_event_records": ms_b}
+    acc_ms = 0.0
+    for name in ("main", "prep", "compact", "seed_merge", "finalize"):
+        v = ix.stat("us_" + name) / 1e3 / bsteps
+        breakdown[{"main": "scan_or_gemm_filter"}.get(name, name) + "_ms"] = v
+        acc_ms += v
+    breakdown["exchange_barriers_launch_gaps_ms"] = ms_b - acc_ms
+    ix.set_option("timing", 0)
+
     # ---- end to end through the host-buffer C-ABI call: pinned queries in, host results out ----
     q_pin = q_dev.cpu().pin_memory()
     q0, q1 = (0, b) if world == 1 else sx.slice_range(b)
@@ -490,6 +504,14 @@ def run_ours(a):
             extra["scan"] = r_
         except Exception as e:
             extra["scan"] = {"error": repr(e)}
+    if not a.no_extra and world == 1 and last_path == 2:
+        try:   # online shape: 64 host threads, one vector per call, against the same handle (library-side load generator)
+            lt = ix.loadtest(q_np[:1024], k, threads=64, calls_per_thread=100, expect_ids=full[0][:1024])
+            lt["workload"] = (f"64 host threads x 100 one-vector ann_query_batch calls, {a.metric} top-{k} over {n}x{d}; concurrent calls "
+                              "are combined into device batches by the library's micro-batcher (QueryIndexThriftController.scala:39-90 shape)")
+            extra["online_single_vector"] = lt
+        except Exception as e:
+            extra["online_single_vector"] = {"error": repr(e)}
     ix_closed = False
     if not a.no_extra and world == 1:
         try:   # configs[2]: single-query L2 top-100 over 10M x 128, batch 1, p50/p99 latency
@@ -599,7 +621,7 @@ def run_ours(a):
                            "per rank: pinned H2D of the batch + three-phase sharded query + slice merge + D2H of the rank's 1/N slice"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "path": {1: "scan", 2: "gemm"}.get(last_path, str(last_path)),
-            "result_digest": digest, "flagged_rows": flagged_rows, "parity_sample": parity, "extra": extra,
+            "result_digest": digest, "flagged_rows": flagged_rows, "parity_sample": parity, "breakdown": breakdown, "extra": extra,
         }
         print(json.dumps(line), flush=True)
         if flagged_rows:

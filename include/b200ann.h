@@ -291,6 +291,7 @@ ANN_API int ann_loadtest(ann_index *ix, const float *queries, int32_t nq, int32_
  *          "timing" (1 = bracket every scan / GEMM-filter launch with CUDA events on its stream),
  *          "coalesce_max_batch" (queries per merged device call of the host entry point's micro-batcher, default 2048; 0 = off),
  *          "coalesce_small_b" (host calls with at most this many queries are combined with concurrent ones, default 32),
+ *          "coalesce_linger_us" (how long a caller that inherits the lead waits for the previous batch's callers to return, default 60),
  *          "device_fallback" (1 = ann_query_batch_device synchronises its stream and re-answers flagged queries with the
  *          exact fallback, like the host entry point always does; 0 = stay asynchronous and report them, default).
  * Stats:   "launches" (kernels launched so far), "last_path", "shadow_bytes", "row_bytes", "n_special", "capacity", "dim",

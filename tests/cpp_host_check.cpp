@@ -1,6 +1,8 @@
 // Compile-and-link check of the C++ host mirror (the-algorithm_b200/host/cpp/b200ann.hpp) against libb200ann.so.
 // Without a GPU every compute entry point must fail loudly: the constructor throws AnnError(ANN_ERR_NO_DEVICE).
 // With a GPU it runs a three-row known-answer query (InnerProduct distances 1 - a.b).
+#include <cuda_runtime.h>
+
 #include <cstdio>
 
 #include "../the-algorithm_b200/host/cpp/b200ann.hpp"
@@ -22,6 +24,35 @@ int main() {
         if (distance(Metric::InnerProduct, {1.0f, 2.0f, 3.0f}, {4.0f, 5.0f, 6.0f}).distance != -31.0f) return 16;
         auto unit = norm({3.0f, 4.0f});                                                               // Metric.scala:285-289
         if (unit.size() != 2 || unit[0] != 0.6f || unit[1] != 0.8f) return 17;
+        // one process, several shards (two GPUs when the box has them, else two shards on one): ComposedQueryable semantics,
+        // ShardApi.scala:72-86 -- the merged answer equals the single index's, ties by id
+        {
+            int ndev = 0;
+            cudaGetDeviceCount(&ndev);
+            ShardedBruteForceIndex sx(Metric::L2, 3, {0, ndev > 1 ? 1 : 0});
+            const int n = 5000;
+            std::vector<int64_t> sids(n);
+            std::vector<float> srows((size_t)n * 3);
+            for (int i = 0; i < n; ++i) {
+                sids[i] = 100000 - i;
+                srows[(size_t)i * 3 + 0] = (float)(i % 71);
+                srows[(size_t)i * 3 + 1] = (float)(i % 13);
+                srows[(size_t)i * 3 + 2] = (float)(i / 1000);
+            }
+            sx.appendBatch(sids.data(), srows.data(), n);
+            BruteForceIndex<int64_t> one(Metric::L2, 3);
+            one.appendBatch(sids.data(), srows.data(), n);
+            const float q[6] = {3.f, 4.f, 1.f, 70.f, 12.f, 4.f};
+            int64_t a_ids[20], b_ids[20];
+            float a_d[20], b_d[20];
+            int32_t a_c[2], b_c[2];
+            sx.batchQueryWithDistance(q, 2, 10, a_ids, a_d, a_c);
+            one.batchQueryWithDistance(q, 2, 10, b_ids, b_d, b_c);
+            if (sx.size() != n || a_c[0] != 10 || a_c[1] != 10) return 18;
+            for (int i = 0; i < 20; ++i)
+                if (a_ids[i] != b_ids[i] || a_d[i] != b_d[i]) return 19;
+            if (sx.query({3.f, 4.f, 1.f}, 1).get().at(0) != a_ids[0]) return 20;
+        }
         std::printf("gpu ok\n");
         return 0;
     } catch (const AnnError& e) {

@@ -15,7 +15,7 @@ def _build(tmp_path, built_lib):
         pytest.skip("no g++")
     exe = tmp_path / "cpp_host_check"
     cmd = [gxx, "-std=c++17", "-O1", "-o", str(exe), str(ROOT / "tests" / "cpp_host_check.cpp"), f"-L{built_lib.parent}",
-           "-lb200ann", f"-Wl,-rpath,{built_lib.parent}", "-L/usr/local/cuda/lib64", "-lcudart", "-pthread"]
+           "-lb200ann", f"-Wl,-rpath,{built_lib.parent}", "-I/usr/local/cuda/include", "-L/usr/local/cuda/lib64", "-lcudart", "-pthread"]
     subprocess.run(cmd, check=True)
     return exe
 
@@ -49,7 +49,17 @@ def test_scala_binding_names_every_abi_entry_point_it_uses():
                         ("size", "ann_size"), ("queryBatch", "ann_query_batch"), ("lastError", "ann_last_error"),
                         ("knnJoin", "ann_knn_join"), ("distancePairs", "ann_distance_pairs"),
                         ("normalizeRows", "ann_normalize_rows"), ("querySeedDevice", "ann_query_seed_device"),
-                        ("queryFinishDevice", "ann_query_finish_device")):
+                        ("queryFinishDevice", "ann_query_finish_device"), ("shardedCreate", "ann_sharded_create"),
+                        ("shardedDestroy", "ann_sharded_destroy"), ("shardedAppendBatch", "ann_sharded_append_batch"),
+                        ("shardedSize", "ann_sharded_size"), ("shardedQueryBatch", "ann_sharded_query_batch"),
+                        ("saveDirectory", "ann_save_directory"), ("loadDirectory", "ann_load_directory"),
+                        ("shardedSaveDirectory", "ann_sharded_save_directory"),
+                        ("shardedLoadDirectory", "ann_sharded_load_directory")):
         assert f"def {native}(" in scala and abi in jni
     for trait in ("extends Appendable[T, BruteForceRuntimeParams.type, D]", "with Queryable[T, BruteForceRuntimeParams.type, D]"):
         assert trait in scala
+    sharded = (ROOT / "the-algorithm_b200" / "host" / "scala" / "GpuShardedBruteForceIndex.scala").read_text()
+    for used in ("shardedCreate", "shardedAppendBatch", "shardedQueryBatch", "shardedSaveDirectory", "shardedLoadDirectory", "shardedDestroy"):
+        assert f"B200AnnNative.{used}(" in sharded
+    for trait in ("extends Appendable[Long, BruteForceRuntimeParams.type, D]", "with Queryable[Long, BruteForceRuntimeParams.type, D]"):
+        assert trait in sharded

@@ -59,7 +59,11 @@ class BruteForceIndex(Appendable, Queryable):
         self._slots = None
         self._slots_version = -1
         self._version = 0          # bumped by every successful append: the id -> slot map is rebuilt when it lags
+        # `_lock` guards the host-side buffer of single-row appends; `_append_lock` serialises appends / updates (id
+        # bookkeeping + the native call).  Queries hold NEITHER during the native call: the library lets appends proceed while
+        # queries run and combines concurrent small queries itself (include/b200ann.h).
         self._lock = threading.RLock()
+        self._append_lock = threading.RLock()
         self._pending_ids: List = []
         self._pending_rows: List[np.ndarray] = []
         # generic id type T: ids that are not int64 live in a host table, the device sees the insertion slot
@@ -92,7 +96,7 @@ class BruteForceIndex(Appendable, Queryable):
         self.dim = dim
 
     def close(self):
-        with self._lock:
+        with self._lock, self._append_lock:
             if self._h:
                 _capi.lib().ann_destroy(self._h)
                 self._h = ctypes.c_void_p()
@@ -147,7 +151,7 @@ class BruteForceIndex(Appendable, Queryable):
         if rows.ndim != 2:
             raise ValueError("rows must be [n, dim]")
         n = rows.shape[0]
-        with self._lock:
+        with self._append_lock:
             if n == 0:
                 return
             self._ensure(rows.shape[1])
@@ -165,7 +169,7 @@ class BruteForceIndex(Appendable, Queryable):
 
     def append_batch_device(self, ids_t, rows_t, stream: int = 0) -> None:
         """rows_t: CUDA float32 [n, dim] tensor, ids_t: CUDA int64 [n] tensor (or None) on this index's device."""
-        with self._lock:
+        with self._append_lock:
             n = int(rows_t.shape[0])
             if n == 0:
                 return
@@ -197,7 +201,7 @@ class BruteForceIndex(Appendable, Queryable):
         """Overwrite the embeddings of existing ids in place; unknown ids are appended (Hnsw.update semantics,
         hnsw/Hnsw.scala:149-182).  With duplicate ids in the index the first inserted one is updated."""
         rows = np.ascontiguousarray(rows, dtype=np.float32)
-        with self._lock:
+        with self._append_lock:
             self.flush()
             smap = self._slot_map() if self._n else {}
             ids = list(ids)
@@ -221,13 +225,12 @@ class BruteForceIndex(Appendable, Queryable):
         return self
 
     def size(self) -> int:
-        with self._lock:
-            self.flush()
-            if not self._h:
-                return 0
-            n = ctypes.c_int64()
-            _capi.check(_capi.lib().ann_size(self._h, ctypes.byref(n)))
-            return int(n.value)
+        self.flush()
+        if not self._h:
+            return 0
+        n = ctypes.c_int64()
+        _capi.check(_capi.lib().ann_size(self._h, ctypes.byref(n)))
+        return int(n.value)
 
     # ---- Queryable -----------------------------------------------------------------------------------------
     def id_of(self, raw):
@@ -242,31 +245,30 @@ class BruteForceIndex(Appendable, Queryable):
         if q.ndim != 2:
             raise ValueError("embeddings must be [b, dim]")
         b, k = q.shape[0], int(num_of_neighbors)
-        with self._lock:
-            self.flush()
-            kk = max(k, 0)
-            if out is not None and self._h and k > 0:
-                out_ids, out_dist, out_cnt = out
-                assert out_ids.shape == (b, kk) and out_ids.dtype == np.int64 and out_ids.flags.c_contiguous
-                assert out_dist.shape == (b, kk) and out_dist.dtype == np.float32 and out_dist.flags.c_contiguous
-                assert out_cnt.shape == (b,) and out_cnt.dtype == np.int32
-            else:
-                out_ids = np.full((b, kk), -1, dtype=np.int64)
-                out_dist = np.full((b, kk), np.inf, dtype=np.float32)
-                out_cnt = np.zeros(b, dtype=np.int32)
-            if k < 0:
-                raise _capi.AnnError(_capi.ANN_ERR_NEGATIVE_K, "numOfNeighbours < 0")
-            if not self._h:  # nothing appended yet: BruteForceIndex.scala:76-89 yields an empty list
-                return out_ids, out_dist, out_cnt
-            _capi.check(_capi.lib().ann_query_batch(self._h, _ptr(q), b, q.shape[1], k, _ptr(out_ids), _ptr(out_dist),
-                                                    _ptr(out_cnt)))
+        self.flush()
+        kk = max(k, 0)
+        if out is not None and self._h and k > 0:
+            out_ids, out_dist, out_cnt = out
+            assert out_ids.shape == (b, kk) and out_ids.dtype == np.int64 and out_ids.flags.c_contiguous
+            assert out_dist.shape == (b, kk) and out_dist.dtype == np.float32 and out_dist.flags.c_contiguous
+            assert out_cnt.shape == (b,) and out_cnt.dtype == np.int32
+        else:
+            out_ids = np.full((b, kk), -1, dtype=np.int64)
+            out_dist = np.full((b, kk), np.inf, dtype=np.float32)
+            out_cnt = np.zeros(b, dtype=np.int32)
+        if k < 0:
+            raise _capi.AnnError(_capi.ANN_ERR_NEGATIVE_K, "numOfNeighbours < 0")
+        if not self._h:  # nothing appended yet: BruteForceIndex.scala:76-89 yields an empty list
             return out_ids, out_dist, out_cnt
+        _capi.check(_capi.lib().ann_query_batch(self._h, _ptr(q), b, q.shape[1], k, _ptr(out_ids), _ptr(out_dist),
+                                                _ptr(out_cnt)))
+        return out_ids, out_dist, out_cnt
 
     def query_batch_device(self, queries_t, k: int, out_ids_t, out_dist_t, out_count_t, stream: int = 0) -> None:
         """Device-pointer query: CUDA tensors in, CUDA tensors out, enqueued on `stream` without synchronising.
         Call raise_pending_error() after the stream has been synchronised."""
-        with self._lock:
-            self.flush()
+        self.flush()
+        if True:
             if not self._h:   # nothing appended yet: an empty list per query (BruteForceIndex.scala:76-89), as on the host path
                 out_ids_t.fill_(-1)
                 out_dist_t.fill_(float("inf"))
@@ -281,8 +283,8 @@ class BruteForceIndex(Appendable, Queryable):
     def query_seed_device(self, queries_t, k: int, seed_keys_t, stream: int = 0) -> None:
         """First half of a sharded query (`ann_query_seed_device`): prepare the batch, score a prefix of this shard and
         publish k bounds per query into `seed_keys_t` ([b, k] int32/uint32 CUDA tensor, normally peer-mapped memory)."""
-        with self._lock:
-            self.flush()
+        self.flush()
+        if True:
             _capi.check(_capi.lib().ann_query_seed_device(
                 self._h, ctypes.c_void_p(queries_t.data_ptr()), int(queries_t.shape[0]), int(queries_t.shape[1]), int(k),
                 ctypes.c_void_p(seed_keys_t.data_ptr()), ctypes.c_void_p(stream)))
@@ -293,7 +295,7 @@ class BruteForceIndex(Appendable, Queryable):
         imply and its candidates for the global top-k are written to the outputs (count may be < k)."""
         world = len(peer_seed_key_ptrs)
         arr = (ctypes.c_void_p * max(world, 1))(*[int(p) for p in peer_seed_key_ptrs])
-        with self._lock:
+        if True:
             _capi.check(_capi.lib().ann_query_finish_device(
                 self._h, ctypes.c_void_p(queries_t.data_ptr()), int(queries_t.shape[0]), int(queries_t.shape[1]), int(k),
                 arr if world else None, world, ctypes.c_void_p(out_ids_t.data_ptr()), ctypes.c_void_p(out_dist_t.data_ptr()),
@@ -304,7 +306,7 @@ class BruteForceIndex(Appendable, Queryable):
         chunks, last compaction; publishes this shard's k best bounds per query into `kth_keys_t` ([b, k] CUDA tensor)."""
         world = len(peer_seed_key_ptrs)
         arr = (ctypes.c_void_p * max(world, 1))(*[int(p) for p in peer_seed_key_ptrs])
-        with self._lock:
+        if True:
             _capi.check(_capi.lib().ann_query_filter_device(
                 self._h, ctypes.c_void_p(queries_t.data_ptr()), int(queries_t.shape[0]), int(queries_t.shape[1]), int(k),
                 arr if world else None, world, ctypes.c_void_p(kth_keys_t.data_ptr()), ctypes.c_void_p(stream)))
@@ -314,7 +316,7 @@ class BruteForceIndex(Appendable, Queryable):
         shards; writes this shard's candidates for the global top-k (count may be < k; -1 = flagged, row invalid)."""
         world = len(peer_kth_key_ptrs)
         arr = (ctypes.c_void_p * max(world, 1))(*[int(p) for p in peer_kth_key_ptrs])
-        with self._lock:
+        if True:
             _capi.check(_capi.lib().ann_query_rescore_device(
                 self._h, ctypes.c_void_p(queries_t.data_ptr()), int(queries_t.shape[0]), int(queries_t.shape[1]), int(k),
                 arr if world else None, world, ctypes.c_void_p(out_ids_t.data_ptr()), ctypes.c_void_p(out_dist_t.data_ptr()),
@@ -347,8 +349,8 @@ class BruteForceIndex(Appendable, Queryable):
 
     def read_rows(self, start: int, n: int):
         """Rows [start, start+n) and their device ids, in insertion order (what toDirectory iterates)."""
-        with self._lock:
-            self.flush()
+        self.flush()
+        if True:
             ids = np.empty(n, dtype=np.int64)
             rows = np.empty((n, self.dim or 0), dtype=np.float32)
             if n:
@@ -361,8 +363,7 @@ class BruteForceIndex(Appendable, Queryable):
         q = np.ascontiguousarray(queries, dtype=np.float32)
         exp = None if expect_ids is None else np.ascontiguousarray(expect_ids, dtype=np.int64)
         st = _capi.AnnLoadStats()
-        with self._lock:
-            self.flush()
+        self.flush()
         _capi.check(_capi.lib().ann_loadtest(self._h, _ptr(q), q.shape[0], q.shape[1], int(k), int(threads), int(calls_per_thread),
                                              _ptr(exp), ctypes.byref(st)))
         return {f: getattr(st, f) for f, _ in _capi.AnnLoadStats._fields_}

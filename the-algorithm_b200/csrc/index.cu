@@ -22,6 +22,7 @@
 #include <utility>
 #include <vector>
 
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 
@@ -146,6 +147,8 @@ struct ann_index {
         bool leader_active = false;
         int max_batch = 2048;   // queries per merged device call; 0 switches coalescing off
         int small_b = 32;       // calls with at most this many queries are coalesced
+        int linger_us = 60;     // a leader that inherits the lead waits this long for the callers of the batch that just
+                                // finished to come back (closed-loop clients re-issue within microseconds); a lone caller never waits
         float* pin_q = nullptr;               // pinned staging of the merged batch
         unsigned char* pin_res = nullptr;
         size_t cap_q = 0, cap_res = 0;
@@ -173,10 +176,16 @@ struct ann_index {
     bool gemm_blocked_by_update = false;   // device entry point: synchronise and run the exact fallback for flagged queries
     // optional CUDA-event timing of the dominant kernel of each path, on the launching stream (bench.py roofline)
     bool timing = false;
+    // label 0 = the dominant kernel of the path (scan / tensor-core filter: the roofline's `achieved`); the others make up the
+    // per-step breakdown bench.py prints with "timing" = 2
+    enum { kLblMain = 0, kLblPrep, kLblCompact, kLblSeedMerge, kLblFinalize, kLblOther, kLblCount };
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pairs;
+    std::vector<int> ev_label;
     size_t ev_used = 0;
+    int timing_level = 0;     // 1 = label 0 only, 2 = every kernel of the query path
     double kernel_ms_total = 0.0;
     long long kernel_launches_timed = 0;
+    double ms_by_label[kLblCount] = {0, 0, 0, 0, 0, 0};
     long long last_candidates = 0;
     std::atomic<long long> launches{0};
     long long last_path = 0, exact_fallback_queries = 0;
@@ -288,13 +297,15 @@ struct TimedScope {
     ann_index* ix;
     cudaStream_t st;
     std::pair<cudaEvent_t, cudaEvent_t>* pr = nullptr;
-    TimedScope(ann_index* i, cudaStream_t s) : ix(i), st(s) {
-        if (!ix->timing) return;
+    TimedScope(ann_index* i, cudaStream_t s, int label = ann_index::kLblMain) : ix(i), st(s) {
+        if (!ix->timing || (label != ann_index::kLblMain && ix->timing_level < 2)) return;
         if (ix->ev_used == ix->ev_pairs.size()) {
             cudaEvent_t a, b;
             if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
             ix->ev_pairs.emplace_back(a, b);
+            ix->ev_label.push_back(0);
         }
+        ix->ev_label[ix->ev_used] = label;
         pr = &ix->ev_pairs[ix->ev_used++];
         cudaEventRecord(pr->first, st);
     }
@@ -303,13 +314,16 @@ struct TimedScope {
     }
 };
 
-// fold finished event pairs into kernel_ms_total (call after the stream has been synchronised)
+// fold finished event pairs into the totals (call after the stream has been synchronised)
 void harvest_timing(ann_index* ix) {
     for (size_t i = 0; i < ix->ev_used; ++i) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, ix->ev_pairs[i].first, ix->ev_pairs[i].second) == cudaSuccess) {
-            ix->kernel_ms_total += ms;
-            ix->kernel_launches_timed++;
+            ix->ms_by_label[ix->ev_label[i]] += ms;
+            if (ix->ev_label[i] == ann_index::kLblMain) {
+                ix->kernel_ms_total += ms;
+                ix->kernel_launches_timed++;
+            }
         }
     }
     ix->ev_used = 0;
@@ -380,7 +394,7 @@ int query_scan(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
     pp.pub_keys = ix->pub_keys.p;
     pp.pub_stride = kPubStride;
     pp.bad_queries = &ix->scalars->bad_queries;
-    CUDA_TRY(launch_prep_queries(pp, st));
+    { TimedScope ts_(ix, st, ann_index::kLblPrep); CUDA_TRY(launch_prep_queries(pp, st)); }
     ix->launches++;
 
     for (int g0 = 0; g0 < b; g0 += group) {
@@ -435,7 +449,7 @@ int query_scan(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
         fp.out_dist = d_out_dist + (size_t)g0 * k_out;
         fp.out_count = d_out_count ? d_out_count + g0 : nullptr;
         fp.k_out = k_out;
-        CUDA_TRY(launch_finalize(fp, gn, st));
+        { TimedScope ts_(ix, st, ann_index::kLblFinalize); CUDA_TRY(launch_finalize(fp, gn, st)); }
         ix->launches++;
     }
     collect_flags_kernel<<<std::min(64, (b + 255) / 256), 256, 0, st>>>(ix->qstate.p, b, ix->scalars);
@@ -483,7 +497,7 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
     pp.pub_stride = 0;
     pp.bad_queries = &ix->scalars->bad_queries;
     if (mode < 2) {
-        CUDA_TRY(launch_prep_queries(pp, st));
+        { TimedScope ts_(ix, st, ann_index::kLblPrep); CUDA_TRY(launch_prep_queries(pp, st)); }
         ix->launches++;
     }
 
@@ -520,7 +534,7 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
             fp.peer_keys = *peers;
             fp.peer_world = world;
         }
-        CUDA_TRY(launch_finalize(fp, b, st));
+        { TimedScope ts_(ix, st, ann_index::kLblFinalize); CUDA_TRY(launch_finalize(fp, b, st)); }
         ix->launches++;
         collect_flags_kernel<<<std::min(64, (b + 255) / 256), 256, 0, st>>>(qs_base, b, ix->scalars);
         CUDA_TRY(cudaGetLastError());
@@ -615,7 +629,7 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
             sp.seed_count = (int)(seed_rows / 32);
             sp.sort_cap = std::max(sp.sort_cap, sp.seed_count);   // every seed entry is loaded
             sp.seed_keys_out = mode == 1 ? seed_keys_out : nullptr;
-            CUDA_TRY(launch_compact_pool(sp, b, st));
+            { TimedScope ts_(ix, st, ann_index::kLblCompact); CUDA_TRY(launch_compact_pool(sp, b, st)); }
             ix->launches++;
         }
         if (mode == 1) {
@@ -626,7 +640,7 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
         if (mode >= 2 && peers && world > 1) {
             // K5c: the k-th best of the union of all shards' published bounds replaces this shard's own seed threshold:
             // as tight as one seed over world * seed_rows rows, for the price of one seed launch per shard
-            CUDA_TRY(launch_seed_merge(*peers, world, qs_base, b, k_eff, st));
+            { TimedScope ts_(ix, st, ann_index::kLblSeedMerge); CUDA_TRY(launch_seed_merge(*peers, world, qs_base, b, k_eff, st)); }
             ix->launches++;
             seen *= world;
         }
@@ -650,7 +664,7 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
         if (rc2) return rc2;
         ix->last_gemm_chunks++;
         if (end >= ix->n) break;
-        CUDA_TRY(launch_compact_pool(fp, b, st));
+        { TimedScope ts_(ix, st, ann_index::kLblCompact); CUDA_TRY(launch_compact_pool(fp, b, st)); }
         ix->launches++;
         begin = end;
         end = std::min<long long>(ix->n, end * growth);
@@ -658,11 +672,11 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
     if (mode == 3) {   // last compaction + publish; the exact finalize follows the second cross-shard round (mode 4)
         SelectParams sp = fp;
         sp.seed_keys_out = seed_keys_out;
-        CUDA_TRY(launch_compact_pool(sp, b, st));
+        { TimedScope ts_(ix, st, ann_index::kLblCompact); CUDA_TRY(launch_compact_pool(sp, b, st)); }
         ix->launches++;
         return ANN_OK;
     }
-    CUDA_TRY(launch_finalize(fp, b, st));
+    { TimedScope ts_(ix, st, ann_index::kLblFinalize); CUDA_TRY(launch_finalize(fp, b, st)); }
     ix->launches++;
     collect_flags_kernel<<<std::min(64, (b + 255) / 256), 256, 0, st>>>(qs_base, b, ix->scalars);
     CUDA_TRY(cudaGetLastError());
@@ -1387,6 +1401,12 @@ int query_coalesced(ann_index* ix, const float* queries, int32_t b, int32_t k, i
             }
         }
         co.leader_active = true;
+        if (me.promoted && co.linger_us > 0 && (int)co.pending.size() < co.max_batch) {
+            // The batch that just finished released its callers a moment ago; without a short linger they arrive just after
+            // this batch is cut and two half-sized groups ping-pong forever (measured: 32 + 32 instead of 64 per device batch).
+            const auto until = std::chrono::steady_clock::now() + std::chrono::microseconds(co.linger_us);
+            while (std::chrono::steady_clock::now() < until) me.cv.wait_until(lk, until);
+        }
         // my batch: me, then every waiting call with my k in arrival order while the merged batch stays within max_batch
         co.pending.erase(std::find(co.pending.begin(), co.pending.end(), &me));
         batch.push_back(&me);
@@ -1532,6 +1552,8 @@ int ann_set_option(ann_index* ix, const char* name, int64_t value) {
     }
     if (!strcmp(name, "timing")) {
         ix->timing = value != 0;
+        ix->timing_level = (int)value;
+        for (double& m : ix->ms_by_label) m = 0.0;
         ix->kernel_ms_total = 0.0;
         ix->kernel_launches_timed = 0;
         ix->ev_used = 0;
@@ -1571,6 +1593,12 @@ int ann_set_option(ann_index* ix, const char* name, int64_t value) {
         ix->co.max_batch = (int)value;
         return ANN_OK;
     }
+    if (!strcmp(name, "coalesce_linger_us")) {
+        if (value < 0 || value > 100000) return fail(ANN_ERR_INVALID_ARGUMENT, "coalesce_linger_us must be in [0, 100000]");
+        std::lock_guard<std::mutex> clk(ix->co.mu);
+        ix->co.linger_us = (int)value;
+        return ANN_OK;
+    }
     if (!strcmp(name, "coalesce_small_b")) {
         if (value < 1) return fail(ANN_ERR_INVALID_ARGUMENT, "coalesce_small_b must be >= 1");
         std::lock_guard<std::mutex> clk(ix->co.mu);
@@ -1595,6 +1623,19 @@ int ann_get_stat(const ann_index* ix, const char* name, int64_t* value) {
         CUDA_TRY(cudaDeviceSynchronize());
         *value = 0;
         return check_device_flags(m, m->stream);
+    }
+    if (!strncmp(name, "us_", 3)) {   // per-kernel-class totals since "timing" = 2 was set; synchronises
+        static const char* const names[] = {"us_main", "us_prep", "us_compact", "us_seed_merge", "us_finalize", "us_other"};
+        for (int l = 0; l < ann_index::kLblCount; ++l)
+            if (!strcmp(name, names[l])) {
+                ann_index* m = const_cast<ann_index*>(ix);
+                std::lock_guard<std::mutex> lk(m->mu);
+                CUDA_TRY(cudaSetDevice(m->device));
+                CUDA_TRY(cudaDeviceSynchronize());
+                harvest_timing(m);
+                *value = (int64_t)(m->ms_by_label[l] * 1000.0);
+                return ANN_OK;
+            }
     }
     if (!strcmp(name, "kernel_us") || !strcmp(name, "kernel_launches_timed")) {
         // dominant-kernel time accumulated since timing was switched on; synchronises the device

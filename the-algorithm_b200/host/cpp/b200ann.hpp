@@ -180,4 +180,65 @@ private:
     ann_index* h_ = nullptr;
 };
 
+// ShardedAppendable + ComposedQueryable (common/ShardApi.scala:34-48, 58-87) over several GPUs of ONE process: the native
+// composed handle (ann_sharded_*).  T = int64 ids only (the merge orders ties by id).
+class ShardedBruteForceIndex : public Appendable<int64_t>, public Queryable<int64_t> {
+public:
+    ShardedBruteForceIndex(Metric metric, int dim, const std::vector<int32_t>& devices, std::launch policy = std::launch::deferred,
+                           int64_t capacity_hint = 0)
+        : dim_(dim), policy_(policy) {
+        ann_config cfg{static_cast<int32_t>(metric), dim, capacity_hint, 0, 0u};
+        check(ann_sharded_create(&cfg, devices.data(), static_cast<int32_t>(devices.size()), &h_));
+    }
+    ~ShardedBruteForceIndex() override { ann_sharded_destroy(h_); }
+    ShardedBruteForceIndex(const ShardedBruteForceIndex&) = delete;
+    ShardedBruteForceIndex& operator=(const ShardedBruteForceIndex&) = delete;
+
+    std::future<void> append(const EntityEmbedding<int64_t>& entity) override {
+        return std::async(policy_, [this, entity] {
+            if (static_cast<int>(entity.embedding.size()) != dim_) throw AnnError(ANN_ERR_DIMENSION_MISMATCH, "embedding dimension");
+            check(ann_sharded_append_batch(h_, &entity.id, entity.embedding.data(), 1));
+        });
+    }
+    void appendBatch(const int64_t* ids, const float* rows, int64_t n) { check(ann_sharded_append_batch(h_, ids, rows, n)); }
+    Queryable<int64_t>& toQueryable() override { return *this; }
+    int64_t size() const {
+        int64_t n = 0;
+        check(ann_sharded_size(h_, &n));
+        return n;
+    }
+    void batchQueryWithDistance(const float* queries, int32_t b, int32_t k, int64_t* out_ids, float* out_dist, int32_t* out_count) {
+        check(ann_sharded_query_batch(h_, queries, b, dim_, k, out_ids, out_dist, out_count));
+    }
+    std::future<std::vector<NeighborWithDistance<int64_t>>> queryWithDistance(const std::vector<float>& embedding, int numOfNeighbors,
+                                                                               BruteForceRuntimeParams = {}) override {
+        return std::async(policy_, [this, embedding, numOfNeighbors] {
+            std::vector<NeighborWithDistance<int64_t>> out;
+            if (numOfNeighbors <= 0) return out;
+            std::vector<int64_t> ids(numOfNeighbors);
+            std::vector<float> dist(numOfNeighbors);
+            int32_t cnt = 0;
+            check(ann_sharded_query_batch(h_, embedding.data(), 1, static_cast<int32_t>(embedding.size()), numOfNeighbors, ids.data(),
+                                          dist.data(), &cnt));
+            for (int j = 0; j < cnt; ++j) out.push_back({ids[j], Distance{dist[j]}});
+            return out;
+        });
+    }
+    std::future<std::vector<int64_t>> query(const std::vector<float>& embedding, int numOfNeighbors, BruteForceRuntimeParams = {}) override {
+        return std::async(policy_, [this, embedding, numOfNeighbors] {
+            std::vector<int64_t> out;
+            for (auto& n : queryWithDistance(embedding, numOfNeighbors).get()) out.push_back(n.neighbor);
+            return out;
+        });
+    }
+    // ShardedSerialization.toDirectory (ShardedSerialization.scala:28-38): shard_<i>/BruteForceFileData, thrift stream
+    void toDirectory(const std::string& directory) { check(ann_sharded_save_directory(h_, directory.c_str(), ANN_ID_INT64_BE, ANN_LAYOUT_FLOAT_TENSOR)); }
+    ann_sharded_index* handle() { return h_; }
+
+private:
+    int dim_;
+    std::launch policy_;
+    ann_sharded_index* h_ = nullptr;
+};
+
 }  // namespace ann

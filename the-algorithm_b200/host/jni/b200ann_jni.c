@@ -94,6 +94,83 @@ NATIVE(jint, queryFinishDevice)(JNIEnv *env, jobject self, jlong handle, jlong d
                                    (float *)(intptr_t)d_out_dist, (int32_t *)(intptr_t)d_out_count, (void *)(intptr_t)stream);
 }
 
+/* ---- one process, several GPUs: ShardedAppendable + ComposedQueryable as one native handle (ann_sharded_*) ---- */
+NATIVE(jlong, shardedCreate)(JNIEnv *env, jobject self, jint metric, jint dim, jlong capacity_hint, jint flags, jintArray devices) {
+    (void)self;
+    ann_config cfg = {metric, dim, capacity_hint, 0, (uint32_t)flags};
+    jsize n = (*env)->GetArrayLength(env, devices);
+    jint *d = (*env)->GetIntArrayElements(env, devices, NULL);
+    ann_sharded_index *sx = NULL;
+    int rc = ann_sharded_create(&cfg, (const int32_t *)d, (int32_t)n, &sx);
+    (*env)->ReleaseIntArrayElements(env, devices, d, JNI_ABORT);
+    return rc == ANN_OK ? (jlong)(intptr_t)sx : 0;
+}
+
+NATIVE(void, shardedDestroy)(JNIEnv *env, jobject self, jlong handle) {
+    (void)env; (void)self;
+    ann_sharded_destroy((ann_sharded_index *)(intptr_t)handle);
+}
+
+NATIVE(jint, shardedAppendBatch)(JNIEnv *env, jobject self, jlong handle, jobject ids, jobject rows, jlong n) {
+    (void)self;
+    return ann_sharded_append_batch((ann_sharded_index *)(intptr_t)handle, (const int64_t *)addr(env, ids),
+                                    (const float *)addr(env, rows), n);
+}
+
+NATIVE(jlong, shardedSize)(JNIEnv *env, jobject self, jlong handle) {
+    (void)env; (void)self;
+    int64_t n = 0;
+    return ann_sharded_size((const ann_sharded_index *)(intptr_t)handle, &n) == ANN_OK ? (jlong)n : -1;
+}
+
+NATIVE(jint, shardedQueryBatch)(JNIEnv *env, jobject self, jlong handle, jobject queries, jint b, jint dim, jint k,
+                                jobject out_ids, jobject out_dist, jobject out_count) {
+    (void)self;
+    return ann_sharded_query_batch((ann_sharded_index *)(intptr_t)handle, (const float *)addr(env, queries), b, dim, k,
+                                   (int64_t *)addr(env, out_ids), (float *)addr(env, out_dist), (int32_t *)addr(env, out_count));
+}
+
+/* ---- the reference's on-disk format: BruteForceFileData thrift stream, shard_<i>/ directories (csrc/persist.cu) ---- */
+NATIVE(jint, saveDirectory)(JNIEnv *env, jobject self, jlong handle, jstring dir, jint id_format, jint layout) {
+    (void)self;
+    const char *d = (*env)->GetStringUTFChars(env, dir, NULL);
+    int rc = ann_save_directory((ann_index *)(intptr_t)handle, d, id_format, layout);
+    (*env)->ReleaseStringUTFChars(env, dir, d);
+    return rc;
+}
+
+NATIVE(jlong, loadDirectory)(JNIEnv *env, jobject self, jint metric, jint dim, jint device, jint flags, jstring dir, jint id_format) {
+    (void)self;
+    ann_config cfg = {metric, dim, 0, device, (uint32_t)flags};
+    const char *d = (*env)->GetStringUTFChars(env, dir, NULL);
+    ann_index *ix = NULL;
+    int rc = ann_load_directory(&cfg, d, id_format, &ix);
+    (*env)->ReleaseStringUTFChars(env, dir, d);
+    return rc == ANN_OK ? (jlong)(intptr_t)ix : 0;
+}
+
+NATIVE(jint, shardedSaveDirectory)(JNIEnv *env, jobject self, jlong handle, jstring dir, jint id_format, jint layout) {
+    (void)self;
+    const char *d = (*env)->GetStringUTFChars(env, dir, NULL);
+    int rc = ann_sharded_save_directory((ann_sharded_index *)(intptr_t)handle, d, id_format, layout);
+    (*env)->ReleaseStringUTFChars(env, dir, d);
+    return rc;
+}
+
+NATIVE(jlong, shardedLoadDirectory)(JNIEnv *env, jobject self, jint metric, jint dim, jint flags, jstring dir, jint id_format,
+                                    jintArray devices) {
+    (void)self;
+    ann_config cfg = {metric, dim, 0, 0, (uint32_t)flags};
+    const char *d = (*env)->GetStringUTFChars(env, dir, NULL);
+    jsize n = (*env)->GetArrayLength(env, devices);
+    jint *dv = (*env)->GetIntArrayElements(env, devices, NULL);
+    ann_sharded_index *sx = NULL;
+    int rc = ann_sharded_load_directory(&cfg, d, id_format, (const int32_t *)dv, (int32_t)n, &sx);
+    (*env)->ReleaseIntArrayElements(env, devices, dv, JNI_ABORT);
+    (*env)->ReleaseStringUTFChars(env, dir, d);
+    return rc == ANN_OK ? (jlong)(intptr_t)sx : 0;
+}
+
 NATIVE(jstring, lastError)(JNIEnv *env, jobject self) {
     (void)self;
     return (*env)->NewStringUTF(env, ann_last_error());

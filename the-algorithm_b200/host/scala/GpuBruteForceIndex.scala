@@ -43,6 +43,19 @@ object B200AnnNative {
   @native def querySeedDevice(handle: Long, dQueries: Long, b: Int, dim: Int, k: Int, dSeedKeys: Long, stream: Long): Int
   @native def queryFinishDevice(handle: Long, dQueries: Long, b: Int, dim: Int, k: Int, peerSeedKeys: ByteBuffer, world: Int,
     dOutIds: Long, dOutDist: Long, dOutCount: Long, stream: Long): Int
+  // one process, several GPUs: ShardedAppendable + ComposedQueryable as ONE native handle (ann_sharded_*; ShardApi.scala:34-87)
+  @native def shardedCreate(metric: Int, dim: Int, capacityHint: Long, flags: Int, devices: Array[Int]): Long
+  @native def shardedDestroy(handle: Long): Unit
+  @native def shardedAppendBatch(handle: Long, ids: ByteBuffer, rows: ByteBuffer, n: Long): Int
+  @native def shardedSize(handle: Long): Long
+  @native def shardedQueryBatch(handle: Long, queries: ByteBuffer, b: Int, dim: Int, k: Int,
+    outIds: ByteBuffer, outDist: ByteBuffer, outCount: ByteBuffer): Int
+  // the reference's own on-disk format, read and written natively (BruteForceIndex.scala:142-161; ThriftIteratorIO.scala:14-56;
+  // ShardedSerialization.scala:28-66): ann_save_directory / ann_load_directory and the sharded variants
+  @native def saveDirectory(handle: Long, directory: String, idFormat: Int, layout: Int): Int
+  @native def loadDirectory(metric: Int, dim: Int, device: Int, flags: Int, directory: String, idFormat: Int): Long
+  @native def shardedSaveDirectory(handle: Long, directory: String, idFormat: Int, layout: Int): Int
+  @native def shardedLoadDirectory(metric: Int, dim: Int, flags: Int, directory: String, idFormat: Int, devices: Array[Int]): Long
   @native def lastError(): String
 }
 
