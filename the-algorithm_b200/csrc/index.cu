@@ -153,6 +153,9 @@ struct ann_index {
         unsigned char* pin_res = nullptr;
         size_t cap_q = 0, cap_res = 0;
         long long batches = 0, merged_calls = 0;
+        std::atomic<int> n_pending{0};                              // pending.size(), readable without the lock
+        int last_batch_calls = 0;                                   // host calls in the merged batch that finished last
+        std::chrono::steady_clock::time_point last_done{};          // ... and when it finished
     } co;
 
     // scratch
@@ -1393,6 +1396,7 @@ int query_coalesced(ann_index* ix, const float* queries, int32_t b, int32_t k, i
     {
         std::unique_lock<std::mutex> lk(co.mu);
         co.pending.push_back(&me);
+        co.n_pending.store((int)co.pending.size(), std::memory_order_release);
         if (co.leader_active) {
             me.cv.wait(lk, [&] { return me.done || me.promoted; });
             if (me.done) {
@@ -1401,11 +1405,20 @@ int query_coalesced(ann_index* ix, const float* queries, int32_t b, int32_t k, i
             }
         }
         co.leader_active = true;
-        if (me.promoted && co.linger_us > 0 && (int)co.pending.size() < co.max_batch) {
-            // The batch that just finished released its callers a moment ago; without a short linger they arrive just after
-            // this batch is cut and two half-sized groups ping-pong forever (measured: 32 + 32 instead of 64 per device batch).
-            const auto until = std::chrono::steady_clock::now() + std::chrono::microseconds(co.linger_us);
-            while (std::chrono::steady_clock::now() < until) me.cv.wait_until(lk, until);
+        // The batch that just finished released its callers a moment ago (closed-loop clients re-issue within microseconds).
+        // Cutting the next batch at once would leave them behind and two half-sized groups would ping-pong forever (measured:
+        // 32 + 32 instead of 64 calls per device batch), so whoever leads right after a multi-call batch waits until that many
+        // calls are waiting again -- at most linger_us.  A lone caller never waits.
+        if (co.linger_us > 0 && co.last_batch_calls > 1) {
+            const auto now = std::chrono::steady_clock::now();
+            const auto until = std::max(now, co.last_done) + std::chrono::microseconds(co.linger_us);
+            if (now - co.last_done < std::chrono::microseconds(4 * co.linger_us)) {
+                const int want = std::min(co.last_batch_calls, co.max_batch);
+                lk.unlock();   // spin (timed waits have ~50 us of timer slack, longer than the whole linger); arrivals need the lock
+                while (co.n_pending.load(std::memory_order_acquire) < want && std::chrono::steady_clock::now() < until) {
+                }
+                lk.lock();
+            }
         }
         // my batch: me, then every waiting call with my k in arrival order while the merged batch stays within max_batch
         co.pending.erase(std::find(co.pending.begin(), co.pending.end(), &me));
@@ -1420,6 +1433,7 @@ int query_coalesced(ann_index* ix, const float* queries, int32_t b, int32_t k, i
                 ++it;
             }
         }
+        co.n_pending.store((int)co.pending.size(), std::memory_order_release);
     }
     int total = 0;
     for (auto* r : batch) total += r->b;
@@ -1474,6 +1488,8 @@ int query_coalesced(ann_index* ix, const float* queries, int32_t b, int32_t k, i
         std::lock_guard<std::mutex> lk(co.mu);
         co.batches++;
         co.merged_calls += (long long)batch.size();
+        co.last_batch_calls = (int)batch.size();
+        co.last_done = std::chrono::steady_clock::now();
         for (auto* r : batch) {
             if (r == &me) continue;
             r->rc = rc;

@@ -32,6 +32,19 @@ __device__ __forceinline__ float widen_half_up(float g, float eps_abs, float eps
     return __fadd_ru(g, __fadd_ru(eps_abs, __fmul_ru(eps_rel, fabsf(g))));
 }
 
+// Slot allocation for a warp: the lanes with `take` get consecutive slots from ONE atomic on `counter` (all 32 lanes must
+// call it).  The plain one-atomic-per-thread form serialises a few hundred shared-memory atomics on a single address per CTA.
+__device__ __forceinline__ int warp_slot(bool take, int* counter) {
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, take);
+    if (m == 0) return 0;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, leader);
+    return base + __popc(m & ((1u << lane) - 1u));
+}
+
 __device__ void bitonic_sort_pairs(uint32_t* key, long long* id, int n2) {
     for (int k = 2; k <= n2; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
@@ -87,9 +100,14 @@ __device__ uint32_t kth_key_radix(const entry_t* buf, int n, int k, uint32_t* hi
         for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
         __syncthreads();
         const uint32_t prefix = prefix_s;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const uint32_t key = (uint32_t)(buf[i] >> 32);
-            if (pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+        for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+            // the keys of one query share their leading bytes, so most lanes of a warp hit the SAME bin: aggregate per bin
+            const int i = i0 + threadIdx.x;
+            const uint32_t key = i < n ? (uint32_t)(buf[i] >> 32) : 0u;
+            const bool on = i < n && (pass == 0 || (key >> (shift + 8)) == (prefix >> (shift + 8)));
+            const uint32_t bin = on ? ((key >> shift) & 255u) : 256u;
+            const unsigned peers = __match_any_sync(0xFFFFFFFFu, bin);
+            if (on && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], (uint32_t)__popc(peers));
         }
         __syncthreads();
         if (threadIdx.x < 32) {
@@ -161,13 +179,17 @@ __device__ bool load_and_threshold(const SelectParams& p, int q, entry_t* buf, u
     if (threadIdx.x == 0) n_s = 0;
     __syncthreads();
     const entry_t* pool = p.pool + (size_t)q * p.pool_cap;
-    for (int i = threadIdx.x; i < pool_n; i += blockDim.x) {
-        entry_t e = pool[i];
-        const float ge = entry_g(e);
-        if (ge <= tau && ge < kSpecialG) {   // special rows scored -1e38 by the tensor-core filter are handled separately
-            int slot = atomicAdd(&n_s, 1);
-            if (slot < sort_cap) buf[slot] = e;
+    for (int i0 = 0; i0 < pool_n; i0 += blockDim.x) {     // whole warps iterate together: one shared-memory atomic per warp
+        const int i = i0 + threadIdx.x;
+        entry_t e = 0;
+        bool keep = false;
+        if (i < pool_n) {
+            e = pool[i];
+            const float ge = entry_g(e);
+            keep = ge <= tau && ge < kSpecialG;   // special rows scored -1e38 by the tensor-core filter are handled separately
         }
+        const int slot = warp_slot(keep, &n_s);
+        if (keep && slot < sort_cap) buf[slot] = e;
     }
     __syncthreads();
     const int n = n_s;
@@ -245,9 +267,12 @@ __global__ void __launch_bounds__(kSelThreads, 4) compact_pool_kernel(SelectPara
     if (threadIdx.x == 0) n_keep = 0;
     __syncthreads();
     entry_t* pool = p.pool + (size_t)q * p.pool_cap;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const entry_t e = buf[i];
-        if (entry_g(e) <= tau) pool[atomicAdd(&n_keep, 1)] = e;
+    for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        const entry_t e = i < n ? buf[i] : 0;
+        const bool keep = i < n && entry_g(e) <= tau;
+        const int slot = warp_slot(keep, &n_keep);
+        if (keep) pool[slot] = e;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -325,17 +350,20 @@ __global__ void __launch_bounds__(kSelThreads, 4) finalize_kernel(SelectParams p
     if (threadIdx.x == 0) n_cand_s = 0;
     __syncthreads();
     uint32_t* crow = ckey;   // row indices first, replaced by the distance keys
-    for (int i = threadIdx.x; i < n + n_spec; i += blockDim.x) {
-        uint32_t row;
+    for (int i0 = 0; i0 < n + n_spec; i0 += blockDim.x) {
+        const int i = i0 + threadIdx.x;
+        uint32_t row = 0;
+        bool keep = false;
         if (i < n) {
             const entry_t e = buf[i];
-            if (!(entry_g(e) <= tau)) continue;
+            keep = entry_g(e) <= tau;
             row = entry_row(e);
-        } else {
+        } else if (i < n + n_spec) {
+            keep = true;
             row = spec_rows[i - n];
         }
-        const int slot = atomicAdd(&n_cand_s, 1);
-        if (slot < exact_cap) crow[slot] = row;
+        const int slot = warp_slot(keep, &n_cand_s);
+        if (keep && slot < exact_cap) crow[slot] = row;
     }
     __syncthreads();
     const int n_cand = n_cand_s;
@@ -605,15 +633,17 @@ __global__ void __launch_bounds__(kSelThreads) exchange_merge_kernel(PeerBlocks 
 // k-th best is <= U -- and tighten this shard's threshold to U + eps (this shard's own error margin for its candidates).
 __global__ void __launch_bounds__(kSelThreads) seed_merge_kernel(PeerSeedKeys pk, int world, QueryState* qstate, int k) {
     extern __shared__ __align__(16) unsigned char sm[];
-    uint32_t* keys = reinterpret_cast<uint32_t*>(sm);   // [world][k]
+    entry_t* keys = reinterpret_cast<entry_t*>(sm);   // [world][k] keys in the entries' high words (the radix select's layout)
+    __shared__ uint32_t hist[256];
     const int q = blockIdx.x;
     const int total = world * k;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
         const int s = i / k, j = i - s * k;
-        keys[i] = __ldcg(pk.keys[s] + (size_t)q * k + j);
+        keys[i] = (entry_t)__ldcg(pk.keys[s] + (size_t)q * k + j) << 32;
     }
     __syncthreads();
-    const uint32_t u = cta_kth_smallest_key(keys, total, k, nullptr);   // pads are 0xFFFFFFFF: fewer than k bounds => no bound
+    // 4 histogram passes instead of a 32-step bisection (84 us -> ~25 us per 4096-query launch, profiles/r02_breakdown.json)
+    const uint32_t u = kth_key_radix(keys, total, k, hist);   // pads are 0xFFFFFFFF: fewer than k bounds => no bound
     if (threadIdx.x == 0 && u < 0xFF800000u) {
         QueryState* qs = qstate + q;
         const float tau_g = widen_half_up(float_from_order_key(u), qs->eps_abs, qs->eps_rel);
@@ -624,7 +654,7 @@ __global__ void __launch_bounds__(kSelThreads) seed_merge_kernel(PeerSeedKeys pk
 
 cudaError_t launch_seed_merge(const PeerSeedKeys& pk, int world, QueryState* qstate, int b, int k, cudaStream_t stream) {
     if (b <= 0 || k <= 0 || world <= 0) return cudaSuccess;
-    const size_t smem = (size_t)world * k * 4;
+    const size_t smem = (size_t)world * k * 8;
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(seed_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
