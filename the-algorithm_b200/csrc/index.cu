@@ -440,6 +440,7 @@ int query_scan(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
         fp.k = k_eff;
         fp.rows = ix->rows;
         fp.ids = ix->ids;
+        fp.row_norm = ix->row_norm;
         fp.n_rows = ix->n;
         fp.dim = ix->dim;
         fp.pitch = ix->pitch;
@@ -519,6 +520,7 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
     fp.k = k_eff;
     fp.rows = ix->rows;
     fp.ids = ix->ids;
+    fp.row_norm = ix->row_norm;
     fp.n_rows = ix->n;
     fp.dim = ix->dim;
     fp.pitch = ix->pitch;

@@ -94,6 +94,7 @@ struct SelectParams {
     // exact rescoring inputs
     const float* rows;
     const int64_t* ids;
+    const float* row_norm;  // [n_rows] |a| rounded up (K1): bounds the summation error of the lane-parallel rescoring
     long long n_rows;
     int dim, pitch, metric, l2_squared;
     int accum_f32;          // ANN_FLAG_ACCUM_F32: exact distances accumulate sequentially in fp32 (oracle accum=1)

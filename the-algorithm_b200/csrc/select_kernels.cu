@@ -405,39 +405,145 @@ __global__ void __launch_bounds__(kSelThreads, 4) finalize_kernel(SelectParams p
         __syncthreads();
         const ExactQuery eq{q64, ACC32 ? 0.0 : nb_s};
         const float nbf = ACC32 ? nbf_s : 0.f;
-        // one thread per candidate row, all candidates in parallel; several CTAs per SM overlap each other's
-        // dependent-miss chains (the kernel is latency bound, so occupancy -- not per-thread ILP -- is what pays)
-        for (int c = threadIdx.x; c < n_cand; c += blockDim.x) {
-            const uint32_t row = crow[c];
-            const float* rp = p.rows + (size_t)row * p.pitch;
-            const float dist = ACC32 ? exact_distance_rows_f32<true, METRIC>(METRIC, rp, q32, nbf, p.dim, p.l2_squared)
-                                     : exact_distance_rows<true, METRIC>(METRIC, rp, eq, p.dim, p.l2_squared);
-            cid[c] = p.ids[row];
-            okey[c] = float_order_key(dist);
+        if (ACC32) {
+            // fp32 convention: the value IS a sequentially rounded fp32 chain, nothing shorter can stand in for it
+            for (int c = threadIdx.x; c < n_cand; c += blockDim.x) {
+                const uint32_t row = crow[c];
+                const float* rp = p.rows + (size_t)row * p.pitch;
+                cid[c] = p.ids[row];
+                okey[c] = float_order_key(exact_distance_rows_f32<true, METRIC>(METRIC, rp, q32, nbf, p.dim, p.l2_squared));
+            }
+        } else {
+            // fp64 convention, 8 lanes per candidate.  The oracle's value is f = fl32(S_seq) with S_seq the sequentially
+            // rounded fp64 sum -- a 200-long dependent chain per row.  ANY summation order gives a sum within
+            // gamma_(d-1) * sum|t_i| of the real sum (the terms t_i themselves are computed identically: products of floats
+            // are exact in fp64, (a-b)^2 is rounded the same way elementwise), so a lane-parallel sum S_par pins S_seq into
+            // [S_par - E, S_par + E], E = 2 d 2^-53 sum|t_i|.  fl32 (and sqrt, and the quotient of Cosine) are monotone, so
+            // when both ends of the interval round to the SAME float, that float is fl32(S_seq) -- bit for bit, with a
+            // 25-long chain and coalesced 128-byte row reads.  Otherwise (about 1 candidate in 10^5) the candidate is
+            // rescored by the sequential chain below.  Exactness is never a matter of probability.
+            uint32_t* redo = okey + exact_cap;            // candidates whose interval straddles a rounding boundary
+            __shared__ int n_redo_s;
+            if (threadIdx.x == 0) n_redo_s = 0;
+            for (int i = p.dim + threadIdx.x; i < p.pitch; i += blockDim.x) q64[i] = 0.0;   // pad columns (rows hold zeros there)
+            __syncthreads();
+            const int sub = threadIdx.x & 7, n4 = p.pitch >> 2;
+            const double du = 2.1 * (double)(p.dim + 4) * 1.1102230246251565e-16;             // 2.1 * (d + 4) * 2^-53
+            const double qn = (double)qs->qnorm;                                               // |b| rounded up
+            for (int c0 = 0; c0 < n_cand; c0 += blockDim.x >> 3) {
+                const int c = c0 + (threadIdx.x >> 3);
+                const bool live = c < n_cand;
+                const uint32_t row = live ? crow[c] : 0u;
+                const float4* a4 = reinterpret_cast<const float4*>(p.rows + (size_t)row * p.pitch);
+                double sx = 0.0, sy = 0.0, sz = 0.0, sw = 0.0, ax = 0.0, ay = 0.0;
+                if (live) {
+                    for (int j = sub; j < n4; j += 8) {
+                        const float4 v = __ldg(a4 + j);
+                        const double* bq = q64 + (j << 2);
+                        if (METRIC == kMetricL2) {
+                            const double d0 = __dsub_rn((double)v.x, bq[0]), d1 = __dsub_rn((double)v.y, bq[1]);
+                            const double d2 = __dsub_rn((double)v.z, bq[2]), d3 = __dsub_rn((double)v.w, bq[3]);
+                            sx = __dadd_rn(sx, __dmul_rn(d0, d0));
+                            sy = __dadd_rn(sy, __dmul_rn(d1, d1));
+                            sz = __dadd_rn(sz, __dmul_rn(d2, d2));
+                            sw = __dadd_rn(sw, __dmul_rn(d3, d3));
+                        } else {
+                            sx = __fma_rn((double)v.x, bq[0], sx);
+                            sy = __fma_rn((double)v.y, bq[1], sy);
+                            sz = __fma_rn((double)v.z, bq[2], sz);
+                            sw = __fma_rn((double)v.w, bq[3], sw);
+                            if (METRIC == kMetricCosine) {
+                                ax = __fma_rn((double)v.x, (double)v.x, ax);
+                                ay = __fma_rn((double)v.y, (double)v.y, ay);
+                                ax = __fma_rn((double)v.z, (double)v.z, ax);
+                                ay = __fma_rn((double)v.w, (double)v.w, ay);
+                            }
+                        }
+                    }
+                }
+                double S = (sx + sy) + (sz + sw), A = ax + ay;
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+                    S += __shfl_xor_sync(0xFFFFFFFFu, S, o);
+                    if (METRIC == kMetricCosine) A += __shfl_xor_sync(0xFFFFFFFFu, A, o);
+                }
+                if (live && sub == 0) {
+                    const double an = (double)p.row_norm[row];                                  // |a| rounded up
+                    float f_lo, f_hi;
+                    if (METRIC == kMetricL2) {
+                        const double E = du * S;
+                        const double lo = fmax(__dsub_rd(S, E), 0.0), hi = __dadd_ru(S, E);
+                        f_lo = __double2float_rn(p.l2_squared ? lo : __dsqrt_rn(lo));
+                        f_hi = __double2float_rn(p.l2_squared ? hi : __dsqrt_rn(hi));
+                    } else if (METRIC == kMetricIP) {
+                        const double E = du * an * qn;
+                        f_lo = __double2float_rn(__dsub_rd(S, E));
+                        f_hi = __double2float_rn(__dadd_ru(S, E));
+                    } else {
+                        const double E = du * an * qn, Ea = du * an * an;
+                        const double d_lo = __dsub_rd(S, E), d_hi = __dadd_ru(S, E);
+                        const double a_lo = fmax(__dsub_rd(A, Ea), 0.0), a_hi = __dadd_ru(A, Ea);
+                        const double sqb = __dsqrt_rn(nb_s);
+                        const double den_lo = __dmul_rn(__dsqrt_rn(a_lo), sqb), den_hi = __dmul_rn(__dsqrt_rn(a_hi), sqb);
+                        // the quotient is monotone in each argument: its extremes over the box are at the four corners
+                        const float c0f = __double2float_rn(__ddiv_rn(d_lo, den_lo)), c1f = __double2float_rn(__ddiv_rn(d_lo, den_hi));
+                        const float c2f = __double2float_rn(__ddiv_rn(d_hi, den_lo)), c3f = __double2float_rn(__ddiv_rn(d_hi, den_hi));
+                        f_lo = fminf(fminf(c0f, c1f), fminf(c2f, c3f));
+                        f_hi = fmaxf(fmaxf(c0f, c1f), fmaxf(c2f, c3f));
+                        if (!(c0f == c0f && c1f == c1f && c2f == c2f && c3f == c3f)) f_lo = NAN;   // fminf / fmaxf drop NaN
+                    }
+                    // certain only if both ends are the same finite float (NaN, +-inf and overflowing bounds go sequential)
+                    if (f_lo == f_hi && fabsf(f_lo) <= 3.4028234e38f && (METRIC != kMetricL2 || S == S)) {
+                        const float dist = METRIC == kMetricL2 ? f_lo : __fsub_rn(1.0f, f_lo);
+                        okey[c] = float_order_key(dist);
+                    } else {
+                        redo[atomicAdd(&n_redo_s, 1)] = (uint32_t)c;
+                    }
+                    cid[c] = p.ids[row];
+                }
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < n_redo_s; i += blockDim.x) {
+                const int c = (int)redo[i];
+                const float* rp = p.rows + (size_t)crow[c] * p.pitch;
+                okey[c] = float_order_key(exact_distance_rows<true, METRIC>(METRIC, rp, eq, p.dim, p.l2_squared));
+            }
         }
         __syncthreads();
         if (n_cand <= kRankSortMax) {
             // Few candidates (the normal case: ~2k): order them by rank counting instead of a bitonic network -- the output
-            // position of a candidate is the number of candidates that precede it under (distance key, id, slot), one pass
-            // of broadcast shared-memory reads and no barriers, against 36 barrier-separated stages for 256 elements.
+            // position of a candidate is the number of candidates that precede it under (distance key, id, slot).  Eight lanes
+            // share one candidate (each counts every 8th rival, three shuffles add up): broadcast shared-memory reads, no barriers.
             const int cnt = min(p.k, n_cand);
-            for (int c = threadIdx.x; c < n_cand; c += blockDim.x) {
-                const uint32_t key = okey[c];
-                const long long id = cid[c];
+            const int sub = threadIdx.x & 7;
+            for (int c0 = 0; c0 < n_cand; c0 += blockDim.x >> 3) {
+                const int c = c0 + (threadIdx.x >> 3);
+                const bool live = c < n_cand;
+                const uint32_t key = live ? okey[c] : 0u;
+                const long long id = live ? cid[c] : 0;
                 int rank = 0, equal = 0;
-                for (int j = 0; j < n_cand; ++j) {       // keys only: two predicated adds per broadcast load
-                    const uint32_t kj = okey[j];
-                    rank += kj < key ? 1 : 0;
-                    equal += kj == key ? 1 : 0;
+                if (live)
+                    for (int j = sub; j < n_cand; j += 8) {
+                        const uint32_t kj = okey[j];
+                        rank += kj < key ? 1 : 0;
+                        equal += kj == key ? 1 : 0;
+                    }
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+                    rank += __shfl_xor_sync(0xFFFFFFFFu, rank, o);
+                    equal += __shfl_xor_sync(0xFFFFFFFFu, equal, o);
                 }
-                if (equal > 1) {                         // exact distance ties (itself included): order those by (id, slot)
-                    for (int j = 0; j < n_cand; ++j) {
+                int tie = 0;
+                if (live && equal > 1)                      // exact distance ties (itself included): order those by (id, slot)
+                    for (int j = sub; j < n_cand; j += 8) {
                         if (okey[j] != key) continue;
                         const long long ij = cid[j];
-                        rank += (ij < id || (ij == id && j < c)) ? 1 : 0;
+                        tie += (ij < id || (ij == id && j < c)) ? 1 : 0;
                     }
-                }
-                if (rank < cnt) {
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) tie += __shfl_xor_sync(0xFFFFFFFFu, tie, o);
+                rank += tie;
+                if (live && sub == 0 && rank < cnt) {
                     oid[rank] = id;
                     od[rank] = float_from_order_key(key);
                 }
@@ -672,7 +778,7 @@ cudaError_t launch_compact_pool(const SelectParams& p, int b, cudaStream_t strea
 
 cudaError_t launch_finalize(const SelectParams& p, int b, cudaStream_t stream) {
     size_t smem = (size_t)sort_cap_of(p) * 8 + (size_t)exact_cap_of(p) * 12;
-    if ((size_t)sort_cap_of(p) * 8 < 8192 + (size_t)exact_cap_of(p) * 4) return cudaErrorInvalidValue;
+    if ((size_t)sort_cap_of(p) * 8 < 8192 + (size_t)exact_cap_of(p) * 8) return cudaErrorInvalidValue;   // q64 | keys | redo list
     if (p.peer_world < 0 || p.peer_world > kMaxPeers || (long long)p.peer_world * p.k > sort_cap_of(p)) return cudaErrorInvalidValue;
     void (*fn)(SelectParams);
     if (p.accum_f32)
