@@ -65,6 +65,9 @@ def parse():
     ap.add_argument("--lat-queries", type=int, default=400, help="sequential single queries in each latency run of the extra block")
     ap.add_argument("--config4-rows", type=int, default=100_000_000,
                     help="total rows of the configs[3] sub-run (Cosine, batch 1024), sharded over the ranks; 0 = skip")
+    ap.add_argument("--config5-rows", type=int, default=50_000_000,
+                    help="rows pre-loaded in the configs[4] streaming sub-run (sharded over the ranks); 0 = skip")
+    ap.add_argument("--config5-appends", type=int, default=1_000_000)
     ap.add_argument("--one-round", action="store_true",
                     help="N > 1: seed round only (A/B of the second cross-shard round that shares the k best bounds)")
     ap.add_argument("--no-share-seeds", action="store_true",
@@ -563,6 +566,78 @@ def run_ours(a):
             ix4.close()
         except Exception as e:
             extra["config4"] = {"error": repr(e)}
+
+    if not a.no_extra and a.config5_rows > 0:
+        try:   # configs[4]: streaming Appendable -- 1M rows appended in host batches, a 256-query batch after every append batch
+            if not ix_closed:
+                ix.close()
+                ix_closed = True
+            torch.cuda.empty_cache()
+            n5, ab5, qb5, total5 = a.config5_rows, 4096, 256, a.config5_appends
+            lo5, hi5 = shard_range(n5, world, rank)
+            # capacity_hint = 0: the storage grows in place while the rows arrive (virtual ranges + mapped chunks, no copies)
+            ix5 = BruteForceIndex(Metric.from_string("Cosine"), FuturePool.immediate_pool(), device=local_rank, capacity_hint=0)
+            g.manual_seed(0x5EED0007)
+            for c0 in range(0, n5, 1_000_000):
+                m = min(1_000_000, n5 - c0)
+                rows = torch.randn((m, d), generator=g, device=dev) / d ** 0.5
+                s_, e_ = max(c0, lo5), min(c0 + m, hi5)
+                if s_ < e_:
+                    ix5.append_batch_device(torch.arange(s_, e_, device=dev, dtype=torch.int64), rows[s_ - c0:e_ - c0].contiguous())
+                del rows
+            sx5 = ShardedBruteForceIndex(ix5, device=dev, share_seeds=not a.no_share_seeds, two_round=not a.one_round) if world > 1 else None
+            rng5 = np.random.default_rng(0x5EED0008)            # the appended rows: same stream on every rank
+            q5_pin = torch.empty((qb5, d), dtype=torch.float32).pin_memory()
+            o5 = (torch.empty((qb5, k), dtype=torch.int64, device=dev), torch.empty((qb5, k), dtype=torch.float32, device=dev),
+                  torch.empty((qb5,), dtype=torch.int32, device=dev))
+            s0_, s1_ = (0, qb5) if world == 1 else sx5.slice_range(qb5)
+            t_app = t_qry = 0.0
+            appended = queried = 0
+            visible = True
+            n_b5 = (total5 + ab5 - 1) // ab5
+            for i in range(n_b5 + 2):                               # two warm-up rounds, not timed
+                timed_ = i >= 2
+                m = min(ab5, total5 - appended) if timed_ else ab5
+                if m <= 0:
+                    break
+                new_rows = (rng5.standard_normal((m, d)) / np.sqrt(d)).astype(np.float32)
+                base = n5 + 10 * total5 + i * ab5 if not timed_ else n5 + appended
+                new_ids = np.arange(base, base + m, dtype=np.int64)
+                barrier()
+                t0 = time.perf_counter()
+                if world == 1:
+                    ix5.append_batch(new_ids, new_rows)             # host rows in: H2D + K1 inside the call
+                else:
+                    sx5.append_routed(new_ids, new_rows)            # round-robin by batch (ShardApi.scala:21-48)
+                torch.cuda.synchronize()
+                t1 = time.perf_counter()
+                q5_pin.copy_(torch.from_numpy(new_rows[:qb5]))      # the queries ARE rows just appended: visibility check
+                qd5 = q5_pin.to(dev, non_blocking=True)
+                if world == 1:
+                    ix5.query_batch_device(qd5, k, o5[0], o5[1], o5[2], stream.cuda_stream)
+                    top1 = o5[0][:, 0].cpu()
+                else:
+                    top1 = sx5.batch_query_device(qd5, k, stream.cuda_stream, deliver="slice")[0][:, 0].cpu()
+                t2 = time.perf_counter()
+                visible &= bool((top1.numpy() == new_ids[s0_:s1_]).all())
+                if timed_:
+                    t_app += t1 - t0
+                    t_qry += t2 - t1
+                    appended += m
+                    queried += qb5
+            ix5.raise_pending_error()
+            t_app, t_qry = max_over_ranks(t_app), max_over_ranks(t_qry)
+            visible = max_over_ranks(0.0 if visible else 1.0) == 0.0
+            extra["config5"] = {"workload": f"configs[4]: {n5}x{d} Cosine pre-loaded over {world} rank(s) into indexes created with capacity_hint = 0, "
+                                            f"{appended} rows appended in host batches of {ab5}, a {qb5}-query batch after every append batch, top-{k}",
+                                "n_gpus": world, "append_rows_per_s": appended / t_app, "queries_per_s": queried / t_qry,
+                                "ms_per_query_batch": 1e3 * t_qry / max(1, queried // qb5), "ms_per_append_batch": 1e3 * t_app / max(1, n_b5),
+                                "appended_rows_visible_to_next_query": visible, "mapped_bytes_rank0": ix5.stat("mapped_bytes"),
+                                "algorithmic_bytes_rank0": ix5.stat("row_bytes") + ix5.stat("shadow_bytes"),
+                                "timing": "host clock around each call incl. H2D of the appended rows / D2H of the answers, max over ranks"}
+            ix5.close()
+        except Exception as e:
+            extra["config5"] = {"error": repr(e)}
 
     # ---- CPU baseline on the host cores (rank 0, N = 1 only; bounded sample) + parity of the sample ----
     cpu, parity = None, None
