@@ -167,6 +167,86 @@ def test_two_rank_shared_seed_thresholds_equal_single_shard(metric):
     assert ret.get(timeout=5) == 1
 
 
+class _FlaggingShard(_OracleShard):
+    """A shard whose bounded selector gives up on query 1 (count = -1: the row is invalid) unless its exact fallback is on
+    -- what the CUDA engine does for thousands of ties or a NaN query."""
+
+    def __init__(self, metric):
+        super().__init__(metric)
+        self.fallback = 0
+
+    def set_option(self, name, value):
+        assert name == "device_fallback"
+        self.fallback = int(value)
+
+    def query_batch_device(self, queries, k, out_ids, out_dist, out_count, stream=0):
+        super().query_batch_device(queries, k, out_ids, out_dist, out_count, stream)
+        if not self.fallback:
+            out_ids[1].fill_(-1)
+            out_dist[1].fill_(float("inf"))
+            out_count[1] = -1
+
+
+def _merge_with_flags(g_ids, g_dist, g_cnt, k, stream=0):
+    """merge_topk_device's contract: a query some shard flagged (count < 0) is delivered as count = -1."""
+    oi, od, oc = _oracle_merge(g_ids, g_dist, torch.clamp(g_cnt, min=0), k)
+    bad = (g_cnt < 0).any(dim=0)
+    oi[bad], od[bad], oc[bad] = -1, float("inf"), -1
+    return oi, od, oc
+
+
+def _worker_slices_and_flags(rank, world, port, metric, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import _pkg
+        _pkg.load()
+        from the_algorithm_b200.ann.distributed import ShardedBruteForceIndex, shard_range
+
+        n, d, b, k = 700, 12, 7, 9
+        rng = np.random.default_rng(3)
+        corpus = (rng.standard_normal((n, d)) / np.sqrt(d)).astype(np.float32)
+        ids = rng.permutation(n).astype(np.int64)
+        q = rng.uniform(-1, 1, (b, d)).astype(np.float32)
+        wi, wd, wc = oracle.query_canonical(metric, corpus, ids, q, k)
+        lo, hi = shard_range(n, world, rank)
+        # slice delivery: this rank receives exactly its rows of the merged batch
+        sx = ShardedBruteForceIndex(_OracleShard(metric), merge=_oracle_merge)
+        sx.append_shard(ids[lo:hi], corpus[lo:hi])
+        q0, q1 = sx.slice_range(b)
+        si, sd, sc = sx.batch_query_device(torch.from_numpy(q), k, deliver="slice")
+        ok = bool(si.shape[0] == q1 - q0 and (si.numpy() == wi[q0:q1]).all() and (sc.numpy() == wc[q0:q1]).all())
+        # flagged rows: the asynchronous form reports them (count = -1 on every rank), the synchronous form answers exactly
+        fx = ShardedBruteForceIndex(_FlaggingShard(metric), merge=_merge_with_flags)
+        fx.append_shard(ids[lo:hi], corpus[lo:hi])
+        ai, ad, ac = fx.batch_query_device(torch.from_numpy(q), k)
+        ok &= bool(ac[1].item() == -1 and (ai[1] == -1).all() and (np.delete(ai.numpy(), 1, 0) == np.delete(wi, 1, 0)).all())
+        bi, bd, bc = fx.batch_query(torch.from_numpy(q), k)
+        ok &= bool((bi.numpy() == wi).all() and (bd.numpy().view(np.uint32) == wd.view(np.uint32)).all() and (bc.numpy() == wc).all())
+        ok &= fx.local.fallback == 0                          # the option is switched back off afterwards
+        t = torch.tensor([1 if ok else 0])
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if rank == 0:
+            ret.put(int(t.item()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_slice_delivery_and_flagged_rows():
+    """deliver="slice" hands each rank its part of the merged batch; a query some shard cannot answer with its bounded
+    selector travels through the merge as count = -1 and `batch_query` re-answers the batch with the exact fallback."""
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_slices_and_flags, args=(r, 2, port, oracle.COSINE, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert ret.get(timeout=5) == 1
+
+
 def test_shard_ranges_cover_everything():
     import _pkg
     _pkg.load()
