@@ -68,6 +68,7 @@ def parse():
     ap.add_argument("--config5-rows", type=int, default=50_000_000,
                     help="rows pre-loaded in the configs[4] streaming sub-run (sharded over the ranks); 0 = skip")
     ap.add_argument("--config5-appends", type=int, default=1_000_000)
+    ap.add_argument("--pull-bounds", action="store_true", help="N > 1: consumers pull the peers' bound arrays (A/B of push delivery)")
     ap.add_argument("--one-round", action="store_true",
                     help="N > 1: seed round only (A/B of the second cross-shard round that shares the k best bounds)")
     ap.add_argument("--no-share-seeds", action="store_true",
@@ -357,7 +358,7 @@ def run_ours(a):
     out_ids = torch.empty((b, k), dtype=torch.int64, device=dev)
     out_dist = torch.empty((b, k), dtype=torch.float32, device=dev)
     out_cnt = torch.empty((b,), dtype=torch.int32, device=dev)
-    sx = ShardedBruteForceIndex(ix, device=dev, share_seeds=not a.no_share_seeds, two_round=not a.one_round) if world > 1 else None
+    sx = ShardedBruteForceIndex(ix, device=dev, share_seeds=not a.no_share_seeds, two_round=not a.one_round, push=not a.pull_bounds) if world > 1 else None
 
     def step_device(queries):
         if world == 1:
@@ -540,7 +541,7 @@ def run_ours(a):
             q4 = (torch.rand((b4, d), generator=g, device=dev) * 2 - 1).contiguous()
             o4 = (torch.empty((b4, k), dtype=torch.int64, device=dev), torch.empty((b4, k), dtype=torch.float32, device=dev),
                   torch.empty((b4,), dtype=torch.int32, device=dev))
-            sx4 = ShardedBruteForceIndex(ix4, device=dev, share_seeds=not a.no_share_seeds, two_round=not a.one_round) if world > 1 else None
+            sx4 = ShardedBruteForceIndex(ix4, device=dev, share_seeds=not a.no_share_seeds, two_round=not a.one_round, push=not a.pull_bounds) if world > 1 else None
 
             def step4():
                 if world == 1:
@@ -585,7 +586,7 @@ def run_ours(a):
                 if s_ < e_:
                     ix5.append_batch_device(torch.arange(s_, e_, device=dev, dtype=torch.int64), rows[s_ - c0:e_ - c0].contiguous())
                 del rows
-            sx5 = ShardedBruteForceIndex(ix5, device=dev, share_seeds=not a.no_share_seeds, two_round=not a.one_round) if world > 1 else None
+            sx5 = ShardedBruteForceIndex(ix5, device=dev, share_seeds=not a.no_share_seeds, two_round=not a.one_round, push=not a.pull_bounds) if world > 1 else None
             rng5 = np.random.default_rng(0x5EED0008)            # the appended rows: same stream on every rank
             q5_pin = torch.empty((qb5, d), dtype=torch.float32).pin_memory()
             o5 = (torch.empty((qb5, k), dtype=torch.int64, device=dev), torch.empty((qb5, k), dtype=torch.float32, device=dev),

@@ -184,6 +184,17 @@ ANN_API int ann_query_rescore_device(ann_index *ix, const float *d_queries, int3
                                      const uint32_t *const *peer_kth_keys, int32_t world, int64_t *d_out_ids,
                                      float *d_out_dist, int32_t *d_out_count, void *stream);
 
+/* The same two publishing phases with PUSH delivery: instead of one local array that every peer then reads over NVLink
+ * (400-byte rows pulled from 7 peers per query are latency-bound: 61 us per 4096-query round at 8 GPUs), the keys are written
+ * straight into this shard's [b*k] block of EVERY peer's receive buffer -- dst[i] / kth_dst[i] is that block inside peer i's
+ * memory as mapped into this process (own copy included) -- and the consuming calls (ann_query_filter_*_device's
+ * peer_seed_keys, ann_query_rescore_device's peer_kth_keys) are given pointers into the LOCAL receive buffer. */
+ANN_API int ann_query_seed_push_device(ann_index *ix, const float *d_queries, int32_t b, int32_t dim, int32_t k,
+                                       uint32_t *const *dst, int32_t n_dst, void *stream);
+ANN_API int ann_query_filter_push_device(ann_index *ix, const float *d_queries, int32_t b, int32_t dim, int32_t k,
+                                         const uint32_t *const *peer_seed_keys, int32_t world, uint32_t *const *kth_dst,
+                                         int32_t n_dst, void *stream);
+
 /* Pull-only form of ann_exchange_merge_device: merge this rank's slice [q_begin, q_begin + q_count) of the batch from all
  * `world` local result blocks (P2P loads) into plain arrays on this device -- d_out_ids / d_out_dist [q_count*k],
  * d_out_count [q_count] (may be NULL).  The merged answer stays partitioned across the ranks: nothing is pushed, and no

@@ -84,6 +84,14 @@ for metric, n, d, b, k in ((InnerProduct, 200_003, 200, 300, 100), (Cosine, 50_0
         ok2 &= bool(si.shape[0] == q1 - q0 and (si.cpu().numpy() == wi[q0:q1]).all()
                     and (sd.cpu().numpy().view(np.uint32) == wd[q0:q1].view(np.uint32)).all() and (sc.cpu().numpy() == wc[q0:q1]).all())
     del sx
+    # the same three phases with PULL delivery of the bounds (consumers read the peers' arrays over NVLink)
+    sx = ShardedBruteForceIndex(ix, device=dev, push=False)
+    for rep in range(2):
+        si, sd, sc = sx.batch_query_device(qd, k, st)
+        torch.cuda.synchronize()
+        ok2 &= bool((si.cpu().numpy() == wi).all() and (sd.cpu().numpy().view(np.uint32) == wd.view(np.uint32)).all()
+                    and (sc.cpu().numpy() == wc).all())
+    del sx
     # the same with the seed round only (A/B of the second cross-shard round)
     sx = ShardedBruteForceIndex(ix, device=dev, two_round=False)
     for rep in range(2):

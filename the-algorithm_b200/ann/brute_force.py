@@ -301,6 +301,26 @@ class BruteForceIndex(Appendable, Queryable):
                 arr if world else None, world, ctypes.c_void_p(out_ids_t.data_ptr()), ctypes.c_void_p(out_dist_t.data_ptr()),
                 None if out_count_t is None else ctypes.c_void_p(out_count_t.data_ptr()), ctypes.c_void_p(stream)))
 
+    def query_seed_push_device(self, queries_t, k: int, dst_ptrs, stream: int = 0) -> None:
+        """`ann_query_seed_push_device`: like `query_seed_device`, but the bounds are written into this shard's block of every
+        peer's receive buffer (`dst_ptrs`: one device address per peer, own copy included)."""
+        n = len(dst_ptrs)
+        arr = (ctypes.c_void_p * n)(*[int(p) for p in dst_ptrs])
+        self.flush()
+        _capi.check(_capi.lib().ann_query_seed_push_device(
+            self._h, ctypes.c_void_p(queries_t.data_ptr()), int(queries_t.shape[0]), int(queries_t.shape[1]), int(k), arr, n,
+            ctypes.c_void_p(stream)))
+
+    def query_filter_push_device(self, queries_t, k: int, seed_src_ptrs, kth_dst_ptrs, stream: int = 0) -> None:
+        """`ann_query_filter_push_device`: seed bounds read from the LOCAL receive buffer (`seed_src_ptrs`), the k best bounds
+        pushed into every peer's receive buffer (`kth_dst_ptrs`)."""
+        w, n = len(seed_src_ptrs), len(kth_dst_ptrs)
+        src = (ctypes.c_void_p * max(w, 1))(*[int(p) for p in seed_src_ptrs])
+        dst = (ctypes.c_void_p * n)(*[int(p) for p in kth_dst_ptrs])
+        _capi.check(_capi.lib().ann_query_filter_push_device(
+            self._h, ctypes.c_void_p(queries_t.data_ptr()), int(queries_t.shape[0]), int(queries_t.shape[1]), int(k),
+            src if w else None, w, dst, n, ctypes.c_void_p(stream)))
+
     def query_filter_device(self, queries_t, k: int, peer_seed_key_ptrs, kth_keys_t, stream: int = 0) -> None:
         """Middle phase of the three-phase sharded query (`ann_query_filter_device`): global seed threshold, tensor-core
         chunks, last compaction; publishes this shard's k best bounds per query into `kth_keys_t` ([b, k] CUDA tensor)."""

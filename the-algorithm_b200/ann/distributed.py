@@ -45,7 +45,7 @@ class ShardedBruteForceIndex:
     all-gather route (default: the CUDA merge kernel)."""
 
     def __init__(self, local, group=None, route: str = "auto", merge: Optional[Callable] = None, device=None,
-                 share_seeds: bool = True, two_round: bool = True):
+                 share_seeds: bool = True, two_round: bool = True, push: bool = True):
         import torch
         import torch.distributed as dist
 
@@ -57,6 +57,7 @@ class ShardedBruteForceIndex:
         self._merge = merge
         self.share_seeds = share_seeds   # fused route: two-phase local query around a cross-shard threshold exchange
         self.two_round = two_round       # ... plus a second exchange of the k best bounds after the last chunk (three phases)
+        self.push = push                 # bounds are pushed into the peers' receive buffers instead of pulled by every consumer
         self._px = {}          # (b, k) -> PeerExchange
         self._gather = {}      # (b, k) -> gathered buffers
         self._own = {}         # (b, k) -> this rank's result arrays (all-gather route)
@@ -154,9 +155,17 @@ class ShardedBruteForceIndex:
             else:
                 if exact or not (self.share_seeds and hasattr(self.local, "query_seed_device")):
                     self.local.query_batch_device(queries, k, px.local.ids, px.local.dist, px.local.count, stream)
+                elif self.two_round and self.push and hasattr(self.local, "query_filter_push_device"):
+                    # three phases around two small exchanges, bounds delivered by PUSH (P2P stores into every peer's receive
+                    # buffer; each consumer then reads local memory): seed bounds, then the k best bounds after the last
+                    # chunk, so that every shard rescores only its share of the global survivors
+                    self.local.query_seed_push_device(queries, k, px.seed_push_dst, stream)
+                    px.seed_barrier()
+                    self.local.query_filter_push_device(queries, k, px.seed_recv_src, px.kth_push_dst, stream)
+                    px.kth_barrier()
+                    self.local.query_rescore_device(queries, k, px.kth_recv_src, px.local.ids, px.local.dist, px.local.count, stream)
                 elif self.two_round and hasattr(self.local, "query_filter_device"):
-                    # three phases around two small exchanges: seed bounds, then the k best bounds after the last chunk, so
-                    # that every shard rescores only its share of the global survivors
+                    # the same with PULL delivery (every consumer reads the peers' arrays over NVLink)
                     self.local.query_seed_device(queries, k, px.seed_keys, stream)
                     px.seed_barrier()
                     self.local.query_filter_device(queries, k, px.seed_ptrs, px.kth_keys, stream)

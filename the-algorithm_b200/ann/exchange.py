@@ -97,7 +97,8 @@ class PeerExchange:
         self._stride = (nb + 255) // 256 * 256
         seed_bytes = (b * k * 4 + 255) // 256 * 256          # this rank's published seed bounds, [b][k] uint32
         # layout: [local block][final block][seed bounds][k-best bounds of the second round]
-        self._buf = symm_mem.empty(2 * self._stride + 2 * seed_bytes, dtype=torch.uint8, device=self.device)
+        #         [seed receive buffer: world blocks][k-best receive buffer: world blocks]   (push delivery)
+        self._buf = symm_mem.empty(2 * self._stride + 2 * seed_bytes + 2 * self.world * seed_bytes, dtype=torch.uint8, device=self.device)
         self._hdl = symm_mem.rendezvous(self._buf, self.group)
         ptrs: List[int] = [int(p) for p in self._hdl.buffer_ptrs]
         assert len(ptrs) == self.world and ptrs[self.rank] == self._buf.data_ptr()
@@ -110,6 +111,14 @@ class PeerExchange:
         self.kth_ptrs = [p + 2 * self._stride + seed_bytes for p in ptrs]
         o2 = 2 * self._stride + seed_bytes
         self.kth_keys = self._buf[o2: o2 + b * k * 4].view(torch.int32).view(b, k)
+        # push delivery: rank r writes its bounds into block r of EVERY rank's receive buffer; consumers read their own buffer
+        o3 = 2 * self._stride + 2 * seed_bytes
+        o4 = o3 + self.world * seed_bytes
+        me = ptrs[self.rank]
+        self.seed_push_dst = [p + o3 + self.rank * seed_bytes for p in ptrs]
+        self.kth_push_dst = [p + o4 + self.rank * seed_bytes for p in ptrs]
+        self.seed_recv_src = [me + o3 + s * seed_bytes for s in range(self.world)]
+        self.kth_recv_src = [me + o4 + s * seed_bytes for s in range(self.world)]
         self.q_begin, q_end = slice_of(self.rank, self.world, b)
         self.q_count = q_end - self.q_begin
         qn = max(self.q_count, 1)

@@ -475,7 +475,7 @@ int query_scan(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
 // all shards (`peers`), so that every shard rescores only its share of the global survivors.
 int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b, int k_eff, int k_out, int64_t* d_out_ids,
                float* d_out_dist, int32_t* d_out_count, cudaStream_t st, int mode = 0, uint32_t* seed_keys_out = nullptr,
-               const PeerSeedKeys* peers = nullptr, int world = 1) {
+               const PeerSeedKeys* peers = nullptr, int world = 1, uint32_t* const* push_dst = nullptr, int n_push = 0) {
     const int b_pad = (b + 127) / 128 * 128;
     CUDA_TRY(ix->q_padded.ensure((size_t)b * ix->pitch));
     const int qkp = (ix->kp + 63) / 64 * 64;
@@ -548,6 +548,21 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
         ix->last_path = 2;
         return ANN_OK;
     }
+    // where modes 1 / 3 publish: one local array, or (push) this shard's block inside every peer's receive buffer
+    auto set_publish = [&](SelectParams& sp) {
+        sp.seed_keys_out = seed_keys_out;
+        sp.n_push = 0;
+        for (int i = 0; i < n_push && i < kMaxPeers; ++i) sp.push_keys[sp.n_push++] = push_dst[i];
+    };
+    auto publish_no_bound = [&]() -> int {
+        const size_t bytes = (size_t)b * k_out * sizeof(uint32_t);
+        if (n_push > 0) {
+            for (int i = 0; i < n_push; ++i) CUDA_TRY(cudaMemsetAsync(push_dst[i], 0xFF, bytes, st));
+        } else if (seed_keys_out) {
+            CUDA_TRY(cudaMemsetAsync(seed_keys_out, 0xFF, bytes, st));
+        }
+        return ANN_OK;
+    };
     const int kHitBudget = ix->gemm_hit_budget;
     auto gemm_launch = [&](long long begin, long long end, int seed_mode) -> int {
         GemmLaunch g{};
@@ -634,7 +649,7 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
             SelectParams sp = fp;
             sp.seed_count = (int)(seed_rows / 32);
             sp.sort_cap = std::max(sp.sort_cap, sp.seed_count);   // every seed entry is loaded
-            sp.seed_keys_out = mode == 1 ? seed_keys_out : nullptr;
+            if (mode == 1) set_publish(sp);
             { TimedScope ts_(ix, st, ann_index::kLblCompact); CUDA_TRY(launch_compact_pool(sp, b, st)); }
             ix->launches++;
         }
@@ -657,7 +672,10 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
         if (end > ix->n) end = ix->n;
     } else if (mode == 1) {
         // too few rows to seed from: nothing to publish, phase 2 runs the unseeded schedule
-        CUDA_TRY(cudaMemsetAsync(seed_keys_out, 0xFF, (size_t)b * k_out * sizeof(uint32_t), st));
+        {
+            int rc2 = publish_no_bound();
+            if (rc2) return rc2;
+        }
         ix->sess.seeded = false;
         ix->sess.seed_rows = 0;
         return ANN_OK;
@@ -677,7 +695,7 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
     }
     if (mode == 3) {   // last compaction + publish; the exact finalize follows the second cross-shard round (mode 4)
         SelectParams sp = fp;
-        sp.seed_keys_out = seed_keys_out;
+        set_publish(sp);
         { TimedScope ts_(ix, st, ann_index::kLblCompact); CUDA_TRY(launch_compact_pool(sp, b, st)); }
         ix->launches++;
         return ANN_OK;
@@ -1118,13 +1136,29 @@ int ann_query_batch_device(ann_index* ix, const float* d_queries, int32_t b, int
 }
 
 // ---- two-phase sharded query: seed (publish this shard's bounds) -> [caller: cross-shard barrier] -> finish ----
+namespace {
+int seed_impl(ann_index* ix, const float* d_queries, int32_t b, int32_t dim, int32_t k, uint32_t* d_seed_keys,
+              uint32_t* const* push_dst, int32_t n_push, void* stream);
+}
 int ann_query_seed_device(ann_index* ix, const float* d_queries, int32_t b, int32_t dim, int32_t k, uint32_t* d_seed_keys,
                           void* stream) {
+    return seed_impl(ix, d_queries, b, dim, k, d_seed_keys, nullptr, 0, stream);
+}
+int ann_query_seed_push_device(ann_index* ix, const float* d_queries, int32_t b, int32_t dim, int32_t k, uint32_t* const* dst,
+                               int32_t n_dst, void* stream) {
+    if (n_dst < 1 || n_dst > kMaxPeers || !dst) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_query_seed_push_device: n_dst must be in [1, 16]");
+    for (int i = 0; i < n_dst; ++i)
+        if (!dst[i]) return fail(ANN_ERR_NULL_POINTER, "ann_query_seed_push_device: NULL destination");
+    return seed_impl(ix, d_queries, b, dim, k, nullptr, dst, n_dst, stream);
+}
+namespace {
+int seed_impl(ann_index* ix, const float* d_queries, int32_t b, int32_t dim, int32_t k, uint32_t* d_seed_keys,
+              uint32_t* const* push_dst, int32_t n_push, void* stream) {
     if (!ix) return fail(ANN_ERR_NULL_POINTER, "ann_query_seed_device: index is NULL");
     if (b < 0) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_query_seed_device: b < 0");
     if (k < 0) return fail(ANN_ERR_NEGATIVE_K, "ann_query_seed_device: k < 0");
     if (dim != ix->dim) return fail(ANN_ERR_DIMENSION_MISMATCH, "ann_query_seed_device: query dimension != index dimension");
-    if (b > 0 && (!d_queries || (k > 0 && !d_seed_keys))) return fail(ANN_ERR_NULL_POINTER, "ann_query_seed_device: NULL buffer");
+    if (b > 0 && (!d_queries || (k > 0 && !d_seed_keys && n_push == 0))) return fail(ANN_ERR_NULL_POINTER, "ann_query_seed_device: NULL buffer");
     std::lock_guard<std::mutex> lk(ix->mu);
     int rc = set_device(ix);
     if (rc) return rc;
@@ -1139,17 +1173,22 @@ int ann_query_seed_device(ann_index* ix, const float* d_queries, int32_t b, int3
     const bool gemm = ix->n > 0 && k_eff <= kMaxK && ix->path_opt != 3 && ix->path_opt != 1 && b <= kMaxGemmBatch &&
                       gemm_eligible(ix, b, k_eff) && (ix->path_opt == 2 || b >= ix->gemm_min_batch);
     if (!gemm) {   // scan / exact paths keep their own thresholds: nothing to publish, the finish call runs the whole query
-        CUDA_TRY(cudaMemsetAsync(d_seed_keys, 0xFF, (size_t)b * k * sizeof(uint32_t), st));
+        if (n_push > 0) {
+            for (int i = 0; i < n_push; ++i) CUDA_TRY(cudaMemsetAsync(push_dst[i], 0xFF, (size_t)b * k * sizeof(uint32_t), st));
+        } else {
+            CUDA_TRY(cudaMemsetAsync(d_seed_keys, 0xFF, (size_t)b * k * sizeof(uint32_t), st));
+        }
         return ANN_OK;
     }
     ix->sess.gemm = true;
     CUDA_TRY(ix->qstate.ensure((size_t)b));
     rc = unit_queries(ix, &d_queries, b, st);
     if (rc) return rc;
-    rc = query_gemm(ix, ix->qstate.p, d_queries, b, k_eff, k, nullptr, nullptr, nullptr, st, 1, d_seed_keys);
+    rc = query_gemm(ix, ix->qstate.p, d_queries, b, k_eff, k, nullptr, nullptr, nullptr, st, 1, d_seed_keys, nullptr, 1, push_dst, n_push);
     if (rc) ix->sess = ann_index::SeedSession{};
     return rc;
 }
+}  // namespace
 
 int ann_query_finish_device(ann_index* ix, const float* d_queries, int32_t b, int32_t dim, int32_t k,
                             const uint32_t* const* peer_seed_keys, int32_t world, int64_t* d_out_ids, float* d_out_dist,
@@ -1224,13 +1263,30 @@ int check_session(ann_index* ix, const char* who, int32_t b, int32_t dim, int32_
 }
 }  // namespace
 
+namespace {
+int filter_impl(ann_index* ix, const float* d_queries, int32_t b, int32_t dim, int32_t k, const uint32_t* const* peer_seed_keys,
+                int32_t world, uint32_t* d_kth_keys, uint32_t* const* push_dst, int32_t n_push, void* stream);
+}
 int ann_query_filter_device(ann_index* ix, const float* d_queries, int32_t b, int32_t dim, int32_t k,
                             const uint32_t* const* peer_seed_keys, int32_t world, uint32_t* d_kth_keys, void* stream) {
+    return filter_impl(ix, d_queries, b, dim, k, peer_seed_keys, world, d_kth_keys, nullptr, 0, stream);
+}
+int ann_query_filter_push_device(ann_index* ix, const float* d_queries, int32_t b, int32_t dim, int32_t k,
+                                 const uint32_t* const* peer_seed_keys, int32_t world, uint32_t* const* kth_dst, int32_t n_dst,
+                                 void* stream) {
+    if (n_dst < 1 || n_dst > kMaxPeers || !kth_dst) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_query_filter_push_device: n_dst must be in [1, 16]");
+    for (int i = 0; i < n_dst; ++i)
+        if (!kth_dst[i]) return fail(ANN_ERR_NULL_POINTER, "ann_query_filter_push_device: NULL destination");
+    return filter_impl(ix, d_queries, b, dim, k, peer_seed_keys, world, nullptr, kth_dst, n_dst, stream);
+}
+namespace {
+int filter_impl(ann_index* ix, const float* d_queries, int32_t b, int32_t dim, int32_t k, const uint32_t* const* peer_seed_keys,
+                int32_t world, uint32_t* d_kth_keys, uint32_t* const* push_dst, int32_t n_push, void* stream) {
     if (!ix) return fail(ANN_ERR_NULL_POINTER, "ann_query_filter_device: index is NULL");
     std::lock_guard<std::mutex> lk(ix->mu);
     int rc = check_session(ix, "ann_query_filter_device", b, dim, k, world, false);
     if (rc) return rc;
-    if (b > 0 && (!d_queries || (k > 0 && !d_kth_keys))) {
+    if (b > 0 && (!d_queries || (k > 0 && !d_kth_keys && n_push == 0))) {
         ix->sess.open = false;
         return fail(ANN_ERR_NULL_POINTER, "ann_query_filter_device: NULL buffer");
     }
@@ -1240,7 +1296,11 @@ int ann_query_filter_device(ann_index* ix, const float* d_queries, int32_t b, in
     ix->sess.filtered = true;
     if (b == 0 || k == 0) return ANN_OK;
     if (!ix->sess.gemm) {   // scan / exact paths: nothing to publish, the rescore call answers the whole local query
-        CUDA_TRY(cudaMemsetAsync(d_kth_keys, 0xFF, (size_t)b * k * sizeof(uint32_t), st));
+        if (n_push > 0) {
+            for (int i = 0; i < n_push; ++i) CUDA_TRY(cudaMemsetAsync(push_dst[i], 0xFF, (size_t)b * k * sizeof(uint32_t), st));
+        } else {
+            CUDA_TRY(cudaMemsetAsync(d_kth_keys, 0xFF, (size_t)b * k * sizeof(uint32_t), st));
+        }
         return ANN_OK;
     }
     PeerSeedKeys pk{};
@@ -1254,11 +1314,11 @@ int ann_query_filter_device(ann_index* ix, const float* d_queries, int32_t b, in
             pk.keys[w++] = peer_seed_keys[s2];
         }
     const int k_eff = (int)std::min<long long>(k, ix->n);
-    if (k_eff < k) CUDA_TRY(cudaMemsetAsync(d_kth_keys, 0xFF, (size_t)b * k * sizeof(uint32_t), st));   // pitch k, k_eff bounds per row
-    rc = query_gemm(ix, ix->qstate.p, d_queries, b, k_eff, k, nullptr, nullptr, nullptr, st, 3, d_kth_keys, &pk, w);
+    rc = query_gemm(ix, ix->qstate.p, d_queries, b, k_eff, k, nullptr, nullptr, nullptr, st, 3, d_kth_keys, &pk, w, push_dst, n_push);
     if (rc) ix->sess.open = false;
     return rc;
 }
+}  // namespace
 
 int ann_query_rescore_device(ann_index* ix, const float* d_queries, int32_t b, int32_t dim, int32_t k,
                              const uint32_t* const* peer_kth_keys, int32_t world, int64_t* d_out_ids, float* d_out_dist,

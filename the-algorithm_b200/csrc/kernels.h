@@ -87,6 +87,9 @@ struct SelectParams {
     uint32_t* seed_keys_out;  // with seed_count: also publish, per query, the k best group maxima as upper bounds on exact
                               // badness (order keys of g + eps, [b][k], 0xFFFFFFFF padded) for the other shards (K5c);
                               // without seed_count (compaction after the last chunk): the k best pool entries, likewise
+    uint32_t* push_keys[kMaxPeers];   // n_push > 0: publish by PUSH instead -- this shard's [b][k] block inside every peer's
+    int n_push;                       // receive buffer (P2P stores are fire-and-forget; pulling 400-byte rows from 7 peers
+                                      // per query was latency-bound: 61 us per 4096-query round at 8 GPUs)
     PeerSeedKeys peer_keys;   // finalize: every shard's bounds published after the last chunk (second cross-shard round)
     int peer_world;           // number of valid peer_keys entries; 0 = single shard, no global bound
     int sort_cap, exact_cap;  // shared-memory capacities (entries) of the approximate and exact stages; 0 = 4096 / 2048.

@@ -8,6 +8,8 @@
 //               rounding to fp32, then `1 - x` in fp32 for Cosine / InnerProduct.
 //   merge     : replaces ComposedQueryable.queryWithDistance's flatten + sort + take (ShardApi.scala:77-85),
 //               ordered by (Float.compare(distance), id) so that R shards give the single-shard answer bit for bit.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -211,13 +213,29 @@ __device__ bool load_and_threshold(const SelectParams& p, int q, entry_t* buf, u
 __global__ void __launch_bounds__(kSelThreads, 4) compact_pool_kernel(SelectParams p) {
     extern __shared__ __align__(16) unsigned char sm[];
     entry_t* buf = reinterpret_cast<entry_t*>(sm);
+    uint32_t* pubk = reinterpret_cast<uint32_t*>(sm + (size_t)sort_cap_of(p) * 8);   // [k] keys to publish (only when publishing)
     __shared__ uint32_t hist[256];
-    __shared__ int n_keep;
+    __shared__ int n_keep, n_pub;
     const int q = blockIdx.x;
     QueryState* qs = p.qstate + q;
+    const bool publishing = p.seed_keys_out != nullptr || p.n_push > 0;
+    // the staged keys go to the local array, or (push mode) into this shard's block of EVERY peer's receive buffer
+    auto publish = [&]() {
+        __syncthreads();
+        if (p.n_push > 0) {
+            for (int d = 0; d < p.n_push; ++d) {
+                uint32_t* out = p.push_keys[d] + (size_t)q * p.k;
+                for (int j = threadIdx.x; j < p.k; j += blockDim.x) out[j] = pubk[j];
+            }
+        } else {
+            uint32_t* out = p.seed_keys_out + (size_t)q * p.k;
+            for (int j = threadIdx.x; j < p.k; j += blockDim.x) out[j] = pubk[j];
+        }
+    };
     auto publish_nothing = [&]() {   // a flagged query publishes "no bound" (never stale keys of an earlier batch)
-        if (p.seed_keys_out)
-            for (int j = threadIdx.x; j < p.k; j += blockDim.x) p.seed_keys_out[(size_t)q * p.k + j] = 0xFFFFFFFFu;
+        if (!publishing) return;
+        for (int j = threadIdx.x; j < p.k; j += blockDim.x) pubk[j] = 0xFFFFFFFFu;
+        publish();
     };
     if (p.seed_count == 0 && qs->pool_count > (uint32_t)p.pool_cap) {
         if (threadIdx.x == 0) atomicOr(&qs->flags, kFlagPoolOverflow);
@@ -231,29 +249,36 @@ __global__ void __launch_bounds__(kSelThreads, 4) compact_pool_kernel(SelectPara
         publish_nothing();
         return;
     }
-    if (p.seed_count > 0) {   // seed entries carry no row: keep only the threshold
-        if (p.seed_keys_out) {
-            // K5c publish: the k best group maxima, each widened to an upper bound on the exact badness of a real row of
-            // this shard (distinct groups => distinct rows).  Order does not matter to the consumer; entries equal to the
-            // k-th key all publish the same value, so the tail is simply filled with it.
-            uint32_t* out = p.seed_keys_out + (size_t)q * p.k;
-            const float ea = qs->eps_abs, er = qs->eps_rel;
-            if (threadIdx.x == 0) n_keep = 0;
-            __syncthreads();
-            if (kk != 0xFFFFFFFFu) {
-                for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                    const uint32_t key = (uint32_t)(buf[i] >> 32);
-                    if (key < kk) {
-                        const int slot = atomicAdd(&n_keep, 1);     // fewer than k entries are strictly below the k-th key
-                        out[slot] = float_order_key(widen_half_up(float_from_order_key(key), ea, er));
-                    }
-                }
-                __syncthreads();
-                const uint32_t fill = float_order_key(widen_half_up(float_from_order_key(kk), ea, er));
-                for (int j = n_keep + threadIdx.x; j < p.k; j += blockDim.x) out[j] = fill;
-            } else {
-                for (int j = threadIdx.x; j < p.k; j += blockDim.x) out[j] = 0xFFFFFFFFu;   // fewer than k groups: no bound
+    // The k best keys of `buf`, each widened to an upper bound on the exact badness of the row (or 32-row group: distinct
+    // groups => distinct rows) that produced it.  Order does not matter to the consumer; entries equal to the k-th key all
+    // publish the same value, so the tail is simply filled with it.  Fewer than k entries: every one is a witness, the rest
+    // is "no bound".
+    auto stage_best = [&]() {
+        const float ea = qs->eps_abs, er = qs->eps_rel;
+        if (threadIdx.x == 0) n_pub = 0;
+        __syncthreads();
+        if (kk != 0xFFFFFFFFu) {
+            for (int i0 = 0; i0 < n; i0 += blockDim.x) {
+                const int i = i0 + threadIdx.x;
+                const uint32_t key = i < n ? (uint32_t)(buf[i] >> 32) : 0xFFFFFFFFu;
+                const bool take = i < n && key < kk;                 // fewer than k entries are strictly below the k-th key
+                const int slot = warp_slot(take, &n_pub);
+                if (take) pubk[slot] = float_order_key(widen_half_up(float_from_order_key(key), ea, er));
             }
+            __syncthreads();
+            const uint32_t fill = float_order_key(widen_half_up(float_from_order_key(kk), ea, er));
+            for (int j = n_pub + threadIdx.x; j < p.k; j += blockDim.x) pubk[j] = fill;
+        } else {
+            for (int i = threadIdx.x; i < min(n, p.k); i += blockDim.x) pubk[i] = float_order_key(widen_half_up(entry_g(buf[i]), ea, er));
+            for (int j = n + threadIdx.x; j < p.k; j += blockDim.x) pubk[j] = 0xFFFFFFFFu;
+        }
+    };
+    if (p.seed_count > 0) {   // seed entries carry no row: keep only the threshold (K5c publish: the k best group maxima)
+        if (publishing) {
+            if (kk != 0xFFFFFFFFu) stage_best();
+            else
+                for (int j = threadIdx.x; j < p.k; j += blockDim.x) pubk[j] = 0xFFFFFFFFu;   // fewer than k groups: no bound
+            publish();
         }
         if (threadIdx.x == 0) {
             qs->pool_count = 0;
@@ -276,29 +301,12 @@ __global__ void __launch_bounds__(kSelThreads, 4) compact_pool_kernel(SelectPara
         qs->pool_count = n_keep;
         qs->tau_key = float_order_key(tau);
     }
-    if (p.seed_keys_out) {
-        // Second cross-shard round (sharded query, after the last chunk): publish this shard's k best approximate keys,
-        // each widened to an upper bound on the exact badness of the row that produced it.  The k-th smallest over all
-        // shards' arrays bounds the GLOBAL k-th best, which lets every shard rescore only its share of the ~2k global
-        // survivors instead of its own ~2k (the local k-th of 1/R of the rows is far looser than the global one).
-        uint32_t* out = p.seed_keys_out + (size_t)q * p.k;
-        const float ea = qs->eps_abs, er = qs->eps_rel;
-        __shared__ int n_pub;
-        if (threadIdx.x == 0) n_pub = 0;
-        __syncthreads();
-        if (kk != 0xFFFFFFFFu) {   // n >= k: entries strictly below the k-th key, then the k-th key itself as often as needed
-            for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                const uint32_t key = (uint32_t)(buf[i] >> 32);
-                if (key < kk) out[atomicAdd(&n_pub, 1)] = float_order_key(widen_half_up(float_from_order_key(key), ea, er));
-            }
-            __syncthreads();
-            const uint32_t fill = float_order_key(widen_half_up(float_from_order_key(kk), ea, er));
-            for (int j = n_pub + threadIdx.x; j < p.k; j += blockDim.x) out[j] = fill;
-        } else {                   // fewer than k candidates under the threshold: every one is a witness, the rest is "no bound"
-            for (int i = threadIdx.x; i < n; i += blockDim.x)
-                out[i] = float_order_key(widen_half_up(entry_g(buf[i]), ea, er));
-            for (int j = n + threadIdx.x; j < p.k; j += blockDim.x) out[j] = 0xFFFFFFFFu;
-        }
+    if (publishing) {
+        // Second cross-shard round (sharded query, after the last chunk): publish this shard's k best approximate keys.  The
+        // k-th smallest over all shards' arrays bounds the GLOBAL k-th best, which lets every shard rescore only its share of
+        // the ~2k global survivors instead of its own ~2k (the local k-th of 1/R of the rows is far looser than the global one).
+        stage_best();
+        publish();
     }
 }
 
@@ -766,7 +774,7 @@ cudaError_t launch_seed_merge(const PeerSeedKeys& pk, int world, QueryState* qst
 }
 
 cudaError_t launch_compact_pool(const SelectParams& p, int b, cudaStream_t stream) {
-    size_t smem = (size_t)sort_cap_of(p) * 8;
+    size_t smem = (size_t)sort_cap_of(p) * 8 + (size_t)std::max(p.k, 1) * 4;   // candidate entries + the keys staged for publishing
     cudaError_t e = cudaFuncSetAttribute(compact_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     compact_pool_kernel<<<b, kSelThreads, smem, stream>>>(p);

@@ -126,8 +126,8 @@ struct Shard {
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
     // per-(b, k) scratch on this device
     float* d_q = nullptr;
-    uint32_t* d_seed = nullptr;
-    uint32_t* d_kth = nullptr;
+    uint32_t* d_seed = nullptr;          // receive buffer [world][b*k]: block s holds shard s's seed bounds (pushed by shard s)
+    uint32_t* d_kth = nullptr;           // likewise for the k best bounds of the second round
     unsigned char* d_local = nullptr;     // result block of this shard's candidates: [ids b*k][dist b*k][count b]
     int64_t* d_sl_ids = nullptr;          // merged slice
     float* d_sl_dist = nullptr;
@@ -174,7 +174,7 @@ cudaError_t regrow(T** p, size_t* cap, size_t want) {
     return e;
 }
 
-int ensure_scratch(Shard& s, int b, int dim, int k, int q_count) {
+int ensure_scratch(Shard& s, int b, int dim, int k, int q_count, int world) {
     SH_TRY(cudaSetDevice(s.device));
     const size_t bk = (size_t)b * std::max(k, 1);
     SH_TRY(regrow(&s.d_q, &s.cap_q, (size_t)b * dim));
@@ -185,8 +185,8 @@ int ensure_scratch(Shard& s, int b, int dim, int k, int q_count) {
         s.d_seed = s.d_kth = nullptr;
         s.d_local = nullptr;
         s.cap_bk = 0;
-        SH_TRY(cudaMalloc(&s.d_seed, bk * 4));
-        SH_TRY(cudaMalloc(&s.d_kth, bk * 4));
+        SH_TRY(cudaMalloc(&s.d_seed, bk * 4 * world));
+        SH_TRY(cudaMalloc(&s.d_kth, bk * 4 * world));
         SH_TRY(cudaMalloc(&s.d_local, bk * 12 + (size_t)b * 4 + 256));
         s.cap_bk = bk;
     }
@@ -411,7 +411,7 @@ int ann_sharded_query_batch(ann_sharded_index* sx, const float* queries, int32_t
     std::atomic<int> failed{0}, flagged{0};
     std::vector<int32_t> cnt_host((size_t)b);
     int32_t* cnt_out = out_count ? out_count : cnt_host.data();
-    std::vector<const uint32_t*> seed_ptrs(R), kth_ptrs(R);
+    std::vector<uint32_t*> recv_seed(R), recv_kth(R);   // every shard's receive buffers (peer-visible)
     std::vector<const void*> local_ptrs(R);
 
     // exact == true: every shard answers with its own exact top-k (device_fallback on), no threshold sharing -- the route for
@@ -436,9 +436,9 @@ int ann_sharded_query_batch(ann_sharded_index* sx, const float* queries, int32_t
                     (void)cudaGetLastError();
                 }
             };
-            step(ensure_scratch(sh, b, dim, k, qn));
-            seed_ptrs[s] = sh.d_seed;
-            kth_ptrs[s] = sh.d_kth;
+            step(ensure_scratch(sh, b, dim, k, qn, R));
+            recv_seed[s] = sh.d_seed;
+            recv_kth[s] = sh.d_kth;
             local_ptrs[s] = sh.d_local;
             int64_t* l_ids = reinterpret_cast<int64_t*>(sh.d_local);
             float* l_dist = reinterpret_cast<float*>(sh.d_local + (size_t)b * k * 8);
@@ -465,15 +465,27 @@ int ann_sharded_query_batch(ann_sharded_index* sx, const float* queries, int32_t
                 }
                 sync_all(2);
             } else {
-                if (ok0 && !rcs[s]) step(ann_query_seed_device(sh.ix, sh.d_q, b, dim, k, sh.d_seed, st));
+                // bounds travel by PUSH: shard s writes its [b*k] block into block s of every shard's receive buffer, and
+                // every consumer reads its own buffer (local HBM) after the phase's events
+                const size_t blk = (size_t)b * k;
+                std::vector<uint32_t*> seed_dst(R), kth_dst(R);
+                std::vector<const uint32_t*> seed_src(R), kth_src(R);
+                for (int t = 0; t < R; ++t) {
+                    seed_dst[t] = recv_seed[t] + (size_t)s * blk;
+                    kth_dst[t] = recv_kth[t] + (size_t)s * blk;
+                    seed_src[t] = sh.d_seed + (size_t)t * blk;
+                    kth_src[t] = sh.d_kth + (size_t)t * blk;
+                }
+                if (ok0 && !failed.load()) step(ann_query_seed_push_device(sh.ix, sh.d_q, b, dim, k, seed_dst.data(), R, st));
                 sync_all(0);
                 if (sx->two_round) {
-                    if (ok0 && !failed.load()) step(ann_query_filter_device(sh.ix, sh.d_q, b, dim, k, seed_ptrs.data(), R, sh.d_kth, st));
+                    if (ok0 && !failed.load())
+                        step(ann_query_filter_push_device(sh.ix, sh.d_q, b, dim, k, seed_src.data(), R, kth_dst.data(), R, st));
                     sync_all(1);
                     if (ok0 && !failed.load())
-                        step(ann_query_rescore_device(sh.ix, sh.d_q, b, dim, k, kth_ptrs.data(), R, l_ids, l_dist, l_cnt, st));
+                        step(ann_query_rescore_device(sh.ix, sh.d_q, b, dim, k, kth_src.data(), R, l_ids, l_dist, l_cnt, st));
                 } else if (ok0 && !failed.load()) {
-                    step(ann_query_finish_device(sh.ix, sh.d_q, b, dim, k, seed_ptrs.data(), R, l_ids, l_dist, l_cnt, st));
+                    step(ann_query_finish_device(sh.ix, sh.d_q, b, dim, k, seed_src.data(), R, l_ids, l_dist, l_cnt, st));
                 }
                 sync_all(2);
             }
