@@ -68,6 +68,7 @@ def parse():
     ap.add_argument("--config5-rows", type=int, default=50_000_000,
                     help="rows pre-loaded in the configs[4] streaming sub-run (sharded over the ranks); 0 = skip")
     ap.add_argument("--config5-appends", type=int, default=1_000_000)
+    ap.add_argument("--full-h2d", action="store_true", help="N > 1, e2e leg: every rank copies the WHOLE query batch from the host (A/B)")
     ap.add_argument("--pull-bounds", action="store_true", help="N > 1: consumers pull the peers' bound arrays (A/B of push delivery)")
     ap.add_argument("--one-round", action="store_true",
                     help="N > 1: seed round only (A/B of the second cross-shard round that shares the k best bounds)")
@@ -413,8 +414,12 @@ def run_ours(a):
     def step_e2e():
         if world == 1:
             return ix.batch_query_with_distance(q_np, k, out=out_np)   # ann_query_batch: H2D, query path, D2H inside the call
-        # N ranks: every rank needs the whole query batch (rows are sharded, queries replicated) and keeps its slice of the answer
-        qd = q_pin.to(dev, non_blocking=True)
+        # N ranks: rows are sharded, queries replicated on the devices -- but the batch crosses PCIe only once: every rank copies
+        # ITS 1/N slice from pinned host memory, pushes it to the peers over NVLink (one barrier), and keeps its slice of the answer
+        if sx.route == "fused" and not a.full_h2d:
+            qd = sx.gather_queries(q_pin[q0:q1], b, k, stream.cuda_stream)
+        else:
+            qd = q_pin.to(dev, non_blocking=True)
         oi, od, oc = step_device(qd)
         h_ids.copy_(oi, non_blocking=True)
         h_dist.copy_(od, non_blocking=True)
@@ -691,10 +696,12 @@ def run_ours(a):
             "dtype_detail": ("bf16 candidate filter on tcgen05 (fp32 accumulate)" if last_path == 2 else "f32 streaming scan")
                             + " + exact rescoring of the survivors: fp64 accumulation, one rounding to fp32 (bit-identical to the oracle)",
             "data": "synthetic", "config": config_dict(a, n_gpus, sx.route if sx else ""),
-            "e2e": {"value": b / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": b * d * 4 * world,
+            "e2e": {"value": b / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": b * d * 4 * (world if (a.full_h2d or (sx and sx.route != "fused")) else 1),
                     "d2h_bytes_per_step": b * k * 12 + b * 4, "ms_per_step": e2e_ms,
                     "api": "ann_query_batch (host buffers)" if world == 1 else
-                           "per rank: pinned H2D of the batch + three-phase sharded query + slice merge + D2H of the rank's 1/N slice"},
+                           ("per rank: pinned H2D of the whole batch" if a.full_h2d else "per rank: pinned H2D of the rank's 1/N slice of the batch + NVLink push all-gather")
+                           + " + three-phase sharded query + slice merge + D2H of the rank's 1/N slice of the answer"},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "path": {1: "scan", 2: "gemm"}.get(last_path, str(last_path)),
             "result_digest": digest, "flagged_rows": flagged_rows, "parity_sample": parity, "breakdown": breakdown, "extra": extra,

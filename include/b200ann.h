@@ -140,6 +140,13 @@ ANN_API int ann_exchange_merge_device(int32_t device, const void *const *peer_lo
                                       int32_t b, int32_t k, int32_t q_begin, int32_t q_count, void *stream);
 ANN_API size_t ann_result_block_bytes(int32_t b, int32_t k);
 
+/* Replicate a device buffer into peers' memory with P2P stores: copies nbytes (a multiple of 16, 16-byte aligned pointers)
+ * from d_src to every peer_dst[i].  This is the all-gather of a PARTITIONED query batch: each GPU copies only its b/R slice
+ * from the host and pushes it into the same rows of every peer's batch buffer, so the queries cross PCIe once instead of R
+ * times; one cross-GPU barrier then makes every copy of the batch complete. */
+ANN_API int ann_peer_push_device(int32_t device, const void *d_src, void *const *peer_dst, int32_t n_dst, size_t nbytes,
+                                 void *stream);
+
 /* The shard-side half of ComposedQueryable.queryWithDistance's fan-out (ShardApi.scala:72-79) when the shards are GPUs of
  * one box: ann_query_batch_device split in two so that the shards can share what they learn before the expensive part.
  *   ann_query_seed_device   prepares the batch, scores a small prefix of this shard's rows and publishes, per query, k

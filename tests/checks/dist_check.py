@@ -83,6 +83,15 @@ for metric, n, d, b, k in ((InnerProduct, 200_003, 200, 300, 100), (Cosine, 50_0
         torch.cuda.synchronize()
         ok2 &= bool(si.shape[0] == q1 - q0 and (si.cpu().numpy() == wi[q0:q1]).all()
                     and (sd.cpu().numpy().view(np.uint32) == wd[q0:q1].view(np.uint32)).all() and (sc.cpu().numpy() == wc[q0:q1]).all())
+    # ... fed by the partitioned query batch: every rank copies only its slice from the host, the rest arrives over NVLink
+    if d % 4 == 0:
+        q_pin = torch.from_numpy(q).pin_memory()
+        for rep in range(2):
+            qg = sx.gather_queries(q_pin[q0:q1], b, k, st)
+            si, sd, sc = sx.batch_query_device(qg, k, st, deliver="slice")
+            torch.cuda.synchronize()
+            ok2 &= bool(torch.equal(qg.cpu(), q_pin) and (si.cpu().numpy() == wi[q0:q1]).all()
+                        and (sd.cpu().numpy().view(np.uint32) == wd[q0:q1].view(np.uint32)).all())
     del sx
     # the same three phases with PULL delivery of the bounds (consumers read the peers' arrays over NVLink)
     sx = ShardedBruteForceIndex(ix, device=dev, push=False)

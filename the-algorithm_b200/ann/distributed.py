@@ -90,8 +90,15 @@ class ShardedBruteForceIndex:
 
         key = (b, k)
         if key not in self._px:
-            self._px[key] = PeerExchange(b, k, self.device, self.group)
+            self._px[key] = PeerExchange(b, k, self.device, self.group, dim=int(getattr(self.local, "dim", 0) or 0))
         return self._px[key]
+
+    def gather_queries(self, host_slice, b: int, k: int, stream: int = 0):
+        """Collective (fused route).  Every rank passes ITS rows `slice_range(b)` of the query batch (pinned CPU tensor) and
+        gets the complete [b, dim] batch on its device: 1/world of the batch crosses this rank's PCIe link, the rest arrives
+        from the peers over NVLink.  Safe to call for the next batch as soon as the previous `batch_query_device` was
+        enqueued: the batch buffer is overwritten only after the barrier every rank enters behind its own query kernels."""
+        return self._exchange_for(b, k).gather_queries(host_slice, stream)
 
     def batch_query_device(self, queries, k: int, stream: int = 0, deliver: str = "all", exact: bool = False):
         """Collective: every rank passes the same [b, dim] batch (on its own device).

@@ -83,7 +83,7 @@ def slice_of(rank: int, world: int, b: int) -> Tuple[int, int]:
 class PeerExchange:
     """Symmetric result blocks of one (b, k) shape across the ranks of a process group + the fused exchange/merge."""
 
-    def __init__(self, b: int, k: int, device, group=None):
+    def __init__(self, b: int, k: int, device, group=None, dim: int = 0):
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
@@ -98,7 +98,10 @@ class PeerExchange:
         seed_bytes = (b * k * 4 + 255) // 256 * 256          # this rank's published seed bounds, [b][k] uint32
         # layout: [local block][final block][seed bounds][k-best bounds of the second round]
         #         [seed receive buffer: world blocks][k-best receive buffer: world blocks]   (push delivery)
-        self._buf = symm_mem.empty(2 * self._stride + 2 * seed_bytes + 2 * self.world * seed_bytes, dtype=torch.uint8, device=self.device)
+        #         [query batch b x dim fp32]   (dim > 0: partitioned H2D + push all-gather, `gather_queries`)
+        q_bytes = (b * dim * 4 + 255) // 256 * 256
+        self._buf = symm_mem.empty(2 * self._stride + 2 * seed_bytes + 2 * self.world * seed_bytes + q_bytes, dtype=torch.uint8,
+                                   device=self.device)
         self._hdl = symm_mem.rendezvous(self._buf, self.group)
         ptrs: List[int] = [int(p) for p in self._hdl.buffer_ptrs]
         assert len(ptrs) == self.world and ptrs[self.rank] == self._buf.data_ptr()
@@ -119,12 +122,34 @@ class PeerExchange:
         self.kth_push_dst = [p + o4 + self.rank * seed_bytes for p in ptrs]
         self.seed_recv_src = [me + o3 + s * seed_bytes for s in range(self.world)]
         self.kth_recv_src = [me + o4 + s * seed_bytes for s in range(self.world)]
+        self.dim = dim
+        o5 = o4 + self.world * seed_bytes
+        self._q_ptrs = [p + o5 for p in ptrs]
+        self.queries = self._buf[o5: o5 + b * dim * 4].view(torch.float32).view(b, dim) if dim else None
         self.q_begin, q_end = slice_of(self.rank, self.world, b)
         self.q_count = q_end - self.q_begin
         qn = max(self.q_count, 1)
         self.slice_ids = torch.empty((qn, k), dtype=torch.int64, device=self.device)[: self.q_count]
         self.slice_dist = torch.empty((qn, k), dtype=torch.float32, device=self.device)[: self.q_count]
         self.slice_count = torch.empty((qn,), dtype=torch.int32, device=self.device)[: self.q_count]
+
+    def gather_queries(self, host_slice, stream: int = 0):
+        """Collective.  `host_slice`: this rank's rows [q_begin, q_begin + q_count) of the query batch (pinned CPU tensor).
+        Copies them into the peer-mapped batch buffer, pushes them into the same rows of every peer's buffer
+        (`ann_peer_push_device`) and waits at one barrier: the batch crosses PCIe once instead of `world` times.  Returns the
+        complete [b, dim] device batch.  Needs dim * 4 * q_begin to be a multiple of 16 (any dim that is a multiple of 4)."""
+        assert self.queries is not None, "PeerExchange was created without dim"
+        if self.q_count:
+            mine = self.queries[self.q_begin: self.q_begin + self.q_count]
+            mine.copy_(host_slice, non_blocking=True)
+            off = self.q_begin * self.dim * 4
+            dst = [p + off for s, p in enumerate(self._q_ptrs) if s != self.rank]
+            if dst:
+                arr = (ctypes.c_void_p * len(dst))(*dst)
+                _capi.check(_capi.lib().ann_peer_push_device(self.device.index or 0, ctypes.c_void_p(self._q_ptrs[self.rank] + off), arr,
+                                                             len(dst), self.q_count * self.dim * 4, ctypes.c_void_p(stream)))
+        self._hdl.barrier(channel=4)
+        return self.queries
 
     def kth_barrier(self) -> None:
         """Collective, between `query_filter_device` and `query_rescore_device`: every rank's k-best bounds are complete."""

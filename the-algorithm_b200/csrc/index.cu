@@ -1614,6 +1614,18 @@ int ann_exchange_merge_device(int32_t device, const void* const* peer_local, voi
     return ANN_OK;
 }
 
+int ann_peer_push_device(int32_t device, const void* d_src, void* const* peer_dst, int32_t n_dst, size_t nbytes, void* stream) {
+    if (n_dst < 0 || n_dst > kMaxPeers) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_peer_push_device: n_dst must be in [0, 16]");
+    if (nbytes == 0 || n_dst == 0) return ANN_OK;
+    if (!d_src || !peer_dst) return fail(ANN_ERR_NULL_POINTER, "ann_peer_push_device: NULL pointer");
+    for (int i = 0; i < n_dst; ++i)
+        if (!peer_dst[i]) return fail(ANN_ERR_NULL_POINTER, "ann_peer_push_device: NULL destination");
+    if ((nbytes & 15) || ((uintptr_t)d_src & 15)) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_peer_push_device: 16-byte alignment required");
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(launch_peer_push(d_src, peer_dst, n_dst, nbytes, (cudaStream_t)stream));
+    return ANN_OK;
+}
+
 size_t ann_result_block_bytes(int32_t b, int32_t k) { return (b < 0 || k < 0) ? 0 : result_block_bytes(b, k); }
 
 int ann_set_option(ann_index* ix, const char* name, int64_t value) {

@@ -135,6 +135,9 @@ inline size_t result_block_bytes(long long b, long long k) { return (size_t)(b *
 cudaError_t launch_exchange_merge(const PeerBlocks& pb, int world, int b, int k, int q_begin, int q_count, cudaStream_t stream,
                                   int64_t* slice_ids = nullptr, float* slice_dist = nullptr, int32_t* slice_count = nullptr);
 
+// copy `nbytes` (multiple of 16, 16-byte aligned) from local `src` to each of `dst[0..n_dst)` with P2P stores
+cudaError_t launch_peer_push(const void* src, void* const* dst, int n_dst, size_t nbytes, cudaStream_t stream);
+
 // K5c: threshold seeding shared between the shards of one index.  Every shard publishes, per query, k witnessed upper
 // bounds on exact badness (SelectParams::seed_keys_out); the k-th smallest over the union of all shards' bounds is a bound
 // on the GLOBAL k-th best, so a shard may discard everything above it (+ its own error margin) even where its own rows

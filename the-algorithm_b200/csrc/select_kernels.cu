@@ -763,6 +763,28 @@ __global__ void __launch_bounds__(kSelThreads) seed_merge_kernel(PeerSeedKeys pk
     }
 }
 
+// ---- replicate a slice to every peer (the all-gather of a partitioned query batch, by push) ----------------------------
+__global__ void __launch_bounds__(256) peer_push_kernel(const uint4* __restrict__ src, PeerBlocks dst, int n_dst, size_t n16) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = src[i];
+        for (int d = 0; d < n_dst; ++d) reinterpret_cast<uint4*>(dst.final_[d])[i] = v;
+    }
+}
+
+cudaError_t launch_peer_push(const void* src, void* const* dst, int n_dst, size_t nbytes, cudaStream_t stream) {
+    if (nbytes == 0 || n_dst <= 0) return cudaSuccess;
+    if (n_dst > kMaxPeers || (nbytes & 15) || ((uintptr_t)src & 15)) return cudaErrorInvalidValue;
+    PeerBlocks pb{};
+    for (int d = 0; d < n_dst; ++d) {
+        if (((uintptr_t)dst[d]) & 15) return cudaErrorInvalidValue;
+        pb.final_[d] = static_cast<unsigned char*>(dst[d]);
+    }
+    const size_t n16 = nbytes / 16;
+    const int grid = (int)std::min<size_t>((n16 + 255) / 256, 148 * 4);
+    peer_push_kernel<<<grid, 256, 0, stream>>>(static_cast<const uint4*>(src), pb, n_dst, n16);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_seed_merge(const PeerSeedKeys& pk, int world, QueryState* qstate, int b, int k, cudaStream_t stream) {
     if (b <= 0 || k <= 0 || world <= 0) return cudaSuccess;
     const size_t smem = (size_t)world * k * 8;
