@@ -68,6 +68,7 @@ def parse():
     ap.add_argument("--config5-rows", type=int, default=50_000_000,
                     help="rows pre-loaded in the configs[4] streaming sub-run (sharded over the ranks); 0 = skip")
     ap.add_argument("--config5-appends", type=int, default=1_000_000)
+    ap.add_argument("--seed-rows", type=int, default=0, help="rows of the threshold-seeding launch per shard (0 = library default 65536)")
     ap.add_argument("--full-h2d", action="store_true", help="N > 1, e2e leg: every rank copies the WHOLE query batch from the host (A/B)")
     ap.add_argument("--pull-bounds", action="store_true", help="N > 1: consumers pull the peers' bound arrays (A/B of push delivery)")
     ap.add_argument("--one-round", action="store_true",
@@ -355,6 +356,8 @@ def run_ours(a):
     q_dev = (torch.rand((b, d), generator=g, device=dev) * 2 - 1).contiguous()
     if a.path:
         ix.set_option("path", a.path)
+    if a.seed_rows:
+        ix.set_option("gemm_seed_rows", a.seed_rows)
 
     out_ids = torch.empty((b, k), dtype=torch.int64, device=dev)
     out_dist = torch.empty((b, k), dtype=torch.float32, device=dev)
