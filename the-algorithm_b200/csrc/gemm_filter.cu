@@ -564,13 +564,7 @@ bool plan_gemm(int kp, int n_qt, size_t smem_optin, GemmPlan* out) {
                 }
             }
         }
-        if (nseg == 1 && n_qt > 1 && getenv("B200ANN_QSTAGES3")) {   // A/B knob: three query stages + ONE row buffer
-            const size_t need = 3 * slot + tile + fixed;
-            if (need <= smem_optin) {
-                *out = GemmPlan{1, 3, 1, 0, (uint32_t)slot, need};
-                return true;
-            }
-        }
+        // (three query stages + ONE row buffer instead of 2 + 2 was measured: 5-8 % slower at 1.25M and 10M rows, round 2)
         {   // streamed query segments (also the fallback for one query tile that is too wide to stay resident)
             const int na_try[] = {nseg == 1 ? 2 : 3, 2};
             for (int nb = (nseg == 1 ? 2 : 1); nb >= 1; --nb)
