@@ -618,7 +618,7 @@ def run_ours(a):
                     ix5.append_batch(new_ids, new_rows)             # host rows in: H2D + K1 inside the call
                 else:
                     sx5.append_routed(new_ids, new_rows)            # round-robin by batch (ShardApi.scala:21-48)
-                torch.cuda.synchronize()
+                barrier()                                           # the JOB's clock: the batch is in place on whichever rank took it
                 t1 = time.perf_counter()
                 q5_pin.copy_(torch.from_numpy(new_rows[:qb5]))      # the queries ARE rows just appended: visibility check
                 qd5 = q5_pin.to(dev, non_blocking=True)
@@ -643,7 +643,8 @@ def run_ours(a):
                                 "ms_per_query_batch": 1e3 * t_qry / max(1, queried // qb5), "ms_per_append_batch": 1e3 * t_app / max(1, n_b5),
                                 "appended_rows_visible_to_next_query": visible, "mapped_bytes_rank0": ix5.stat("mapped_bytes"),
                                 "algorithmic_bytes_rank0": ix5.stat("row_bytes") + ix5.stat("shadow_bytes"),
-                                "timing": "host clock around each call incl. H2D of the appended rows / D2H of the answers, max over ranks"}
+                                "timing": "host wall clock of the whole job: every append batch is timed to the barrier behind it (one rank takes it, the "
+                                          "others wait), every query batch to the D2H of the answers; max over ranks"}
             ix5.close()
         except Exception as e:
             extra["config5"] = {"error": repr(e)}
