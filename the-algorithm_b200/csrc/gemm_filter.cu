@@ -40,6 +40,8 @@ namespace {
 constexpr int kEpiWarp0 = 4;
 constexpr int gemm_threads(int epi_warps) { return 32 * (kEpiWarp0 + epi_warps); }
 constexpr int kTileRows = 128;        // rows (and queries) staged per CTA per tile
+constexpr int kTauTiles = 16;         // query tiles whose thresholds fit the shared-memory table (b <= 4096 with CG = 2)
+constexpr size_t kTauBytes = (size_t)kTauTiles * kTileRows * sizeof(uint32_t);
 
 struct alignas(64) GemmTmaps {
     CUtensorMap q64, q32, q16, r64, r32, r16;
@@ -57,6 +59,7 @@ struct GemmArgs {
     int na_stages, nb_stages;         // query-segment ring slots / row-tile buffers
     int a_resident;                   // the batch is one query tile: its segments are loaded once and never released
     uint32_t a_slot_stride;           // bytes between query-segment slots (1024-aligned)
+    int tau_smem;                     // thresholds of all query tiles are staged in shared memory (n_qt <= kTauTiles)
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -193,6 +196,7 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
     uint64_t* t_full = bars + 22;    // 2
     uint64_t* t_empty = bars + 24;   // 2
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+    uint32_t* tau_tab = reinterpret_cast<uint32_t*>(bars + 28);   // [kTauTiles][kTileRows], present when a.tau_smem
 
     const KBlocks kb(a.kp_mma);
     // K segments: the 64-wide blocks are dealt out evenly, the narrow tail blocks (32 / 16 wide) go with the last segment
@@ -346,7 +350,20 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
         const int half = e >> 2;                      // which slice of the N columns
         constexpr int COLS_PER_WARP = N_TILE / (EW / 4);
         const int q_lane = (int)rank * kTileRows + quarter * 32 + lane;
+        // Thresholds are constant for the launch and a thread meets the same n_qt of them for every row tile: they are staged
+        // in shared memory once.  (A global load per tile sat on the scoreboard of the slot-reserving atomic: ncu showed
+        // the epilogue's first stall of every tile there, 7 % of its samples in a hit-dense chunk.)
+        const bool tau_smem = a.tau_smem != 0;
+        if (tau_smem) {
+            if (half == 0)
+                for (int qt = 0; qt < a.n_qt; ++qt) {
+                    const int q = qt * N_TILE + q_lane;
+                    tau_tab[qt * kTileRows + quarter * 32 + lane] = q < a.b ? __ldcg(&a.qstate[q].tau_key) : 0u;
+                }
+            asm volatile("bar.sync 1, %0;" ::"r"(EW * 32) : "memory");
+        }
         auto load_tau = [&](int qt) -> uint32_t {
+            if (tau_smem) return tau_tab[qt * kTileRows + quarter * 32 + lane];
             const int q = qt * N_TILE + q_lane;
             return q < a.b ? __ldcg(&a.qstate[q].tau_key) : 0u;
         };
@@ -415,40 +432,57 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
                         for (int j = 2; j < 8; ++j) gm[g] = fmaxf(gm[g], v[8 * g + j]);
                     }
                     const bool any = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3])) >= thr;
-                    // Rare path, kept SMALL on purpose: the kernel has to stay inside the 32 KB instruction cache (a 32x
-                    // unrolled hit handler -- tried twice, 42-45 KB of code -- costs 5-40 % because it stalls the MMA warp).
-                    // Build this lane's hit mask, OR it across the warp, and visit every column some lane hit by re-reading
-                    // that single column from TMEM (warp-uniform address).  A 32-way select on v[] (switch, or a 5-level
-                    // select tree) measured 1-2 % slower on the whole batch in same-box A/B runs.
+                    // Hit path.  It has to stay SMALL: the kernel must fit the 32 KB instruction cache (a 32x unrolled handler --
+                    // tried twice, 42-45 KB of code -- costs 5-40 % because it stalls the MMA warp).
+                    // Fast case, no TMEM re-read and nothing warp-wide: an 8-column group with exactly ONE hit -- its value is
+                    // the group maximum already in a register, its column the set bit of the group's compare mask.  Groups with
+                    // two or more hits, partial tiles and threads whose hit registers are full take the slow case: OR the
+                    // masks across the warp and re-read every such column from TMEM (warp-uniform address).  (A 32-way select on
+                    // v[] -- switch, or a 5-level select tree -- measured 1-2 % slower on the whole batch.)
                     if (__any_sync(0xFFFFFFFFu, any) && col0 < valid_cols) {
-                        uint32_t mask = 0;
+                        const int left = valid_cols - col0;
+                        uint32_t mask = 0;            // columns of this lane left to the slow case
 #pragma unroll
                         for (int g = 0; g < 4; ++g)
                             if (gm[g] >= thr) {   // only the 8-column groups that hold a hit are expanded
+                                uint32_t m8 = 0;
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) mask |= (v[8 * g + j] >= thr) ? (1u << (8 * g + j)) : 0u;
-                            }
-                        const int left = valid_cols - col0;
-                        if (left < 32) mask &= (1u << left) - 1u;
-                        uint32_t um = __reduce_or_sync(0xFFFFFFFFu, mask);
-                        while (um) {
-                            const int j = __ffs(um) - 1;
-                            um &= um - 1;
-                            float x;
-                            tmem_ld1(t_lane + c0 + j, &x);
-                            tmem_ld_wait();
-                            if ((mask >> j) & 1u) {
-                                const uint32_t row = (uint32_t)(tile_row0 + col0 + j);
-                                if (ccnt < kHitRegs) {
+                                for (int j = 0; j < 8; ++j) m8 |= (v[8 * g + j] >= thr) ? (1u << j) : 0u;
+                                if ((m8 & (m8 - 1u)) == 0u && ccnt < kHitRegs && left >= 32) {
+                                    const uint32_t row = (uint32_t)(tile_row0 + col0 + 8 * g + (__ffs(m8) - 1));
 #pragma unroll
                                     for (int i = 0; i < kHitRegs; ++i)
                                         if (i == ccnt) {
-                                            cv[i] = x;
+                                            cv[i] = gm[g];
                                             cr[i] = row;
                                         }
                                     ++ccnt;
                                 } else {
-                                    emit_now(q, x, row);   // dense regions (first chunk): straight to the pool
+                                    mask |= m8 << (8 * g);
+                                }
+                            }
+                        if (left < 32) mask &= (1u << left) - 1u;
+                        if (__any_sync(0xFFFFFFFFu, mask != 0u)) {
+                            uint32_t um = __reduce_or_sync(0xFFFFFFFFu, mask);
+                            while (um) {
+                                const int j = __ffs(um) - 1;
+                                um &= um - 1;
+                                float x;
+                                tmem_ld1(t_lane + c0 + j, &x);
+                                tmem_ld_wait();
+                                if ((mask >> j) & 1u) {
+                                    const uint32_t row = (uint32_t)(tile_row0 + col0 + j);
+                                    if (ccnt < kHitRegs) {
+#pragma unroll
+                                        for (int i = 0; i < kHitRegs; ++i)
+                                            if (i == ccnt) {
+                                                cv[i] = x;
+                                                cr[i] = row;
+                                            }
+                                        ++ccnt;
+                                    } else {
+                                        emit_now(q, x, row);   // dense regions (first chunk): straight to the pool
+                                    }
                                 }
                             }
                         }
@@ -617,6 +651,7 @@ cudaError_t launch_gemm_filter(const GemmLaunch& g, cudaStream_t stream) {
     int clusters = g.sm_count / cg;
     if (clusters > n_rt) clusters = n_rt;
     GemmPlan plan;
+    size_t optin = 232448;
     {
         cudaDeviceProp prop;
         int dev = 0;
@@ -626,14 +661,17 @@ cudaError_t launch_gemm_filter(const GemmLaunch& g, cudaStream_t stream) {
             cudaGetDeviceProperties(&prop, dev);
             optin_cache[dev] = prop.sharedMemPerBlockOptin;
         }
-        if (!plan_gemm(kp, a.n_qt, dev < 16 ? optin_cache[dev] : 232448, &plan)) return cudaErrorInvalidValue;
+        if (dev < 16) optin = optin_cache[dev];
+        if (!plan_gemm(kp, a.n_qt, optin, &plan)) return cudaErrorInvalidValue;
     }
     a.nseg = plan.nseg;
     a.na_stages = plan.na;
     a.nb_stages = plan.nb;
     a.a_resident = plan.a_resident;
     a.a_slot_stride = plan.a_slot_stride;
-    const size_t smem = plan.smem;
+    // the threshold table rides behind the barriers when the plan leaves room for it (it does for every dim <= 208)
+    a.tau_smem = (!g.seed_mode && a.n_qt <= kTauTiles && plan.smem + kTauBytes <= optin) ? 1 : 0;
+    const size_t smem = plan.smem + (a.tau_smem ? kTauBytes : 0);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(clusters * cg);
     cfg.dynamicSmemBytes = smem;
