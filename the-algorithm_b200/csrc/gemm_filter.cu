@@ -354,16 +354,24 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
         // in shared memory once.  (A global load per tile sat on the scoreboard of the slot-reserving atomic: ncu showed
         // the epilogue's first stall of every tile there, 7 % of its samples in a hit-dense chunk.)
         const bool tau_smem = a.tau_smem != 0;
+        const uint32_t tau_addr = smem_u32(tau_tab) + (uint32_t)(quarter * 32 + lane) * 4u;   // + qt * kTileRows * 4
         if (tau_smem) {
-            if (half == 0)
+            if (half == 0) {
+#pragma unroll 1
                 for (int qt = 0; qt < a.n_qt; ++qt) {
                     const int q = qt * N_TILE + q_lane;
-                    tau_tab[qt * kTileRows + quarter * 32 + lane] = q < a.b ? __ldcg(&a.qstate[q].tau_key) : 0u;
+                    const uint32_t t = q < a.b ? __ldcg(&a.qstate[q].tau_key) : 0u;
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(tau_addr + (uint32_t)qt * (kTileRows * 4u)), "r"(t) : "memory");
                 }
+            }
             asm volatile("bar.sync 1, %0;" ::"r"(EW * 32) : "memory");
         }
         auto load_tau = [&](int qt) -> uint32_t {
-            if (tau_smem) return tau_tab[qt * kTileRows + quarter * 32 + lane];
+            if (tau_smem) {
+                uint32_t t;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(t) : "r"(tau_addr + (uint32_t)qt * (kTileRows * 4u)));
+                return t;
+            }
             const int q = qt * N_TILE + q_lane;
             return q < a.b ? __ldcg(&a.qstate[q].tau_key) : 0u;
         };
@@ -403,6 +411,7 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
                 float cv[kHitRegs];
                 uint32_t cr[kHitRegs];
                 int ccnt = 0;
+                float seed_m = -INFINITY;
 #pragma unroll 1
                 for (int c0 = 0; c0 < COLS_PER_WARP; c0 += 32) {
                     float v[32];
@@ -410,16 +419,14 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
                     tmem_ld_wait();
                     const int col0 = half * COLS_PER_WARP + c0;
                     if constexpr (SEED) {
-                        // threshold seeding: the best score of each 32-row group goes to a fixed pool slot.  The k-th best
-                        // of these group maxima bounds the k-th best row from below (k distinct groups => k rows).
+                        // threshold seeding: the best score of each group of COLS_PER_WARP rows (this warp's columns of the
+                        // tile) goes to a fixed pool slot.  The k-th best of these group maxima bounds the k-th best row from
+                        // below (k distinct groups => k rows).  One 8-byte store per thread and tile: the stores of a warp go
+                        // to 32 different queries' pools (32 sectors), and with 32-row groups -- four stores per tile --
+                        // they slowed the seed launch to 1050 TFLOP/s.
                         const int left = valid_cols - col0;
-                        float m = -INFINITY;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) m = fmaxf(m, j < left ? v[j] : -INFINITY);
-                        if (q_ok && left > 0) {
-                            const uint32_t slot = (uint32_t)((tile_row0 - a.row_begin + col0) >> 5);
-                            if (slot < (uint32_t)a.pool_cap) a.pool[(size_t)q * a.pool_cap + slot] = make_entry(-m, 0xFFFFFFFFu);
-                        }
+                        for (int j = 0; j < 32; ++j) seed_m = fmaxf(seed_m, j < left ? v[j] : -INFINITY);
                         continue;
                     }
                     // four independent max chains (one per 8 columns) instead of one 32-long dependent chain: with two
@@ -481,11 +488,20 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
                                             }
                                         ++ccnt;
                                     } else {
-                                        emit_now(q, x, row);   // dense regions (first chunk): straight to the pool
+                                        // registers full: straight to the pool.  Rare on purpose -- the store waits for the
+                                        // atomic's round trip with the accumulator still held (measured: parking a hit that
+                                        // could have been parked costs 1.5 % of a 1.25M-row batch)
+                                        emit_now(q, x, row);
                                     }
                                 }
                             }
                         }
+                    }
+                }
+                if constexpr (SEED) {
+                    if (q_ok && half * COLS_PER_WARP < valid_cols) {
+                        const uint32_t slot = (uint32_t)((tile_row0 - a.row_begin) / COLS_PER_WARP) + (uint32_t)half;
+                        if (slot < (uint32_t)a.pool_cap) a.pool[(size_t)q * a.pool_cap + slot] = make_entry(-seed_m, 0xFFFFFFFFu);
                     }
                 }
                 // The next tile's threshold was requested at the top of this tile; pin its arrival HERE, before the slot
@@ -615,6 +631,10 @@ bool plan_gemm(int kp, int n_qt, size_t smem_optin, GemmPlan* out) {
 }
 
 }  // namespace
+
+// rows per seed group (one pool entry each) of a seed-mode launch: the columns one epilogue warp owns (seed launches run
+// with 8 epilogue warps)
+int gemm_seed_group_rows(int cta_group) { return kTileRows * (cta_group == 2 ? 2 : 1) / (8 / 4); }
 
 // 1 when some shared-memory plan exists for this operand width (any batch size), else 0: the caller must use the scan.
 int gemm_row_stages(int kp, size_t smem_optin) {

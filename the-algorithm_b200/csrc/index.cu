@@ -174,6 +174,7 @@ struct ann_index {
     // options / stats
     int path_opt = 0, gemm_min_batch = 2, gemm_cta_group = 2, gemm_epi_warps = 0;
     int gemm_hit_budget = 500;        // candidates a chunk of the GEMM path may add per query (sets the chunk schedule)
+    int gemm_growth_pct = 0;          // chunk growth factor in percent (0 = derived from the hit budget)
     int gemm_small_select = 1;        // GEMM path: 2048 / 1024-entry selector stages (4 CTAs per SM) instead of 4096 / 2048
     long long gemm_seed_rows = 0;     // rows of the threshold-seeding launch (0 = as many as the pool has slots for)
     bool device_fallback = false;
@@ -581,8 +582,9 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
         // ~1.5e-4 hits per score the epilogue is the bottleneck and wants 16 warps (same-process A/B, tools/ab_options.py:
         // 2.82 -> 2.52 ms per 4096-query batch over 1.25M rows; neutral at 10M rows where sparse chunks dominate)
         // With a single resident query tile (b <= 256) the launch is HBM bound and 8 warps measured 8 % faster.
-        g.epi_warps = ix->gemm_epi_warps ? ix->gemm_epi_warps
-                                         : ((!seed_mode && b > 256 && (double)(end - begin) * 1.5e-4 < (double)kHitBudget) ? 16 : 8);
+        g.epi_warps = seed_mode ? 8   // the seed group is the column range of one of 8 epilogue warps (gemm_seed_group_rows)
+                      : ix->gemm_epi_warps ? ix->gemm_epi_warps
+                                         : ((b > 256 && (double)(end - begin) * 1.5e-4 < (double)kHitBudget) ? 16 : 8);
         g.nb_stages = gemm_row_stages(ix->kp, ix->smem_optin);
         g.sm_count = ix->sm_count;
         g.qstate = qs_base;
@@ -630,15 +632,19 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
     //   chunks : then [0, c1), [c1, c2), ... sized so that each adds roughly kHitBudget candidates per query.
     // Seeding is an extra pass over its rows (the first chunk scores them again), so it is kept short: 65536 rows (2048
     // group maxima, >= 8 groups per neighbour up to k = 256) measured 1.6 % faster than 131072 on the 10M x 200 batch.
-    long long seed_rows = std::min<long long>(ix->n / 256 * 256, std::min<long long>((long long)kGemmPoolCap * 32, std::max<long long>(65536, 256LL * k_eff)));
+    // One pool entry per group of G rows (128 with CTA pairs): 65536 rows give 512 group maxima, 5 per neighbour at k = 100
+    // (the k-th best of them sits where the 111th best row does); larger k seeds over 4 groups per neighbour.
+    const long long G = gemm_seed_group_rows(ix->gemm_cta_group);
+    long long seed_rows = std::min<long long>(ix->n / 256 * 256, std::min<long long>((long long)kGemmPoolCap * G, std::max<long long>(65536, 4 * G * k_eff)));
     if (ix->gemm_seed_rows > 0) seed_rows = std::min<long long>(seed_rows, ix->gemm_seed_rows / 256 * 256);
-    bool use_seed = seed_rows >= 128LL * k_eff && seed_rows >= 4096;
+    bool use_seed = seed_rows >= 2 * G * k_eff && seed_rows >= 4096;
     if (mode >= 2) {   // what phase 1 decided and did
         use_seed = ix->sess.seeded;
         seed_rows = ix->sess.seed_rows;
     }
     // a chunk `growth` times the rows seen so far adds about (growth - 1) * 1.9 * k candidates per query
-    int growth = (int)std::min<double>(8.0, std::max<double>(2.0, 1.0 + kHitBudget / (1.9 * std::max(1, k_eff))));
+    double growth = std::floor(std::min<double>(8.0, std::max<double>(2.0, 1.0 + kHitBudget / (1.9 * std::max(1, k_eff)))));
+    if (ix->gemm_growth_pct > 0) growth = ix->gemm_growth_pct / 100.0;
     long long begin = 0, end;
     ix->last_gemm_chunks = 0;
     if (use_seed) {
@@ -647,7 +653,7 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
             int rc2 = gemm_launch(0, seed_rows, 1);
             if (rc2) return rc2;
             SelectParams sp = fp;
-            sp.seed_count = (int)(seed_rows / 32);
+            sp.seed_count = (int)(seed_rows / G);
             sp.sort_cap = std::max(sp.sort_cap, sp.seed_count);   // every seed entry is loaded
             if (mode == 1) set_publish(sp);
             { TimedScope ts_(ix, st, ann_index::kLblCompact); CUDA_TRY(launch_compact_pool(sp, b, st)); }
@@ -691,7 +697,7 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
         { TimedScope ts_(ix, st, ann_index::kLblCompact); CUDA_TRY(launch_compact_pool(fp, b, st)); }
         ix->launches++;
         begin = end;
-        end = std::min<long long>(ix->n, end * growth);
+        end = std::min<long long>(ix->n, ((long long)((double)end * growth) + 255) / 256 * 256);
     }
     if (mode == 3) {   // last compaction + publish; the exact finalize follows the second cross-shard round (mode 4)
         SelectParams sp = fp;
@@ -1656,6 +1662,11 @@ int ann_set_option(ann_index* ix, const char* name, int64_t value) {
     }
     if (!strcmp(name, "gemm_small_select")) {
         ix->gemm_small_select = value ? 1 : 0;
+        return ANN_OK;
+    }
+    if (!strcmp(name, "gemm_growth_pct")) {
+        if (value != 0 && (value < 125 || value > 800)) return fail(ANN_ERR_INVALID_ARGUMENT, "gemm_growth_pct must be 0 (auto) or in [125, 800]");
+        ix->gemm_growth_pct = (int)value;
         return ANN_OK;
     }
     if (!strcmp(name, "gemm_seed_rows")) {

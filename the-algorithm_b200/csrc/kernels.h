@@ -178,6 +178,7 @@ struct GemmLaunch {
     int pool_cap;
 };
 cudaError_t launch_gemm_filter(const GemmLaunch& g, cudaStream_t stream);
+int gemm_seed_group_rows(int cta_group);
 int gemm_row_stages(int kp, size_t smem_optin);   // 1 when a shared-memory plan exists for this operand width, else 0 (use the scan)
 
 }  // namespace b200ann
