@@ -71,6 +71,8 @@ def parse():
     ap.add_argument("--seed-rows", type=int, default=0, help="rows of the threshold-seeding launch per shard (0 = library default 65536)")
     ap.add_argument("--full-h2d", action="store_true", help="N > 1, e2e leg: every rank copies the WHOLE query batch from the host (A/B)")
     ap.add_argument("--pull-bounds", action="store_true", help="N > 1: consumers pull the peers' bound arrays (A/B of push delivery)")
+    ap.add_argument("--full-seeds", action="store_true",
+                    help="N > 1: every rank seeds every query and delivers k bounds per query (A/B of sliced seeding)")
     ap.add_argument("--one-round", action="store_true",
                     help="N > 1: seed round only (A/B of the second cross-shard round that shares the k best bounds)")
     ap.add_argument("--no-share-seeds", action="store_true",
@@ -362,7 +364,8 @@ def run_ours(a):
     out_ids = torch.empty((b, k), dtype=torch.int64, device=dev)
     out_dist = torch.empty((b, k), dtype=torch.float32, device=dev)
     out_cnt = torch.empty((b,), dtype=torch.int32, device=dev)
-    sx = ShardedBruteForceIndex(ix, device=dev, share_seeds=not a.no_share_seeds, two_round=not a.one_round, push=not a.pull_bounds) if world > 1 else None
+    sx = ShardedBruteForceIndex(ix, device=dev, share_seeds=not a.no_share_seeds, two_round=not a.one_round, push=not a.pull_bounds,
+                                sliced_seeds=not a.full_seeds) if world > 1 else None
 
     def step_device(queries):
         if world == 1:
@@ -549,7 +552,8 @@ def run_ours(a):
             q4 = (torch.rand((b4, d), generator=g, device=dev) * 2 - 1).contiguous()
             o4 = (torch.empty((b4, k), dtype=torch.int64, device=dev), torch.empty((b4, k), dtype=torch.float32, device=dev),
                   torch.empty((b4,), dtype=torch.int32, device=dev))
-            sx4 = ShardedBruteForceIndex(ix4, device=dev, share_seeds=not a.no_share_seeds, two_round=not a.one_round, push=not a.pull_bounds) if world > 1 else None
+            sx4 = ShardedBruteForceIndex(ix4, device=dev, share_seeds=not a.no_share_seeds, two_round=not a.one_round, push=not a.pull_bounds,
+                                sliced_seeds=not a.full_seeds) if world > 1 else None
 
             def step4():
                 if world == 1:
@@ -594,7 +598,8 @@ def run_ours(a):
                 if s_ < e_:
                     ix5.append_batch_device(torch.arange(s_, e_, device=dev, dtype=torch.int64), rows[s_ - c0:e_ - c0].contiguous())
                 del rows
-            sx5 = ShardedBruteForceIndex(ix5, device=dev, share_seeds=not a.no_share_seeds, two_round=not a.one_round, push=not a.pull_bounds) if world > 1 else None
+            sx5 = ShardedBruteForceIndex(ix5, device=dev, share_seeds=not a.no_share_seeds, two_round=not a.one_round, push=not a.pull_bounds,
+                                sliced_seeds=not a.full_seeds) if world > 1 else None
             rng5 = np.random.default_rng(0x5EED0008)            # the appended rows: same stream on every rank
             q5_pin = torch.empty((qb5, d), dtype=torch.float32).pin_memory()
             o5 = (torch.empty((qb5, k), dtype=torch.int64, device=dev), torch.empty((qb5, k), dtype=torch.float32, device=dev),

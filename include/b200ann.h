@@ -202,6 +202,28 @@ ANN_API int ann_query_filter_push_device(ann_index *ix, const float *d_queries, 
                                          const uint32_t *const *peer_seed_keys, int32_t world, uint32_t *const *kth_dst,
                                          int32_t n_dst, void *stream);
 
+/* SLICED seeding (round 1 of the sharded query, replaces ann_query_seed_push_device + the seed half of
+ * ann_query_filter_push_device).  Instead of every shard seeding ALL b queries over a short prefix, publishing k bounds per
+ * query and every consumer selecting the k-th smallest of the R*k bounds, shard s seeds only ITS slice
+ * [q_begin, q_begin + q_count) of the batch, over n_slices times the rows, and publishes ONE bound per query: the same
+ * tensor-core work per shard, the same number of rows seen per query, k times less to exchange and no selection kernel.
+ *   ann_query_seed_slice_push_device   dst[i] = the [b] uint32 bound array inside peer i's memory (own copy included); this
+ *                                      shard writes entries [q_begin, q_begin + q_count) of each (0xFFFFFFFF = no bound);
+ *                                                                                               -- barrier --
+ *   ann_query_filter_bounds_push_device  d_bounds = the LOCAL [b] array every slice owner has written; thresholds of all b
+ *                                      queries come from it (plus this shard's own error margin); then as
+ *                                      ann_query_filter_push_device (chunks, last compaction, k best bounds pushed to kth_dst);
+ *                                                                                               -- barrier --
+ *   ann_query_rescore_device           unchanged.
+ * The slices of the shards must tile [0, b).  A shard too small to seed publishes "no bound" for its slice; the queries of
+ * that slice are then flagged on the other shards (count = -1) and re-answered by the callers' exact fallback. */
+ANN_API int ann_query_seed_slice_push_device(ann_index *ix, const float *d_queries, int32_t b, int32_t dim, int32_t k,
+                                             int32_t q_begin, int32_t q_count, int32_t n_slices, uint32_t *const *dst,
+                                             int32_t n_dst, void *stream);
+ANN_API int ann_query_filter_bounds_push_device(ann_index *ix, const float *d_queries, int32_t b, int32_t dim, int32_t k,
+                                                const uint32_t *d_bounds, int32_t world, uint32_t *const *kth_dst,
+                                                int32_t n_dst, void *stream);
+
 /* Pull-only form of ann_exchange_merge_device: merge this rank's slice [q_begin, q_begin + q_count) of the batch from all
  * `world` local result blocks (P2P loads) into plain arrays on this device -- d_out_ids / d_out_dist [q_count*k],
  * d_out_count [q_count] (may be NULL).  The merged answer stays partitioned across the ranks: nothing is pushed, and no
@@ -228,7 +250,9 @@ ANN_API int ann_sharded_query_batch(ann_sharded_index *sx, const float *queries,
                                     int64_t *out_ids, float *out_dist, int32_t *out_count);
 /* Borrow shard `shard` (owned by the composed handle) and its row count. */
 ANN_API int ann_sharded_shard(ann_sharded_index *sx, int32_t shard, ann_index **out, int64_t *rows);
-/* "two_round" (1 = seed + k-best rounds, default; 0 = seed round only); any other name is applied to every shard.
+/* "two_round" (1 = seed + k-best rounds, default; 0 = seed round only), "sliced_seeds" (two_round only; 1 = every shard
+ * seeds its slice of the batch and delivers one bound per query, default; 0 = every shard seeds every query and delivers k
+ * bounds per query); any other name is applied to every shard.
  * Stats: "shards", "peer_access", "fallback_batches", "queries"; any other name is summed over the shards. */
 ANN_API int ann_sharded_set_option(ann_sharded_index *sx, const char *name, int64_t value);
 ANN_API int ann_sharded_get_stat(const ann_sharded_index *sx, const char *name, int64_t *value);
@@ -306,6 +330,7 @@ ANN_API int ann_loadtest(ann_index *ix, const float *queries, int32_t nq, int32_
 /* Tuning / introspection.
  * Options: "path" (0 auto, 1 streaming scan, 2 tensor-core GEMM filter, 3 exact fallback for every query), "gemm_min_batch", "gemm_cta_group" (1|2), "gemm_epi_warps" (0 auto, 8, 16),
  *          "gemm_hit_budget" (candidates one chunk may add per query, default 500), "gemm_seed_rows" (0 = default 65536),
+ *          "gemm_growth_pct" (chunk growth factor in percent, 0 = derived from the hit budget),
  *          "timing" (1 = bracket every scan / GEMM-filter launch with CUDA events on its stream),
  *          "coalesce_max_batch" (queries per merged device call of the host entry point's micro-batcher, default 2048; 0 = off),
  *          "coalesce_small_b" (host calls with at most this many queries are combined with concurrent ones, default 32),

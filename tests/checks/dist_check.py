@@ -101,6 +101,14 @@ for metric, n, d, b, k in ((InnerProduct, 200_003, 200, 300, 100), (Cosine, 50_0
         ok2 &= bool((si.cpu().numpy() == wi).all() and (sd.cpu().numpy().view(np.uint32) == wd.view(np.uint32)).all()
                     and (sc.cpu().numpy() == wc).all())
     del sx
+    # push delivery with every shard seeding every query (k bounds per query; A/B of sliced seeding, the default above)
+    sx = ShardedBruteForceIndex(ix, device=dev, sliced_seeds=False)
+    for rep in range(2):
+        si, sd, sc = sx.batch_query_device(qd, k, st)
+        torch.cuda.synchronize()
+        ok2 &= bool((si.cpu().numpy() == wi).all() and (sd.cpu().numpy().view(np.uint32) == wd.view(np.uint32)).all()
+                    and (sc.cpu().numpy() == wc).all())
+    del sx
     # the same with the seed round only (A/B of the second cross-shard round)
     sx = ShardedBruteForceIndex(ix, device=dev, two_round=False)
     for rep in range(2):

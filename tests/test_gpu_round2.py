@@ -170,18 +170,21 @@ def _devices(shards):
     return [s % n for s in range(shards)]       # one GPU: every shard on it (same code path, events instead of NVLink)
 
 
-@pytest.mark.parametrize("two_round", [1, 0])
+@pytest.mark.parametrize("two_round,sliced", [(1, 1), (1, 0), (0, 0)])
 @pytest.mark.parametrize("mi", [0, 1, 2])
 @pytest.mark.parametrize("shards,n,d,b,k", [(2, 70_001, 200, 130, 100), (3, 50_000, 64, 40, 10), (8, 400_000, 128, 64, 100),
-                                            (4, 9000, 32, 7, 100), (2, 150, 16, 5, 100)])
-def test_in_process_sharded_handle_equals_single_index(two_round, mi, shards, n, d, b, k):
-    """ann_sharded_* (one process, R shards, CUDA events between the phases): bit for bit the single-index oracle answer."""
+                                            (4, 9000, 32, 7, 100), (2, 150, 16, 5, 100), (2, 300_000, 64, 300, 50)])
+def test_in_process_sharded_handle_equals_single_index(two_round, sliced, mi, shards, n, d, b, k):
+    """ann_sharded_* (one process, R shards, CUDA events between the phases): bit for bit the single-index oracle answer --
+    with sliced seeding (every shard seeds its slice of the batch, one bound per query), with every shard seeding every
+    query (k bounds per query), and with the seed round only."""
     from the_algorithm_b200.ann.sharded import GpuShardedBruteForceIndex
 
     m = metrics()[mi]
     corpus, ids, q = make(n, d, b, seed=n + shards, dup=True)
     sx = GpuShardedBruteForceIndex(m, G["FuturePool"].immediate_pool(), dim=d, devices=_devices(shards))
     sx.set_option("two_round", two_round)
+    sx.set_option("sliced_seeds", sliced)
     half = n // 2
     sx.append_batch(ids[:half], corpus[:half])         # two appends: every shard holds two non-adjacent row ranges
     sx.append_batch(ids[half:], corpus[half:])

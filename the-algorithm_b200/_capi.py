@@ -37,6 +37,7 @@ SYMBOLS = (
     "ann_query_batch_device", "ann_merge_topk_device", "ann_exchange_merge_device", "ann_result_block_bytes", "ann_query_seed_device", "ann_query_finish_device",
     "ann_query_filter_device", "ann_query_rescore_device", "ann_exchange_merge_slice_device",
     "ann_query_seed_push_device", "ann_query_filter_push_device", "ann_peer_push_device",
+    "ann_query_seed_slice_push_device", "ann_query_filter_bounds_push_device",
     "ann_sharded_create", "ann_sharded_destroy", "ann_sharded_append_batch", "ann_sharded_size", "ann_sharded_query_batch",
     "ann_sharded_shard", "ann_sharded_set_option", "ann_sharded_get_stat",
     "ann_save_directory", "ann_load_directory", "ann_sharded_save_directory", "ann_sharded_load_directory",
@@ -106,6 +107,10 @@ def lib() -> ctypes.CDLL:
         L.ann_query_seed_push_device.argtypes = [vp, vp, i32, i32, i32, ctypes.POINTER(vp), i32, vp]
         L.ann_query_filter_push_device.restype = ctypes.c_int
         L.ann_query_filter_push_device.argtypes = [vp, vp, i32, i32, i32, ctypes.POINTER(vp), i32, ctypes.POINTER(vp), i32, vp]
+        L.ann_query_seed_slice_push_device.restype = ctypes.c_int
+        L.ann_query_seed_slice_push_device.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, ctypes.POINTER(vp), i32, vp]
+        L.ann_query_filter_bounds_push_device.restype = ctypes.c_int
+        L.ann_query_filter_bounds_push_device.argtypes = [vp, vp, i32, i32, i32, vp, i32, ctypes.POINTER(vp), i32, vp]
         L.ann_peer_push_device.restype = ctypes.c_int
         L.ann_peer_push_device.argtypes = [i32, vp, ctypes.POINTER(vp), i32, ctypes.c_size_t, vp]
         L.ann_query_rescore_device.restype = ctypes.c_int

@@ -321,6 +321,26 @@ class BruteForceIndex(Appendable, Queryable):
             self._h, ctypes.c_void_p(queries_t.data_ptr()), int(queries_t.shape[0]), int(queries_t.shape[1]), int(k),
             src if w else None, w, dst, n, ctypes.c_void_p(stream)))
 
+    def query_seed_slice_push_device(self, queries_t, k: int, q_begin: int, q_count: int, n_slices: int, dst_ptrs, stream: int = 0) -> None:
+        """`ann_query_seed_slice_push_device` (sliced seeding): seed only the queries [q_begin, q_begin + q_count) over
+        `n_slices` times the rows and write ONE bound per query into entries [q_begin, ...) of every peer's [b] bound array
+        (`dst_ptrs`: the array's device address inside every peer, own copy included)."""
+        n = len(dst_ptrs)
+        arr = (ctypes.c_void_p * n)(*[int(p) for p in dst_ptrs])
+        self.flush()
+        _capi.check(_capi.lib().ann_query_seed_slice_push_device(
+            self._h, ctypes.c_void_p(queries_t.data_ptr()), int(queries_t.shape[0]), int(queries_t.shape[1]), int(k), int(q_begin),
+            int(q_count), int(n_slices), arr, n, ctypes.c_void_p(stream)))
+
+    def query_filter_bounds_push_device(self, queries_t, k: int, bounds_ptr: int, world: int, kth_dst_ptrs, stream: int = 0) -> None:
+        """`ann_query_filter_bounds_push_device`: thresholds from the LOCAL [b] bound array the slice owners filled, then the
+        chunks, the last compaction and the k best bounds pushed into every peer's receive buffer (`kth_dst_ptrs`)."""
+        n = len(kth_dst_ptrs)
+        dst = (ctypes.c_void_p * n)(*[int(p) for p in kth_dst_ptrs])
+        _capi.check(_capi.lib().ann_query_filter_bounds_push_device(
+            self._h, ctypes.c_void_p(queries_t.data_ptr()), int(queries_t.shape[0]), int(queries_t.shape[1]), int(k),
+            ctypes.c_void_p(int(bounds_ptr)), int(world), dst, n, ctypes.c_void_p(stream)))
+
     def query_filter_device(self, queries_t, k: int, peer_seed_key_ptrs, kth_keys_t, stream: int = 0) -> None:
         """Middle phase of the three-phase sharded query (`ann_query_filter_device`): global seed threshold, tensor-core
         chunks, last compaction; publishes this shard's k best bounds per query into `kth_keys_t` ([b, k] CUDA tensor)."""

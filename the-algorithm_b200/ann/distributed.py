@@ -45,7 +45,7 @@ class ShardedBruteForceIndex:
     all-gather route (default: the CUDA merge kernel)."""
 
     def __init__(self, local, group=None, route: str = "auto", merge: Optional[Callable] = None, device=None,
-                 share_seeds: bool = True, two_round: bool = True, push: bool = True):
+                 share_seeds: bool = True, two_round: bool = True, push: bool = True, sliced_seeds: bool = True):
         import torch
         import torch.distributed as dist
 
@@ -58,6 +58,7 @@ class ShardedBruteForceIndex:
         self.share_seeds = share_seeds   # fused route: two-phase local query around a cross-shard threshold exchange
         self.two_round = two_round       # ... plus a second exchange of the k best bounds after the last chunk (three phases)
         self.push = push                 # bounds are pushed into the peers' receive buffers instead of pulled by every consumer
+        self.sliced_seeds = sliced_seeds  # first round: every rank seeds its SLICE of the batch and delivers one bound per query
         self._px = {}          # (b, k) -> PeerExchange
         self._gather = {}      # (b, k) -> gathered buffers
         self._own = {}         # (b, k) -> this rank's result arrays (all-gather route)
@@ -162,6 +163,15 @@ class ShardedBruteForceIndex:
             else:
                 if exact or not (self.share_seeds and hasattr(self.local, "query_seed_device")):
                     self.local.query_batch_device(queries, k, px.local.ids, px.local.dist, px.local.count, stream)
+                elif self.two_round and self.push and self.sliced_seeds and hasattr(self.local, "query_seed_slice_push_device"):
+                    # SLICED seeding: this rank seeds only ITS slice of the batch, over `world` times the rows, and writes one
+                    # bound per query into every rank's bound array; then the k best bounds after the last chunk, by push
+                    q0, q1 = self.slice_range(b)
+                    self.local.query_seed_slice_push_device(queries, k, q0, q1 - q0, self.world, px.bound_dst, stream)
+                    px.seed_barrier()
+                    self.local.query_filter_bounds_push_device(queries, k, px.bound_src, self.world, px.kth_push_dst, stream)
+                    px.kth_barrier()
+                    self.local.query_rescore_device(queries, k, px.kth_recv_src, px.local.ids, px.local.dist, px.local.count, stream)
                 elif self.two_round and self.push and hasattr(self.local, "query_filter_push_device"):
                     # three phases around two small exchanges, bounds delivered by PUSH (P2P stores into every peer's receive
                     # buffer; each consumer then reads local memory): seed bounds, then the k best bounds after the last

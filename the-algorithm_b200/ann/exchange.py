@@ -120,6 +120,9 @@ class PeerExchange:
         me = ptrs[self.rank]
         self.seed_push_dst = [p + o3 + self.rank * seed_bytes for p in ptrs]
         self.kth_push_dst = [p + o4 + self.rank * seed_bytes for p in ptrs]
+        # sliced seeding: ONE bound per query, written by the query's slice owner into the head of every rank's seed receive buffer
+        self.bound_dst = [p + o3 for p in ptrs]
+        self.bound_src = me + o3
         self.seed_recv_src = [me + o3 + s * seed_bytes for s in range(self.world)]
         self.kth_recv_src = [me + o4 + s * seed_bytes for s in range(self.world)]
         self.dim = dim

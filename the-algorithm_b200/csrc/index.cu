@@ -203,6 +203,7 @@ struct ann_index {
         bool seeded = false;      // ... and a seed launch ran: this shard's bounds are published
         bool clobbered = false;   // another call touched the scratch or the rows in between
         bool filtered = false;    // ann_query_filter_device ran: only ann_query_rescore_device may follow
+        bool sliced = false;      // sliced seeding: this shard seeded only its slice of the batch, over `scale` x the rows
         int b = 0, k = 0;
         long long seed_rows = 0;
     } sess;
@@ -474,9 +475,20 @@ int query_scan(ann_index* ix, const float* d_queries, int b, int k_eff, int k_ou
 // mode 3 / 4 split mode 2 once more around a SECOND cross-shard round: 3 = thresholds + chunks + last compaction, which
 // publishes this shard's k best approximate bounds into `seed_keys_out`; 4 = exact finalize against the k-th best bound of
 // all shards (`peers`), so that every shard rescores only its share of the global survivors.
+// Sliced seeding (`slice` != nullptr): in mode 1 the shard seeds only the queries [q_begin, q_begin + q_count) but over
+// `scale` times the rows, and publishes ONE bound per query (the k-th best group maximum as an upper bound) into every
+// peer's [b] array; in mode 3 the thresholds of all b queries come from the array the slice owners filled (`bounds`).
+// Same GEMM work per shard as seeding every query over a short prefix, the same rows seen per query as the union of all
+// shards' prefixes -- but k times less to exchange and no k-th-of-the-union selection on the consumer side.
+struct SliceSeed {
+    int q_begin = 0, q_count = 0, scale = 1;
+    const uint32_t* bounds = nullptr;
+};
+
 int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b, int k_eff, int k_out, int64_t* d_out_ids,
                float* d_out_dist, int32_t* d_out_count, cudaStream_t st, int mode = 0, uint32_t* seed_keys_out = nullptr,
-               const PeerSeedKeys* peers = nullptr, int world = 1, uint32_t* const* push_dst = nullptr, int n_push = 0) {
+               const PeerSeedKeys* peers = nullptr, int world = 1, uint32_t* const* push_dst = nullptr, int n_push = 0,
+               const SliceSeed* slice = nullptr) {
     const int b_pad = (b + 127) / 128 * 128;
     CUDA_TRY(ix->q_padded.ensure((size_t)b * ix->pitch));
     const int qkp = (ix->kp + 63) / 64 * 64;
@@ -565,16 +577,17 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
         return ANN_OK;
     };
     const int kHitBudget = ix->gemm_hit_budget;
-    auto gemm_launch = [&](long long begin, long long end, int seed_mode) -> int {
+    auto gemm_launch = [&](long long begin, long long end, int seed_mode, int q_first = 0, int q_n = -1) -> int {
+        if (q_n < 0) q_n = b;
         GemmLaunch g{};
-        g.q_shadow = ix->q_shadow.p;
+        g.q_shadow = ix->q_shadow.p + (size_t)q_first * qkp;   // a query sub-range: the operand rows behind it stay addressable
         g.qkp = qkp;
         g.shadow = ix->shadow;
         g.n_rows_total = ix->n;
         g.row_begin = begin;
         g.row_end = end;
-        g.b = b;
-        g.b_pad = b_pad;
+        g.b = q_n;
+        g.b_pad = b_pad - q_first;
         g.kp = ix->kp;
         g.cta_group = ix->gemm_cta_group;
         g.seed_mode = seed_mode;
@@ -587,8 +600,8 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
                                          : ((b > 256 && (double)(end - begin) * 1.5e-4 < (double)kHitBudget) ? 16 : 8);
         g.nb_stages = gemm_row_stages(ix->kp, ix->smem_optin);
         g.sm_count = ix->sm_count;
-        g.qstate = qs_base;
-        g.pool = ix->pool.p;
+        g.qstate = qs_base + q_first;
+        g.pool = ix->pool.p + (size_t)q_first * kGemmPoolCap;
         g.pool_cap = kGemmPoolCap;
         cudaEvent_t dbg0 = nullptr, dbg1 = nullptr;
         const bool dbg = getenv("B200ANN_DEBUG") != nullptr;
@@ -619,7 +632,7 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
                 sum += x.pool_count;
             }
             fprintf(stderr, "[b200ann] gemm%s [%lld,%lld): %.3f ms %.1f TFLOP/s; pool_count min %u mean %.1f max %u tau[0]=%g\n",
-                    seed_mode ? " seed" : "", begin, end, dms, 2.0 * (double)(end - begin) * ix->dim * b / (dms * 1e-3) / 1e12, mn,
+                    seed_mode ? " seed" : "", begin, end, dms, 2.0 * (double)(end - begin) * ix->dim * q_n / (dms * 1e-3) / 1e12, mn,
                     sum / b, mx, float_from_order_key(h[0].tau_key));
         }
         return ANN_OK;
@@ -635,12 +648,15 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
     // One pool entry per group of G rows (128 with CTA pairs): 65536 rows give 512 group maxima, 5 per neighbour at k = 100
     // (the k-th best of them sits where the 111th best row does); larger k seeds over 4 groups per neighbour.
     const long long G = gemm_seed_group_rows(ix->gemm_cta_group);
-    long long seed_rows = std::min<long long>(ix->n / 256 * 256, std::min<long long>((long long)kGemmPoolCap * G, std::max<long long>(65536, 4 * G * k_eff)));
-    if (ix->gemm_seed_rows > 0) seed_rows = std::min<long long>(seed_rows, ix->gemm_seed_rows / 256 * 256);
+    const long long seed_scale = (mode == 1 && slice) ? std::max(1, slice->scale) : 1;
+    long long seed_rows = std::min<long long>(ix->n / 256 * 256, std::min<long long>((long long)kGemmPoolCap * G, std::max<long long>(65536, 4 * G * k_eff) * seed_scale));
+    if (ix->gemm_seed_rows > 0) seed_rows = std::min<long long>(seed_rows, ix->gemm_seed_rows * seed_scale / 256 * 256);
     bool use_seed = seed_rows >= 2 * G * k_eff && seed_rows >= 4096;
+    bool sliced = mode == 1 && slice != nullptr;
     if (mode >= 2) {   // what phase 1 decided and did
         use_seed = ix->sess.seeded;
         seed_rows = ix->sess.seed_rows;
+        sliced = ix->sess.sliced;
     }
     // a chunk `growth` times the rows seen so far adds about (growth - 1) * 1.9 * k candidates per query
     double growth = std::floor(std::min<double>(8.0, std::max<double>(2.0, 1.0 + kHitBudget / (1.9 * std::max(1, k_eff)))));
@@ -649,7 +665,23 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
     ix->last_gemm_chunks = 0;
     if (use_seed) {
         double seen = (double)seed_rows;   // rows the threshold has been learnt from
-        if (mode < 2) {
+        if (mode < 2 && sliced) {
+            if (slice->q_count > 0) {
+                int rc2 = gemm_launch(0, seed_rows, 1, slice->q_begin, slice->q_count);
+                if (rc2) return rc2;
+                SelectParams sp = fp;
+                sp.qstate = qs_base + slice->q_begin;
+                sp.pool = ix->pool.p + (size_t)slice->q_begin * kGemmPoolCap;
+                sp.seed_count = (int)(seed_rows / G);
+                sp.sort_cap = std::max(sp.sort_cap, sp.seed_count);
+                sp.pub_single = 1;
+                sp.seed_keys_out = seed_keys_out ? seed_keys_out + slice->q_begin : nullptr;
+                sp.n_push = 0;
+                for (int i = 0; i < n_push && i < kMaxPeers; ++i) sp.push_keys[sp.n_push++] = push_dst[i] + slice->q_begin;
+                { TimedScope ts_(ix, st, ann_index::kLblCompact); CUDA_TRY(launch_compact_pool(sp, slice->q_count, st)); }
+                ix->launches++;
+            }
+        } else if (mode < 2) {
             int rc2 = gemm_launch(0, seed_rows, 1);
             if (rc2) return rc2;
             SelectParams sp = fp;
@@ -662,9 +694,17 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
         if (mode == 1) {
             ix->sess.seeded = true;
             ix->sess.seed_rows = seed_rows;
+            ix->sess.sliced = sliced;
             return ANN_OK;
         }
-        if (mode >= 2 && peers && world > 1) {
+        if (mode >= 2 && sliced) {
+            // every query's bound was learnt by its slice owner from seed_rows rows of THAT shard: as tight as this shard's
+            // own seed over as many rows, and nothing to select
+            if (slice && slice->bounds) {
+                { TimedScope ts_(ix, st, ann_index::kLblSeedMerge); CUDA_TRY(launch_apply_bounds(slice->bounds, qs_base, b, st)); }
+                ix->launches++;
+            }
+        } else if (mode >= 2 && peers && world > 1) {
             // K5c: the k-th best of the union of all shards' published bounds replaces this shard's own seed threshold:
             // as tight as one seed over world * seed_rows rows, for the price of one seed launch per shard
             { TimedScope ts_(ix, st, ann_index::kLblSeedMerge); CUDA_TRY(launch_seed_merge(*peers, world, qs_base, b, k_eff, st)); }
@@ -678,14 +718,21 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
         if (end > ix->n) end = ix->n;
     } else if (mode == 1) {
         // too few rows to seed from: nothing to publish, phase 2 runs the unseeded schedule
-        {
+        if (sliced) {
+            const size_t bytes = (size_t)slice->q_count * sizeof(uint32_t);
+            for (int i = 0; i < n_push && bytes; ++i) CUDA_TRY(cudaMemsetAsync(push_dst[i] + slice->q_begin, 0xFF, bytes, st));
+            if (n_push == 0 && seed_keys_out && bytes) CUDA_TRY(cudaMemsetAsync(seed_keys_out + slice->q_begin, 0xFF, bytes, st));
+        } else {
             int rc2 = publish_no_bound();
             if (rc2) return rc2;
         }
         ix->sess.seeded = false;
         ix->sess.seed_rows = 0;
+        ix->sess.sliced = sliced;
         return ANN_OK;
     } else {
+        // (mode 3 after an unseeded phase 1: bounds other slice owners delivered still help -- a shard too small to seed
+        // is too small for them to matter, so they are simply not applied)
         // no seed: the first chunk is scored with tau = +inf (every row is a candidate), so it must fit the pool
         end = std::min<long long>(ix->n, kGemmPoolCap / 2);
     }
@@ -1144,22 +1191,36 @@ int ann_query_batch_device(ann_index* ix, const float* d_queries, int32_t b, int
 // ---- two-phase sharded query: seed (publish this shard's bounds) -> [caller: cross-shard barrier] -> finish ----
 namespace {
 int seed_impl(ann_index* ix, const float* d_queries, int32_t b, int32_t dim, int32_t k, uint32_t* d_seed_keys,
-              uint32_t* const* push_dst, int32_t n_push, void* stream);
+              uint32_t* const* push_dst, int32_t n_push, void* stream, const SliceSeed* slice);
 }
 int ann_query_seed_device(ann_index* ix, const float* d_queries, int32_t b, int32_t dim, int32_t k, uint32_t* d_seed_keys,
                           void* stream) {
-    return seed_impl(ix, d_queries, b, dim, k, d_seed_keys, nullptr, 0, stream);
+    return seed_impl(ix, d_queries, b, dim, k, d_seed_keys, nullptr, 0, stream, nullptr);
+}
+int ann_query_seed_slice_push_device(ann_index* ix, const float* d_queries, int32_t b, int32_t dim, int32_t k, int32_t q_begin,
+                                     int32_t q_count, int32_t n_slices, uint32_t* const* dst, int32_t n_dst, void* stream) {
+    if (n_dst < 1 || n_dst > kMaxPeers || !dst) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_query_seed_slice_push_device: n_dst must be in [1, 16]");
+    for (int i = 0; i < n_dst; ++i)
+        if (!dst[i]) return fail(ANN_ERR_NULL_POINTER, "ann_query_seed_slice_push_device: NULL destination");
+    if (q_begin < 0 || q_count < 0 || (long long)q_begin + q_count > b)
+        return fail(ANN_ERR_INVALID_ARGUMENT, "ann_query_seed_slice_push_device: query slice outside the batch");
+    if (n_slices < 1 || n_slices > kMaxPeers) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_query_seed_slice_push_device: n_slices must be in [1, 16]");
+    SliceSeed sl;
+    sl.q_begin = q_begin;
+    sl.q_count = q_count;
+    sl.scale = n_slices;
+    return seed_impl(ix, d_queries, b, dim, k, nullptr, dst, n_dst, stream, &sl);
 }
 int ann_query_seed_push_device(ann_index* ix, const float* d_queries, int32_t b, int32_t dim, int32_t k, uint32_t* const* dst,
                                int32_t n_dst, void* stream) {
     if (n_dst < 1 || n_dst > kMaxPeers || !dst) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_query_seed_push_device: n_dst must be in [1, 16]");
     for (int i = 0; i < n_dst; ++i)
         if (!dst[i]) return fail(ANN_ERR_NULL_POINTER, "ann_query_seed_push_device: NULL destination");
-    return seed_impl(ix, d_queries, b, dim, k, nullptr, dst, n_dst, stream);
+    return seed_impl(ix, d_queries, b, dim, k, nullptr, dst, n_dst, stream, nullptr);
 }
 namespace {
 int seed_impl(ann_index* ix, const float* d_queries, int32_t b, int32_t dim, int32_t k, uint32_t* d_seed_keys,
-              uint32_t* const* push_dst, int32_t n_push, void* stream) {
+              uint32_t* const* push_dst, int32_t n_push, void* stream, const SliceSeed* slice) {
     if (!ix) return fail(ANN_ERR_NULL_POINTER, "ann_query_seed_device: index is NULL");
     if (b < 0) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_query_seed_device: b < 0");
     if (k < 0) return fail(ANN_ERR_NEGATIVE_K, "ann_query_seed_device: k < 0");
@@ -1178,8 +1239,12 @@ int seed_impl(ann_index* ix, const float* d_queries, int32_t b, int32_t dim, int
     constexpr int kMaxGemmBatch = 16384;
     const bool gemm = ix->n > 0 && k_eff <= kMaxK && ix->path_opt != 3 && ix->path_opt != 1 && b <= kMaxGemmBatch &&
                       gemm_eligible(ix, b, k_eff) && (ix->path_opt == 2 || b >= ix->gemm_min_batch);
+    ix->sess.sliced = slice != nullptr;
     if (!gemm) {   // scan / exact paths keep their own thresholds: nothing to publish, the finish call runs the whole query
-        if (n_push > 0) {
+        if (slice) {   // one "no bound" per query of the slice
+            for (int i = 0; i < n_push && slice->q_count > 0; ++i)
+                CUDA_TRY(cudaMemsetAsync(push_dst[i] + slice->q_begin, 0xFF, (size_t)slice->q_count * sizeof(uint32_t), st));
+        } else if (n_push > 0) {
             for (int i = 0; i < n_push; ++i) CUDA_TRY(cudaMemsetAsync(push_dst[i], 0xFF, (size_t)b * k * sizeof(uint32_t), st));
         } else {
             CUDA_TRY(cudaMemsetAsync(d_seed_keys, 0xFF, (size_t)b * k * sizeof(uint32_t), st));
@@ -1190,7 +1255,7 @@ int seed_impl(ann_index* ix, const float* d_queries, int32_t b, int32_t dim, int
     CUDA_TRY(ix->qstate.ensure((size_t)b));
     rc = unit_queries(ix, &d_queries, b, st);
     if (rc) return rc;
-    rc = query_gemm(ix, ix->qstate.p, d_queries, b, k_eff, k, nullptr, nullptr, nullptr, st, 1, d_seed_keys, nullptr, 1, push_dst, n_push);
+    rc = query_gemm(ix, ix->qstate.p, d_queries, b, k_eff, k, nullptr, nullptr, nullptr, st, 1, d_seed_keys, nullptr, 1, push_dst, n_push, slice);
     if (rc) ix->sess = ann_index::SeedSession{};
     return rc;
 }
@@ -1271,11 +1336,19 @@ int check_session(ann_index* ix, const char* who, int32_t b, int32_t dim, int32_
 
 namespace {
 int filter_impl(ann_index* ix, const float* d_queries, int32_t b, int32_t dim, int32_t k, const uint32_t* const* peer_seed_keys,
-                int32_t world, uint32_t* d_kth_keys, uint32_t* const* push_dst, int32_t n_push, void* stream);
+                int32_t world, uint32_t* d_kth_keys, uint32_t* const* push_dst, int32_t n_push, void* stream, const uint32_t* d_bounds);
 }
 int ann_query_filter_device(ann_index* ix, const float* d_queries, int32_t b, int32_t dim, int32_t k,
                             const uint32_t* const* peer_seed_keys, int32_t world, uint32_t* d_kth_keys, void* stream) {
-    return filter_impl(ix, d_queries, b, dim, k, peer_seed_keys, world, d_kth_keys, nullptr, 0, stream);
+    return filter_impl(ix, d_queries, b, dim, k, peer_seed_keys, world, d_kth_keys, nullptr, 0, stream, nullptr);
+}
+int ann_query_filter_bounds_push_device(ann_index* ix, const float* d_queries, int32_t b, int32_t dim, int32_t k,
+                                        const uint32_t* d_bounds, int32_t world, uint32_t* const* kth_dst, int32_t n_dst, void* stream) {
+    if (n_dst < 1 || n_dst > kMaxPeers || !kth_dst) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_query_filter_bounds_push_device: n_dst must be in [1, 16]");
+    for (int i = 0; i < n_dst; ++i)
+        if (!kth_dst[i]) return fail(ANN_ERR_NULL_POINTER, "ann_query_filter_bounds_push_device: NULL destination");
+    if (b > 0 && k > 0 && !d_bounds) return fail(ANN_ERR_NULL_POINTER, "ann_query_filter_bounds_push_device: NULL bound array");
+    return filter_impl(ix, d_queries, b, dim, k, nullptr, world, nullptr, kth_dst, n_dst, stream, d_bounds);
 }
 int ann_query_filter_push_device(ann_index* ix, const float* d_queries, int32_t b, int32_t dim, int32_t k,
                                  const uint32_t* const* peer_seed_keys, int32_t world, uint32_t* const* kth_dst, int32_t n_dst,
@@ -1283,11 +1356,11 @@ int ann_query_filter_push_device(ann_index* ix, const float* d_queries, int32_t 
     if (n_dst < 1 || n_dst > kMaxPeers || !kth_dst) return fail(ANN_ERR_INVALID_ARGUMENT, "ann_query_filter_push_device: n_dst must be in [1, 16]");
     for (int i = 0; i < n_dst; ++i)
         if (!kth_dst[i]) return fail(ANN_ERR_NULL_POINTER, "ann_query_filter_push_device: NULL destination");
-    return filter_impl(ix, d_queries, b, dim, k, peer_seed_keys, world, nullptr, kth_dst, n_dst, stream);
+    return filter_impl(ix, d_queries, b, dim, k, peer_seed_keys, world, nullptr, kth_dst, n_dst, stream, nullptr);
 }
 namespace {
 int filter_impl(ann_index* ix, const float* d_queries, int32_t b, int32_t dim, int32_t k, const uint32_t* const* peer_seed_keys,
-                int32_t world, uint32_t* d_kth_keys, uint32_t* const* push_dst, int32_t n_push, void* stream) {
+                int32_t world, uint32_t* d_kth_keys, uint32_t* const* push_dst, int32_t n_push, void* stream, const uint32_t* d_bounds) {
     if (!ix) return fail(ANN_ERR_NULL_POINTER, "ann_query_filter_device: index is NULL");
     std::lock_guard<std::mutex> lk(ix->mu);
     int rc = check_session(ix, "ann_query_filter_device", b, dim, k, world, false);
@@ -1320,7 +1393,14 @@ int filter_impl(ann_index* ix, const float* d_queries, int32_t b, int32_t dim, i
             pk.keys[w++] = peer_seed_keys[s2];
         }
     const int k_eff = (int)std::min<long long>(k, ix->n);
-    rc = query_gemm(ix, ix->qstate.p, d_queries, b, k_eff, k, nullptr, nullptr, nullptr, st, 3, d_kth_keys, &pk, w, push_dst, n_push);
+    if ((d_bounds != nullptr) != ix->sess.sliced) {
+        ix->sess.open = false;
+        return fail(ANN_ERR_INVALID_ARGUMENT, "ann_query_filter_device: the seed call and the filter call must both be sliced or both be not");
+    }
+    SliceSeed sl;
+    sl.bounds = d_bounds;
+    rc = query_gemm(ix, ix->qstate.p, d_queries, b, k_eff, k, nullptr, nullptr, nullptr, st, 3, d_kth_keys, &pk, w, push_dst, n_push,
+                    d_bounds ? &sl : nullptr);
     if (rc) ix->sess.open = false;
     return rc;
 }

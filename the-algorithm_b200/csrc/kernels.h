@@ -90,6 +90,8 @@ struct SelectParams {
     uint32_t* push_keys[kMaxPeers];   // n_push > 0: publish by PUSH instead -- this shard's [b][k] block inside every peer's
     int n_push;                       // receive buffer (P2P stores are fire-and-forget; pulling 400-byte rows from 7 peers
                                       // per query was latency-bound: 61 us per 4096-query round at 8 GPUs)
+    int pub_single;                   // seed compaction of a query SLICE (sliced seeding): publish ONE key per query -- the
+                                      // k-th best group maximum as an upper bound -- at push_keys[d][q] / seed_keys_out[q]
     PeerSeedKeys peer_keys;   // finalize: every shard's bounds published after the last chunk (second cross-shard round)
     int peer_world;           // number of valid peer_keys entries; 0 = single shard, no global bound
     int sort_cap, exact_cap;  // shared-memory capacities (entries) of the approximate and exact stages; 0 = 4096 / 2048.
@@ -112,6 +114,8 @@ struct SelectParams {
 cudaError_t launch_compact_pool(const SelectParams& p, int b, cudaStream_t stream);
 // compaction + exact fp64 rescoring + (distance, id) ordering + output
 cudaError_t launch_finalize(const SelectParams& p, int b, cudaStream_t stream);
+// sliced seeding, consumer side: tau_q <- min(tau_q, bound_q + this shard's margin) for the b bounds the slice owners delivered
+cudaError_t launch_apply_bounds(const uint32_t* bounds, QueryState* qstate, int b, cudaStream_t stream);
 // fill outputs for k == 0 / empty index
 cudaError_t launch_fill_empty(int64_t* out_ids, float* out_dist, int32_t* out_count, int b, int k_out, cudaStream_t stream);
 

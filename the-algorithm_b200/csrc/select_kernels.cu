@@ -232,8 +232,18 @@ __global__ void __launch_bounds__(kSelThreads, 4) compact_pool_kernel(SelectPara
             for (int j = threadIdx.x; j < p.k; j += blockDim.x) out[j] = pubk[j];
         }
     };
+    auto publish_one = [&](uint32_t key) {   // sliced seeding: one bound per query, to every peer's [b] array
+        if (threadIdx.x < max(p.n_push, 1)) {
+            uint32_t* out = p.n_push > 0 ? p.push_keys[threadIdx.x] : p.seed_keys_out;
+            out[q] = key;
+        }
+    };
     auto publish_nothing = [&]() {   // a flagged query publishes "no bound" (never stale keys of an earlier batch)
         if (!publishing) return;
+        if (p.pub_single) {
+            publish_one(0xFFFFFFFFu);
+            return;
+        }
         for (int j = threadIdx.x; j < p.k; j += blockDim.x) pubk[j] = 0xFFFFFFFFu;
         publish();
     };
@@ -274,7 +284,10 @@ __global__ void __launch_bounds__(kSelThreads, 4) compact_pool_kernel(SelectPara
         }
     };
     if (p.seed_count > 0) {   // seed entries carry no row: keep only the threshold (K5c publish: the k best group maxima)
-        if (publishing) {
+        if (publishing && p.pub_single) {
+            // the k-th best group maximum, widened to an upper bound on the exact badness of the k-th best of k real rows
+            publish_one(kk != 0xFFFFFFFFu ? float_order_key(widen_half_up(float_from_order_key(kk), qs->eps_abs, qs->eps_rel)) : 0xFFFFFFFFu);
+        } else if (publishing) {
             if (kk != 0xFFFFFFFFu) stage_best();
             else
                 for (int j = threadIdx.x; j < p.k; j += blockDim.x) pubk[j] = 0xFFFFFFFFu;   // fewer than k groups: no bound
@@ -761,6 +774,23 @@ __global__ void __launch_bounds__(kSelThreads) seed_merge_kernel(PeerSeedKeys pk
         const uint32_t tg = float_order_key(tau_g);
         if (tg < qs->tau_key) qs->tau_key = tg;
     }
+}
+
+// ---- sliced seeding, consumer side: one delivered bound per query -> this shard's threshold -------------------------------
+__global__ void __launch_bounds__(256) apply_bounds_kernel(const uint32_t* __restrict__ bounds, QueryState* qstate, int b) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= b) return;
+    const uint32_t u = __ldcg(bounds + q);
+    if (u >= 0xFF800000u) return;                       // the owner had no bound for this query
+    QueryState* qs = qstate + q;
+    const uint32_t tg = float_order_key(widen_half_up(float_from_order_key(u), qs->eps_abs, qs->eps_rel));
+    if (tg < qs->tau_key) qs->tau_key = tg;
+}
+
+cudaError_t launch_apply_bounds(const uint32_t* bounds, QueryState* qstate, int b, cudaStream_t stream) {
+    if (b <= 0) return cudaSuccess;
+    apply_bounds_kernel<<<(b + 255) / 256, 256, 0, stream>>>(bounds, qstate, b);
+    return cudaGetLastError();
 }
 
 // ---- replicate a slice to every peer (the all-gather of a partitioned query batch, by push) ----------------------------

@@ -147,6 +147,9 @@ struct ann_sharded_index {
     SpinBarrier* bar = nullptr;
     bool peer_ok = true;      // every pair of devices can map each other; else the merge is staged through the host
     int two_round = 1;        // 1 = share the k best bounds after the last chunk (slice-sized rescoring), 0 = seed round only
+    int sliced_seeds = 1;     // two_round only: 1 = every shard seeds ITS slice of the batch over R x the rows and delivers one
+                              // bound per query (ann_query_seed_slice_push_device), 0 = every shard seeds every query and
+                              // delivers k bounds per query (ann_query_seed_push_device)
     long long queries = 0, fallback_batches = 0;
 };
 
@@ -323,6 +326,10 @@ int ann_sharded_shard(ann_sharded_index* sx, int32_t shard, ann_index** out, int
 int ann_sharded_set_option(ann_sharded_index* sx, const char* name, int64_t value) {
     if (!sx || !name) return report_error(ANN_ERR_NULL_POINTER, "ann_sharded_set_option: NULL argument");
     std::lock_guard<std::mutex> lk(sx->mu);
+    if (!strcmp(name, "sliced_seeds")) {
+        sx->sliced_seeds = value ? 1 : 0;
+        return ANN_OK;
+    }
     if (!strcmp(name, "two_round")) {
         sx->two_round = value ? 1 : 0;
         return ANN_OK;
@@ -476,9 +483,22 @@ int ann_sharded_query_batch(ann_sharded_index* sx, const float* queries, int32_t
                     seed_src[t] = sh.d_seed + (size_t)t * blk;
                     kth_src[t] = sh.d_kth + (size_t)t * blk;
                 }
-                if (ok0 && !failed.load()) step(ann_query_seed_push_device(sh.ix, sh.d_q, b, dim, k, seed_dst.data(), R, st));
+                const bool sliced = sx->two_round && sx->sliced_seeds;
+                if (sliced) {
+                    // one bound per query, written by the query's slice owner into the head of every shard's seed buffer
+                    if (ok0 && !failed.load())
+                        step(ann_query_seed_slice_push_device(sh.ix, sh.d_q, b, dim, k, q0, qn, R, recv_seed.data(), R, st));
+                } else if (ok0 && !failed.load()) {
+                    step(ann_query_seed_push_device(sh.ix, sh.d_q, b, dim, k, seed_dst.data(), R, st));
+                }
                 sync_all(0);
-                if (sx->two_round) {
+                if (sliced) {
+                    if (ok0 && !failed.load())
+                        step(ann_query_filter_bounds_push_device(sh.ix, sh.d_q, b, dim, k, sh.d_seed, R, kth_dst.data(), R, st));
+                    sync_all(1);
+                    if (ok0 && !failed.load())
+                        step(ann_query_rescore_device(sh.ix, sh.d_q, b, dim, k, kth_src.data(), R, l_ids, l_dist, l_cnt, st));
+                } else if (sx->two_round) {
                     if (ok0 && !failed.load())
                         step(ann_query_filter_push_device(sh.ix, sh.d_q, b, dim, k, seed_src.data(), R, kth_dst.data(), R, st));
                     sync_all(1);
