@@ -197,7 +197,9 @@ __device__ bool load_and_threshold(const SelectParams& p, int q, entry_t* buf, u
         return false;
     }
     if (kth_key_out) *kth_key_out = 0xFFFFFFFFu;
-    if (n >= p.k && p.k > 0) {
+    // With the shards' round-2 bounds in hand (this shard's own k best among them) the cut above is already at least as tight
+    // as this shard's own k-th best + margin: the second selection would be four more histogram passes for nothing.
+    if (n >= p.k && p.k > 0 && !(p.peer_world > 0 && !kth_key_out)) {
         const uint32_t kk = kth_key_radix(buf, n, p.k, hist);
         tau = fminf(tau, widen(float_from_order_key(kk), eps_abs, eps_rel));
         if (kth_key_out) *kth_key_out = kk;
