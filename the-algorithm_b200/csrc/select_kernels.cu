@@ -329,6 +329,8 @@ __global__ void __launch_bounds__(kCompactThreads, 8) compact_pool_kernel(Select
 }
 
 // ---- finalize: survivors + specials -> exact distances -> (distance, id) order -> outputs -------------------
+// (4 CTAs per SM on purpose: 5 / 6 per SM -- 48 / 40 registers -- measured 0.311 -> 0.326 / 0.351 ms per 4096-query batch; the
+// kernel waits on scattered 800-byte row reads, 3.5 TB/s of DRAM traffic, and more CTAs only add contention)
 template <int METRIC, bool ACC32>
 __global__ void __launch_bounds__(kSelThreads, 4) finalize_kernel(SelectParams p) {
     extern __shared__ __align__(16) unsigned char sm[];
