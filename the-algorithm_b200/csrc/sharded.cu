@@ -123,7 +123,7 @@ struct Shard {
     int device = 0;
     ann_index* ix = nullptr;
     cudaStream_t st = nullptr;
-    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // phases 0..2 of the query, 3 = query batch gathered
     // per-(b, k) scratch on this device
     float* d_q = nullptr;
     uint32_t* d_seed = nullptr;          // receive buffer [world][b*k]: block s holds shard s's seed bounds (pushed by shard s)
@@ -420,6 +420,17 @@ int ann_sharded_query_batch(ann_sharded_index* sx, const float* queries, int32_t
     int32_t* cnt_out = out_count ? out_count : cnt_host.data();
     std::vector<uint32_t*> recv_seed(R), recv_kth(R);   // every shard's receive buffers (peer-visible)
     std::vector<const void*> local_ptrs(R);
+    std::vector<float*> q_ptrs(R);                       // every shard's query batch buffer
+    // The batch crosses PCIe ONCE: every shard copies its slice of the queries from the caller's buffer and pushes it into
+    // the peers' batch buffers over NVLink (the caller's memory is usually pageable -- a JVM direct buffer -- and R staged
+    // copies of the whole batch cost R times the host-side staging).  Needs 16-byte aligned slices; else every shard copies
+    // the whole batch.
+    bool gather_q = R > 1 && sx->peer_ok;
+    for (int t = 0; t < R && gather_q; ++t) {
+        int t0, tn;
+        slice_of(t, R, b, &t0, &tn);
+        if (((size_t)t0 * dim * sizeof(float)) % 16 || ((size_t)tn * dim * sizeof(float)) % 16) gather_q = false;
+    }
 
     // exact == true: every shard answers with its own exact top-k (device_fallback on), no threshold sharing -- the route for
     // batches in which some shard's bounded selector flagged a query
@@ -447,16 +458,13 @@ int ann_sharded_query_batch(ann_sharded_index* sx, const float* queries, int32_t
             recv_seed[s] = sh.d_seed;
             recv_kth[s] = sh.d_kth;
             local_ptrs[s] = sh.d_local;
+            q_ptrs[s] = sh.d_q;
             int64_t* l_ids = reinterpret_cast<int64_t*>(sh.d_local);
             float* l_dist = reinterpret_cast<float*>(sh.d_local + (size_t)b * k * 8);
             int32_t* l_cnt = reinterpret_cast<int32_t*>(sh.d_local + (size_t)b * k * 12);
             sx->bar->wait();   // pointer tables complete; a failed allocation is visible to everyone
             const bool ok0 = !failed.load();
             cudaStream_t st = sh.st;
-            if (ok0) {
-                cuda_step(cudaSetDevice(sh.device), "cudaSetDevice");
-                cuda_step(cudaMemcpyAsync(sh.d_q, queries, (size_t)b * dim * sizeof(float), cudaMemcpyHostToDevice, st), "H2D queries");
-            }
             auto sync_all = [&](int phase) {   // my phase is enqueued -> everyone's is -> my stream waits for all of them
                 if (ok0) cuda_step(cudaEventRecord(sh.ev[phase], st), "cudaEventRecord");
                 sx->bar->wait();
@@ -464,6 +472,20 @@ int ann_sharded_query_batch(ann_sharded_index* sx, const float* queries, int32_t
                     for (int t = 0; t < R; ++t)
                         if (t != s) cuda_step(cudaStreamWaitEvent(st, sx->sh[t].ev[phase], 0), "cudaStreamWaitEvent");
             };
+            if (ok0) cuda_step(cudaSetDevice(sh.device), "cudaSetDevice");
+            if (gather_q) {
+                if (ok0 && qn > 0) {
+                    const size_t off = (size_t)q0 * dim, bytes = (size_t)qn * dim * sizeof(float);
+                    cuda_step(cudaMemcpyAsync(sh.d_q + off, queries + off, bytes, cudaMemcpyHostToDevice, st), "H2D query slice");
+                    std::vector<void*> dst;
+                    for (int t = 0; t < R; ++t)
+                        if (t != s) dst.push_back(q_ptrs[t] + off);
+                    cuda_step(launch_peer_push(sh.d_q + off, dst.data(), (int)dst.size(), bytes, st), "query slice push");
+                }
+                sync_all(3);
+            } else if (ok0) {
+                cuda_step(cudaMemcpyAsync(sh.d_q, queries, (size_t)b * dim * sizeof(float), cudaMemcpyHostToDevice, st), "H2D queries");
+            }
             if (exact) {
                 if (ok0 && !rcs[s]) {
                     step(ann_set_option(sh.ix, "device_fallback", 1));
