@@ -73,16 +73,25 @@ class GpuShardedBruteForceIndex(Appendable, Queryable):
         return out
 
     # ---- ComposedQueryable -------------------------------------------------------------------------------------
-    def batch_query_with_distance(self, embeddings, num_of_neighbors: int):
+    def batch_query_with_distance(self, embeddings, num_of_neighbors: int, out=None):
+        """`out` = (ids [b,k] int64, dist [b,k] float32, count [b] int32) C-contiguous arrays to write into (e.g. pinned
+        buffers reused from call to call); the library fills every slot, so they need no initialisation."""
         q = np.ascontiguousarray(embeddings, dtype=np.float32)
         if q.ndim != 2:
             raise ValueError("embeddings must be [b, dim]")
         b, k = q.shape[0], int(num_of_neighbors)
         if k < 0:
             raise _capi.AnnError(_capi.ANN_ERR_NEGATIVE_K, "numOfNeighbours < 0")
-        out_ids = np.full((b, k), -1, dtype=np.int64)
-        out_dist = np.full((b, k), np.inf, dtype=np.float32)
-        out_cnt = np.zeros(b, dtype=np.int32)
+        if out is not None:
+            out_ids, out_dist, out_cnt = out
+            if (out_ids.shape != (b, k) or out_dist.shape != (b, k) or out_cnt.shape != (b,) or out_ids.dtype != np.int64
+                    or out_dist.dtype != np.float32 or out_cnt.dtype != np.int32
+                    or not (out_ids.flags.c_contiguous and out_dist.flags.c_contiguous and out_cnt.flags.c_contiguous)):
+                raise ValueError("out must be C-contiguous (int64 [b,k], float32 [b,k], int32 [b])")
+        else:
+            out_ids = np.full((b, k), -1, dtype=np.int64)
+            out_dist = np.full((b, k), np.inf, dtype=np.float32)
+            out_cnt = np.zeros(b, dtype=np.int32)
         _capi.check(_capi.lib().ann_sharded_query_batch(self._h, _ptr(q), b, q.shape[1], k, _ptr(out_ids), _ptr(out_dist), _ptr(out_cnt)))
         return out_ids, out_dist, out_cnt
 
