@@ -237,6 +237,68 @@ def test_in_process_sharded_handle_errors_and_empty():
         GpuShardedBruteForceIndex(G["L2"], G["FuturePool"].immediate_pool(), dim=8, devices=[99])
 
 
+@pytest.mark.parametrize("mi", [0, 1, 2])
+def test_sliced_seed_protocol_by_hand_and_its_argument_checks(mi):
+    """ann_query_seed_slice_push_device -> ann_query_filter_bounds_push_device -> ann_query_rescore_device driven shard by shard
+    (two shards on one device, one stream: what ann/distributed.py and csrc/sharded.cu do across GPUs); the merged lists are
+    the single-index oracle answer.  Then the session rules of the sliced calls."""
+    import torch
+
+    m = metrics()[mi]
+    n, d, b, k, R = 200_000, 64, 96, 20, 2
+    corpus, ids, q = make(n, d, b, seed=5, dup=True)
+    dev = torch.device("cuda", 0)
+    shards = []
+    for r in range(R):
+        lo, hi = r * n // R, (r + 1) * n // R
+        ix = G["BruteForceIndex"].apply(m, G["FuturePool"].immediate_pool())
+        ix.append_batch(ids[lo:hi], corpus[lo:hi])
+        ix.set_option("path", 2)
+        shards.append(ix)
+    qd = torch.from_numpy(q).to(dev)
+    st = torch.cuda.current_stream().cuda_stream
+    bounds = [torch.zeros((b,), dtype=torch.int32, device=dev) for _ in range(R)]          # every shard's [b] bound array
+    kth = [torch.empty((R, b, k), dtype=torch.int32, device=dev) for _ in range(R)]        # receive buffers [source shard][b][k]
+    outs = [(torch.empty((b, k), dtype=torch.int64, device=dev), torch.empty((b, k), dtype=torch.float32, device=dev),
+             torch.empty((b,), dtype=torch.int32, device=dev)) for _ in range(R)]
+    for rep in range(2):
+        for r in range(R):
+            q0, q1 = r * b // R, (r + 1) * b // R
+            shards[r].query_seed_slice_push_device(qd, k, q0, q1 - q0, R, [t.data_ptr() for t in bounds], st)
+        for r in range(R):
+            shards[r].query_filter_bounds_push_device(qd, k, bounds[r].data_ptr(), R, [kth[t][r].data_ptr() for t in range(R)], st)
+        for r in range(R):
+            shards[r].query_rescore_device(qd, k, [kth[r][s_].data_ptr() for s_ in range(R)], *outs[r], st)
+        torch.cuda.synchronize()
+        assert all(int((bounds[r].view(torch.int32) == -1).sum()) == 0 for r in range(R))      # every query got a bound from its owner
+        want = oracle.query_canonical(m.ordinal, corpus, ids, q, k)
+        for qi in range(b):
+            rows = []
+            for r in range(R):
+                c = int(outs[r][2][qi])
+                assert 0 <= c <= k
+                di = outs[r][1][qi, :c].cpu().numpy()
+                ii = outs[r][0][qi, :c].cpu().numpy()
+                rows += [(float(x), int(i)) for x, i in zip(di, ii)]
+            rows.sort(key=lambda t: (np.inf if np.isnan(t[0]) else t[0], t[1]))        # canonical order: (distance, id)
+            assert [t[1] for t in rows[:k]] == want[0][qi, :int(want[2][qi])].tolist()
+    AnnError, capi = G["_capi"].AnnError, G["_capi"]
+    with pytest.raises(AnnError) as e:                                                     # slice outside the batch
+        shards[0].query_seed_slice_push_device(qd, k, b - 4, 8, R, [t.data_ptr() for t in bounds], st)
+    assert e.value.code == capi.ANN_ERR_INVALID_ARGUMENT
+    shards[0].query_seed_slice_push_device(qd, k, 0, b // 2, R, [t.data_ptr() for t in bounds], st)
+    with pytest.raises(AnnError) as e:                                                     # a sliced seed needs the bounds form of the filter
+        shards[0].query_filter_push_device(qd, k, [kth[0][s_].data_ptr() for s_ in range(R)], [kth[t][0].data_ptr() for t in range(R)], st)
+    assert e.value.code == capi.ANN_ERR_INVALID_ARGUMENT
+    shards[0].query_seed_slice_push_device(qd, k, 0, b // 2, R, [t.data_ptr() for t in bounds], st)
+    with pytest.raises(AnnError) as e:                                                     # ... and cannot be finished in one round
+        shards[0].query_finish_device(qd, k, [kth[0][s_].data_ptr() for s_ in range(R)], *outs[0], st)
+    assert e.value.code == capi.ANN_ERR_INVALID_ARGUMENT
+    torch.cuda.synchronize()
+    for ix in shards:
+        ix.close()
+
+
 # ------------------------------------------------------------------------------------------------ the reference's on-disk format
 @pytest.mark.parametrize("layout", [0, 2])
 def test_thrift_directory_round_trip(tmp_path, layout):

@@ -1277,6 +1277,11 @@ int ann_query_finish_device(ann_index* ix, const float* d_queries, int32_t b, in
     const ann_index::SeedSession sess = ix->sess;
     if (!sess.open || sess.b != b || sess.k != k || sess.filtered)
         return fail(ANN_ERR_INVALID_ARGUMENT, "ann_query_finish_device: no pending ann_query_seed_device call with this (b, k)");
+    if (sess.sliced) {
+        ix->sess.open = false;
+        return fail(ANN_ERR_INVALID_ARGUMENT,
+                    "ann_query_finish_device: the pending seed call was sliced (one bound per query); ann_query_filter_bounds_push_device must follow it");
+    }
     if (sess.clobbered) {
         ix->sess.open = false;
         return fail(ANN_ERR_INVALID_ARGUMENT,
