@@ -253,7 +253,7 @@ ANN_API int ann_sharded_shard(ann_sharded_index *sx, int32_t shard, ann_index **
 /* "two_round" (1 = seed + k-best rounds, default; 0 = seed round only), "sliced_seeds" (two_round only; 1 = every shard
  * seeds its slice of the batch and delivers one bound per query, default; 0 = every shard seeds every query and delivers k
  * bounds per query); any other name is applied to every shard.
- * Stats: "shards", "peer_access", "fallback_batches", "queries"; any other name is summed over the shards. */
+ * Stats: "shards", "peer_access", "fallback_batches", "queries", "dim"; any other name is summed over the shards. */
 ANN_API int ann_sharded_set_option(ann_sharded_index *sx, const char *name, int64_t value);
 ANN_API int ann_sharded_get_stat(const ann_sharded_index *sx, const char *name, int64_t *value);
 
@@ -334,7 +334,7 @@ ANN_API int ann_loadtest(ann_index *ix, const float *queries, int32_t nq, int32_
  *          "timing" (1 = bracket every scan / GEMM-filter launch with CUDA events on its stream),
  *          "coalesce_max_batch" (queries per merged device call of the host entry point's micro-batcher, default 2048; 0 = off),
  *          "coalesce_small_b" (host calls with at most this many queries are combined with concurrent ones, default 32),
- *          "coalesce_linger_us" (how long a caller that inherits the lead waits for the previous batch's callers to return, default 60),
+ *          "coalesce_linger_us" (how long a caller that inherits the lead waits for the previous batch's callers to return, default 100),
  *          "device_fallback" (1 = ann_query_batch_device synchronises its stream and re-answers flagged queries with the
  *          exact fallback, like the host entry point always does; 0 = stay asynchronous and report them, default).
  * Stats:   "launches" (kernels launched so far), "last_path", "shadow_bytes", "row_bytes", "n_special", "capacity", "dim",

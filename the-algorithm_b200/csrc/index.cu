@@ -1061,7 +1061,9 @@ void ann_destroy(ann_index* ix) {
 
 int ann_size(const ann_index* ix, int64_t* n) {
     if (!ix || !n) return fail(ANN_ERR_NULL_POINTER, "ann_size: NULL argument");
-    *n = ix->n;
+    // lock-free like linkedQueue.size (BruteForceIndex.scala:34-36): a size() poll must not wait behind a running query
+    // batch, which holds `mu` for its whole duration; pairs with the release store in append_and_publish
+    *n = __atomic_load_n(&ix->n, __ATOMIC_ACQUIRE);
     return ANN_OK;
 }
 
@@ -1137,7 +1139,7 @@ int append_and_publish(ann_index* ix, const int64_t* ids, const float* rows, int
     CUDA_TRY(cudaStreamSynchronize(st));
     std::lock_guard<std::mutex> lk(ix->mu);
     if (ix->sess.open) ix->sess.clobbered = true;   // new rows may raise the error bounds a pending sharded query was prepared with
-    ix->n += n;
+    __atomic_store_n(&ix->n, ix->n + n, __ATOMIC_RELEASE);   // ann_size reads it without `mu`
     ix->n_special = ix->h_scalars->n_special;
     return ANN_OK;
 }

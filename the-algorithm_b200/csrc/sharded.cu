@@ -347,6 +347,7 @@ int ann_sharded_get_stat(const ann_sharded_index* sx, const char* name, int64_t*
     else if (!strcmp(name, "peer_access")) *value = sx->peer_ok ? 1 : 0;
     else if (!strcmp(name, "fallback_batches")) *value = sx->fallback_batches;
     else if (!strcmp(name, "queries")) *value = sx->queries;
+    else if (!strcmp(name, "dim")) *value = sx->cfg.dim;   // one dimension, not a sum over the shards
     else {   // sums over the shards ("launches", "row_bytes", ...)
         int64_t t = 0;
         for (const Shard& s : sx->sh) {

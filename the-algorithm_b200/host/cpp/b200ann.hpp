@@ -171,6 +171,12 @@ public:
         check(ann_query_batch(h_, queries, b, dim_, k, out_ids, out_dist, out_count));
     }
 
+    // Updatable.update (Api.scala:148-150), batched: overwrite the rows stored at insertion slots `slots` (ann_update_batch)
+    void updateBatch(const int64_t* slots, const float* rows, int64_t n) { check(ann_update_batch(h_, slots, rows, n)); }
+
+    // SerializableBruteForceIndex.toDirectory (BruteForceIndex.scala:142-161): BruteForceFileData thrift stream + _SUCCESS
+    void toDirectory(const std::string& directory) { check(ann_save_directory(h_, directory.c_str(), ANN_ID_INT64_BE, ANN_LAYOUT_FLOAT_TENSOR)); }
+
     ann_index* handle() { return h_; }
 
 private:

@@ -1,11 +1,15 @@
 /* b200ann_jni.c -- JNI shim between com.twitter.ann.brute_force.B200AnnNative (host/scala/GpuBruteForceIndex.scala) and
- * the C ABI (include/b200ann.h).  One function per entry point, no logic: direct ByteBuffers are unwrapped to plain
- * pointers and passed through.  Same boundary shape as the reference's SWIG Faiss binding
+ * the C ABI (include/b200ann.h).  One function per entry point and one piece of logic: direct ByteBuffers are unwrapped to
+ * plain pointers AFTER their capacity has been checked against what the call will read or write, so a buffer sized for the
+ * wrong (b, k, dim) is refused (ANN_ERR_INVALID_ARGUMENT, message through lastError) instead of overrunning the JVM's
+ * native heap.  Same boundary shape as the reference's SWIG Faiss binding
  * (ann/src/main/java/com/twitter/ann/faiss/swig/swigfaissJNI.java:267-269: opaque long handle + flat buffers).
  *
  * Build (where a JDK exists):  gcc -shared -fPIC -I$JAVA_HOME/include -I$JAVA_HOME/include/linux \
  *                                  b200ann_jni.c -L../../lib -lb200ann -o libb200ann_jni.so
- * This image has no jni.h, so the body is compiled only when the header is present; the guard keeps `make` green. */
+ * This image has no jni.h, so the body is compiled only when the header is present; the guard keeps `make` green.
+ * tests/test_jni_host.py compiles the body against a stand-in header (tests/jni_stub/jni.h) and runs every entry point
+ * below against a mock JNIEnv (tests/jni_host_check.c). */
 #if defined(__has_include)
 #if __has_include(<jni.h>)
 #define B200ANN_HAVE_JNI 1
@@ -21,6 +25,25 @@
 
 static void *addr(JNIEnv *env, jobject buf) { return buf ? (*env)->GetDirectBufferAddress(env, buf) : NULL; }
 
+/* message of the last call this shim itself refused on this thread (lastError returns it once, then the library's) */
+static __thread const char *g_shim_error = NULL;
+
+/* 1 when `buf` is a direct buffer with room for `bytes` (a NULL buffer passes: the C ABI decides whether it is optional) */
+static int fits(JNIEnv *env, jobject buf, int64_t bytes, const char *what) {
+    if (!buf || bytes <= 0) return 1;
+    if ((*env)->GetDirectBufferAddress(env, buf) != NULL && (int64_t)(*env)->GetDirectBufferCapacity(env, buf) >= bytes) return 1;
+    g_shim_error = what;
+    return 0;
+}
+#define REQUIRE(buf, bytes, what) \
+    do { if (!fits(env, (buf), (int64_t)(bytes), "b200ann_jni: " what " is not a direct ByteBuffer large enough for this call")) return ANN_ERR_INVALID_ARGUMENT; } while (0)
+/* dimension of an existing handle (0 when it cannot be read: the C ABI then reports the real problem) */
+static int64_t dim_of(jlong handle) {
+    int64_t d = 0;
+    return (handle && ann_get_stat((const ann_index *)(intptr_t)handle, "dim", &d) == ANN_OK) ? d : 0;
+}
+static int64_t pos(int64_t v) { return v > 0 ? v : 0; }
+
 NATIVE(jlong, create)(JNIEnv *env, jobject self, jint metric, jint dim, jlong capacity_hint, jint device, jint flags) {
     (void)env; (void)self;
     ann_config cfg = {metric, dim, capacity_hint, device, (uint32_t)flags};
@@ -35,6 +58,8 @@ NATIVE(void, destroy)(JNIEnv *env, jobject self, jlong handle) {
 
 NATIVE(jint, appendBatch)(JNIEnv *env, jobject self, jlong handle, jobject ids, jobject rows, jlong n) {
     (void)self;
+    REQUIRE(ids, pos(n) * 8, "ids");
+    REQUIRE(rows, pos(n) * dim_of(handle) * 4, "rows");
     return ann_append_batch((ann_index *)(intptr_t)handle, (const int64_t *)addr(env, ids), (const float *)addr(env, rows), n);
 }
 
@@ -47,6 +72,10 @@ NATIVE(jlong, size)(JNIEnv *env, jobject self, jlong handle) {
 NATIVE(jint, queryBatch)(JNIEnv *env, jobject self, jlong handle, jobject queries, jint b, jint dim, jint k, jobject out_ids,
                          jobject out_dist, jobject out_count) {
     (void)self;
+    REQUIRE(queries, pos(b) * pos(dim) * 4, "queries");
+    REQUIRE(out_ids, pos(b) * pos(k) * 8, "outIds");
+    REQUIRE(out_dist, pos(b) * pos(k) * 4, "outDist");
+    REQUIRE(out_count, pos(b) * 4, "outCount");
     return ann_query_batch((ann_index *)(intptr_t)handle, (const float *)addr(env, queries), b, dim, k,
                            (int64_t *)addr(env, out_ids), (float *)addr(env, out_dist), (int32_t *)addr(env, out_count));
 }
@@ -56,6 +85,12 @@ NATIVE(jint, knnJoin)(JNIEnv *env, jobject self, jint metric, jint dim, jint dev
                       jobject corpus_rows, jlong n, jobject queries, jlong nq, jint k, jlong corpus_tile_rows, jint query_tile,
                       jobject out_ids, jobject out_dist, jobject out_count) {
     (void)self;
+    REQUIRE(corpus_ids, pos(n) * 8, "corpusIds");
+    REQUIRE(corpus_rows, pos(n) * pos(dim) * 4, "corpusRows");
+    REQUIRE(queries, pos(nq) * pos(dim) * 4, "queries");
+    REQUIRE(out_ids, pos(nq) * pos(k) * 8, "outIds");
+    REQUIRE(out_dist, pos(nq) * pos(k) * 4, "outDist");
+    REQUIRE(out_count, pos(nq) * 4, "outCount");
     ann_config cfg = {metric, dim, 0, device, (uint32_t)flags};
     return ann_knn_join(&cfg, (const int64_t *)addr(env, corpus_ids), (const float *)addr(env, corpus_rows), n,
                         (const float *)addr(env, queries), nq, k, corpus_tile_rows, query_tile, (int64_t *)addr(env, out_ids),
@@ -66,12 +101,17 @@ NATIVE(jint, knnJoin)(JNIEnv *env, jobject self, jint metric, jint dim, jint dev
 NATIVE(jint, distancePairs)(JNIEnv *env, jobject self, jint metric, jint flags, jint dim, jobject a, jobject b, jlong n,
                             jobject out, jint device) {
     (void)self;
+    REQUIRE(a, pos(n) * pos(dim) * 4, "a");
+    REQUIRE(b, pos(n) * pos(dim) * 4, "b");
+    REQUIRE(out, pos(n) * 4, "out");
     return ann_distance_pairs(metric, (uint32_t)flags, dim, (const float *)addr(env, a), (const float *)addr(env, b), n,
                               (float *)addr(env, out), device);
 }
 
 NATIVE(jint, normalizeRows)(JNIEnv *env, jobject self, jint dim, jobject rows, jlong n, jobject out, jint device) {
     (void)self;
+    REQUIRE(rows, pos(n) * pos(dim) * 4, "rows");
+    REQUIRE(out, pos(n) * pos(dim) * 4, "out");
     return ann_normalize_rows(dim, (const float *)addr(env, rows), n, (float *)addr(env, out), device);
 }
 
@@ -89,6 +129,7 @@ NATIVE(jint, queryFinishDevice)(JNIEnv *env, jobject self, jlong handle, jlong d
                                 jobject peer_seed_keys, jint world, jlong d_out_ids, jlong d_out_dist, jlong d_out_count,
                                 jlong stream) {
     (void)self;
+    REQUIRE(peer_seed_keys, pos(world) * 8, "peerSeedKeys");
     return ann_query_finish_device((ann_index *)(intptr_t)handle, (const float *)(intptr_t)d_queries, b, dim, k,
                                    (const uint32_t *const *)addr(env, peer_seed_keys), world, (int64_t *)(intptr_t)d_out_ids,
                                    (float *)(intptr_t)d_out_dist, (int32_t *)(intptr_t)d_out_count, (void *)(intptr_t)stream);
@@ -113,6 +154,10 @@ NATIVE(void, shardedDestroy)(JNIEnv *env, jobject self, jlong handle) {
 
 NATIVE(jint, shardedAppendBatch)(JNIEnv *env, jobject self, jlong handle, jobject ids, jobject rows, jlong n) {
     (void)self;
+    int64_t d = 0;
+    if (handle && ann_sharded_get_stat((const ann_sharded_index *)(intptr_t)handle, "dim", &d) != ANN_OK) d = 0;
+    REQUIRE(ids, pos(n) * 8, "ids");
+    REQUIRE(rows, pos(n) * d * 4, "rows");
     return ann_sharded_append_batch((ann_sharded_index *)(intptr_t)handle, (const int64_t *)addr(env, ids),
                                     (const float *)addr(env, rows), n);
 }
@@ -126,6 +171,10 @@ NATIVE(jlong, shardedSize)(JNIEnv *env, jobject self, jlong handle) {
 NATIVE(jint, shardedQueryBatch)(JNIEnv *env, jobject self, jlong handle, jobject queries, jint b, jint dim, jint k,
                                 jobject out_ids, jobject out_dist, jobject out_count) {
     (void)self;
+    REQUIRE(queries, pos(b) * pos(dim) * 4, "queries");
+    REQUIRE(out_ids, pos(b) * pos(k) * 8, "outIds");
+    REQUIRE(out_dist, pos(b) * pos(k) * 4, "outDist");
+    REQUIRE(out_count, pos(b) * 4, "outCount");
     return ann_sharded_query_batch((ann_sharded_index *)(intptr_t)handle, (const float *)addr(env, queries), b, dim, k,
                                    (int64_t *)addr(env, out_ids), (float *)addr(env, out_dist), (int32_t *)addr(env, out_count));
 }
@@ -171,9 +220,50 @@ NATIVE(jlong, shardedLoadDirectory)(JNIEnv *env, jobject self, jint metric, jint
     return rc == ANN_OK ? (jlong)(intptr_t)sx : 0;
 }
 
+/* Updatable.update (Api.scala:148-150), batched: overwrite the rows stored at `slots` (ann_update_batch) */
+NATIVE(jint, updateBatch)(JNIEnv *env, jobject self, jlong handle, jobject slots, jobject rows, jlong n) {
+    (void)self;
+    REQUIRE(slots, pos(n) * 8, "slots");
+    REQUIRE(rows, pos(n) * dim_of(handle) * 4, "rows");
+    return ann_update_batch((ann_index *)(intptr_t)handle, (const int64_t *)addr(env, slots), (const float *)addr(env, rows), n);
+}
+
+/* rows [start, start + n) and their ids back into direct buffers (ann_read_rows): what toDirectory iterates */
+NATIVE(jint, readRows)(JNIEnv *env, jobject self, jlong handle, jlong start, jlong n, jobject out_ids, jobject out_rows) {
+    (void)self;
+    REQUIRE(out_ids, pos(n) * 8, "outIds");
+    REQUIRE(out_rows, pos(n) * dim_of(handle) * 4, "outRows");
+    return ann_read_rows((ann_index *)(intptr_t)handle, start, n, (int64_t *)addr(env, out_ids), (float *)addr(env, out_rows));
+}
+
+NATIVE(jint, setOption)(JNIEnv *env, jobject self, jlong handle, jstring name, jlong value) {
+    (void)self;
+    const char *s = name ? (*env)->GetStringUTFChars(env, name, NULL) : NULL;
+    int rc = ann_set_option((ann_index *)(intptr_t)handle, s, value);
+    if (s) (*env)->ReleaseStringUTFChars(env, name, s);
+    return rc;
+}
+
+/* a stat by name, or Long.MIN_VALUE when the call failed (see lastError) */
+NATIVE(jlong, getStat)(JNIEnv *env, jobject self, jlong handle, jstring name) {
+    (void)self;
+    const char *s = name ? (*env)->GetStringUTFChars(env, name, NULL) : NULL;
+    int64_t v = 0;
+    int rc = ann_get_stat((const ann_index *)(intptr_t)handle, s, &v);
+    if (s) (*env)->ReleaseStringUTFChars(env, name, s);
+    return rc == ANN_OK ? (jlong)v : (jlong)INT64_MIN;
+}
+
+NATIVE(jint, version)(JNIEnv *env, jobject self) {
+    (void)env; (void)self;
+    return ann_version();
+}
+
 NATIVE(jstring, lastError)(JNIEnv *env, jobject self) {
     (void)self;
-    return (*env)->NewStringUTF(env, ann_last_error());
+    const char *own = g_shim_error;
+    g_shim_error = NULL;
+    return (*env)->NewStringUTF(env, own ? own : ann_last_error());
 }
 #else
 /* no JDK in this image: nothing to compile */

@@ -14,6 +14,7 @@ import com.twitter.ann.common.EntityEmbedding
 import com.twitter.ann.common.Metric
 import com.twitter.ann.common.NeighborWithDistance
 import com.twitter.ann.common.Queryable
+import com.twitter.ann.common.Updatable
 import com.twitter.ann.common.{Cosine, InnerProduct, L2}
 import com.twitter.util.Future
 import com.twitter.util.FuturePool
@@ -56,6 +57,16 @@ object B200AnnNative {
   @native def loadDirectory(metric: Int, dim: Int, device: Int, flags: Int, directory: String, idFormat: Int): Long
   @native def shardedSaveDirectory(handle: Long, directory: String, idFormat: Int, layout: Int): Int
   @native def shardedLoadDirectory(metric: Int, dim: Int, flags: Int, directory: String, idFormat: Int, devices: Array[Int]): Long
+  // Updatable.update (common/Api.scala:148-150), batched: overwrite the rows stored at insertion slots (ann_update_batch)
+  @native def updateBatch(handle: Long, slots: ByteBuffer, rows: ByteBuffer, n: Long): Int
+  // rows [start, start + n) and their ids back into direct buffers (ann_read_rows)
+  @native def readRows(handle: Long, start: Long, n: Long, outIds: ByteBuffer, outRows: ByteBuffer): Int
+  // tuning / introspection by name (ann_set_option / ann_get_stat; getStat returns Long.MinValue on failure)
+  @native def setOption(handle: Long, name: String, value: Long): Int
+  @native def getStat(handle: Long, name: String): Long
+  @native def version(): Int
+  // message of the last failed call on this thread; the shim refuses direct buffers too small for a call before the
+  // library could overrun them, and reports that here as well
   @native def lastError(): String
 }
 
@@ -81,6 +92,22 @@ object GpuBruteForceIndex {
     initialEmbeddings.grouped(65536).foreach(batch => index.appendBatch(batch))
     index
   }
+
+  /** BruteForceDeserialization.fromDirectory (BruteForceDeserialization.scala:42-63) for Long ids: reads the
+   * `BruteForceFileData` thrift stream written by SerializableBruteForceIndex.toDirectory -- or by `toDirectory` below --
+   * straight into device memory (ann_load_directory).  The dimension is taken from the first record. */
+  def fromDirectory[D <: Distance[D]](
+    directory: String,
+    metric: Metric[D],
+    futurePool: FuturePool,
+    device: Int = 0
+  ): GpuBruteForceIndex[Long, D] = {
+    val h = B200AnnNative.loadDirectory(ordinal(metric), 0, device, 0, directory, 0)
+    if (h == 0L) throw new RuntimeException(B200AnnNative.lastError())
+    val index = new GpuBruteForceIndex[Long, D](metric, futurePool, device)
+    index.adopt(h)
+    index
+  }
 }
 
 class GpuBruteForceIndex[T, D <: Distance[D]] private (
@@ -89,12 +116,32 @@ class GpuBruteForceIndex[T, D <: Distance[D]] private (
   device: Int)
     extends Appendable[T, BruteForceRuntimeParams.type, D]
     with Queryable[T, BruteForceRuntimeParams.type, D]
+    with Updatable[T]
     with AutoCloseable {
 
   private[this] var handle: Long = 0L
   private[this] var dim: Int = -1
   private[this] val slotTable = new java.util.ArrayList[T]() // used only when T is not Long
   private[this] var nativeIds = true
+  // id -> insertion slot of its FIRST occurrence (what Updatable.update rewrites); filled as rows are appended
+  private[this] val slotOf = new java.util.HashMap[T, java.lang.Long]()
+  private[this] var appended: Long = 0L
+
+  /** takes over a handle that ann_load_directory filled (Long ids); the id -> slot map is rebuilt from the device */
+  private[brute_force] def adopt(loaded: Long): Unit = synchronized {
+    handle = loaded
+    dim = B200AnnNative.getStat(loaded, "dim").toInt
+    appended = B200AnnNative.size(loaded)
+    var start = 0L
+    while (start < appended) {
+      val n = math.min(1L << 20, appended - start)
+      val ids = direct((n * 8).toInt)
+      check(B200AnnNative.readRows(handle, start, n, ids, null))
+      var i = 0
+      while (i < n) { slotOf.putIfAbsent(ids.getLong(i * 8).asInstanceOf[T], start + i); i += 1 }
+      start += n
+    }
+  }
 
   private[this] def check(rc: Int): Unit =
     if (rc != 0) throw new RuntimeException(s"b200ann error $rc: ${B200AnnNative.lastError()}")
@@ -130,7 +177,39 @@ class GpuBruteForceIndex[T, D <: Distance[D]] private (
         while (i < d) { rows.putFloat(e.embedding(i)); i += 1 }
       }
       check(B200AnnNative.appendBatch(handle, ids, rows, batch.size.toLong))
+      // only after the native call succeeded, so a failed append cannot desynchronise id and slot
+      batch.foreach { e => slotOf.putIfAbsent(e.id, appended); appended += 1 }
     }
+  }
+
+  /** Updatable.update (Api.scala:148-150; hnsw/Hnsw.scala:149-182 is the in-tree implementation) for a whole batch: the
+   * embedding stored under each id is overwritten in place, norms and the bf16 shadow row are refreshed (ann_update_batch).
+   * An unknown id is an error, as in Hnsw.update. */
+  def updateBatch(batch: Seq[EntityEmbedding[T]]): Unit = synchronized {
+    if (batch.nonEmpty) {
+      val slots = direct(batch.size * 8)
+      val rows = direct(batch.size * dim * 4)
+      batch.foreach { e =>
+        val slot = slotOf.get(e.id)
+        if (slot == null) throw new IllegalArgumentException(s"update of an id that was never appended: ${e.id}")
+        if (e.embedding.length != dim) throw new IllegalArgumentException(s"embedding dimension ${e.embedding.length} != index dimension $dim")
+        slots.putLong(slot)
+        var i = 0
+        while (i < dim) { rows.putFloat(e.embedding(i)); i += 1 }
+      }
+      check(B200AnnNative.updateBatch(handle, slots, rows, batch.size.toLong))
+    }
+  }
+
+  override def update(entity: EntityEmbedding[T]): Future[Unit] = futurePool { updateBatch(Seq(entity)) }
+
+  /** SerializableBruteForceIndex.toDirectory (BruteForceIndex.scala:142-161): `BruteForceFileData` as a TBinaryProtocol
+   * PersistedEmbedding stream + `_SUCCESS`, written natively (ann_save_directory); Long ids only (8 bytes big-endian,
+   * AnnInjections.scala:8-12).  BruteForceDeserialization.fromDirectory reads it back, as does `fromDirectory` above. */
+  def toDirectory(directory: String): Unit = synchronized {
+    if (!nativeIds) throw new UnsupportedOperationException("toDirectory needs Long ids (other id types live in the JVM-side slot table)")
+    if (handle == 0L) throw new IllegalStateException("toDirectory on an index that never saw a row (dimension unknown)")
+    check(B200AnnNative.saveDirectory(handle, directory, 1, 0))
   }
 
   // Appendable.append, BruteForceIndex.scala:48-52
