@@ -97,3 +97,94 @@ def test_end_of_stream_and_errors(built_lib):
     assert rc == _capi.ANN_ERR_INVALID_ARGUMENT
     rc, *_ = decode(hand_record(1, [1.0]), id_format=_capi.ANN_ID_INT32_BE)                  # 8-byte id refused when Int was asked for
     assert rc == _capi.ANN_ERR_INVALID_ARGUMENT
+
+
+# ---- robustness: no read past the end of the input, malformed records are errors (not a silent end of stream) ----------
+class GuardedBuffer:
+    """`data` placed so that its last byte is the last byte of a page, with a PROT_NONE page right behind it: a decoder
+    that reads one byte too far dies with SIGSEGV instead of passing by luck."""
+
+    def __init__(self, data: bytes):
+        import mmap
+        self.page = mmap.PAGESIZE
+        self.libc = ctypes.CDLL(None, use_errno=True)
+        self.libc.mmap.restype = ctypes.c_void_p
+        self.libc.mmap.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_long]
+        self.libc.mprotect.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+        self.libc.munmap.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+        n_pages = (len(data) + self.page - 1) // self.page + 1
+        self.size = (n_pages + 1) * self.page
+        base = self.libc.mmap(None, self.size, mmap.PROT_READ | mmap.PROT_WRITE, mmap.MAP_PRIVATE | mmap.MAP_ANONYMOUS, -1, 0)
+        assert base not in (None, ctypes.c_void_p(-1).value)
+        self.base = base
+        guard = base + n_pages * self.page
+        assert self.libc.mprotect(guard, self.page, 0) == 0      # prot 0 = PROT_NONE
+        self.addr = guard - len(data)
+        ctypes.memmove(self.addr, data, len(data)) if data else None
+        self.len = len(data)
+
+    def close(self):
+        self.libc.munmap(self.base, self.size)
+
+
+def decode_guarded(data, id_format=_capi.ANN_ID_AUTO, cap=64):
+    L = _capi.lib()
+    g = GuardedBuffer(data)
+    try:
+        idv, dim, used = ctypes.c_int64(), ctypes.c_int32(), ctypes.c_int64()
+        row = np.zeros(cap, dtype=np.float32)
+        rc = L.ann_persisted_embedding_decode(ctypes.cast(g.addr, ctypes.POINTER(ctypes.c_ubyte)), g.len, id_format, ctypes.byref(idv),
+                                              row.ctypes.data, cap, ctypes.byref(dim), ctypes.byref(used))
+        return rc, idv.value, row[: max(0, min(dim.value, cap))].copy(), used.value, dim.value
+    finally:
+        g.close()
+
+
+@pytest.mark.parametrize("layout", [0, 1, 2])
+@pytest.mark.parametrize("id_format", [_capi.ANN_ID_INT64_BE, _capi.ANN_ID_INT32_BE])
+def test_every_truncation_ends_the_stream_without_reading_past_the_input(built_lib, layout, id_format):
+    row = np.arange(1, 6, dtype=np.float32) * 0.5
+    data = encode(77, row, id_format=id_format, layout=layout)
+    rc, idv, got, used, dim = decode_guarded(data)
+    assert rc == 0 and idv == 77 and used == len(data) and got.tolist() == row.tolist()
+    for cut in range(len(data)):      # every proper prefix: a partial trailing record is the end of the stream
+        rc, _, _, used, dim = decode_guarded(data[:cut])
+        assert rc == 0 and used == 0 and dim == 0, cut
+
+
+def test_mutated_records_never_crash_and_never_end_the_stream_silently_mid_record(built_lib):
+    rng = np.random.default_rng(20261019)
+    base = [encode(5, np.linspace(-1, 1, 9, dtype=np.float32), layout=l) for l in (0, 1, 2)]
+    base.append(hand_record(9, [1.5, 2.5], shape=True))
+    outcomes = {"ok": 0, "eos": 0, "error": 0}
+    for it in range(3000):
+        data = bytearray(base[it % len(base)])
+        for _ in range(int(rng.integers(1, 4))):
+            data[int(rng.integers(0, len(data)))] = int(rng.integers(0, 256))
+        rc, idv, got, used, dim = decode_guarded(bytes(data))      # a read past the input would be a SIGSEGV here
+        assert rc in (0, _capi.ANN_ERR_INVALID_ARGUMENT), rc
+        if rc == 0:
+            assert 0 <= used <= len(data) and dim >= 0
+            outcomes["ok" if used else "eos"] += 1
+        else:
+            outcomes["error"] += 1
+    # all three happen: mutations of padding-like bytes still decode, longer declared sizes run off the end, broken type
+    # bytes / negative sizes are errors
+    assert min(outcomes.values()) > 0, outcomes
+
+
+def test_malformed_record_in_mid_stream_is_an_error_not_a_short_index(built_lib):
+    """Only END_OF_FILE ends the reference's iterator (ThriftIteratorIO.scala:42-49); a TProtocolException propagates.  A
+    record whose embedding holds an unknown thrift type, with a good record BEHIND it, must not load as a shorter index."""
+    good = hand_record(1, [1.0, 2.0])
+    bad = bytearray(hand_record(2, [3.0, 4.0]))
+    pos = bad.index(fh(15, 1)) + 3      # element-type byte of list<double>: 4 -> 99 (no such TType)
+    assert bad[pos] == 4
+    bad[pos] = 99
+    stream = bytes(bad) + good
+    rc, *_ = decode_guarded(stream)
+    assert rc == _capi.ANN_ERR_INVALID_ARGUMENT
+    neg = bytearray(hand_record(2, [3.0, 4.0]))
+    neg[pos + 1: pos + 5] = struct.pack(">i", -7)      # negative list length
+    rc, *_ = decode_guarded(bytes(neg) + good)
+    assert rc == _capi.ANN_ERR_INVALID_ARGUMENT

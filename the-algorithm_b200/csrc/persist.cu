@@ -238,7 +238,10 @@ int read_record(Reader& r, int id_format, int64_t* id, std::vector<float>* row) 
             have_id = true;
         } else if (fid == 2 && type == T_STRUCT) {
             if (!walk_struct(r, &f, 0)) {
-                if (f.bad) return perr(ANN_ERR_INVALID_ARGUMENT, "BruteForceFileData: malformed embedding struct");
+                // only running off the end of the file ends the stream quietly (TTransportException.END_OF_FILE,
+                // ThriftIteratorIO.scala:42-49); a record that is malformed where it stands (negative size, unknown type,
+                // absurd nesting) is an error there (TProtocolException propagates) and here
+                if (f.bad || !r.eof) return perr(ANN_ERR_INVALID_ARGUMENT, "BruteForceFileData: malformed embedding struct");
                 return 0;
             }
         } else if (!skip_value(r, type, 0)) {
