@@ -134,7 +134,7 @@ class GpuShardedBruteForceIndex(Appendable, Queryable):
         self._h = ctypes.c_void_p()
         _capi.check(_capi.lib().ann_sharded_load_directory(ctypes.byref(cfg), os.fsencode(str(directory)), id_format, arr,
                                                            len(self.devices), ctypes.byref(self._h)))
-        self.dim = self.stat("dim") // max(len(self.devices), 1)     # "dim" is summed over the shards like every per-shard stat
+        self.dim = self.stat("dim")     # the composed handle's dimension (not summed over the shards)
         return self
 
     fromDirectory = from_directory

@@ -65,6 +65,7 @@ constexpr int kScanGroup = 64;       // queries finalized together on the scan p
 constexpr int kScanPoolCap = 16384;  // pool entries per query, scan path
 constexpr int kGemmPoolCap = 4096;   // pool entries per query, gemm path
 constexpr int kPubStride = 256;
+constexpr size_t kSmallResultBytes = 256 << 10;   // host queries whose whole result fits go through the pinned landing zone
 
 struct DeviceScalars {
     uint32_t max_norm_bits;
@@ -127,6 +128,11 @@ struct ann_index {
     std::mutex mu, append_mu;
     cudaStream_t append_stream = nullptr;
     DeviceScalars* h_scalars = nullptr;   // pinned host mirror of the scalars' header (read back with the append's own sync)
+    // pinned landing zone for SMALL query results (guarded by `mu`): a device->host copy into the caller's pageable memory
+    // blocks the host until it has landed, so the four copies of a host query (ids, distances, counts, flag word) were four
+    // serial round trips; into pinned memory they are queued back to back behind the kernels and ONE synchronisation
+    // covers them, then the rows are copied to the caller on the host (a single-vector result is 1.2 KB)
+    unsigned char* h_res = nullptr;
 
     long long cap = 0, n = 0, max_rows = 0;
     // storage: virtual ranges reserved once, physical memory mapped behind the rows as they arrive (grows in place)
@@ -981,6 +987,10 @@ int ann_create(const ann_config* cfg, ann_index** out) {
     if (cudaHostAlloc(&ix->h_scalars, sizeof(DeviceScalars), cudaHostAllocDefault) != cudaSuccess)
         return cleanup(fail(ANN_ERR_OUT_OF_MEMORY, "cudaHostAlloc failed"));
     memset(ix->h_scalars, 0, sizeof(DeviceScalars));
+    if (cudaHostAlloc(&ix->h_res, kSmallResultBytes, cudaHostAllocDefault) != cudaSuccess) {
+        (void)cudaGetLastError();
+        ix->h_res = nullptr;   // not fatal: results then go straight to the caller's buffers, as before
+    }
     if (cudaMemsetAsync(ix->scalars, 0, sizeof(DeviceScalars), ix->stream) != cudaSuccess)
         return cleanup(fail(ANN_ERR_CUDA, "cudaMemset failed"));
     // Address ranges for the whole life of the index: as many rows as could ever fit the device (192 GB of fp32 rows, local
@@ -1033,6 +1043,7 @@ void ann_destroy(ann_index* ix) {
     ix->vm_shadow.release();
     cudaFree(ix->scalars);
     if (ix->h_scalars) cudaFreeHost(ix->h_scalars);
+    if (ix->h_res) cudaFreeHost(ix->h_res);
     if (ix->co.pin_q) cudaFreeHost(ix->co.pin_q);
     if (ix->co.pin_res) cudaFreeHost(ix->co.pin_res);
     if (ix->append_stream) cudaStreamDestroy(ix->append_stream);
@@ -1472,7 +1483,8 @@ int ann_exchange_merge_slice_device(int32_t device, const void* const* peer_loca
 namespace {
 
 // The host-buffer query: H2D, query path, D2H, exact fallback for flagged queries.  Takes `mu`.
-int query_host(ann_index* ix, const float* queries, int32_t b, int32_t k, int64_t* out_ids, float* out_dist, int32_t* out_count) {
+int query_host(ann_index* ix, const float* queries, int32_t b, int32_t k, int64_t* out_ids, float* out_dist, int32_t* out_count,
+               bool dest_pinned = false) {
     std::lock_guard<std::mutex> lk(ix->mu);
     int rc = set_device(ix);
     if (rc) return rc;
@@ -1491,14 +1503,29 @@ int query_host(ann_index* ix, const float* queries, int32_t b, int32_t k, int64_
     if (rc) return rc;
     // one round trip in the common case: results and the sticky flag word come back together
     DeviceScalars hs{};
+    const size_t ids_bytes = (size_t)b * k * sizeof(int64_t), dist_bytes = (size_t)b * k * sizeof(float), cnt_bytes = (size_t)b * sizeof(int32_t);
+    const size_t hdr_off = (ids_bytes + dist_bytes + cnt_bytes + 15) / 16 * 16;
+    const bool landing = !dest_pinned && ix->h_res != nullptr && hdr_off + kScalarsHeader <= kSmallResultBytes;   // see ann_index::h_res
     auto copy_out = [&]() -> int {
+        unsigned char* const h_ids = landing ? ix->h_res : reinterpret_cast<unsigned char*>(out_ids);
+        unsigned char* const h_dist = landing ? ix->h_res + ids_bytes : reinterpret_cast<unsigned char*>(out_dist);
+        unsigned char* const h_cnt = landing ? ix->h_res + ids_bytes + dist_bytes : reinterpret_cast<unsigned char*>(out_count);
+        void* const h_hdr = landing ? static_cast<void*>(ix->h_res + hdr_off) : static_cast<void*>(&hs);
         if (k > 0) {
-            CUDA_TRY(cudaMemcpyAsync(out_ids, ix->out_ids.p, (size_t)b * k * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-            CUDA_TRY(cudaMemcpyAsync(out_dist, ix->out_dist.p, (size_t)b * k * sizeof(float), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(h_ids, ix->out_ids.p, ids_bytes, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(h_dist, ix->out_dist.p, dist_bytes, cudaMemcpyDeviceToHost, st));
         }
-        if (out_count) CUDA_TRY(cudaMemcpyAsync(out_count, ix->out_count.p, (size_t)b * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(&hs, ix->scalars, kScalarsHeader, cudaMemcpyDeviceToHost, st));
+        if (out_count) CUDA_TRY(cudaMemcpyAsync(h_cnt, ix->out_count.p, cnt_bytes, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(h_hdr, ix->scalars, kScalarsHeader, cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
+        if (landing) {
+            if (k > 0) {
+                memcpy(out_ids, h_ids, ids_bytes);
+                memcpy(out_dist, h_dist, dist_bytes);
+            }
+            if (out_count) memcpy(out_count, h_cnt, cnt_bytes);
+            memcpy(&hs, h_hdr, kScalarsHeader);
+        }
         return ANN_OK;
     };
     rc = copy_out();
@@ -1626,7 +1653,7 @@ int query_coalesced(ann_index* ix, const float* queries, int32_t b, int32_t k, i
             int64_t* s_ids = reinterpret_cast<int64_t*>(co.pin_res);
             float* s_dist = reinterpret_cast<float*>(co.pin_res + (size_t)total * k * 8);
             int32_t* s_cnt = reinterpret_cast<int32_t*>(co.pin_res + (size_t)total * k * 12);
-            rc = query_host(ix, co.pin_q, total, k, s_ids, s_dist, s_cnt);
+            rc = query_host(ix, co.pin_q, total, k, s_ids, s_dist, s_cnt, /*dest_pinned=*/true);
             if (rc) err = g_last_error;
             else {
                 size_t row = 0;
