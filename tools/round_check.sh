@@ -13,6 +13,8 @@ timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/b
 # the ncu passes profile the headline step only (--no-extra: no sub-runs); every number printed under ncu is ignored
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/ncu_launches_$TAG.log 2>&1; echo NCU_LAUNCHES_EXIT $?
+# SKIP_FULL=1: no `--set full` captures (for a pass whose kernels are byte-identical to the previous capture's)
+if [ -n "$SKIP_FULL" ]; then ls -la gpurun_out | tail -12; exit 0; fi
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_filter -s 12 -c 6 -f -o gpurun_out/gemm_$TAG \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extra > gpurun_out/ncu_full_$TAG.log 2>&1; echo NCU_FULL_EXIT $?
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:finalize_kernel -s 3 -c 1 -f -o gpurun_out/finalize_$TAG \
