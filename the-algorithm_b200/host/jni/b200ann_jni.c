@@ -25,7 +25,8 @@
 
 static void *addr(JNIEnv *env, jobject buf) { return buf ? (*env)->GetDirectBufferAddress(env, buf) : NULL; }
 
-/* message of the last call this shim itself refused on this thread (lastError returns it once, then the library's) */
+/* message of the LAST native call on this thread when the shim itself refused it; every native clears it on entry, so
+ * lastError reports the shim's message only for the call that produced it and the library's (ann_last_error) otherwise */
 static __thread const char *g_shim_error = NULL;
 
 /* 1 when `buf` is a direct buffer with room for `bytes` (a NULL buffer passes: the C ABI decides whether it is optional) */
@@ -45,6 +46,7 @@ static int64_t dim_of(jlong handle) {
 static int64_t pos(int64_t v) { return v > 0 ? v : 0; }
 
 NATIVE(jlong, create)(JNIEnv *env, jobject self, jint metric, jint dim, jlong capacity_hint, jint device, jint flags) {
+    g_shim_error = NULL;
     (void)env; (void)self;
     ann_config cfg = {metric, dim, capacity_hint, device, (uint32_t)flags};
     ann_index *ix = NULL;
@@ -52,11 +54,13 @@ NATIVE(jlong, create)(JNIEnv *env, jobject self, jint metric, jint dim, jlong ca
 }
 
 NATIVE(void, destroy)(JNIEnv *env, jobject self, jlong handle) {
+    g_shim_error = NULL;
     (void)env; (void)self;
     ann_destroy((ann_index *)(intptr_t)handle);
 }
 
 NATIVE(jint, appendBatch)(JNIEnv *env, jobject self, jlong handle, jobject ids, jobject rows, jlong n) {
+    g_shim_error = NULL;
     (void)self;
     REQUIRE(ids, pos(n) * 8, "ids");
     REQUIRE(rows, pos(n) * dim_of(handle) * 4, "rows");
@@ -64,6 +68,7 @@ NATIVE(jint, appendBatch)(JNIEnv *env, jobject self, jlong handle, jobject ids, 
 }
 
 NATIVE(jlong, size)(JNIEnv *env, jobject self, jlong handle) {
+    g_shim_error = NULL;
     (void)env; (void)self;
     int64_t n = 0;
     return ann_size((const ann_index *)(intptr_t)handle, &n) == ANN_OK ? (jlong)n : -1;
@@ -71,6 +76,7 @@ NATIVE(jlong, size)(JNIEnv *env, jobject self, jlong handle) {
 
 NATIVE(jint, queryBatch)(JNIEnv *env, jobject self, jlong handle, jobject queries, jint b, jint dim, jint k, jobject out_ids,
                          jobject out_dist, jobject out_count) {
+    g_shim_error = NULL;
     (void)self;
     REQUIRE(queries, pos(b) * pos(dim) * 4, "queries");
     REQUIRE(out_ids, pos(b) * pos(k) * 8, "outIds");
@@ -84,6 +90,7 @@ NATIVE(jint, queryBatch)(JNIEnv *env, jobject self, jlong handle, jobject querie
 NATIVE(jint, knnJoin)(JNIEnv *env, jobject self, jint metric, jint dim, jint device, jint flags, jobject corpus_ids,
                       jobject corpus_rows, jlong n, jobject queries, jlong nq, jint k, jlong corpus_tile_rows, jint query_tile,
                       jobject out_ids, jobject out_dist, jobject out_count) {
+    g_shim_error = NULL;
     (void)self;
     REQUIRE(corpus_ids, pos(n) * 8, "corpusIds");
     REQUIRE(corpus_rows, pos(n) * pos(dim) * 4, "corpusRows");
@@ -100,6 +107,7 @@ NATIVE(jint, knnJoin)(JNIEnv *env, jobject self, jint metric, jint dim, jint dev
 /* Metric.distance for n plain pairs / MetricUtil.norm (Metric.scala:76-86, 285-289): host buffers, computed on the device */
 NATIVE(jint, distancePairs)(JNIEnv *env, jobject self, jint metric, jint flags, jint dim, jobject a, jobject b, jlong n,
                             jobject out, jint device) {
+    g_shim_error = NULL;
     (void)self;
     REQUIRE(a, pos(n) * pos(dim) * 4, "a");
     REQUIRE(b, pos(n) * pos(dim) * 4, "b");
@@ -109,6 +117,7 @@ NATIVE(jint, distancePairs)(JNIEnv *env, jobject self, jint metric, jint flags, 
 }
 
 NATIVE(jint, normalizeRows)(JNIEnv *env, jobject self, jint dim, jobject rows, jlong n, jobject out, jint device) {
+    g_shim_error = NULL;
     (void)self;
     REQUIRE(rows, pos(n) * pos(dim) * 4, "rows");
     REQUIRE(out, pos(n) * pos(dim) * 4, "out");
@@ -120,6 +129,7 @@ NATIVE(jint, normalizeRows)(JNIEnv *env, jobject self, jint dim, jobject rows, j
  * (CUDA IPC); peerSeedKeys is a direct buffer holding `world` 64-bit device addresses. */
 NATIVE(jint, querySeedDevice)(JNIEnv *env, jobject self, jlong handle, jlong d_queries, jint b, jint dim, jint k,
                               jlong d_seed_keys, jlong stream) {
+    g_shim_error = NULL;
     (void)env; (void)self;
     return ann_query_seed_device((ann_index *)(intptr_t)handle, (const float *)(intptr_t)d_queries, b, dim, k,
                                  (uint32_t *)(intptr_t)d_seed_keys, (void *)(intptr_t)stream);
@@ -128,6 +138,7 @@ NATIVE(jint, querySeedDevice)(JNIEnv *env, jobject self, jlong handle, jlong d_q
 NATIVE(jint, queryFinishDevice)(JNIEnv *env, jobject self, jlong handle, jlong d_queries, jint b, jint dim, jint k,
                                 jobject peer_seed_keys, jint world, jlong d_out_ids, jlong d_out_dist, jlong d_out_count,
                                 jlong stream) {
+    g_shim_error = NULL;
     (void)self;
     REQUIRE(peer_seed_keys, pos(world) * 8, "peerSeedKeys");
     return ann_query_finish_device((ann_index *)(intptr_t)handle, (const float *)(intptr_t)d_queries, b, dim, k,
@@ -137,6 +148,7 @@ NATIVE(jint, queryFinishDevice)(JNIEnv *env, jobject self, jlong handle, jlong d
 
 /* ---- one process, several GPUs: ShardedAppendable + ComposedQueryable as one native handle (ann_sharded_*) ---- */
 NATIVE(jlong, shardedCreate)(JNIEnv *env, jobject self, jint metric, jint dim, jlong capacity_hint, jint flags, jintArray devices) {
+    g_shim_error = NULL;
     (void)self;
     ann_config cfg = {metric, dim, capacity_hint, 0, (uint32_t)flags};
     jsize n = (*env)->GetArrayLength(env, devices);
@@ -148,11 +160,13 @@ NATIVE(jlong, shardedCreate)(JNIEnv *env, jobject self, jint metric, jint dim, j
 }
 
 NATIVE(void, shardedDestroy)(JNIEnv *env, jobject self, jlong handle) {
+    g_shim_error = NULL;
     (void)env; (void)self;
     ann_sharded_destroy((ann_sharded_index *)(intptr_t)handle);
 }
 
 NATIVE(jint, shardedAppendBatch)(JNIEnv *env, jobject self, jlong handle, jobject ids, jobject rows, jlong n) {
+    g_shim_error = NULL;
     (void)self;
     int64_t d = 0;
     if (handle && ann_sharded_get_stat((const ann_sharded_index *)(intptr_t)handle, "dim", &d) != ANN_OK) d = 0;
@@ -163,6 +177,7 @@ NATIVE(jint, shardedAppendBatch)(JNIEnv *env, jobject self, jlong handle, jobjec
 }
 
 NATIVE(jlong, shardedSize)(JNIEnv *env, jobject self, jlong handle) {
+    g_shim_error = NULL;
     (void)env; (void)self;
     int64_t n = 0;
     return ann_sharded_size((const ann_sharded_index *)(intptr_t)handle, &n) == ANN_OK ? (jlong)n : -1;
@@ -170,6 +185,7 @@ NATIVE(jlong, shardedSize)(JNIEnv *env, jobject self, jlong handle) {
 
 NATIVE(jint, shardedQueryBatch)(JNIEnv *env, jobject self, jlong handle, jobject queries, jint b, jint dim, jint k,
                                 jobject out_ids, jobject out_dist, jobject out_count) {
+    g_shim_error = NULL;
     (void)self;
     REQUIRE(queries, pos(b) * pos(dim) * 4, "queries");
     REQUIRE(out_ids, pos(b) * pos(k) * 8, "outIds");
@@ -181,6 +197,7 @@ NATIVE(jint, shardedQueryBatch)(JNIEnv *env, jobject self, jlong handle, jobject
 
 /* ---- the reference's on-disk format: BruteForceFileData thrift stream, shard_<i>/ directories (csrc/persist.cu) ---- */
 NATIVE(jint, saveDirectory)(JNIEnv *env, jobject self, jlong handle, jstring dir, jint id_format, jint layout) {
+    g_shim_error = NULL;
     (void)self;
     const char *d = (*env)->GetStringUTFChars(env, dir, NULL);
     int rc = ann_save_directory((ann_index *)(intptr_t)handle, d, id_format, layout);
@@ -189,6 +206,7 @@ NATIVE(jint, saveDirectory)(JNIEnv *env, jobject self, jlong handle, jstring dir
 }
 
 NATIVE(jlong, loadDirectory)(JNIEnv *env, jobject self, jint metric, jint dim, jint device, jint flags, jstring dir, jint id_format) {
+    g_shim_error = NULL;
     (void)self;
     ann_config cfg = {metric, dim, 0, device, (uint32_t)flags};
     const char *d = (*env)->GetStringUTFChars(env, dir, NULL);
@@ -199,6 +217,7 @@ NATIVE(jlong, loadDirectory)(JNIEnv *env, jobject self, jint metric, jint dim, j
 }
 
 NATIVE(jint, shardedSaveDirectory)(JNIEnv *env, jobject self, jlong handle, jstring dir, jint id_format, jint layout) {
+    g_shim_error = NULL;
     (void)self;
     const char *d = (*env)->GetStringUTFChars(env, dir, NULL);
     int rc = ann_sharded_save_directory((ann_sharded_index *)(intptr_t)handle, d, id_format, layout);
@@ -208,6 +227,7 @@ NATIVE(jint, shardedSaveDirectory)(JNIEnv *env, jobject self, jlong handle, jstr
 
 NATIVE(jlong, shardedLoadDirectory)(JNIEnv *env, jobject self, jint metric, jint dim, jint flags, jstring dir, jint id_format,
                                     jintArray devices) {
+    g_shim_error = NULL;
     (void)self;
     ann_config cfg = {metric, dim, 0, 0, (uint32_t)flags};
     const char *d = (*env)->GetStringUTFChars(env, dir, NULL);
@@ -222,6 +242,7 @@ NATIVE(jlong, shardedLoadDirectory)(JNIEnv *env, jobject self, jint metric, jint
 
 /* Updatable.update (Api.scala:148-150), batched: overwrite the rows stored at `slots` (ann_update_batch) */
 NATIVE(jint, updateBatch)(JNIEnv *env, jobject self, jlong handle, jobject slots, jobject rows, jlong n) {
+    g_shim_error = NULL;
     (void)self;
     REQUIRE(slots, pos(n) * 8, "slots");
     REQUIRE(rows, pos(n) * dim_of(handle) * 4, "rows");
@@ -230,6 +251,7 @@ NATIVE(jint, updateBatch)(JNIEnv *env, jobject self, jlong handle, jobject slots
 
 /* rows [start, start + n) and their ids back into direct buffers (ann_read_rows): what toDirectory iterates */
 NATIVE(jint, readRows)(JNIEnv *env, jobject self, jlong handle, jlong start, jlong n, jobject out_ids, jobject out_rows) {
+    g_shim_error = NULL;
     (void)self;
     REQUIRE(out_ids, pos(n) * 8, "outIds");
     REQUIRE(out_rows, pos(n) * dim_of(handle) * 4, "outRows");
@@ -237,6 +259,7 @@ NATIVE(jint, readRows)(JNIEnv *env, jobject self, jlong handle, jlong start, jlo
 }
 
 NATIVE(jint, setOption)(JNIEnv *env, jobject self, jlong handle, jstring name, jlong value) {
+    g_shim_error = NULL;
     (void)self;
     const char *s = name ? (*env)->GetStringUTFChars(env, name, NULL) : NULL;
     int rc = ann_set_option((ann_index *)(intptr_t)handle, s, value);
@@ -246,6 +269,7 @@ NATIVE(jint, setOption)(JNIEnv *env, jobject self, jlong handle, jstring name, j
 
 /* a stat by name, or Long.MIN_VALUE when the call failed (see lastError) */
 NATIVE(jlong, getStat)(JNIEnv *env, jobject self, jlong handle, jstring name) {
+    g_shim_error = NULL;
     (void)self;
     const char *s = name ? (*env)->GetStringUTFChars(env, name, NULL) : NULL;
     int64_t v = 0;
@@ -255,15 +279,14 @@ NATIVE(jlong, getStat)(JNIEnv *env, jobject self, jlong handle, jstring name) {
 }
 
 NATIVE(jint, version)(JNIEnv *env, jobject self) {
+    g_shim_error = NULL;
     (void)env; (void)self;
     return ann_version();
 }
 
 NATIVE(jstring, lastError)(JNIEnv *env, jobject self) {
     (void)self;
-    const char *own = g_shim_error;
-    g_shim_error = NULL;
-    return (*env)->NewStringUTF(env, own ? own : ann_last_error());
+    return (*env)->NewStringUTF(env, g_shim_error ? g_shim_error : ann_last_error());
 }
 #else
 /* no JDK in this image: nothing to compile */
