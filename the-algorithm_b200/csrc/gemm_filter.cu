@@ -33,7 +33,7 @@ namespace b200ann {
 
 namespace {
 
-// warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 spare, 4.. epilogue.  The epilogue runs with EW = 8 or 16 warps (template parameter):
+// warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 second MMA issuer (or spare), 4.. epilogue.  The epilogue runs with EW = 8 or 16 warps (template parameter):
 // the filter is a string of dependent compares, and in hit-dense chunks two warps per scheduler leave its fixed latencies
 // exposed (IPC 0.38 in ncu), so those launches use four per scheduler (+25 % there); in hit-sparse chunks the epilogue
 // keeps up anyway and the extra warps only take issue slots from the MMA warp (-1..5 %), so they use eight.
@@ -60,6 +60,7 @@ struct GemmArgs {
     int a_resident;                   // the batch is one query tile: its segments are loaded once and never released
     uint32_t a_slot_stride;           // bytes between query-segment slots (1024-aligned)
     int tau_smem;                     // thresholds of all query tiles are staged in shared memory (n_qt <= kTauTiles)
+    int mma_warps;                    // 1, or 2: warps 1 and 3 of the leader CTA issue the MMAs of alternate query tiles
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -223,7 +224,7 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
         }
         for (int i = 0; i < 3; ++i) {
             mbar_init(&b_full[i], 1);
-            mbar_init(&b_empty[i], 1);
+            mbar_init(&b_empty[i], a.mma_warps == 2 ? 2 : 1);   // every MMA issuer hands a row tile back
         }
         mbar_fence_init();
     }
@@ -282,9 +283,19 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
                 }
             }
         }
-    } else if (warp == 1) {
-        // ================================ MMA issuer (leader CTA, one thread) ================================
+    } else if (warp == 1 || (warp == 3 && a.mma_warps == 2)) {
+        // ================================ MMA issuer (leader CTA, one thread per issuing warp) ================================
+        // ONE thread issuing every tcgen05.mma is itself the limit of this kernel: ncu's instruction sampling of the headline
+        // launch shows warp 1 busy 91 % of the time, spread evenly over the ~34 SASS instructions nvcc needs per MMA
+        // (descriptor arithmetic + an ELECT / R2UR.BROADCAST loop per operand), 3.7 clocks each -- 447 instructions per
+        // 256 x 256 x 208 tile against the 1664 clocks its 13 MMAs occupy the tensor pipe, which therefore idles ~15 %
+        // even with no hit to handle.  With mma_warps == 2 warps 1 and 3 alternate query tiles: issuer W owns accumulator
+        // stage W and query slot W (both are the tile counter's parity), waits and commits on the same barriers as before, and
+        // each has two tile times to issue one tile.  tcgen05.commit tracks the MMAs of the EXECUTING thread, so a tile's
+        // t_full / a_empty commits stay exact; the row tile is released when both issuers have committed (b_empty counts 2).
         if (leader && lane == 0) {
+            const bool dual = !SEG && a.mma_warps == 2;
+            const uint32_t my_parity = warp == 3 ? 1u : 0u;
             // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7, 10), K-major both, N>>3 at 17, M>>4 at 24
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_TILE >> 3) << 17) | ((uint32_t)(N_TILE >> 4) << 24);
             uint32_t ga = 0, gt = 0, it = 0;
@@ -294,6 +305,10 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
                 const uint32_t b_addr = smem_u32(smB0 + (size_t)bs * tile_stride);
                 for (int qt = 0; qt < a.n_qt; ++qt, ++gt) {
                     const uint32_t s = gt & 1;                    // accumulator stage
+                    if (dual && s != my_parity) {                 // the other issuer's tile (nseg == 1: one slot per tile)
+                        ++ga;
+                        continue;
+                    }
                     mbar_wait(&t_empty[s], ((gt >> 1) & 1) ^ 1);
                     const uint32_t d_tmem = tmem_base + s * N_TILE;
                     uint32_t acc = 0;
@@ -691,6 +706,9 @@ cudaError_t launch_gemm_filter(const GemmLaunch& g, cudaStream_t stream) {
     a.a_slot_stride = plan.a_slot_stride;
     // the threshold table rides behind the barriers when the plan leaves room for it (it does for every dim <= 208)
     a.tau_smem = (!g.seed_mode && a.n_qt <= kTauTiles && plan.smem + kTauBytes <= optin) ? 1 : 0;
+    // two MMA issuers need the tile counter's parity to name both the accumulator stage and the query slot: whole-K query
+    // stages in a ring of two, more than one query tile per row tile
+    a.mma_warps = (g.mma_warps == 2 && plan.nseg == 1 && !plan.a_resident && plan.na == 2) ? 2 : 1;
     const size_t smem = plan.smem + (a.tau_smem ? kTauBytes : 0);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(clusters * cg);

@@ -179,6 +179,7 @@ struct ann_index {
 
     // options / stats
     int path_opt = 0, gemm_min_batch = 2, gemm_cta_group = 2, gemm_epi_warps = 0;
+    int gemm_mma_warps = 2;           // MMA-issuing threads per CTA pair (2: warps 1 and 3 alternate query tiles; 1 = round 1's single issuer)
     int gemm_hit_budget = 500;        // candidates a chunk of the GEMM path may add per query (sets the chunk schedule)
     int gemm_growth_pct = 0;          // chunk growth factor in percent (0 = derived from the hit budget)
     int gemm_small_select = 1;        // GEMM path: 2048 / 1024-entry selector stages (4 CTAs per SM) instead of 4096 / 2048
@@ -604,6 +605,7 @@ int query_gemm(ann_index* ix, QueryState* qs_base, const float* d_queries, int b
         g.epi_warps = seed_mode ? 8   // the seed group is the column range of one of 8 epilogue warps (gemm_seed_group_rows)
                       : ix->gemm_epi_warps ? ix->gemm_epi_warps
                                          : ((b > 256 && (double)(end - begin) * 1.5e-4 < (double)kHitBudget) ? 16 : 8);
+        g.mma_warps = ix->gemm_mma_warps;
         g.nb_stages = gemm_row_stages(ix->kp, ix->smem_optin);
         g.sm_count = ix->sm_count;
         g.qstate = qs_base + q_first;
@@ -1791,6 +1793,11 @@ int ann_set_option(ann_index* ix, const char* name, int64_t value) {
     if (!strcmp(name, "gemm_epi_warps")) {
         if (value != 0 && value != 8 && value != 16) return fail(ANN_ERR_INVALID_ARGUMENT, "gemm_epi_warps must be 0 (auto), 8 or 16");
         ix->gemm_epi_warps = (int)value;
+        return ANN_OK;
+    }
+    if (!strcmp(name, "gemm_mma_warps")) {
+        if (value != 1 && value != 2) return fail(ANN_ERR_INVALID_ARGUMENT, "gemm_mma_warps must be 1 or 2");
+        ix->gemm_mma_warps = (int)value;
         return ANN_OK;
     }
     if (!strcmp(name, "gemm_cta_group")) {

@@ -175,6 +175,7 @@ struct GemmLaunch {
     int cta_group;              // 1 or 2 (tcgen05 cta_group)
     int seed_mode;              // 1: threshold seeding launch (group maxima at fixed pool slots)
     int epi_warps;              // 8 or 16 epilogue warps (hit-dense chunks want 16); anything else = 8
+    int mma_warps;              // 1 or 2 MMA-issuing threads (2: warps 1 and 3 alternate query tiles); anything else = default
     int nb_stages;              // from gemm_row_stages()
     int sm_count;
     QueryState* qstate;
