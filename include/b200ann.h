@@ -329,6 +329,7 @@ ANN_API int ann_loadtest(ann_index *ix, const float *queries, int32_t nq, int32_
 
 /* Tuning / introspection.
  * Options: "path" (0 auto, 1 streaming scan, 2 tensor-core GEMM filter, 3 exact fallback for every query), "gemm_min_batch", "gemm_cta_group" (1|2), "gemm_epi_warps" (0 auto, 8, 16),
+ *          "gemm_mma_warps" (MMA-issuing threads per CTA pair: 2 = two warps alternate query tiles, default; 1 = a single issuer),
  *          "gemm_hit_budget" (candidates one chunk may add per query, default 500), "gemm_seed_rows" (0 = default 65536),
  *          "gemm_growth_pct" (chunk growth factor in percent, 0 = derived from the hit budget),
  *          "timing" (1 = bracket every scan / GEMM-filter launch with CUDA events on its stream),

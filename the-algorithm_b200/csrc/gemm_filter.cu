@@ -15,8 +15,9 @@
 // stages only its half of both operands and the pair's tensor cores read both halves.  A row tile stays in
 // shared memory while every query tile streams past it (queries come from L2), so the shadow matrix is read
 // from HBM exactly once per batch.  Both operands are double buffered (TMA -> smem, mbarrier full/empty), the
-// accumulator is double buffered in TMEM (2 x N columns), and 16 epilogue warps drain one accumulator while
-// the next tile's MMAs run.
+// accumulator is double buffered in TMEM (2 x N columns), two threads of the leader CTA issue the MMAs of alternate
+// query tiles (one issuer alone is instruction-issue-bound, see the MMA section), and 8 or 16 epilogue warps drain one
+// accumulator while the next tile's MMAs run.
 //
 // K is not padded to the 128-byte swizzle width in HBM: a K of e.g. 208 is staged as 3 blocks of 64 (128B
 // swizzle) + 1 block of 16 (32B swizzle), each with its own tensor map / UMMA descriptor, TMA zero-filling
