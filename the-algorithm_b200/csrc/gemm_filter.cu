@@ -310,13 +310,15 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
                         ++ga;
                         continue;
                     }
-                    mbar_wait(&t_empty[s], ((gt >> 1) & 1) ^ 1);
                     const uint32_t d_tmem = tmem_base + s * N_TILE;
                     uint32_t acc = 0;
                     for (int sg = 0; sg < nseg; ++sg, ++ga) {
                         const uint32_t slot = a_resident ? (uint32_t)sg : a_slot(ga);
                         if (!a_resident) mbar_wait(&a_full[slot], a_phase(ga));
                         else if (it == 0) mbar_wait(&a_full[slot], 0);
+                        // the accumulator stage last: its hand-off from the epilogue is the round trip that paces the large
+                        // launches, the query slot is ready long before it
+                        if (sg == 0) mbar_wait(&t_empty[s], ((gt >> 1) & 1) ^ 1);
                         tc_fence_after();
                         const uint32_t a_addr = smem_u32(smA0 + (size_t)slot * a.a_slot_stride);
                         const int n64 = seg_n64(sg);
