@@ -323,13 +323,18 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
                         const uint32_t a_addr = smem_u32(smA0 + (size_t)slot * a.a_slot_stride);
                         const int n64 = seg_n64(sg);
                         const uint32_t b_seg = b_addr + (uint32_t)seg_first64(sg) * 16384u;
+                        // descriptors by addition: the start-address field is the low 14 bits (address >> 4; shared memory
+                        // is < 256 KB, so the field never carries out): +2 per 16-column step, +1024 per 64-column block
+                        uint64_t da = smem_desc(a_addr, 1024, 2), db = smem_desc(b_seg, 1024, 2);
+#pragma unroll 1
                         for (int i = 0; i < n64; ++i) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                umma_bf16<CG>(d_tmem, smem_desc(a_addr + i * 16384 + j * 32, 1024, 2),
-                                              smem_desc(b_seg + i * 16384 + j * 32, 1024, 2), idesc, acc);
+                                umma_bf16<CG>(d_tmem, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc, acc);
                                 acc = 1;
                             }
+                            da += 1024;
+                            db += 1024;
                         }
                         if (sg == nseg - 1) {
                             uint32_t a_off = (uint32_t)n64 * 16384u, b_off = (uint32_t)kb.nb64 * 16384u;
