@@ -287,10 +287,10 @@ gemm_filter_kernel(const __grid_constant__ GemmTmaps tm, const GemmArgs a) {
     } else if (warp == 1 || (warp == 3 && a.mma_warps == 2)) {
         // ================================ MMA issuer (leader CTA, one thread per issuing warp) ================================
         // ONE thread issuing every tcgen05.mma is itself the limit of this kernel: ncu's instruction sampling of the headline
-        // launch shows warp 1 busy 91 % of the time, spread evenly over the ~34 SASS instructions nvcc needs per MMA
-        // (descriptor arithmetic + an ELECT / R2UR.BROADCAST loop per operand), 3.7 clocks each -- 447 instructions per
-        // 256 x 256 x 208 tile against the 1664 clocks its 13 MMAs occupy the tensor pipe, which therefore idles ~15 %
-        // even with no hit to handle.  With mma_warps == 2 warps 1 and 3 alternate query tiles: issuer W owns accumulator
+        // launch showed warp 1 busy 91 % of the time, spread evenly over the ~34 SASS instructions nvcc then needed per
+        // MMA (descriptor arithmetic + an ELECT / R2UR.BROADCAST loop per operand; 19 since the descriptors are formed by
+        // addition below), 3.7 clocks each -- 447 instructions per 256 x 256 x 208 tile against the 1664 clocks its 13
+        // MMAs occupy the tensor pipe, which therefore idled ~15 % even with no hit to handle.  With mma_warps == 2 warps 1 and 3 alternate query tiles: issuer W owns accumulator
         // stage W and query slot W (both are the tile counter's parity), waits and commits on the same barriers as before, and
         // each has two tile times to issue one tile.  tcgen05.commit tracks the MMAs of the EXECUTING thread, so a tile's
         // t_full / a_empty commits stay exact; the row tile is released when both issuers have committed (b_empty counts 2).
