@@ -88,3 +88,13 @@ def test_every_native_the_scala_classes_call_is_declared():
 def test_stub_header_says_what_it_is():
     text = (ROOT / "tests" / "jni_stub" / "jni.h").read_text()
     assert "TEST STAND-IN, not the JDK header" in text
+
+
+def test_scala_sources_are_bracket_balanced():
+    """No scalac here: at least the brackets of the shipped Scala sources balance (comments and string literals stripped)."""
+    for f in SCALA.glob("*.scala"):
+        t = re.sub(r"//.*", "", f.read_text())
+        t = re.sub(r"/\*.*?\*/", "", t, flags=re.S)
+        t = re.sub(r's?"(\\.|[^"\\])*"', '""', t)
+        for o, c in ("()", "[]", "{}"):
+            assert t.count(o) == t.count(c), (f.name, o, t.count(o), t.count(c))
